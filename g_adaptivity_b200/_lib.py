@@ -1,0 +1,80 @@
+"""ctypes binding of the C-ABI CUDA library (`include/gadapt.h`).
+
+The library is built ahead of time by `g_adaptivity_b200/build.py` into
+`g_adaptivity_b200/libgadapt_b200.so`.  There is no fallback: if the library is missing or a
+call fails, a `RuntimeError` is raised -- the product path never computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgadapt_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gadapt.h declaration by declaration
+SIGNATURES = {
+    "gad_version": (_i, []),
+    "gad_last_error": (C.c_char_p, []),
+    "gad_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "gad_graph_workspace_bytes": (_sz, [_i64, _i64, _i64, _i]),
+    "gad_graph_build": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gad_graph_check_tiles": (_i, [_p, _p, _i64, _p, _i, _p, _p]),
+    "gad_prepare_weights": (_i, [_p, _p, _p, _i, _i, _i, _f, _p, _p]),
+    "gad_weight_grads": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
+    "gad_pack_features": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _p]),
+    "gad_deform_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "gad_deform_fwd": (_i, [_p, _p, _i64, _i64, _p, _i, _i, _i, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "gad_deform_bwd_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "gad_deform_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p,
+                            _p, _sz, _p]),
+    "gad_conv_fwd": (_i, [_p, _p, _p, _i64, _i64, _p, _i, _p, _p, _p, _p]),
+    "gad_conv_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "gad_mesh_loss": (_i, [_p, _p, _i64, _i, _f, _p, _p, _p, _p]),
+    "gad_mesh_loss_workspace_bytes": (_sz, [_i64]),
+}
+
+
+def load():
+    """Load the shared library (once) and declare every entry point of `include/gadapt.h`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m g_adaptivity_b200.build` "
+                "(there is no CPU or PyTorch fallback for the deformer hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here == header and library out of sync
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().gad_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "gadapt kernels take contiguous tensors"
+    return t.data_ptr()

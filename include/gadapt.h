@@ -1,0 +1,145 @@
+/*
+ * gadapt.h -- C ABI of the B200 (sm_100a) g-adaptivity deformer hot path.
+ *
+ * Drop-in boundary for the GNN mesh-deformer of JRowbottomGit/g-adaptivity.  The reference has no
+ * FFI of its own: its seam is the Python class surface `GNN(dataset, opt).forward(data)`
+ * (src/GNN.py:144-306) and the operator `GRAND_plusConv.forward(x, edge_index, ...)`
+ * (src/GRAND_plus.py:204-267).  These entry points are what a ctypes binding under that surface
+ * calls; the host-side mirror that does so lives in g_adaptivity_b200/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `host_`;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *     performs no allocation and no host synchronisation (callers own all buffers, including
+ *     the workspaces sized by the *_workspace_bytes queries);
+ *   - return value 0 = OK, non-zero = error (message via gad_last_error(), thread-local);
+ *   - no global mutable state: calls on distinct streams are re-entrant;
+ *   - node-state tensors are row-major [N, CE] fp32 where CE (2, 4 or 8) is the number of live
+ *     channels padded to a vector width.  With the reference's identity encoder
+ *     (src/GNN.py:75-83) channels >= in_dim are exactly zero for the whole integration, so
+ *     CE = pad(min(in_dim, hidden_dim)); the operator seam uses CE = hidden_dim.
+ *   - the q/k projections of src/GRAND_plus.py:225-226 enter the kernels as the bilinear form
+ *       s_e = <q_i, k_j> / (sqrt(C) T) = x_i^T M x_j + u^T x_j + (terms constant over the in-edges of i)
+ *     with M = c Wq^T Wk, u = c Wk^T bq, c = 1/(sqrt(C) T); the row-constant terms cancel in the
+ *     segment softmax (src/GRAND_plus.py:333), which is also why d/d(lin_key.bias) == 0.
+ */
+#ifndef GADAPT_H_
+#define GADAPT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAD_OK 0
+#define GAD_ERR_ARG 1
+#define GAD_ERR_CUDA 2
+#define GAD_ERR_UNSUPPORTED 3
+
+#define GAD_METHOD_EULER 0 /* x <- x + tau * F(x)          src/GNN.py:288-291                */
+#define GAD_METHOD_RK4 1   /* one classical RK4 step of F per layer (extension)  */
+
+/* gad_graph_build writes this many int32 values to `info` */
+#define GAD_INFO_WORDS 8
+#define GAD_INFO_E 0            /* number of edges after filtering / loops               */
+#define GAD_INFO_MAX_IN_DEG 1
+#define GAD_INFO_MAX_OUT_DEG 2
+#define GAD_INFO_CROSS_TILE 3   /* edges whose endpoints lie in different tiles (gad_graph_check_tiles) */
+
+int gad_version(void);
+const char* gad_last_error(void);
+/* Device properties the host-side planner needs (SM count, opt-in shared memory per block). */
+int gad_device_info(int* host_sm_count, int* host_smem_optin_bytes, int* host_l2_bytes);
+
+/* ---- K0: mesh-graph builder ------------------------------------------------------------
+ * Replaces the per-call prologue of GNN.forward (src/GNN.py:206-223): boolean-mask filtering of
+ * `edge_index`, appended corner self-loops, optional remove_self_loops + add_self_loops, and the
+ * scatter/gather index structures PyG derives implicitly.  Produces
+ *   filt_edge_index  int64 [2, Emax]  the edge list the reference's conv layers see, same order
+ *   rowptr/col/eid   CSR by destination, rows in STABLE edge-list order (eid = edge position)
+ *   t_rowptr/t_dst/t_slot  transpose (by source, stable) with the CSR slot of every edge
+ * Emax = E0 + K + (self_loops ? N : 0).  The edge count E lands in info[GAD_INFO_E].
+ * An edge e < E0 is dropped when any of the three masks is set (mask pointers may be NULL).
+ * `extra_loops` are K node ids that each get one self-loop appended after the kept edges.
+ */
+size_t gad_graph_workspace_bytes(int64_t E0, int64_t K, int64_t N, int self_loops);
+int gad_graph_build(const int64_t* edge_index, int64_t E0,
+                    const uint8_t* mask_to_boundary, const uint8_t* mask_to_corner,
+                    const uint8_t* mask_diff_boundary,
+                    const int64_t* extra_loops, int64_t K, int self_loops, int64_t N,
+                    int64_t* filt_edge_index, int32_t* rowptr, int32_t* col, int32_t* eid,
+                    int32_t* t_rowptr, int32_t* t_dst, int32_t* t_slot, int32_t* info,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* Counts edges that leave their tile (tile_ptr int32 [T+1], node offsets) into info[GAD_INFO_CROSS_TILE]. */
+int gad_graph_check_tiles(const int32_t* rowptr, const int32_t* col, int64_t N,
+                          const int32_t* tile_ptr, int T, int32_t* info, void* stream);
+
+/* ---- weights ----------------------------------------------------------------------------
+ * Mu[l] = { M (CE x CE, row-major, M[a][b]), u (CE) } for each of the Lw weight sets
+ * (Lw = 1 when share_conv, src/GNN.py:131-137).  Wq/Wk are [Lw, C, C] ([out, in] like
+ * torch Linear), bq [Lw, C].  Only the first min(CE, C) input columns are live.
+ */
+int gad_prepare_weights(const float* Wq, const float* bq, const float* Wk, int Lw, int C, int CE,
+                        float inv_temp, float* Mu, void* stream);
+/* Chain rule from (G_M, G_u) back to the Linear parameters; gbk is identically zero. */
+int gad_weight_grads(const float* Wq, const float* bq, const float* Wk, const float* gMu, int Lw,
+                     int C, int CE, float inv_temp, float* gWq, float* gbq, float* gWk, float* gbk,
+                     void* stream);
+
+/* ---- feature assembly (src/GNN.py:225-239 + identity encoder :75-83,270) -----------------
+ * x0[i] = [x_comp[i, 0:dim], f[i] * f_scale, uu[i] * uu_scale, 0...] truncated/padded to CE.
+ * f / uu may be NULL (feature switched off); *_scale may be NULL (= 1).
+ */
+int gad_pack_features(const float* x_comp, const float* f, const float* uu, const float* f_scale,
+                      const float* uu_scale, int64_t N, int dim, int CE, float* x0, void* stream);
+
+/* ---- deformer forward ---------------------------------------------------------------------
+ * The whole of src/GNN.py:270-299: L layers of  x <- x + tau_l (A(x) x - x)  (or RK4 steps) and
+ * the final slice to the first `dim` channels.  tau is a DEVICE array [L] (learn_step or not).
+ * tile_ptr != NULL selects the mesh-resident kernel (one CTA per tile, state in shared memory
+ * across all layers); tile_ptr == NULL selects the streaming kernels (one launch per F-eval).
+ * states (optional) receives x^0 .. x^{L-1}  as [L, N, CE] for the backward.
+ * workspace: gad_deform_workspace_bytes(N, CE, method) bytes (streaming path scratch).
+ */
+size_t gad_deform_workspace_bytes(int64_t N, int CE, int method);
+int gad_deform_fwd(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E,
+                   const int32_t* tile_ptr, int T, int max_tile_nodes, int max_tile_edges,
+                   const float* x0, int dim, int CE, const float* Mu, int Lw, const float* tau, int L,
+                   int method, float* x_phys, float* states, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ---- deformer backward (Euler) ---------------------------------------------------------------
+ * Cotangent g_xphys [N, dim] -> gMu [Lw, CE*CE+CE] (G_M, G_u), g_tau [L] (may be NULL),
+ * g_x0 [N, CE] (may be NULL).  Deterministic: no floating-point atomics.
+ * workspace: gad_deform_bwd_workspace_bytes(...) bytes.
+ */
+size_t gad_deform_bwd_workspace_bytes(int64_t N, int CE, int T, int L);
+int gad_deform_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr,
+                   const int32_t* t_dst, int64_t N, int64_t E, const int32_t* tile_ptr, int T,
+                   int max_tile_nodes, int max_tile_edges, const float* states,
+                   const float* g_xphys, int dim, int CE, const float* Mu, int Lw, const float* tau,
+                   int L, float* gMu, float* g_tau, float* g_x0, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --
+ * res = A(x) x - x  for x [N, CE];  alpha (optional) [E] in filtered edge-list order.
+ */
+int gad_conv_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t N, int64_t E,
+                 const float* x, int CE, const float* Mu, float* res, float* alpha, void* stream);
+int gad_conv_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr,
+                 const int32_t* t_dst, int64_t N, int64_t E, const float* x, const float* g_res,
+                 int CE, const float* Mu, float* gMu, float* g_x, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* ---- loss seam used by the training step (run_GNN.py:80-84,103-106): mean |out - target| or
+ * mean (out - target)^2 over N*dim entries; writes the cotangent and a per-call loss scalar. */
+int gad_mesh_loss(const float* out, const float* target, int64_t count, int kind /*0 l1, 1 mse*/,
+                  float grad_scale, float* loss, float* g_out, void* workspace, void* stream);
+size_t gad_mesh_loss_workspace_bytes(int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GADAPT_H_ */

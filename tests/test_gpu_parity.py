@@ -1,0 +1,376 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Bars (SURVEY section 4 item 3 / BASELINE north_star): graph arrays bit-exact; relocated coordinates
+max|d| / max|ref| <= 1e-5 in fp32; parameter gradients <= 1e-4 relative (lin_key.bias is
+analytically zero and is checked against an absolute bound instead).
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gad_testutil as util
+from g_adaptivity_b200 import GNN, GRAND_plusConv, MeshGraph, synth
+from g_adaptivity_b200 import functional as GF
+from oracle import gnn_oracle
+
+pytestmark = pytest.mark.gpu
+
+COORD_TOL = 1e-5
+GRAD_TOL = 1e-4
+NAMES = util.golden_names()
+
+
+def cuda_model(dataset, opt_cpu, state_dict=None, **extra):
+    opt = copy.deepcopy(opt_cpu)
+    opt["device"] = "cuda"
+    opt.update(extra)
+    m = GNN(dataset, opt).to("cuda")
+    if state_dict is not None:
+        m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+def oracle_model(dataset, opt_cpu, state_dict=None):
+    m = gnn_oracle.GNNRef(dataset, copy.deepcopy(opt_cpu))
+    if state_dict is not None:
+        m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+def grads_of(model):
+    return {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def check_grads(got, ref, tol=GRAD_TOL):
+    assert sorted(k for k in got if "lin_skip" not in k) == sorted(ref)
+    scale = max(g.abs().max().item() for n, g in ref.items() if "lin_key.bias" not in n)
+    for n, g in ref.items():
+        if "lin_key.bias" in n:
+            # analytically zero (softmax shift invariance); the reference holds rounding noise here
+            assert got[n].abs().max().item() <= 1e-4 * max(scale, 1e-12), n
+            continue
+        denom = max(g.abs().max().item(), 1e-3 * scale, 1e-12)
+        err = (got[n] - g).abs().max().item() / denom
+        assert err <= tol, (n, err)
+
+
+# --------------------------------------------------------------------------------------
+# K0: graph builder, bit-exact
+# --------------------------------------------------------------------------------------
+def _graph_case(data, opt, dim):
+    ei = gnn_oracle.filtered_edge_index(data, opt, dim)
+    N = data.x_comp.shape[0]
+    ds = synth.SyntheticDataset(dim, opt["mesh_dims"])
+    m = cuda_model(ds, opt)
+    g = m._graph(data, torch.device("cuda"))
+    assert g.E == ei.shape[1]
+    assert torch.equal(g.edge_index.cpu(), ei)
+    rowptr, col, eid = gnn_oracle.csr_by_destination(ei, N)
+    assert torch.equal(g.rowptr.cpu(), rowptr)
+    assert torch.equal(g.col.cpu(), col)
+    assert torch.equal(g.eid.cpu(), eid)
+    t_rowptr, t_dst, t_eid = gnn_oracle.csc_by_source(ei, N)
+    assert torch.equal(g.t_rowptr.cpu(), t_rowptr)
+    assert torch.equal(g.t_dst.cpu(), t_dst)
+    # t_slot links every CSC entry to the CSR slot of the same edge
+    slot_of_edge = torch.empty(ei.shape[1], dtype=torch.int64)
+    slot_of_edge[eid.long()] = torch.arange(ei.shape[1])
+    assert torch.equal(g.t_slot.cpu().long(), slot_of_edge[t_eid.long()])
+    deg = torch.diff(rowptr)
+    assert g.max_in_deg == int(deg.max())
+    return g
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_graph_builder_matches_reference_edge_list(name):
+    fx = util.load_golden(name)
+    opt = util.fixture_opt(fx)
+    data = util.fixture_batch(fx)
+    g = _graph_case(data, opt, len(fx["mesh_dims_list"][0]))
+    assert torch.equal(g.edge_index.cpu(), fx["edge_index_filtered"])
+
+
+@pytest.mark.parametrize("mesh_dims,B,over", [
+    ((30, 30), 256, {}), ((200,), 512, {}), ((50, 50), 16, {"self_loops": True}),
+    ((200, 200), 1, {}), ((17, 17), 5, {"fix_boundary": False}),
+])
+def test_graph_builder_bit_exact_at_size(mesh_dims, B, over):
+    opt = synth.default_opt(mesh_dims, **over)
+    data = synth.make_batch(mesh_dims, B, seed=1)
+    g = _graph_case(data, opt, len(mesh_dims))
+    if mesh_dims == (200, 200):
+        assert g.tile_ptr is None          # too large for one CTA -> streaming kernels
+    else:
+        assert g.tile_ptr is not None
+
+
+def test_graph_builder_empty_and_ragged_inputs():
+    dev = torch.device("cuda")
+    # no edges at all: every row empty
+    g = MeshGraph.build(torch.zeros((2, 0), dtype=torch.long), 5, device=dev)
+    assert g.E == 0 and torch.equal(g.rowptr.cpu(), torch.zeros(6, dtype=torch.int32))
+    # all edges masked away, only the appended loops survive
+    ei = torch.tensor([[0, 1, 2], [1, 2, 0]])
+    m = torch.ones(3, dtype=torch.bool)
+    g = MeshGraph.build(ei, 3, masks=(m, None, None), extra_loops=torch.tensor([2, 0]), device=dev)
+    assert g.E == 2 and g.edge_index.cpu().tolist() == [[2, 0], [2, 0]]
+    # duplicate edges and a hub row keep stable order
+    ei = torch.tensor([[3, 1, 3, 2, 1, 0, 3], [0, 0, 0, 0, 0, 0, 0]])
+    g = MeshGraph.build(ei, 4, device=dev)
+    assert g.col.cpu().tolist() == [3, 1, 3, 2, 1, 0, 3] and g.eid.cpu().tolist() == list(range(7))
+    # out-of-range node id is an error, not a crash
+    with pytest.raises(ValueError):
+        MeshGraph.build(torch.tensor([[0, 7], [1, 0]]), 3, device=dev)
+
+
+# --------------------------------------------------------------------------------------
+# deformer forward / backward against the golden fixtures (reference's own source)
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("force_stream", [False, True])
+@pytest.mark.parametrize("name", NAMES)
+def test_deformer_matches_reference_fixture(name, force_stream):
+    fx = util.load_golden(name)
+    opt = util.fixture_opt(fx)
+    data = util.fixture_batch(fx)
+    model = cuda_model(util.fixture_dataset(fx), opt, fx["state_dict"], gad_force_stream=force_stream)
+    model.train()
+    out = model(data)
+    assert out.shape == fx["x_phys"].shape
+    err = util.rel_err(out, fx["x_phys"])
+    assert err <= COORD_TOL, err
+    # attention of the last layer, reference edge order
+    conv = model.conv_layers[-1]
+    assert torch.equal(conv.stored_ei.cpu(), fx["edge_index_filtered"])
+    alpha = conv.stored_alpha.cpu()
+    assert alpha.shape == fx["alpha_last"].shape
+    assert (alpha - fx["alpha_last"]).abs().max().item() <= 2e-5
+    target = data.x_phys.cuda()
+    target = target if target.dim() == 2 else target.unsqueeze(-1)
+    loss = F.l1_loss(out, target)
+    assert abs(loss.item() - fx["loss"]) <= 1e-5 * max(abs(fx["loss"]), 1e-6)
+    loss.backward()
+    check_grads(grads_of(model), fx["grads"])
+    assert model.conv_layers[0].lin_skip.weight.grad is None
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE configs against the oracle on the same seeded inputs
+# --------------------------------------------------------------------------------------
+def _compare_with_oracle(mesh_dims, B, over=None, burgers=False, backward=True, seed=0, wscale=1.0, **extra):
+    over = over or {}
+    opt = synth.burgers_opt(mesh_dims, **over) if burgers else synth.default_opt(mesh_dims, **over)
+    dim = len(mesh_dims)
+    ds = synth.SyntheticDataset(dim, mesh_dims)
+    data = synth.make_batch(mesh_dims, B, seed=seed, burgers=burgers)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if "lin_key" in n or "lin_query" in n:
+                p.mul_(wscale)
+    model = cuda_model(ds, opt, ref.state_dict(), **extra)
+    model.train()
+    out = model(data)
+    ref_out = ref(data)
+    err = util.rel_err(out, ref_out)
+    assert err <= COORD_TOL, err
+    if backward:
+        gnn_oracle.mesh_loss(ref_out, data.x_phys).backward()
+        tgt = data.x_phys.cuda()
+        F.l1_loss(out, tgt if tgt.dim() == 2 else tgt.unsqueeze(-1)).backward()
+        check_grads(grads_of(model), {n: p.grad for n, p in ref.named_parameters() if p.grad is not None})
+    return model, out, ref_out, data
+
+
+def test_config1_15x15_single_mesh():
+    _compare_with_oracle((15, 15), 1)
+
+
+@pytest.mark.parametrize("force_stream", [False, True])
+def test_config2_30x30_batch256_fwd_bwd(force_stream):
+    model, out, ref_out, data = _compare_with_oracle((30, 30), 256, gad_force_stream=force_stream)
+    assert (model.last_graph.tile_ptr is None) == force_stream
+    # size-independent properties on the full batch
+    n = 30
+    o = out.detach().cpu().view(256, n, n, 2)
+    x = data.x_comp.view(256, n, n, 2)
+    for (iy, ix) in ((0, 0), (0, n - 1), (n - 1, 0), (n - 1, n - 1)):      # corners are fixed points
+        assert torch.equal(o[:, iy, ix], x[:, iy, ix])
+    assert o[:, :, 0, 0].abs().max() <= 1e-6 and (o[:, :, -1, 0] - 1).abs().max() <= 1e-6   # sides stay on sides
+    assert o[:, 0, :, 1].abs().max() <= 1e-6 and (o[:, -1, :, 1] - 1).abs().max() <= 1e-6
+
+
+def test_config3_burgers_1d_200_repeated_calls():
+    """Burgers roll-out pattern (src/utils_eval_Burgers.py:269,297): same graph, new uu each call."""
+    mesh_dims, B = (200,), 1024
+    opt = synth.burgers_opt(mesh_dims)
+    ds = synth.SyntheticDataset(1, mesh_dims)
+    data = synth.make_batch(mesh_dims, B, seed=0, burgers=True)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    model = cuda_model(ds, opt, ref.state_dict())
+    model.eval()
+    ref.eval()
+    rng = np.random.default_rng(0)
+    with torch.no_grad():
+        for call in range(4):
+            out = model(data)
+            ref_out = ref(data)
+            assert util.rel_err(out, ref_out) <= COORD_TOL
+            assert out.shape == (B * 200, 1)
+            # end points of every 1-D mesh are fixed (self-loop only)
+            o = out.cpu().view(B, 200)
+            assert torch.equal(o[:, 0], data.x_comp.view(B, 200)[:, 0]) and torch.equal(o[:, -1], data.x_comp.view(B, 200)[:, -1])
+            x = data.x_comp.view(B, 200).numpy()
+            amp, ph = rng.uniform(0.1, 0.3), rng.uniform(0, 1)
+            data.uu_tensor = torch.from_numpy((amp * np.exp(-((x - 0.3 - 0.1 * call - 0.05 * ph) ** 2) / 0.01)).astype(np.float32).reshape(-1))
+    assert model._graphs.misses == 1 and model._graphs.hits == 3     # topology cached across calls
+
+
+def test_config4_200x200_rk4_64_steps_forward():
+    over = {"ode_method": "rk4", "num_layers": 64}
+    model, out, ref_out, data = _compare_with_oracle((200, 200), 1, over=over, backward=False)
+    assert model.last_graph.tile_ptr is None
+
+
+def test_rk4_mesh_resident_matches_oracle():
+    over = {"ode_method": "rk4", "num_layers": 6}
+    model, *_ = _compare_with_oracle((20, 20), 7, over=over, backward=False)
+    assert model.last_graph.tile_ptr is not None
+
+
+def test_config5_slice_50x50_batch64_fwd_bwd():
+    model, *_ = _compare_with_oracle((50, 50), 64)
+    assert model.last_graph.tile_ptr is not None and model.last_graph.max_tile_nodes == 2500
+
+
+def test_scaled_weights_stress_softmax():
+    # x4 weights: logits 16x larger -> near one-hot attention; parity is still within the bar
+    _compare_with_oracle((24, 24), 8, wscale=4.0)
+
+
+def test_variable_size_batch_and_tile_packing():
+    sizes = [[5, 5], [9, 9], [30, 30], [7, 7], [12, 12], [6, 6], [20, 20]] * 3
+    opt = synth.default_opt(sizes[0])
+    ds = synth.SyntheticDataset(2, sizes[0])
+    data = synth.make_mixed_batch(sizes, seed=3)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    ref_out = ref(data)
+    gnn_oracle.mesh_loss(ref_out, data.x_phys).backward()
+    ref_grads = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    outs = []
+    for tile_nodes in (64, 512, 1024, 3000):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_tile_nodes=tile_nodes)
+        model.train()
+        out = model(data)
+        assert util.rel_err(out, ref_out) <= COORD_TOL
+        F.l1_loss(out, data.x_phys.cuda()).backward()
+        check_grads(grads_of(model), ref_grads)
+        outs.append(out.detach().cpu())
+        if model.last_graph.tile_ptr is not None:
+            tp = model.last_graph.tile_ptr.cpu().numpy()
+            bounds = np.concatenate([[0], np.cumsum([a * b for a, b in sizes])])
+            assert set(tp.tolist()) <= set(bounds.tolist())          # tiles never split a mesh
+    for o in outs[1:]:
+        assert util.rel_err(o, outs[0]) <= 1e-6      # the tiling does not change the arithmetic
+
+
+def test_run_to_run_determinism():
+    mesh_dims, B = (30, 30), 64
+    opt = synth.default_opt(mesh_dims)
+    ds = synth.SyntheticDataset(2, mesh_dims)
+    data = synth.make_batch(mesh_dims, B, seed=9)
+    res = []
+    for _ in range(3):
+        torch.manual_seed(1)
+        model = cuda_model(ds, opt)
+        model.train()
+        out = model(data)
+        F.l1_loss(out, data.x_phys.cuda()).backward()
+        res.append((out.detach().cpu(), grads_of(model)))
+    for out, gr in res[1:]:
+        assert torch.equal(out, res[0][0])
+        for n in gr:
+            assert torch.equal(gr[n], res[0][1][n]), n       # no floating-point atomics anywhere
+
+
+def test_input_gradients_match_autograd():
+    mesh_dims, B = (9, 9), 3
+    opt = synth.default_opt(mesh_dims)
+    ds = synth.SyntheticDataset(2, mesh_dims)
+    data = synth.make_batch(mesh_dims, B, seed=2)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    rd = data.clone()
+    for k in ("x_comp", "f_tensor", "uu_tensor"):
+        getattr(rd, k).requires_grad_(True)
+    gnn_oracle.mesh_loss(ref(rd), data.x_phys).backward()
+    model = cuda_model(ds, opt, ref.state_dict())
+    gd = data.clone().to("cuda")
+    for k in ("x_comp", "f_tensor", "uu_tensor"):
+        getattr(gd, k).requires_grad_(True)
+    F.l1_loss(model(gd), gd.x_phys).backward()
+    for k in ("x_comp", "f_tensor", "uu_tensor"):
+        a, b = getattr(gd, k).grad.cpu(), getattr(rd, k).grad
+        assert (a - b).abs().max().item() <= GRAD_TOL * max(b.abs().max().item(), 1e-12), k
+
+
+# --------------------------------------------------------------------------------------
+# operator seam and the loss helper
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("conv_type", ["GRAND_plus", "GRAND"])
+@pytest.mark.parametrize("C", [8, 4, 2])
+def test_operator_seam_single_layer(conv_type, C):
+    md = (12, 12)
+    opt = synth.default_opt(md, conv_type=conv_type, hidden_dim=C)
+    data = synth.make_batch(md, 3, seed=5)
+    ei = gnn_oracle.filtered_edge_index(data, opt, 2)
+    N = data.x_comp.shape[0]
+    torch.manual_seed(7)
+    x = torch.randn(N, C)
+    ref_cls = gnn_oracle.GRANDPlusConvRef if conv_type == "GRAND_plus" else gnn_oracle.GRANDConvRef
+    ref = ref_cls(copy.deepcopy(opt), C, C, heads=1)
+    from g_adaptivity_b200.GNN import get_conv
+    conv = get_conv(copy.deepcopy(opt), conv_type, C, C, 8).cuda()
+    conv.load_state_dict(ref.state_dict())
+    xr = x.clone().requires_grad_(True)
+    xg = x.clone().cuda().requires_grad_(True)
+    args = (None, None) if conv_type == "GRAND_plus" else ()
+    r_ref = ref(xr, ei, *args)
+    r_gpu = conv(xg, ei.cuda(), *args)
+    assert util.rel_err(r_gpu, r_ref) <= COORD_TOL
+    assert (conv.stored_alpha.cpu() - ref.stored_alpha).abs().max().item() <= 2e-5
+    assert torch.equal(conv.stored_ei.cpu(), ei)
+    w = torch.randn(N, C)
+    (r_ref * w).sum().backward()
+    (r_gpu * w.cuda()).sum().backward()
+    assert util.rel_err(xg.grad, xr.grad) <= GRAD_TOL
+    got = {n: p.grad.cpu() for n, p in conv.named_parameters() if p.grad is not None}
+    check_grads(got, {n: p.grad for n, p in ref.named_parameters() if p.grad is not None})
+
+
+@pytest.mark.parametrize("kind", ["l1", "mse"])
+def test_mesh_loss_kernel(kind):
+    torch.manual_seed(0)
+    a = torch.randn(100_003, 2, device="cuda")
+    b = torch.randn(100_003, 2, device="cuda")
+    loss, g = GF.mesh_loss(a, b, kind)
+    ar = a.clone().requires_grad_(True)
+    ref = F.l1_loss(ar, b) if kind == "l1" else F.mse_loss(ar, b)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (g - ar.grad).abs().max().item() <= 1e-9
+
+
+def test_no_cpu_fallback():
+    opt = synth.default_opt((6, 6))      # device='cpu'
+    m = GNN(synth.SyntheticDataset(2, (6, 6)), opt)
+    with pytest.raises(RuntimeError):
+        m(synth.make_batch((6, 6), 1))
+    conv = GRAND_plusConv(opt, 8, 8, heads=1, concat=False, bias=False, root_weight=False)
+    with pytest.raises(RuntimeError):
+        conv(torch.zeros(4, 8), torch.zeros((2, 0), dtype=torch.long))

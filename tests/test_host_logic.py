@@ -1,0 +1,151 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import g_adaptivity_b200 as gad
+from g_adaptivity_b200 import _lib, build as gad_build, graph, synth
+from g_adaptivity_b200 import functional as GF
+from g_adaptivity_b200 import params as gparams
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    gad_build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "gadapt.h")).read()
+    declared = set(re.findall(r"\b(gad_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in gadapt.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.gad_version() >= 100
+
+
+def test_workspace_queries_need_no_gpu(lib):
+    assert lib.gad_graph_workspace_bytes(1000, 4, 225, 0) > 0
+    assert lib.gad_graph_workspace_bytes(1000, 4, 225, 1) > lib.gad_graph_workspace_bytes(1000, 4, 225, 0)
+    a = lib.gad_deform_workspace_bytes(1000, 4, 0)
+    b = lib.gad_deform_workspace_bytes(1000, 4, 1)
+    assert b > a >= 2 * 1000 * 4 * 4
+
+
+def test_argument_errors_are_reported_not_crashed(lib):
+    rc = lib.gad_prepare_weights(None, None, None, 1, 8, 4, 1.0, None, None)
+    assert rc == 1 and b"null" in lib.gad_last_error()
+    rc = lib.gad_deform_fwd(None, None, 10, 10, None, 0, 0, 0, None, 2, 3, None, 1, None, 4, 0, None, None, None, 0, None)
+    assert rc != 0
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    opt = synth.default_opt((6, 6), device="cuda")
+    model = gad.GNN(synth.SyntheticDataset(2, (6, 6)), opt)
+    with pytest.raises((RuntimeError, AssertionError)):
+        model(synth.make_batch((6, 6), 1))
+    opt = synth.default_opt((6, 6), device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gad.GNN(synth.SyntheticDataset(2, (6, 6)), opt)(synth.make_batch((6, 6), 1))
+    with pytest.raises(RuntimeError):
+        GF.pack_features(torch.zeros(4, 2), None, None, None, None, 4)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "g_adaptivity_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_plan_tiles():
+    tp = graph.plan_tiles([900] * 5, target_nodes=1024)
+    assert tp.tolist() == [0, 900, 1800, 2700, 3600, 4500]
+    tp = graph.plan_tiles([200] * 11, target_nodes=1024)
+    assert tp.tolist() == [0, 1000, 2000, 2200]
+    tp = graph.plan_tiles([25, 2500, 49, 36], target_nodes=1024)
+    assert tp.tolist() == [0, 25, 2525, 2610]
+    assert graph.plan_tiles([40000], target_nodes=1024) is None        # single 200x200 mesh -> streaming
+    assert graph.plan_tiles([], target_nodes=1024).tolist() == [0]
+    # the shared-memory model mirrors csrc/fused_kernels.cu (50x50, CE=4 fits one CTA on B200)
+    assert graph._bwd_smem_bytes(2500, 14212, 4) < 227 * 1024
+    assert graph._bwd_smem_bytes(3072, 18000, 4) > 227 * 1024
+
+
+def test_live_channels():
+    assert GF.live_channels(4, 8) == (4, 4)
+    assert GF.live_channels(2, 8) == (2, 2)
+    assert GF.live_channels(3, 8) == (3, 4)
+    assert GF.live_channels(4, 2) == (2, 2)
+    assert GF.live_channels(8, 8) == (8, 8)
+    with pytest.raises(NotImplementedError):
+        GF.live_channels(20, 16)
+
+
+def test_model_surface_matches_reference_contract():
+    opt = synth.default_opt((15, 15), device="cuda", learn_step=True)
+    m = gad.GNN(synth.SyntheticDataset(2, (15, 15)), opt)
+    keys = set(m.state_dict())
+    assert "enc.weight" in keys and {f"steps.{i}" for i in range(4)} <= keys
+    for i in range(4):
+        for leaf in ("lin_key.weight", "lin_key.bias", "lin_query.weight", "lin_query.bias", "lin_skip.weight"):
+            assert f"conv_layers.{i}.{leaf}" in keys
+    assert m.conv_layers[0] is m.conv_layers[3]          # share_conv: one instance (GNN.py:131-137)
+    assert not m.enc.weight.requires_grad
+    assert opt["hidden_dims_list"] == [2, 1, 1]           # written back (GNN.py:161)
+    assert torch.equal(m.enc.weight, torch.eye(8, 4))
+    # a reference state_dict (golden fixture) loads strictly
+    import gad_testutil as util
+    fx = util.load_golden("learn_step_6x6")
+    m.load_state_dict(fx["state_dict"], strict=True)
+    m2 = gad.GNN(synth.SyntheticDataset(2, (6, 6)), synth.default_opt((6, 6), share_conv=False, num_layers=3))
+    assert m2.conv_layers[0] is not m2.conv_layers[1]
+
+
+@pytest.mark.parametrize("over,exc", [
+    ({"conv_type": "GCN"}, NotImplementedError), ({"conv_type": "GAT_plus"}, NotImplementedError),
+    ({"enc": "lin_layer"}, NotImplementedError), ({"dropout": 0.5}, NotImplementedError),
+    ({"gnn_inc_glob_feat_f": True}, NotImplementedError), ({"loss_type": "pde_loss"}, NotImplementedError),
+    ({"reg_skew": True}, NotImplementedError), ({"softmax_temp_type": "learnable_a"}, NotImplementedError),
+    ({"residual": False}, NotImplementedError), ({"ode_method": "dopri5"}, ValueError),
+])
+def test_unsupported_options_raise(over, exc):
+    opt = synth.default_opt((6, 6), **over)
+    with pytest.raises(exc):
+        gad.GNN(synth.SyntheticDataset(2, (6, 6)), opt)
+
+
+def test_params_mirror_defaults_and_presets():
+    opt = gparams.get_params([])
+    assert opt["hidden_dim"] == 8 and opt["num_layers"] == 4 and opt["time_step"] == 0.1
+    assert opt["fix_boundary"] == "True" and opt["softmax_temp_type"] is None and opt["mesh_dims"] == [10, 10]
+    opt = gparams.tf_sweep_args(opt)
+    assert opt["fix_boundary"] is True and opt["self_loops"] is False and opt["show_mesh_evol_plots"] is True
+    opt = gparams.run_params(opt)
+    assert opt["conv_type"] == "GRAND_plus" and opt["mesh_dims"] == [11, 11] and opt["gnn_inc_feat_uu"] is True
+    assert opt["gnn_inc_glob_feat_f"] is False and opt["share_conv"] is True and opt["enc"] == "identity"
+    b = gparams.run_params(gparams.tf_sweep_args(gparams.get_params(["--pde_type", "Burgers"])))
+    assert b["conv_type"] == "GRAND" and b["mesh_dims"] == [21] and b["gnn_inc_feat_f"] is False
+    assert b["loss_type"] == "modular" and b["num_eval_time_steps"] == 20
+    assert gparams.get_arg_list([15, 15]) == [15, 15] and gparams.get_arg_list(["[20, 20]"]) == [20, 20]
+    o = gparams.get_params(["--mesh_dims", "30", "30", "--ode_method", "rk4"])
+    assert o["ode_method"] == "rk4"
+
+
+def test_corner_loops_follow_reference_order():
+    data = synth.make_batch((5, 5), 3)
+    ids = graph.corner_loops(data, 2, [5, 5], [25, 25, 25]).tolist()
+    assert ids == [0, 4, 20, 24, 25, 29, 45, 49, 50, 54, 70, 74]
+    d1 = synth.make_batch((7,), 2)
+    assert graph.corner_loops(d1, 1, [7], [7, 7]).tolist() == [0, 6, 7, 13]
