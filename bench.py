@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Headline benchmark: mesh-nodes/s through the deformer forward+backward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): batched 2D 30x30 meshes, batch 256 per GPU, 4 Euler layers,
+hidden 8, fp32, L1 mesh loss -- one STEP is one full training pass over one batch:
+pack features -> fold weights -> fused forward -> loss/cotangent -> fused backward -> weight
+gradients -> [NCCL gradient all-reduce when N > 1] -> Adam.  Weak scaling: every rank owns its
+own 256-mesh shard (no data-path collective).
+
+L2 hygiene: the timed loop walks a ring of R distinct resident batches (own features, own graph
+arrays) whose read-only footprint exceeds the 126 MB L2 several times over, so no step finds
+its inputs in L2 ("config.l2").
+
+Printed JSON (rank 0, one line): `value` = nodes/s with inputs resident in HBM (CUDA-graph
+replay, device-timed, max over ranks); `e2e` = the same step driven from pinned HOST buffers
+through `DeformerTrainer.step_from_host` (H2D of features/targets and D2H of the loss inside the
+timed region); `roofline` = algorithmic bytes of the dominant kernel (fused backward) / its
+CUDA-event duration against the measured HBM peak; `cpu_baseline` = the CPU oracle (port of the
+reference path) timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+MESH_DIMS = (30, 30)
+MESHES_PER_GPU = 256
+NUM_LAYERS = 4
+METRIC = "mesh_nodes_per_sec_deformer_fwd_bwd"
+UNIT = "nodes/s"
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic bytes: per node per F-evaluation, fp32 state, int32 indices
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(n_nodes: int, n_edges: int, c_eff: int, L: int, in_dim: int, dim: int):
+    dbar = n_edges / n_nodes
+    b_f = 8 * c_eff + 4 * dbar + 4
+    b_b = 12 * c_eff + 2 * (4 * dbar + 4)
+    fwd = L * b_f + 4 * in_dim + 4 * dim
+    bwd = L * b_b + 4 * dim
+    return {"dbar": dbar, "fwd_per_node": fwd, "bwd_per_node": bwd, "step_per_node": fwd + bwd}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.t0 = self.t1 = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self, start: bool):
+        if start:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        lo = (self.t0 or 0) - 0.05
+        hi = (self.t1 or time.time()) + 0.05
+        rows = [r for t, r in self.rows if lo <= t <= hi] or [r for _, r in self.rows]
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------
+def time_cpu_oracle(steps: int, warmup: int, budget_s: float = 25.0):
+    """fwd + L1 loss + autograd backward of the CPU oracle (pure-PyTorch port of the reference
+    path; PyG itself is not installable here) on the full 256-mesh batch, all host threads."""
+    import copy
+    from g_adaptivity_b200 import synth
+    from oracle import gnn_oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    opt = synth.default_opt(MESH_DIMS, num_layers=NUM_LAYERS)
+    ds = synth.SyntheticDataset(2, MESH_DIMS)
+    data = synth.make_batch(MESH_DIMS, MESHES_PER_GPU, seed=0)
+    torch.manual_seed(42)
+    model = gnn_oracle.GNNRef(ds, copy.deepcopy(opt))
+    model.train()
+    n_nodes = data.x_comp.shape[0]
+
+    def one():
+        model.zero_grad(set_to_none=True)
+        out = model(data)
+        gnn_oracle.mesh_loss(out, data.x_phys).backward()
+
+    for _ in range(max(1, warmup)):
+        one()
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": n_nodes / (ms * 1e-3), "ms_per_step": ms, "cores": cores, "steps": len(times),
+            "sample": f"{MESHES_PER_GPU} meshes of {MESH_DIMS[0]}x{MESH_DIMS[1]} ({n_nodes} nodes), "
+                      f"fwd + L1 loss + autograd bwd, torch CPU {torch.get_num_threads()} threads, "
+                      f"mean of {len(times)} steps"}
+
+
+def run_reference(args, rank: int, world: int):
+    """Reference arm: the reference's CPU implementation of the path.  The reference itself cannot
+    run here (torch_geometric / Firedrake absent), so this times the oracle port."""
+    if rank != 0:
+        return
+    r = time_cpu_oracle(min(args.steps, 40), min(args.warmup, 3), budget_s=90.0)
+    n_nodes = MESHES_PER_GPU * MESH_DIMS[0] * MESH_DIMS[1]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2: {MESHES_PER_GPU} x {MESH_DIMS[0]}x{MESH_DIMS[1]} meshes, fwd+bwd, L={NUM_LAYERS}, hidden 8",
+                   "nodes_per_step": n_nodes, "device": "host CPU"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ring", type=int, default=16, help="distinct resident batches walked by the timed loop")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from g_adaptivity_b200 import GNN, _lib, synth
+    from g_adaptivity_b200.trainer import DeformerTrainer
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the deformer has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    R = max(1, args.ring)
+
+    # ---- workload ----------------------------------------------------------------------
+    opt = synth.default_opt(MESH_DIMS, num_layers=NUM_LAYERS, device=str(dev), gad_store_alpha=False)
+    ds = synth.SyntheticDataset(2, MESH_DIMS)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev)
+    trainer = DeformerTrainer(model, use_cuda_graph=not args.no_graph)
+    trainer.broadcast_parameters()
+    host_batches = []
+    for r in range(R):
+        first = (rank * R + r) * MESHES_PER_GPU
+        b = synth.make_batch(MESH_DIMS, MESHES_PER_GPU, seed=1000, first_mesh_id=first)
+        b.pin_memory()
+        host_batches.append(b)
+        trainer.add_batch(b)
+    s0 = trainer.slots[0]
+    n_nodes, n_edges = s0.N, s0.graph.E
+    in_dim = sum(model.in_dims)
+    ab = algorithmic_bytes(n_nodes, n_edges, model.live, NUM_LAYERS, in_dim, model.dim)
+    ro_bytes = sum(t.numel() * t.element_size() for s in trainer.slots for t in
+                   (s.x_comp, s.f, s.uu, s.target, s.graph.rowptr, s.graph.col, s.graph.t_rowptr, s.graph.t_dst))
+    lib = _lib.load()
+
+    if not args.no_graph:
+        for sid in range(R):
+            trainer.capture(sid)
+    trainer.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+
+    # ---- device-resident timing: W warm-up + exactly K timed steps -------------------------
+    for i in range(W):
+        trainer.step(i % R)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.gad_launch_count()
+    clocks.mark(True)
+    ev0.record(trainer.stream)
+    for i in range(K):
+        trainer.step(i % R)
+    ev1.record(trainer.stream)
+    barrier()
+    clocks.mark(False)
+    ms_total = ev0.elapsed_time(ev1)
+    eager_launches = lib.gad_launch_count() - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * n_nodes / (ms_step * 1e-3)
+
+    # kernels per step: counted once from an eager issue of the same step
+    l0 = lib.gad_launch_count()
+    trainer._issue(s0, trainer.stream.cuda_stream)
+    trainer.synchronize()
+    launches_per_step = lib.gad_launch_count() - l0
+    gpu_launches = int(launches_per_step * K) if not args.no_graph else int(eager_launches)
+
+    # ---- dominant-kernel timing (CUDA events on the launching stream, eager issue) ----------
+    kt = {"fwd": [], "bwd": []}
+    P = _lib.ptr
+    nk = min(max(K, 20), 200)
+    evs = []
+    for i in range(nk):
+        s = trainer.slots[i % R]
+        g = s.graph
+        st = trainer.stream.cuda_stream
+        with torch.cuda.stream(trainer.stream):
+            lib.gad_prepare_weights(P(trainer.Wq), P(trainer.bq), P(trainer.Wk), trainer.Lw, trainer.C, trainer.CE,
+                                    model.inv_temp, P(trainer.Mu), st)
+            lib.gad_pack_features(P(s.x_comp), P(s.f), P(s.uu), None, None, s.N, model.dim, trainer.CE, P(s.states), st)
+            a0, a1, b0, b1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            a0.record(trainer.stream)
+            lib.gad_deform_fwd(P(g.rowptr), P(g.col), s.N, g.E, P(g.tile_ptr), g.T, g.max_tile_nodes, g.max_tile_edges,
+                               P(s.states), model.dim, trainer.CE, P(trainer.Mu), trainer.Lw, P(trainer.tau), trainer.L, 0,
+                               P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, st)
+            a1.record(trainer.stream)
+            lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * model.dim, 0, 1.0 / (s.N * model.dim), P(s.loss), P(s.g_out),
+                              P(s.loss_ws), st)
+            b0.record(trainer.stream)
+            lib.gad_deform_bwd(P(g.rowptr), P(g.col), P(g.t_rowptr), P(g.t_dst), s.N, g.E, P(g.tile_ptr), g.T,
+                               g.max_tile_nodes, g.max_tile_edges, P(s.states), P(s.g_out), model.dim, trainer.CE,
+                               P(trainer.Mu), trainer.Lw, P(trainer.tau), trainer.L, P(trainer.gMu), P(trainer.gtau), None,
+                               P(s.bwd_ws), s.bwd_ws_bytes, st)
+            b1.record(trainer.stream)
+        evs.append((a0, a1, b0, b1))
+    trainer.synchronize()
+    for a0, a1, b0, b1 in evs[5:]:
+        kt["fwd"].append(a0.elapsed_time(a1))
+        kt["bwd"].append(b0.elapsed_time(b1))
+    fwd_ms, bwd_ms = statistics.median(kt["fwd"]), statistics.median(kt["bwd"])
+    peak, peak_src = measured_peaks()
+    bwd_bytes = ab["bwd_per_node"] * n_nodes
+    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_fused_bwd (+k_fused_reduce)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bwd_bytes, "kernel_ms": bwd_ms,
+                "fwd_kernel_ms": fwd_ms, "fwd_achieved_gbs": ab["fwd_per_node"] * n_nodes / (fwd_ms * 1e-3) / 1e9,
+                "step_bytes_per_node": ab["step_per_node"],
+                "step_frac": (value / world) * ab["step_per_node"] / 1e9 / peak,
+                "timing": "CUDA events on the launching stream around the kernel, median of eager launches after the timed region"}
+
+    # ---- end-to-end: pinned host buffers in, loss out, every step --------------------------
+    e2e = None
+    if not args.skip_e2e:
+        ke = min(K, 300)
+        for i in range(3):
+            trainer.step_from_host(i % R, host_batches[i % R])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            trainer.step_from_host(i % R, host_batches[i % R])
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * n_nodes * ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(s0.h2d_bytes),
+               "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * dt / ke, "steps": ke,
+               "api": "DeformerTrainer.step_from_host (pinned H2D of x_comp/f/uu/target, graph replay, D2H loss)"}
+
+    clk = clocks.stop() if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and not args.skip_cpu:
+        r = time_cpu_oracle(steps=20, warmup=1, budget_s=20.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "ms_per_step": r["ms_per_step"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"cfg2: {MESHES_PER_GPU} x {MESH_DIMS[0]}x{MESH_DIMS[1]} meshes per GPU, fwd+bwd train step "
+                            f"(L={NUM_LAYERS} Euler layers, hidden 8, L1 mesh loss, Adam"
+                            + (", NCCL grad all-reduce" if world > 1 else "") + ")",
+                "nodes_per_step_per_gpu": n_nodes, "edges_per_step_per_gpu": n_edges, "live_channels": model.live,
+                "l2": f"ring of {R} distinct resident batches, {ro_bytes / 1e6:.0f} MB read-only inputs (> 126 MB L2)",
+                "launch": "eager" if args.no_graph else "cuda-graph replay",
+                "tiles": s0.graph.T, "max_tile_nodes": s0.graph.max_tile_nodes,
+            },
+            "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": int(launches_per_step),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

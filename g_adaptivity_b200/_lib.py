@@ -26,6 +26,7 @@ _sz = C.c_size_t
 SIGNATURES = {
     "gad_version": (_i, []),
     "gad_last_error": (C.c_char_p, []),
+    "gad_launch_count": (C.c_longlong, []),
     "gad_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "gad_graph_workspace_bytes": (_sz, [_i64, _i64, _i64, _i]),
     "gad_graph_build": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -42,6 +43,7 @@ SIGNATURES = {
     "gad_conv_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "gad_mesh_loss": (_i, [_p, _p, _i64, _i, _f, _p, _p, _p, _p]),
     "gad_mesh_loss_workspace_bytes": (_sz, [_i64]),
+    "gad_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p, _p]),
 }
 
 

@@ -2,6 +2,8 @@
 // mesh-resident kernels (fused_kernels.cu) and the streaming kernels (stream_kernels.cu).
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace gad {
@@ -14,6 +16,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static int g_sm_count = 0, g_smem_optin = 0, g_l2 = 0;
 
@@ -66,6 +71,8 @@ using namespace gad;
 extern "C" int gad_version(void) { return 100; }
 
 extern "C" const char* gad_last_error(void) { return g_err; }
+
+extern "C" long long gad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int gad_device_info(int* host_sm_count, int* host_smem_optin_bytes, int* host_l2_bytes) {
     int n = 0;

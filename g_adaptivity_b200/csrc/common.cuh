@@ -11,6 +11,7 @@
 namespace gad {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n);   // host-side tally of kernel launches issued by this library
 
 #define GAD_CHECK_ARG(cond, ...)            \
     do {                                    \
@@ -32,6 +33,7 @@ void set_error(const char* fmt, ...);
 
 #define GAD_LAUNCH_CHECK()                                                               \
     do {                                                                                 \
+        gad::count_launch(1);                                                            \
         cudaError_t err__ = cudaGetLastError();                                          \
         if (err__ != cudaSuccess) {                                                      \
             gad::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,     \

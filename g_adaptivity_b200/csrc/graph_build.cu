@@ -108,6 +108,7 @@ cudaError_t exclusive_scan(const int32_t* in, int32_t* out, int64_t n, int32_t* 
     k_scan_tile<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, sums, n);
     k_scan_sums<<<1, 1024, 0, st>>>(sums, tiles, total);
     k_scan_add<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(out, sums, n, nullptr);
+    count_launch(3);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,241 @@
+"""Data-parallel training step of the deformer, CUDA-graph captured.
+
+The reference trains with the loop of `src/run_GNN.py:95-131` (forward, L1 mesh loss, autograd
+backward, `torch.optim.Adam`), single process.  `DeformerTrainer` runs the same step as one
+replayable CUDA graph per resident batch ("slot"):
+
+    pack features -> fold weights (M, u) -> fused forward -> loss + cotangent -> fused backward
+    -> weight gradients -> [gradient all-reduce over NCCL] -> Adam
+
+Sharding: a batch is a disjoint union of meshes, so ranks take contiguous shards of
+whole meshes with no data-path collective; the only exchange is the all-reduce of the flat
+gradient (144 + L floats).  The mesh loss is a mean over ALL nodes of the global batch
+(`F.l1_loss`, run_GNN.py:80-84): every rank scales its cotangent by 1/(count_local * world) and
+the all-reduce sums.
+
+The model's parameters are re-pointed at views of one flat buffer (as DDP buckets do), so the
+kernels, the all-reduce and Adam all work on contiguous memory and `model.state_dict()` /
+`load_state_dict()` keep working unchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import functional as GF
+from .GNN import GNN
+
+
+class _Slot:
+    """Device-resident inputs, outputs and scratch of one batch."""
+    pass
+
+
+class DeformerTrainer:
+    def __init__(self, model: GNN, lr: Optional[float] = None, weight_decay: Optional[float] = None,
+                 betas=(0.9, 0.999), eps: float = 1e-8, loss_fn: Optional[str] = None,
+                 process_group=None, use_cuda_graph: bool = True):
+        self.model = model
+        opt = model.opt
+        self.opt = opt
+        self.dev = model._device()
+        self.lr = float(opt.get("lr", 1e-3) if lr is None else lr)
+        self.wd = float(opt.get("decay", 0.0) if weight_decay is None else weight_decay)
+        self.betas, self.eps = betas, eps
+        self.loss_kind = (opt.get("loss_fn", "l1") if loss_fn is None else loss_fn)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graph = use_cuda_graph
+        self.L = int(opt["num_layers"])
+        self.Lw = 1 if opt["share_conv"] else self.L
+        self.C = int(opt["hidden_dim"])
+        self.CE = model.CE
+        self.dim = model.dim
+        self.method = GF.METHODS[opt.get("ode_method", "euler")]
+        if self.method != GF.METHOD_EULER:
+            raise NotImplementedError("training through ode_method='rk4' is not implemented")
+        self._flatten_parameters()
+        self.slots: List[_Slot] = []
+        self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.lib = _lib.load()
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    # ------------------------------------------------------------------------------------
+    def _flatten_parameters(self):
+        """flat = [Wq (Lw,C,C) | bq (Lw,C) | Wk (Lw,C,C) | bk (Lw,C) | steps (L, if learn_step)]."""
+        m, Lw, C = self.model, self.Lw, self.C
+        convs = [m.conv_layers[0]] if self.opt["share_conv"] else list(m.conv_layers)
+        nW, nb = Lw * C * C, Lw * C
+        nsteps = self.L if self.opt["learn_step"] else 0
+        n = 2 * nW + 2 * nb + nsteps
+        flat = torch.empty(n, dtype=torch.float32, device=self.dev)
+        gflat = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        o = 0
+        self.Wq = flat[o:o + nW].view(Lw, C, C); self.gWq = gflat[o:o + nW].view(Lw, C, C); o += nW
+        self.bq = flat[o:o + nb].view(Lw, C); self.gbq = gflat[o:o + nb].view(Lw, C); o += nb
+        self.Wk = flat[o:o + nW].view(Lw, C, C); self.gWk = gflat[o:o + nW].view(Lw, C, C); o += nW
+        self.bk = flat[o:o + nb].view(Lw, C); self.gbk = gflat[o:o + nb].view(Lw, C); o += nb
+        with torch.no_grad():
+            for l, c in enumerate(convs):
+                for view, gview, p in ((self.Wq, self.gWq, c.lin_query.weight), (self.bq, self.gbq, c.lin_query.bias),
+                                       (self.Wk, self.gWk, c.lin_key.weight), (self.bk, self.gbk, c.lin_key.bias)):
+                    view[l].copy_(p.detach().to(self.dev))
+                    p.data = view[l]
+                    p.grad = gview[l]
+            if nsteps:
+                self.tau = flat[o:o + nsteps]
+                self.gtau = gflat[o:o + nsteps]
+                for l, s in enumerate(m.steps):
+                    self.tau[l:l + 1].copy_(s.detach().to(self.dev).reshape(1))
+                    s.data = self.tau[l:l + 1]
+                    s.grad = self.gtau[l:l + 1]
+            else:
+                self.tau = torch.full((self.L,), float(self.opt["time_step"]), dtype=torch.float32, device=self.dev)
+                self.gtau = None
+        self.flat, self.gflat = flat, gflat
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.Mu = torch.empty((Lw, self.CE * self.CE + self.CE), dtype=torch.float32, device=self.dev)
+        self.gMu = torch.empty_like(self.Mu)
+
+    def broadcast_parameters(self, src: int = 0):
+        if self.world > 1:
+            dist.broadcast(self.flat, src=src, group=self.pg)
+
+    # ------------------------------------------------------------------------------------
+    def add_batch(self, data) -> int:
+        """Make `data` (host or device Batch) resident: build/cached graph, static input buffers,
+        saved-state and scratch buffers.  Returns the slot id."""
+        m, dev, lib = self.model, self.dev, self.lib
+        s = _Slot()
+        with torch.cuda.device(dev):
+            s.graph = m._graph(data, dev)
+            N = s.graph.N
+            s.N = N
+            f32 = dict(dtype=torch.float32, device=dev)
+            xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
+            s.x_comp = torch.empty((N, self.dim), **f32)
+            s.f = torch.empty(N, **f32) if self.opt["gnn_inc_feat_f"] else None
+            s.uu = torch.empty(N, **f32) if self.opt["gnn_inc_feat_uu"] else None
+            s.target = torch.empty((N, self.dim), **f32)
+            s.states = torch.empty((self.L, N, self.CE), **f32)
+            s.x_phys = torch.empty((N, self.dim), **f32)
+            s.g_out = torch.empty((N, self.dim), **f32)
+            s.loss = torch.zeros(1, **f32)
+            s.loss_ws = torch.empty(lib.gad_mesh_loss_workspace_bytes(N * self.dim), dtype=torch.uint8, device=dev)
+            T = s.graph.T if s.graph.tile_ptr is not None else 0
+            s.bwd_ws_bytes = lib.gad_deform_bwd_workspace_bytes(N, self.CE, T, self.L)
+            s.bwd_ws = torch.empty(s.bwd_ws_bytes, dtype=torch.uint8, device=dev)
+            s.fwd_ws_bytes = 0 if T else lib.gad_deform_workspace_bytes(N, self.CE, self.method)
+            s.fwd_ws = torch.empty(max(s.fwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
+            s.h2d_bytes = 0
+        self.slots.append(s)
+        sid = len(self.slots) - 1
+        self.load_inputs(sid, data)
+        return sid
+
+    def load_inputs(self, sid: int, data, non_blocking: bool = True):
+        """Copy one batch's node features and target mesh (host, ideally pinned) into the slot."""
+        s = self.slots[sid]
+        xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
+        tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
+        nbytes = 0
+        with torch.cuda.stream(self.stream):
+            s.x_comp.copy_(xc, non_blocking=non_blocking); nbytes += xc.numel() * 4
+            s.target.copy_(tg, non_blocking=non_blocking); nbytes += tg.numel() * 4
+            if s.f is not None:
+                s.f.copy_(data.f_tensor, non_blocking=non_blocking); nbytes += data.f_tensor.numel() * 4
+            if s.uu is not None:
+                s.uu.copy_(data.uu_tensor, non_blocking=non_blocking); nbytes += data.uu_tensor.numel() * 4
+        s.h2d_bytes = nbytes
+        return nbytes
+
+    # ------------------------------------------------------------------------------------
+    def _issue(self, s: _Slot, stream_ptr: int, with_optimizer: bool = True, stage: str = "all"):
+        """Enqueue the kernels of one training step on `stream_ptr` (captured or eager)."""
+        lib, P, chk = self.lib, _lib.ptr, _lib.check
+        g = s.graph
+        CE, L, Lw, C, dim = self.CE, self.L, self.Lw, self.C, self.dim
+        tiles = g.tile_ptr is not None and not self.opt.get("gad_force_stream", False)
+        inv_temp = self.model.inv_temp
+        if stage in ("all", "pre"):
+            chk(lib.gad_prepare_weights(P(self.Wq), P(self.bq), P(self.Wk), Lw, C, CE, inv_temp, P(self.Mu), stream_ptr),
+                "gad_prepare_weights")
+            chk(lib.gad_pack_features(P(s.x_comp), P(s.f), P(s.uu), None, None, s.N, dim, CE, P(s.states), stream_ptr),
+                "gad_pack_features")
+            chk(lib.gad_deform_fwd(P(g.rowptr), P(g.col), s.N, g.E, P(g.tile_ptr) if tiles else None, g.T if tiles else 0,
+                                   g.max_tile_nodes, g.max_tile_edges, P(s.states), dim, CE, P(self.Mu), Lw, P(self.tau), L,
+                                   self.method, P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, stream_ptr),
+                "gad_deform_fwd")
+            chk(lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * dim, 0 if self.loss_kind == "l1" else 1,
+                                  1.0 / (s.N * dim * self.world), P(s.loss), P(s.g_out), P(s.loss_ws), stream_ptr),
+                "gad_mesh_loss")
+            chk(lib.gad_deform_bwd(P(g.rowptr), P(g.col), P(g.t_rowptr), P(g.t_dst), s.N, g.E,
+                                   P(g.tile_ptr) if tiles else None, g.T if tiles else 0, g.max_tile_nodes,
+                                   g.max_tile_edges, P(s.states), P(s.g_out), dim, CE, P(self.Mu), Lw, P(self.tau), L,
+                                   P(self.gMu), P(self.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, stream_ptr),
+                "gad_deform_bwd")
+            chk(lib.gad_weight_grads(P(self.Wq), P(self.bq), P(self.Wk), P(self.gMu), Lw, C, CE, inv_temp, P(self.gWq),
+                                     P(self.gbq), P(self.gWk), P(self.gbk), stream_ptr), "gad_weight_grads")
+        if stage in ("all", "post") and with_optimizer:
+            b1, b2 = self.betas
+            chk(lib.gad_adam_step(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.flat.numel(),
+                                  self.lr, b1, b2, self.eps, self.wd, 1.0, P(self.step_count), stream_ptr),
+                "gad_adam_step")
+
+    def _allreduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def capture(self, sid: int):
+        """Capture the step of slot `sid` into a CUDA graph (gradient all-reduce included)."""
+        s = self.slots[sid]
+        with torch.cuda.device(self.dev):
+            # warm up on the side stream (first-call attribute setting, NCCL communicator set-up)
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(self.stream):
+                saved = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_count)]
+                for _ in range(2):
+                    self._issue(s, self.stream.cuda_stream, stage="pre")
+                    self._allreduce()
+                    self._issue(s, self.stream.cuda_stream, stage="post")
+                for t, v in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_count), saved):
+                    t.copy_(v)
+            self.stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                cs = torch.cuda.current_stream(self.dev).cuda_stream
+                self._issue(s, cs, stage="pre")
+                self._allreduce()
+                self._issue(s, cs, stage="post")
+            self.graphs[sid] = g
+
+    def step(self, sid: int):
+        """One training step on the resident batch `sid` (asynchronous; loss stays on the device)."""
+        if self.use_graph:
+            if sid not in self.graphs:
+                self.capture(sid)
+            with torch.cuda.stream(self.stream):
+                self.graphs[sid].replay()
+        else:
+            with torch.cuda.stream(self.stream):
+                s = self.slots[sid]
+                self._issue(s, self.stream.cuda_stream, stage="pre")
+                self._allreduce()
+                self._issue(s, self.stream.cuda_stream, stage="post")
+        return self.slots[sid].loss
+
+    def step_from_host(self, sid: int, data) -> float:
+        """End-to-end step: host (pinned) inputs -> device, train step, loss back to the host."""
+        self.load_inputs(sid, data)
+        loss = self.step(sid)
+        with torch.cuda.stream(self.stream):
+            out = loss.to("cpu", non_blocking=False)
+        return float(out)
+
+    def synchronize(self):
+        self.stream.synchronize()

@@ -50,6 +50,8 @@ extern "C" {
 
 int gad_version(void);
 const char* gad_last_error(void);
+/* Number of kernel launches this library has issued (or captured into a CUDA graph) so far. */
+long long gad_launch_count(void);
 /* Device properties the host-side planner needs (SM count, opt-in shared memory per block). */
 int gad_device_info(int* host_sm_count, int* host_smem_optin_bytes, int* host_l2_bytes);
 
@@ -138,6 +140,14 @@ int gad_conv_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_row
 int gad_mesh_loss(const float* out, const float* target, int64_t count, int kind /*0 l1, 1 mse*/,
                   float grad_scale, float* loss, float* g_out, void* workspace, void* stream);
 size_t gad_mesh_loss_workspace_bytes(int64_t count);
+
+/* ---- optimiser step on the flat parameter vector (run_GNN.py:88,128,131: torch.optim.Adam) ----
+ * torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected moments).
+ * `step` is a DEVICE int64 counter incremented by the kernel, so the call is CUDA-graph replayable.
+ * grad_scale multiplies the gradient first (e.g. 1/world after a SUM all-reduce). */
+int gad_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                  int64_t* step, void* stream);
 
 #ifdef __cplusplus
 }

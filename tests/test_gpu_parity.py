@@ -192,7 +192,7 @@ def test_config1_15x15_single_mesh():
 @pytest.mark.parametrize("force_stream", [False, True])
 def test_config2_30x30_batch256_fwd_bwd(force_stream):
     model, out, ref_out, data = _compare_with_oracle((30, 30), 256, gad_force_stream=force_stream)
-    assert (model.last_graph.tile_ptr is None) == force_stream
+    assert model.last_graph.tile_ptr is not None      # the plan exists; force_stream only bypasses it
     # size-independent properties on the full batch
     n = 30
     o = out.detach().cpu().view(256, n, n, 2)
