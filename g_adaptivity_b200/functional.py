@@ -218,8 +218,7 @@ class DeformFunction(torch.autograd.Function):
         pack_features(x_comp.detach(), None if f is None else f.detach(), None if uu is None else uu.detach(),
                       f_scale, uu_scale, CE, out=x0)
         x_phys = deform_forward(graph, x0, dim, Mu, tau_d, method, states=states, force_stream=force_stream)
-        if needs and method != METHOD_EULER:
-            raise NotImplementedError("backward through ode_method='rk4' is not implemented (forward-only extension)")
+        ctx.method = method
         ctx.graph, ctx.dim, ctx.CE, ctx.inv_temp, ctx.force_stream = graph, dim, CE, inv_temp, force_stream
         ctx.has_f, ctx.has_uu = f is not None, uu is not None
         ctx.normalised = (f_scale is not None) or (uu_scale is not None)
@@ -231,6 +230,8 @@ class DeformFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_xphys):
+        if ctx.method != METHOD_EULER:
+            raise NotImplementedError("backward through ode_method='rk4' is not implemented (forward-only extension)")
         states, Mu, tau_d, Wq, bq, Wk = ctx.saved_tensors
         ni = ctx.needs_input_grad
         want_gx0 = ni[0] or ni[1] or ni[2]
