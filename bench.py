@@ -301,14 +301,14 @@ def main():
             lib.gad_pack_features(P(s.x_comp), P(s.f), P(s.uu), None, None, s.N, model.dim, trainer.CE, P(s.states), st)
             a0, a1, b0, b1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             a0.record(trainer.stream)
-            lib.gad_deform_fwd(P(g.rowptr), P(g.col), s.N, g.E, P(g.tile_ptr), g.T, g.max_tile_nodes, g.max_tile_edges,
+            lib.gad_deform_fwd(P(g.rowptr), P(g.col_walk), s.N, g.E, P(g.tile_ptr), g.T, g.max_tile_nodes, g.max_tile_edges,
                                P(s.states), model.dim, trainer.CE, P(trainer.Mu), trainer.Lw, P(trainer.tau), trainer.L, 0,
                                P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, st)
             a1.record(trainer.stream)
             lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * model.dim, 0, 1.0 / (s.N * model.dim), P(s.loss), P(s.g_out),
                               P(s.loss_ws), st)
             b0.record(trainer.stream)
-            lib.gad_deform_bwd(P(g.rowptr), P(g.col), P(g.t_rowptr), P(g.t_dst), s.N, g.E, P(g.tile_ptr), g.T,
+            lib.gad_deform_bwd(P(g.rowptr), P(g.col_walk), P(g.t_rowptr), P(g.t_dst_walk), s.N, g.E, P(g.tile_ptr), g.T,
                                g.max_tile_nodes, g.max_tile_edges, P(s.states), P(s.g_out), model.dim, trainer.CE,
                                P(trainer.Mu), trainer.Lw, P(trainer.tau), trainer.L, P(trainer.gMu), P(trainer.gtau), None,
                                P(s.bwd_ws), s.bwd_ws_bytes, st)

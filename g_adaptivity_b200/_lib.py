@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgadapt_b200.so")
+# GAD_LIB selects another build of the same library (kernel-variant experiments, scripts/kbench.py)
+LIB_PATH = os.environ.get("GAD_LIB") or os.path.join(_HERE, "libgadapt_b200.so")
 
 _lib = None
 _lock = threading.Lock()
@@ -30,6 +31,7 @@ SIGNATURES = {
     "gad_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "gad_graph_workspace_bytes": (_sz, [_i64, _i64, _i64, _i]),
     "gad_graph_build": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gad_graph_sort_rows": (_i, [_p, _p, _i64, _p, _p]),
     "gad_graph_check_tiles": (_i, [_p, _p, _i64, _p, _i, _p, _p]),
     "gad_prepare_weights": (_i, [_p, _p, _p, _i, _i, _i, _f, _p, _p]),
     "gad_weight_grads": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p]),

@@ -1,21 +1,24 @@
 """Ahead-of-time build of the C-ABI CUDA library (sm_100a only), in-tree.
 
-    python -m g_adaptivity_b200.build [--force] [--verbose]
+    python -m g_adaptivity_b200.build [--force] [--verbose] [--out NAME.so] [-D MACRO[=V] ...]
 
 Produces `g_adaptivity_b200/libgadapt_b200.so` from `g_adaptivity_b200/csrc/*.cu` with
 `nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo`.  No torch headers are involved: the
 library is plain CUDA behind `include/gadapt.h` and is loaded with ctypes (`_lib.py`).  nvcc
 cross-compiles without a GPU, so this runs in the build container; the .so travels to the GPU box
 with the repo snapshot (it is git-ignored, not gpurun-ignored).
+
+`--out` / `-D` build a kernel variant next to the default library (selected at run time with the
+GAD_LIB environment variable; used by scripts/kbench.py to compare variants on the GPU box).
 """
 from __future__ import annotations
 
 import argparse
 import concurrent.futures as cf
+import hashlib
 import os
 import shutil
 import subprocess
-import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
@@ -25,10 +28,8 @@ BUILD = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libgadapt_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false", "-Xcompiler", "-fPIC",
-              "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC]
-# --use_fast_math is NOT enabled: expf/logf/division stay IEEE-accurate (parity bar 1e-5).
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+# no --use_fast_math: expf / logf / division stay accurate unless a kernel asks for an intrinsic
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC]
 
 
 def nvcc() -> str:
@@ -47,16 +48,20 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(p) for p in paths)
 
 
-def up_to_date() -> bool:
-    return os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime()
+def up_to_date(lib: str = LIB) -> bool:
+    return os.path.exists(lib) and os.path.getmtime(lib) >= _deps_mtime()
 
 
-def _compile(src: str, verbose: bool) -> str:
-    obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
-    cmd = [nvcc()] + ARCH + NVCC_FLAGS + ["-c", src, "-o", obj]
+def _compile(src: str, objdir: str, defines, verbose: bool) -> str:
+    base = os.path.basename(src)[:-3]
+    obj = os.path.join(objdir, base + ".o")
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(INCLUDE, "gadapt.h")]
+    newest = max(os.path.getmtime(p) for p in [src, __file__] + hdrs)
+    if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
+        return obj
+    cmd = [nvcc()] + ARCH + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(BUILD, os.path.basename(src)[:-3] + ".ptxas.log")
-    with open(log, "w") as fh:
+    with open(os.path.join(objdir, base + ".ptxas.log"), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
@@ -65,23 +70,32 @@ def _compile(src: str, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
-        return LIB
-    os.makedirs(BUILD, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()) -> str:
+    defines = list(defines)
+    if not os.path.isabs(out):
+        out = os.path.join(PKG, out)
+    if not force and up_to_date(out):
+        return out
+    tag = hashlib.md5(" ".join(sorted(defines)).encode()).hexdigest()[:8] if defines else "default"
+    objdir = os.path.join(BUILD, tag)
+    if force and os.path.isdir(objdir):
+        shutil.rmtree(objdir)
+    os.makedirs(objdir, exist_ok=True)
     srcs = sources()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
-    cmd = [nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
+        objs = list(ex.map(lambda s: _compile(s, objdir, defines, verbose), srcs))
+    cmd = [nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", out] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--out", default=LIB)
+    ap.add_argument("-D", dest="defines", action="append", default=[])
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, out=a.out, defines=a.defines))

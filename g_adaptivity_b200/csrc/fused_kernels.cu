@@ -27,6 +27,13 @@ namespace {
 
 typedef uint16_t lidx_t;  // tile-local node index (tiles hold < 65536 nodes)
 
+#ifndef GAD_FWD_MINB
+#define GAD_FWD_MINB 2   // min resident CTAs per SM the kernels are compiled for (register cap)
+#endif
+#ifndef GAD_BWD_MINB
+#define GAD_BWD_MINB 2
+#endif
+
 struct FwdSmem {
     size_t x_off, col_off, row_off, mu_off, total;
 };
@@ -60,7 +67,7 @@ struct MaxThreads {
 constexpr int MAX_FUSED_TILE_NODES = 4 * 768;
 
 template <int CE, int NPT, int METHOD>
-__global__ void __launch_bounds__(MaxThreads<NPT>::value) k_fused_fwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+__global__ void __launch_bounds__(MaxThreads<NPT>::value, GAD_FWD_MINB) k_fused_fwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                     const int32_t* __restrict__ tile_ptr, int cap_nodes, int cap_edges,
                                                     const float* __restrict__ x0, int dim,
                                                     const float* __restrict__ Mu_g, int Lw,
@@ -212,7 +219,7 @@ __host__ __device__ inline BwdSmem bwd_layout(int cap_nodes, int cap_edges, int 
 // sum <g^{l+1}, F(x^l)> (the gradient of a learnable step) when per_layer, else unused; when the
 // weights are shared but g_tau is wanted, tau_partials [T, L] carries it.
 template <int CE, int NPT>
-__global__ void __launch_bounds__(MaxThreads<NPT>::value) k_fused_bwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+__global__ void __launch_bounds__(MaxThreads<NPT>::value, GAD_BWD_MINB) k_fused_bwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                     const int32_t* __restrict__ t_rowptr, const int32_t* __restrict__ t_dst,
                                                     const int32_t* __restrict__ tile_ptr, int cap_nodes, int cap_edges,
                                                     const float* __restrict__ states, const float* __restrict__ g_xphys,
@@ -380,6 +387,8 @@ int set_smem(K kernel, size_t bytes) {
     GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "tile needs %zu B of shared memory (> %d): use smaller tiles", bytes,
                   smem_optin_bytes());
     GAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // let several CTAs share an SM: without this the driver picks the smallest carve-out that fits ONE block
+    GAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return GAD_OK;
 }
 

@@ -16,18 +16,50 @@
 //     D_i = <g_o, o_i>;  da_e = <g_o, x_j>;  ds_e = alpha_e (da_e - D_i);  t_i = sum_e ds_e x_j
 //     G_M += x_i (x) t_i;  G_u += t_i;  g_x[i] += M t_i                      (destination pass)
 //     g_x[j] += alpha_e g_o[i] + ds_e p_i                                    (source pass)
+//
+// Row caching.  Mesh rows are short (in-degree <= 7), so a row of up to GAD_ROW_W neighbours is
+// gathered ONCE into registers (all gathers issued back to back -> memory-level parallelism) and
+// max / exp / aggregate / backward terms are computed from registers; longer rows fall back to
+// multi-pass loops over the row.
 #pragma once
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
 
+// ---- build-time variant switches (defaults = shipped configuration) -------------------------
+#ifndef GAD_FAST_EXP
+#define GAD_FAST_EXP 0      // 1: ex2.approx-based __expf instead of expf
+#endif
+#ifndef GAD_ROW_W
+#define GAD_ROW_W 0         // register-cached row width; 0 disables row caching (measured: slower at 127 regs)
+#endif
+#ifndef GAD_BWD_ROWCACHE
+#define GAD_BWD_ROWCACHE 1  // destination pass of the backward also row-cached
+#endif
+
 namespace gad {
+
+__device__ __forceinline__ float gexp(float x) {
+#if GAD_FAST_EXP
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
 
 template <int CE>
 struct Row {
     float v[CE];
 };
+
+template <int CE>
+__device__ __forceinline__ Row<CE> zero_row() {
+    Row<CE> r;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) r.v[c] = 0.f;
+    return r;
+}
 
 template <int CE>
 __device__ __forceinline__ Row<CE> load_row(const float* __restrict__ base, int64_t i) {
@@ -101,31 +133,59 @@ struct SoftmaxStats {
     float rZ;   // 1 / sum exp(s - m)    (0 for an empty row)
 };
 
+// Rows longer than the register cache (and builds with GAD_ROW_W == 0) use the row-cached code
+// only when CE * GAD_ROW_W registers are affordable: CE = 8 keeps the multi-pass loops.
+template <int CE>
+struct RowCache {
+    static constexpr int W = (CE <= 4) ? GAD_ROW_W : 0;
+};
+
 // One F-evaluation at node i.  X: state rows (global or shared), indexed by the entries of `col`
-// (already relative to X).  Returns k_i = o_i - x_i; o_i and the softmax stats on request.
+// (already relative to X).  Returns k_i = o_i - x_i; o_i, the softmax stats and p_i on request.
 template <int CE, typename ColT>
 __device__ __forceinline__ Row<CE> node_feval(const float* __restrict__ X, const ColT* __restrict__ col,
                                               int e_begin, int e_end, const Row<CE>& xi,
                                               const float* __restrict__ Mu, Row<CE>* o_out = nullptr,
                                               SoftmaxStats* st_out = nullptr, Row<CE>* p_out = nullptr) {
     const Row<CE> p = project<CE>(Mu, xi);
-    float m = -CUDART_INF_F;
-    for (int e = e_begin; e < e_end; ++e) {
-        const Row<CE> xj = load_row<CE>(X, (int64_t)col[e]);
-        m = fmaxf(m, dot<CE>(p, xj));
-    }
-    float Z = 0.f;
-    Row<CE> o;
+    const int deg = e_end - e_begin;
+    float m = -CUDART_INF_F, Z = 0.f;
+    Row<CE> o = zero_row<CE>();
+    constexpr int W = RowCache<CE>::W;
+    if (W > 0 && deg <= W) {
+        Row<CE> xj[W > 0 ? W : 1];
+        float s[W > 0 ? W : 1];
 #pragma unroll
-    for (int c = 0; c < CE; ++c) o.v[c] = 0.f;
-    for (int e = e_begin; e < e_end; ++e) {
-        const Row<CE> xj = load_row<CE>(X, (int64_t)col[e]);
-        const float w = expf(dot<CE>(p, xj) - m);
-        Z += w;
+        for (int q = 0; q < W; ++q) {
+            if (q < deg) {
+                xj[q] = load_row<CE>(X, (int64_t)col[e_begin + q]);
+                s[q] = dot<CE>(p, xj[q]);
+                m = fmaxf(m, s[q]);
+            }
+        }
 #pragma unroll
-        for (int c = 0; c < CE; ++c) o.v[c] = fmaf(w, xj.v[c], o.v[c]);
+        for (int q = 0; q < W; ++q) {
+            if (q < deg) {
+                const float w = gexp(s[q] - m);
+                Z += w;
+#pragma unroll
+                for (int c = 0; c < CE; ++c) o.v[c] = fmaf(w, xj[q].v[c], o.v[c]);
+            }
+        }
+    } else {
+        for (int e = e_begin; e < e_end; ++e) {
+            const Row<CE> xj = load_row<CE>(X, (int64_t)col[e]);
+            m = fmaxf(m, dot<CE>(p, xj));
+        }
+        for (int e = e_begin; e < e_end; ++e) {
+            const Row<CE> xj = load_row<CE>(X, (int64_t)col[e]);
+            const float w = gexp(dot<CE>(p, xj) - m);
+            Z += w;
+#pragma unroll
+            for (int c = 0; c < CE; ++c) o.v[c] = fmaf(w, xj.v[c], o.v[c]);
+        }
     }
-    const float rZ = (e_end > e_begin) ? 1.0f / Z : 0.f;
+    const float rZ = (deg > 0) ? 1.0f / Z : 0.f;
     Row<CE> k;
 #pragma unroll
     for (int c = 0; c < CE; ++c) {
@@ -134,7 +194,7 @@ __device__ __forceinline__ Row<CE> node_feval(const float* __restrict__ X, const
     }
     if (o_out) *o_out = o;
     if (st_out) {
-        st_out->m = (e_end > e_begin) ? m : 0.f;
+        st_out->m = (deg > 0) ? m : 0.f;
         st_out->rZ = rZ;
     }
     if (p_out) *p_out = p;
@@ -159,24 +219,70 @@ __device__ __forceinline__ Row<CE> node_bwd_dst(const float* __restrict__ X, con
                                                 const Row<CE>& gplus, float a, float b,
                                                 const float* __restrict__ Mu, DstRec<CE>* rec,
                                                 float* __restrict__ acc, float* gb_acc) {
-    Row<CE> o, p;
-    SoftmaxStats st;
-    const Row<CE> k = node_feval<CE, ColT>(X, col, e_begin, e_end, xi, Mu, &o, &st, &p);
+    const int deg = e_end - e_begin;
     Row<CE> go;
 #pragma unroll
     for (int c = 0; c < CE; ++c) go.v[c] = b * gplus.v[c];
-    const float D = dot<CE>(go, o);
-    *gb_acc += dot<CE>(gplus, k);
-    Row<CE> t;
+    Row<CE> t = zero_row<CE>();
+    Row<CE> p, o;
+    float D, m, rZ;
+    constexpr int W = GAD_BWD_ROWCACHE ? RowCache<CE>::W : 0;
+    if (W > 0 && deg <= W) {
+        p = project<CE>(Mu, xi);
+        Row<CE> xj[W > 0 ? W : 1];
+        float s[W > 0 ? W : 1], da[W > 0 ? W : 1];
+        m = -CUDART_INF_F;
 #pragma unroll
-    for (int c = 0; c < CE; ++c) t.v[c] = 0.f;
-    for (int e = e_begin; e < e_end; ++e) {
-        const Row<CE> xj = load_row<CE>(X, (int64_t)col[e]);
-        const float alpha = expf(dot<CE>(p, xj) - st.m) * st.rZ;
-        const float ds = alpha * (dot<CE>(go, xj) - D);
+        for (int q = 0; q < W; ++q) {
+            if (q < deg) {
+                xj[q] = load_row<CE>(X, (int64_t)col[e_begin + q]);
+                s[q] = dot<CE>(p, xj[q]);
+                da[q] = dot<CE>(go, xj[q]);
+                m = fmaxf(m, s[q]);
+            }
+        }
+        float Z = 0.f;
+        o = zero_row<CE>();
 #pragma unroll
-        for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj.v[c], t.v[c]);
+        for (int q = 0; q < W; ++q) {
+            if (q < deg) {
+                s[q] = gexp(s[q] - m);          // s[q] now holds w_q
+                Z += s[q];
+#pragma unroll
+                for (int c = 0; c < CE; ++c) o.v[c] = fmaf(s[q], xj[q].v[c], o.v[c]);
+            }
+        }
+        rZ = (deg > 0) ? 1.0f / Z : 0.f;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
+        D = dot<CE>(go, o);
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            if (q < deg) {
+                const float ds = (s[q] * rZ) * (da[q] - D);
+#pragma unroll
+                for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj[q].v[c], t.v[c]);
+            }
+        }
+        if (deg == 0) m = 0.f;
+    } else {
+        SoftmaxStats st;
+        node_feval<CE, ColT>(X, col, e_begin, e_end, xi, Mu, &o, &st, &p);
+        m = st.m;
+        rZ = st.rZ;
+        D = dot<CE>(go, o);
+        for (int e = e_begin; e < e_end; ++e) {
+            const Row<CE> xj = load_row<CE>(X, (int64_t)col[e]);
+            const float alpha = gexp(dot<CE>(p, xj) - m) * rZ;
+            const float ds = alpha * (dot<CE>(go, xj) - D);
+#pragma unroll
+            for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj.v[c], t.v[c]);
+        }
     }
+    float gb = 0.f;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) gb = fmaf(gplus.v[c], o.v[c] - xi.v[c], gb);
+    *gb_acc += gb;
 #pragma unroll
     for (int aa = 0; aa < CE; ++aa)
 #pragma unroll
@@ -186,7 +292,7 @@ __device__ __forceinline__ Row<CE> node_bwd_dst(const float* __restrict__ X, con
     rec->p = p;
     rec->D = D;
     // alpha_e = exp(s_e - lse);  lse = m + log Z.  Empty row: never read by a source pass.
-    rec->lse = (e_end > e_begin) ? st.m - logf(st.rZ) : 0.f;
+    rec->lse = (deg > 0) ? m - logf(rZ) : 0.f;
     const Row<CE> Mt = apply_M<CE>(Mu, t);
     Row<CE> gs;
 #pragma unroll
@@ -200,15 +306,14 @@ template <int CE, typename ColT>
 __device__ __forceinline__ Row<CE> node_bwd_src(const float* __restrict__ P, const float2* __restrict__ DL,
                                                 const float* __restrict__ G, const ColT* __restrict__ tdst,
                                                 int e_begin, int e_end, const Row<CE>& xj, float b) {
-    Row<CE> accv;
-#pragma unroll
-    for (int c = 0; c < CE; ++c) accv.v[c] = 0.f;
+    Row<CE> accv = zero_row<CE>();
+#pragma unroll 2
     for (int e = e_begin; e < e_end; ++e) {
         const int64_t i = (int64_t)tdst[e];
         const Row<CE> p = load_row<CE>(P, i);
         const Row<CE> gp = load_row<CE>(G, i);
         const float2 dl = DL[i];
-        const float alpha = expf(dot<CE>(p, xj) - dl.y);
+        const float alpha = gexp(dot<CE>(p, xj) - dl.y);
         const float da = b * dot<CE>(gp, xj);
         const float ds = alpha * (da - dl.x);
         const float ab = alpha * b;
@@ -218,8 +323,8 @@ __device__ __forceinline__ Row<CE> node_bwd_src(const float* __restrict__ P, con
     return accv;
 }
 
-// Deterministic block-wide sum of `n` per-thread accumulators into out[0..n) (thread 0..n-1
-// hold the result in smem `red` on return; caller copies).  red must hold n * (blockDim/32) floats.
+// Deterministic block-wide sum of NACC per-thread accumulators into out[0..NACC).
+// red must hold NACC * (blockDim/32) floats.
 template <int NACC>
 __device__ __forceinline__ void block_reduce(float (&acc)[NACC], float* __restrict__ red,
                                              float* __restrict__ out) {

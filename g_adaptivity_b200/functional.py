@@ -110,7 +110,7 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
     with torch.cuda.device(x0.device):
         _lib.check(lib.gad_deform_fwd(
-            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), N, graph.E,
+            _lib.ptr(graph.rowptr), _lib.ptr(graph.col_walk), N, graph.E,
             _lib.ptr(graph.tile_ptr) if use_tiles else None, graph.T if use_tiles else 0,
             graph.max_tile_nodes, graph.max_tile_edges, _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L,
             method, _lib.ptr(x_phys), _lib.ptr(states), _lib.ptr(ws), ws_bytes, _stream(x0)), "gad_deform_fwd")
@@ -135,7 +135,7 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.gad_deform_bwd(
-            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.t_rowptr), _lib.ptr(graph.t_dst), N, graph.E,
+            _lib.ptr(graph.rowptr), _lib.ptr(graph.col_walk), _lib.ptr(graph.t_rowptr), _lib.ptr(graph.t_dst_walk), N, graph.E,
             _lib.ptr(graph.tile_ptr) if use_tiles else None, T, graph.max_tile_nodes, graph.max_tile_edges,
             _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, _lib.ptr(gMu),
             _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes, _stream(states)), "gad_deform_bwd")

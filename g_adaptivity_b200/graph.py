@@ -61,6 +61,7 @@ class MeshGraph:
         self.edge_index = None      # int64 [2, E]  filtered list, reference order (conv.stored_ei)
         self.rowptr = self.col = self.eid = None
         self.t_rowptr = self.t_dst = self.t_slot = None
+        self.col_walk = self.t_dst_walk = None   # per-row ascending copies used by the deformer kernels
         self.max_in_deg = self.max_out_deg = 0
         self.tile_ptr = None        # int32 [T+1] on device, or None -> streaming kernels
         self.T = 0
@@ -125,6 +126,15 @@ class MeshGraph:
         g.edge_index = filt[:, :E].contiguous() if E != filt.shape[1] else filt
         g.col, g.eid, g.t_dst, g.t_slot = col[:E], eid[:E], t_dst[:E], t_slot[:E]
         g._info = info
+        # row-sorted copies: what the deformer kernels walk (see gad_graph_sort_rows)
+        g.col_walk = torch.empty_like(g.col)
+        g.t_dst_walk = torch.empty_like(g.t_dst)
+        if E > 0:
+            with torch.cuda.device(device):
+                _lib.check(lib.gad_graph_sort_rows(_lib.ptr(g.rowptr), _lib.ptr(g.col), N, _lib.ptr(g.col_walk), stream),
+                           "gad_graph_sort_rows")
+                _lib.check(lib.gad_graph_sort_rows(_lib.ptr(g.t_rowptr), _lib.ptr(g.t_dst), N, _lib.ptr(g.t_dst_walk),
+                                                   stream), "gad_graph_sort_rows")
         if mesh_sizes is not None:
             g.plan(mesh_sizes, ce=ce, tile_target=tile_target)
         return g

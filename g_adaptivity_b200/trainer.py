@@ -167,14 +167,14 @@ class DeformerTrainer:
                 "gad_prepare_weights")
             chk(lib.gad_pack_features(P(s.x_comp), P(s.f), P(s.uu), None, None, s.N, dim, CE, P(s.states), stream_ptr),
                 "gad_pack_features")
-            chk(lib.gad_deform_fwd(P(g.rowptr), P(g.col), s.N, g.E, P(g.tile_ptr) if tiles else None, g.T if tiles else 0,
+            chk(lib.gad_deform_fwd(P(g.rowptr), P(g.col_walk), s.N, g.E, P(g.tile_ptr) if tiles else None, g.T if tiles else 0,
                                    g.max_tile_nodes, g.max_tile_edges, P(s.states), dim, CE, P(self.Mu), Lw, P(self.tau), L,
                                    self.method, P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, stream_ptr),
                 "gad_deform_fwd")
             chk(lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * dim, 0 if self.loss_kind == "l1" else 1,
                                   1.0 / (s.N * dim * self.world), P(s.loss), P(s.g_out), P(s.loss_ws), stream_ptr),
                 "gad_mesh_loss")
-            chk(lib.gad_deform_bwd(P(g.rowptr), P(g.col), P(g.t_rowptr), P(g.t_dst), s.N, g.E,
+            chk(lib.gad_deform_bwd(P(g.rowptr), P(g.col_walk), P(g.t_rowptr), P(g.t_dst_walk), s.N, g.E,
                                    P(g.tile_ptr) if tiles else None, g.T if tiles else 0, g.max_tile_nodes,
                                    g.max_tile_edges, P(s.states), P(s.g_out), dim, CE, P(self.Mu), Lw, P(self.tau), L,
                                    P(self.gMu), P(self.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, stream_ptr),

@@ -74,6 +74,10 @@ int gad_graph_build(const int64_t* edge_index, int64_t E0,
                     int64_t* filt_edge_index, int32_t* rowptr, int32_t* col, int32_t* eid,
                     int32_t* t_rowptr, int32_t* t_dst, int32_t* t_slot, int32_t* info,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* Per-row ascending copy of a CSR (ptr = rowptr, idx = col) or CSC (t_rowptr, t_dst) index array:
+ * the order in which the deformer kernels walk a row (bank-conflict-free gathers on structured
+ * meshes).  The canonical, stable-ordered arrays are left untouched. */
+int gad_graph_sort_rows(const int32_t* ptr, const int32_t* idx, int64_t N, int32_t* idx_sorted, void* stream);
 /* Counts edges that leave their tile (tile_ptr int32 [T+1], node offsets) into info[GAD_INFO_CROSS_TILE]. */
 int gad_graph_check_tiles(const int32_t* rowptr, const int32_t* col, int64_t N,
                           const int32_t* tile_ptr, int T, int32_t* info, void* stream);
