@@ -157,7 +157,8 @@ class GNN(nn.Module):
 
     def _graph(self, data, dev) -> MeshGraph:
         opt = self.opt
-        flags = (bool(opt["fix_boundary"]), bool(opt["self_loops"]), self.CE, str(dev), opt.get("gad_tile_nodes"))
+        flags = (bool(opt["fix_boundary"]), bool(opt["self_loops"]), self.CE, str(dev), opt.get("gad_tile_nodes"),
+                 bool(opt.get("gad_no_ell", False)))
         key = GraphCache.key_of(data, flags)
         g = self._graphs.get(key)
         if g is not None:
@@ -169,7 +170,8 @@ class GNN(nn.Module):
             masks = (data.to_boundary_edge_mask, data.to_corner_nodes_mask, data.diff_boundary_edges_mask)
             loops = corner_loops(data, self.dim, opt["mesh_dims"], sizes)
         g = MeshGraph.build(data.edge_index, N, masks=masks, extra_loops=loops, self_loops=bool(opt["self_loops"]),
-                            mesh_sizes=sizes, device=dev, ce=self.CE, tile_target=opt.get("gad_tile_nodes"))
+                            mesh_sizes=sizes, device=dev, ce=self.CE, tile_target=opt.get("gad_tile_nodes"),
+                            use_ell=not opt.get("gad_no_ell", False))
         keep = (data.edge_index, data.batch) + tuple(m for m in masks)
         self._graphs.put(key, g, keep)
         return g

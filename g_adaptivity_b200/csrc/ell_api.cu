@@ -1,0 +1,319 @@
+// Host side of the mesh-resident ELL kernels (ell_kernels.cuh): the ELL topology builder, the
+// launch planner (threads per CTA, ELL rows in shared memory or streamed from L2), the fixed-order
+// reduction of the per-tile partials, and the C-ABI entry points of include/gadapt.h.
+#include <stdlib.h>
+
+#include "ell_kernels.cuh"
+
+namespace gad {
+namespace ell {
+
+GAD_ELL_DECLARE(2, 2)
+GAD_ELL_DECLARE(2, 3)
+GAD_ELL_DECLARE(2, 6)
+GAD_ELL_DECLARE(2, 7)
+GAD_ELL_DECLARE(4, 2)
+GAD_ELL_DECLARE(4, 3)
+GAD_ELL_DECLARE(4, 6)
+GAD_ELL_DECLARE(4, 7)
+
+namespace {
+
+// ---- ELL rows from the CSR / CSC walk arrays -----------------------------------------------
+// One CTA per tile.  ell[i] = { (nbr_q - n0) * ROWBYTES as uint16, q < 7 ; degree }.
+__global__ void k_build_ell(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                            const int32_t* __restrict__ tile_ptr, int T, int rowbytes, uint4* __restrict__ ell,
+                            int32_t* __restrict__ bad) {
+    const int t = blockIdx.x;
+    if (t >= T) return;
+    const int n0 = tile_ptr[t], n1 = tile_ptr[t + 1];
+    for (int i = n0 + threadIdx.x; i < n1; i += blockDim.x) {
+        const int b = ptr[i], e = ptr[i + 1];
+        const int deg = e - b;
+        uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool ok = (deg <= ELL_SLOTS);
+        for (int q = 0; q < ELL_SLOTS; ++q) {
+            if (q < deg && ok) {
+                const int j = idx[b + q];
+                const long long off = (long long)(j - n0) * rowbytes;
+                if (j < n0 || j >= n1 || off > 0xffff) ok = false;
+                else h[q] = (uint32_t)off;
+            }
+        }
+        if (!ok) {
+            atomicAdd(bad, 1);
+            for (int q = 0; q < 8; ++q) h[q] = 0;
+        } else {
+            h[7] = (uint32_t)deg;
+        }
+        ell[i] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    }
+}
+
+// ---- fixed-order reduction of the per-tile partials -------------------------------------------
+// One warp per output column: columns [0, slots*nacc) are (G_M, G_u[, g_tau]) per weight slot,
+// then L step-size columns (shared weights) and one loss column.
+__global__ void k_ell_reduce(const float* __restrict__ partials, int T, int slots, int nacc, int musz,
+                             float* __restrict__ gMu, const float* __restrict__ tau_partials, int L,
+                             float* __restrict__ g_tau, const float* __restrict__ loss_partials, float loss_scale,
+                             float* __restrict__ loss) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int ncol = slots * nacc;
+    const float* src = nullptr;
+    int stride = 0;
+    if (w < ncol) {
+        src = partials + w;
+        stride = ncol;
+    } else if (w < ncol + L) {
+        if (!(tau_partials && g_tau)) return;
+        src = tau_partials + (w - ncol);
+        stride = L;
+    } else if (w == ncol + L) {
+        if (!(loss_partials && loss)) return;
+        src = loss_partials;
+        stride = 1;
+    } else {
+        return;
+    }
+    float s = 0.f;
+    for (int t = lane; t < T; t += 32) s += src[(size_t)t * stride];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane != 0) return;
+    if (w < ncol) {
+        const int l = w / nacc, a = w % nacc;
+        if (a < musz) gMu[(size_t)l * musz + a] = s;
+        else if (g_tau && slots > 1) g_tau[l] = s;
+    } else if (w < ncol + L) {
+        g_tau[w - ncol] = s;
+    } else {
+        loss[0] = s * loss_scale;
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+struct Plan {
+    int w;        // instantiated slot count (2, 3, 6, 7)
+    int ells;     // ELL rows staged in shared memory
+    int threads;
+};
+
+// Per-SM shared memory: 228 KB minus 1 KB reserved per resident CTA.
+constexpr size_t SMEM_PER_SM = 233472;
+
+int make_plan(int CE, int kind, int max_tile_nodes, int max_deg, Plan* p) {
+    GAD_CHECK_ARG(CE == 2 || CE == 4, "ELL kernels are instantiated for CE = 2 and 4 (got %d)", CE);
+    GAD_CHECK_ARG(max_deg >= 0 && max_deg <= ELL_SLOTS, "ELL kernels need degree <= %d (got %d)", ELL_SLOTS, max_deg);
+    GAD_CHECK_ARG(max_tile_nodes > 0 && (long long)max_tile_nodes * CE * 4 <= 0x10000,
+                  "ELL kernels: tile of %d nodes exceeds the 16-bit row offsets", max_tile_nodes);
+    p->w = max_deg <= 2 ? 2 : (max_deg <= 3 ? 3 : (max_deg <= 6 ? 6 : 7));
+    const int nw = GAD_ELL_MAXT / 32;
+    const size_t with = make_layout(CE, kind, max_tile_nodes, true, nw).total + 1024;
+    const size_t without = make_layout(CE, kind, max_tile_nodes, false, nw).total + 1024;
+    const size_t optin = (size_t)smem_optin_bytes() + 1024;
+    int ells;
+    if (2 * with <= SMEM_PER_SM) ells = 1;                 // two CTAs per SM either way
+    else if (2 * without <= SMEM_PER_SM) ells = 0;         // keep the second CTA
+    else if (with <= optin) ells = 1;
+    else if (without <= optin) ells = 0;
+    else {
+        set_error("ELL kernels: a tile of %d nodes needs %zu B of shared memory (> %zu)", max_tile_nodes, without, optin);
+        return GAD_ERR_UNSUPPORTED;
+    }
+    ells = env_int("GAD_ELL_SMEM", ells);
+    p->ells = ells ? 1 : 0;
+    const size_t bytes = p->ells ? with : without;
+    const bool two = 2 * bytes <= SMEM_PER_SM;
+    int target = env_int("GAD_ELL_THREADS", two ? GAD_ELL_MAXT / 2 : GAD_ELL_MAXT);
+    if (target > GAD_ELL_MAXT) target = GAD_ELL_MAXT;
+    if (target < 32) target = 32;
+    const int rounds = (max_tile_nodes + target - 1) / target;
+    int th = (max_tile_nodes + rounds - 1) / rounds;
+    th = ((th + 31) / 32) * 32;
+    if (th < 64) th = 64;
+    if (th > GAD_ELL_MAXT) th = GAD_ELL_MAXT;
+    p->threads = th;
+    return GAD_OK;
+}
+
+int dispatch(int CE, const Plan& p, int which, const Args& a, int method, cudaStream_t st) {
+#define GAD_ELL_CASE(CE_, W_) \
+    if (CE == CE_ && p.w == W_) return ell_launch_c##CE_##w##W_(which, a, method, p.ells, p.threads, st)
+    GAD_ELL_CASE(2, 2);
+    GAD_ELL_CASE(2, 3);
+    GAD_ELL_CASE(2, 6);
+    GAD_ELL_CASE(2, 7);
+    GAD_ELL_CASE(4, 2);
+    GAD_ELL_CASE(4, 3);
+    GAD_ELL_CASE(4, 6);
+    GAD_ELL_CASE(4, 7);
+#undef GAD_ELL_CASE
+    set_error("ELL kernels: no instantiation for CE=%d W=%d", CE, p.w);
+    return GAD_ERR_UNSUPPORTED;
+}
+
+size_t ws_floats(int CE, int T, int L) {
+    const int NACC = CE * CE + CE + 1;
+    return (size_t)T * L * NACC + (size_t)T * L + (size_t)T + 64;
+}
+
+int reduce_partials(int CE, int T, int Lw, int L, float* ws, float* gMu, float* g_tau, float loss_scale, float* loss,
+                    cudaStream_t st) {
+    const int NACC = CE * CE + CE + 1, MUSZ = CE * CE + CE;
+    const int slots = Lw > 1 ? L : 1;
+    float* partials = ws;
+    float* tau_partials = (g_tau && Lw == 1) ? ws + (size_t)T * L * NACC : nullptr;
+    float* loss_partials = loss ? ws + (size_t)T * L * NACC + (size_t)T * L : nullptr;
+    const int ncol = slots * NACC + L + 1;
+    k_ell_reduce<<<(ncol + 7) / 8, 256, 0, st>>>(partials, T, slots, NACC, MUSZ, gMu, tau_partials, L, g_tau,
+                                                 loss_partials, loss_scale, loss);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+}  // namespace
+}  // namespace ell
+}  // namespace gad
+
+using namespace gad;
+using namespace gad::ell;
+
+extern "C" int gad_graph_build_ell(const int32_t* ptr, const int32_t* idx, int64_t N, const int32_t* tile_ptr, int T,
+                                   int CE, void* ell_rows, int32_t* info, void* stream) {
+    GAD_CHECK_ARG(ptr && idx && tile_ptr && ell_rows && info && N > 0 && T > 0, "gad_graph_build_ell: bad arguments");
+    GAD_CHECK_ARG(CE == 2 || CE == 4, "gad_graph_build_ell: CE must be 2 or 4 (got %d)", CE);
+    k_build_ell<<<T, 256, 0, as_stream(stream)>>>(ptr, idx, tile_ptr, T, CE * 4, reinterpret_cast<uint4*>(ell_rows),
+                                                 info + GAD_INFO_ELL_BAD);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+extern "C" int gad_ell_supported(int CE, int max_tile_nodes, int max_deg, int train) {
+    Plan p;
+    if (CE != 2 && CE != 4) return 0;
+    if (max_deg > ELL_SLOTS || max_tile_nodes <= 0 || (long long)max_tile_nodes * CE * 4 > 0x10000) return 0;
+    if (make_plan(CE, KIND_FWD_RK4, max_tile_nodes, max_deg, &p) != GAD_OK) return 0;
+    if (train && make_plan(CE, KIND_BWD, max_tile_nodes, max_deg, &p) != GAD_OK) return 0;
+    return 1;
+}
+
+extern "C" size_t gad_ell_workspace_bytes(int CE, int T, int L) { return ws_floats(CE, T > 0 ? T : 1, L) * sizeof(float); }
+
+extern "C" int gad_deform_fwd_ell(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T, int max_tile_nodes,
+                                  int max_deg, const float* x0, int dim, int CE, const float* Mu, int Lw,
+                                  const float* tau, int L, int method, float* x_phys, float* states, void* stream) {
+    GAD_CHECK_ARG(ell_in && tile_ptr && x0 && Mu && tau && x_phys, "gad_deform_fwd_ell: null pointer");
+    GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
+                  "gad_deform_fwd_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
+    GAD_CHECK_ARG(method == GAD_METHOD_EULER || method == GAD_METHOD_RK4, "gad_deform_fwd_ell: unknown method %d", method);
+    GAD_CHECK_ARG(!states || states == x0, "gad_deform_fwd_ell: when states is given, x0 must alias states[0]");
+    Plan p;
+    int rc = make_plan(CE, method == GAD_METHOD_RK4 ? KIND_FWD_RK4 : KIND_FWD, max_tile_nodes, max_deg, &p);
+    if (rc) return rc;
+    Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(ell_in);
+    a.tile_ptr = tile_ptr;
+    a.T = T;
+    a.cap_nodes = max_tile_nodes;
+    a.N = N;
+    a.Mu = Mu;
+    a.tau = tau;
+    a.Lw = Lw;
+    a.L = L;
+    a.dim = dim;
+    a.x0 = x0;
+    a.x_phys = x_phys;
+    a.states = states;
+    return dispatch(CE, p, 0, a, method, as_stream(stream));
+}
+
+extern "C" int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
+                                  int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
+                                  int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,
+                                  float* g_x0, void* workspace, size_t workspace_bytes, void* stream) {
+    GAD_CHECK_ARG(ell_in && ell_out && tile_ptr && states && g_xphys && Mu && tau && gMu && workspace,
+                  "gad_deform_bwd_ell: null pointer");
+    GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
+                  "gad_deform_bwd_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
+    GAD_CHECK_ARG(workspace_bytes >= ws_floats(CE, T, L) * sizeof(float), "gad_deform_bwd_ell: workspace too small");
+    Plan p;
+    int rc = make_plan(CE, KIND_BWD, max_tile_nodes, max_deg, &p);
+    if (rc) return rc;
+    const int NACC = CE * CE + CE + 1;
+    float* ws = reinterpret_cast<float*>(workspace);
+    Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(ell_in);
+    a.ell_out = reinterpret_cast<const uint4*>(ell_out);
+    a.tile_ptr = tile_ptr;
+    a.T = T;
+    a.cap_nodes = max_tile_nodes;
+    a.N = N;
+    a.Mu = Mu;
+    a.tau = tau;
+    a.Lw = Lw;
+    a.L = L;
+    a.dim = dim;
+    a.states = const_cast<float*>(states);
+    a.g_xphys = g_xphys;
+    a.partials = ws;
+    a.tau_partials = (g_tau && Lw == 1) ? ws + (size_t)T * L * NACC : nullptr;
+    a.g_x0 = g_x0;
+    cudaStream_t st = as_stream(stream);
+    if ((rc = dispatch(CE, p, 1, a, GAD_METHOD_EULER, st))) return rc;
+    return reduce_partials(CE, T, Lw, L, ws, gMu, g_tau, 0.f, nullptr, st);
+}
+
+extern "C" int gad_deform_train_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
+                                    int max_tile_nodes, int max_deg, const float* x_comp, const float* f,
+                                    const float* uu, const float* f_scale, const float* uu_scale, const float* target,
+                                    int dim, int CE, const float* Mu, int Lw, const float* tau, int L, int loss_kind,
+                                    float grad_scale, float loss_scale, float* states, float* gMu, float* g_tau,
+                                    float* loss, float* x_phys, void* workspace, size_t workspace_bytes, void* stream) {
+    GAD_CHECK_ARG(ell_in && ell_out && tile_ptr && x_comp && target && Mu && tau && states && gMu && loss && workspace,
+                  "gad_deform_train_ell: null pointer");
+    GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
+                  "gad_deform_train_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
+    GAD_CHECK_ARG(dim + (f ? 1 : 0) + (uu ? 1 : 0) <= CE, "gad_deform_train_ell: %d input features exceed CE=%d",
+                  dim + (f ? 1 : 0) + (uu ? 1 : 0), CE);
+    GAD_CHECK_ARG(loss_kind == 0 || loss_kind == 1, "gad_deform_train_ell: unknown loss kind %d", loss_kind);
+    GAD_CHECK_ARG(workspace_bytes >= ws_floats(CE, T, L) * sizeof(float), "gad_deform_train_ell: workspace too small");
+    Plan p;
+    int rc = make_plan(CE, KIND_BWD, max_tile_nodes, max_deg, &p);
+    if (rc) return rc;
+    const int NACC = CE * CE + CE + 1;
+    float* ws = reinterpret_cast<float*>(workspace);
+    Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(ell_in);
+    a.ell_out = reinterpret_cast<const uint4*>(ell_out);
+    a.tile_ptr = tile_ptr;
+    a.T = T;
+    a.cap_nodes = max_tile_nodes;
+    a.N = N;
+    a.Mu = Mu;
+    a.tau = tau;
+    a.Lw = Lw;
+    a.L = L;
+    a.dim = dim;
+    a.x_phys = x_phys;
+    a.states = states;
+    a.partials = ws;
+    a.tau_partials = (g_tau && Lw == 1) ? ws + (size_t)T * L * NACC : nullptr;
+    a.g_x0 = nullptr;
+    a.x_comp = x_comp;
+    a.f = f;
+    a.uu = uu;
+    a.f_scale = f_scale;
+    a.uu_scale = uu_scale;
+    a.target = target;
+    a.loss_kind = loss_kind;
+    a.grad_scale = grad_scale;
+    a.loss_partials = ws + (size_t)T * L * NACC + (size_t)T * L;
+    cudaStream_t st = as_stream(stream);
+    if ((rc = dispatch(CE, p, 2, a, GAD_METHOD_EULER, st))) return rc;
+    return reduce_partials(CE, T, Lw, L, ws, gMu, g_tau, loss_scale, loss, st);
+}

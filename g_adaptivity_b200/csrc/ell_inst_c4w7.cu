@@ -1,0 +1,9 @@
+// Instantiation unit of the mesh-resident ELL kernels for CE = 4 live channels and 7 neighbour
+// slots per row (one translation unit per combination so that nvcc compiles them in parallel).
+#include "ell_kernels.cuh"
+
+namespace gad {
+namespace ell {
+GAD_ELL_INSTANTIATE(4, 7)
+}  // namespace ell
+}  // namespace gad

@@ -1,0 +1,621 @@
+// Mesh-resident ELL kernels: the whole multi-layer integration of a tile in ONE launch, and the
+// whole training pass (forward, mesh loss, backward) of a tile in ONE launch.
+//
+// A batch is a disjoint union of meshes (PyG Batch semantics), so a contiguous node
+// range that does not split a mesh ("tile", planned on the host) is closed under the edge
+// relation.  A CTA owns a tile at a time (persistent loop over tiles): the tile's node state lives
+// in shared memory for all L layers (src/GNN.py:273-296) and HBM is touched only for the inputs,
+// the saved layer states and the outputs.  Topology is the ELL form of ell_math.cuh (one 128-bit
+// row per node and direction, byte offsets pre-multiplied), staged into shared memory by 1-D TMA
+// bulk copies (cp.async.bulk + mbarrier) together with the initial state, or -- for tiles whose
+// state alone fills the SM (50x50 meshes) -- streamed from L2 with a one-row software prefetch.
+//
+// Thread mapping: thread t owns nodes t, t + nthr, t + 2 nthr, ... of the tile, in every phase, so
+// values a node carries between phases (gradient rows) are only ever touched by one thread and
+// need no synchronisation; consecutive lanes own consecutive rows, which on row-major structured
+// meshes makes the q-th neighbour gather of a warp hit consecutive shared-memory rows.
+//
+// Forward, per layer:    read X_cur (gathers), write X_nxt[i]          -> 1 barrier per layer
+// Backward, per layer:   phase A (destination pass) reads X, writes GO / P / DL / GS[i]
+//                        phase B (source pass) gathers GO / P / DL, writes GS[j], X[j] <- x^{l-1}
+//                                                                      -> 2 barriers per layer
+// Weight gradients: per-thread register accumulators, fixed-order block reduction, per-tile
+// partials summed by a second tiny kernel.  No floating-point atomics: bit-reproducible.
+#pragma once
+
+#include "common.cuh"
+#include "ell_math.cuh"
+
+namespace gad {
+namespace ell {
+
+#ifndef GAD_ELL_MAXT
+#define GAD_ELL_MAXT 640    // largest CTA; with 1 CTA of 640 or 2 CTAs of 320 threads: <= 96 registers
+#endif
+#ifndef GAD_ELL_MINB
+#define GAD_ELL_MINB 1
+#endif
+
+enum Kind { KIND_FWD = 0, KIND_FWD_RK4 = 1, KIND_BWD = 2 };
+
+struct Layout {
+    uint32_t xa, xb, p, gs, dl, ein, eout, mu, red, bar, total;
+};
+
+__host__ __device__ inline Layout make_layout(int CE, int kind, int cap_nodes, bool ells, int nwarps) {
+    Layout s{};
+    size_t o = 0;
+    auto bump = [&](size_t bytes) {
+        const size_t at = o;
+        o = (o + bytes + 127) & ~size_t(127);
+        return (uint32_t)at;
+    };
+    const size_t rows = (size_t)cap_nodes * CE * sizeof(float);
+    s.xa = bump(rows);
+    s.xb = bump(rows);
+    if (kind != KIND_FWD) {
+        s.p = bump(rows);    // RK4: base state;   backward: p_i rows
+        s.gs = bump(rows);   // RK4: accumulator;  backward: per-node gradient carry
+    }
+    if (kind == KIND_BWD) s.dl = bump((size_t)cap_nodes * 8);
+    if (ells) {
+        s.ein = bump((size_t)cap_nodes * 16);
+        if (kind == KIND_BWD) s.eout = bump((size_t)cap_nodes * 16);
+    }
+    s.mu = bump((size_t)(CE * CE + CE) * sizeof(float));
+    if (kind == KIND_BWD) s.red = bump((size_t)(CE * CE + CE + 1) * nwarps * sizeof(float));
+    s.bar = bump(16);
+    s.total = (uint32_t)o;
+    return s;
+}
+
+struct Args {
+    // topology
+    const uint4* ell_in;
+    const uint4* ell_out;
+    const int32_t* tile_ptr;
+    int T, cap_nodes;
+    int64_t N;
+    // model
+    const float* Mu;
+    const float* tau;
+    int Lw, L, dim;
+    // forward
+    const float* x0;        // [N, CE] (forward kernel)
+    float* x_phys;          // [N, dim] (may be null in the train kernel)
+    float* states;          // [L, N, CE]: written by forward / train, read by backward / train
+    // backward
+    const float* g_xphys;   // [N, dim]
+    float* partials;        // [T, slots, NACC]
+    float* tau_partials;    // [T, L] or null
+    float* g_x0;            // [N, CE] or null
+    // train: fused feature assembly + loss
+    const float* x_comp;
+    const float* f;
+    const float* uu;
+    const float* f_scale;
+    const float* uu_scale;
+    const float* target;    // [N, dim]
+    int loss_kind;          // 0: L1, 1: MSE
+    float grad_scale;       // cotangent = grad_scale * d|out - target| (or d(out - target)^2)
+    float* loss_partials;   // [T] sum over the tile of |d| or d^2
+};
+
+template <int CE>
+__device__ __forceinline__ Row<CE> load_row_cg(const float* base, int64_t i) {
+    Row<CE> r;
+    if constexpr (CE == 2) {
+        const float2 t = __ldcg(reinterpret_cast<const float2*>(base + i * 2));
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+    } else {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(base + i * CE));
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+        r.v[2] = t.z;
+        r.v[3] = t.w;
+    }
+    return r;
+}
+
+template <int CE>
+__device__ __forceinline__ void store_dims(float* __restrict__ out, int64_t i, int dim, const Row<CE>& r) {
+    if (dim == 2) {
+        *reinterpret_cast<float2*>(out + i * 2) = make_float2(r.v[0], r.v[1]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < CE; ++c)
+            if (c < dim) out[i * dim + c] = r.v[c];
+    }
+}
+
+template <int CE>
+__device__ __forceinline__ Row<CE> load_dims(const float* __restrict__ in, int64_t i, int dim) {
+    Row<CE> r;
+    if (dim == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(in + i * 2);
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+#pragma unroll
+        for (int c = 2; c < CE; ++c) r.v[c] = 0.f;
+    } else {
+#pragma unroll
+        for (int c = 0; c < CE; ++c) r.v[c] = (c < dim) ? in[i * dim + c] : 0.f;
+    }
+    return r;
+}
+
+// Per-tile view of the ELL rows: shared memory (staged by TMA) or global memory (L2-resident).
+template <bool ELLS>
+struct EllView {
+    const uint4* base;   // shared: tile-local rows; global: rows of the whole batch + n0
+    __device__ __forceinline__ uint4 get(int i) const {
+        if constexpr (ELLS) return base[i];
+        else return __ldg(base + i);
+    }
+};
+
+// ============================================================================================
+// forward
+// ============================================================================================
+template <int CE, int W, bool ELLS, int METHOD>
+__global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Args a) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const Layout lay = make_layout(CE, METHOD == GAD_METHOD_RK4 ? KIND_FWD_RK4 : KIND_FWD, a.cap_nodes, ELLS,
+                                   (nthr + 31) >> 5);
+    unsigned char* Xc = smem + lay.xa;
+    unsigned char* Xn = smem + lay.xb;
+    unsigned char* XB = smem + lay.p;    // RK4 only
+    unsigned char* AC = smem + lay.gs;   // RK4 only
+    float* Mu = reinterpret_cast<float*>(smem + lay.mu);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    uint32_t parity = 0;
+    const size_t state_stride = (size_t)a.N * CE;
+
+    for (int tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
+        const int n0 = a.tile_ptr[tile];
+        const int NT = a.tile_ptr[tile + 1] - n0;
+        __syncthreads();   // previous tile fully consumed (and the mbarrier initialised)
+        const float* x0t = a.x0 + (size_t)n0 * CE;
+        const bool bulk_x = ((reinterpret_cast<uintptr_t>(x0t) & 15) == 0) && (((uint32_t)NT * RB) % 16 == 0);
+        const uint32_t tx = (ELLS ? (uint32_t)NT * 16u : 0u) + (bulk_x ? (uint32_t)NT * RB : 0u);
+        if (tid == 0 && tx) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(bar, tx);
+            if (ELLS) bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
+            if (bulk_x) bulk_g2s(Xc, x0t, (uint32_t)NT * RB, bar);
+        }
+        if (!bulk_x)
+            for (int i = tid; i < NT; i += nthr) sts_row<CE>(Xc, i * RB, load_row<CE>(a.x0, (int64_t)n0 + i));
+        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+        if (tx) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        __syncthreads();
+        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
+
+        for (int l = 0; l < a.L; ++l) {
+            if (a.Lw > 1 && l > 0) {
+                for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+                __syncthreads();
+            }
+            const float h = a.tau[l];
+            const bool last = (l == a.L - 1);
+            float* st_out = (a.states && !last) ? a.states + (size_t)(l + 1) * state_stride : nullptr;
+            if constexpr (METHOD == GAD_METHOD_EULER) {
+                uint4 e_nx = (tid < NT) ? Ein.get(tid) : make_uint4(0, 0, 0, 0);
+                for (int i = tid; i < NT; i += nthr) {
+                    const uint4 e = e_nx;
+                    if (i + nthr < NT) e_nx = Ein.get(i + nthr);
+                    const Row<CE> y = lds_row<CE>(Xc, i * RB);
+                    const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mu);
+                    Row<CE> xn;
+#pragma unroll
+                    for (int c = 0; c < CE; ++c) xn.v[c] = fmaf(h, k.v[c], y.v[c]);
+                    sts_row<CE>(Xn, i * RB, xn);
+                    if (st_out) store_row<CE>(st_out, (int64_t)n0 + i, xn);
+                    if (last) store_dims<CE>(a.x_phys, (int64_t)n0 + i, a.dim, xn);   // decoder = identity slice
+                }
+                __syncthreads();
+                unsigned char* t = Xc;
+                Xc = Xn;
+                Xn = t;
+            } else {
+                // classical RK4 on F(y) = A(y) y - y (extension): the stage input lives in
+                // the ping-pong buffers, the step's base state and the k-accumulator in XB / AC.
+                const float cin[4] = {0.5f * h, 0.5f * h, h, 0.f};
+                const float wacc[4] = {1.f, 2.f, 2.f, 1.f};
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    for (int i = tid; i < NT; i += nthr) {
+                        const uint4 e = Ein.get(i);
+                        const Row<CE> y = lds_row<CE>(Xc, i * RB);
+                        const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mu);
+                        Row<CE> base, acc, out;
+                        if (s == 0) {
+                            base = y;
+                            acc = k;
+                            sts_row<CE>(XB, i * RB, y);
+                        } else {
+                            base = lds_row<CE>(XB, i * RB);
+                            acc = lds_row<CE>(AC, i * RB);
+#pragma unroll
+                            for (int c = 0; c < CE; ++c) acc.v[c] = fmaf(wacc[s], k.v[c], acc.v[c]);
+                        }
+                        if (s < 3) {
+                            sts_row<CE>(AC, i * RB, acc);
+#pragma unroll
+                            for (int c = 0; c < CE; ++c) out.v[c] = fmaf(cin[s], k.v[c], base.v[c]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CE; ++c) out.v[c] = fmaf(h * (1.0f / 6.0f), acc.v[c], base.v[c]);
+                            if (st_out) store_row<CE>(st_out, (int64_t)n0 + i, out);
+                            if (last) store_dims<CE>(a.x_phys, (int64_t)n0 + i, a.dim, out);
+                        }
+                        sts_row<CE>(Xn, i * RB, out);
+                    }
+                    __syncthreads();
+                    unsigned char* t = Xc;
+                    Xc = Xn;
+                    Xn = t;
+                }
+            }
+        }
+    }
+}
+
+// ============================================================================================
+// backward of one tile (shared by the backward and the train kernels)
+// ============================================================================================
+// On entry (all visible to the CTA): X = x^{L-1} rows, GS = dL/dx^L rows, Mu = weights of layer
+// L-1.  acc: per-thread (G_M, G_u[, g_tau]) accumulators, zero on entry.
+template <int CE, int W, bool ELLS>
+__device__ __forceinline__ void tile_backward(const Args& a, int tile, int n0, int NT, unsigned char* X,
+                                              unsigned char* GO, unsigned char* P, unsigned char* DL,
+                                              unsigned char* GS, const EllView<ELLS>& Ein,
+                                              const EllView<ELLS>& Eout, float* Mu, float* red) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    constexpr int NACC = MUSZ + 1;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const bool per_layer = (a.Lw > 1);
+    const int slots = per_layer ? a.L : 1;
+    const size_t state_stride = (size_t)a.N * CE;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+
+    for (int l = a.L - 1; l >= 0; --l) {
+        if (per_layer && l < a.L - 1) {
+            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+            __syncthreads();
+        }
+        const float b = a.tau[l];
+        float gtau = 0.f;
+        // ---- phase A: destination pass ------------------------------------------------------
+        {
+            uint4 e_nx = (tid < NT) ? Ein.get(tid) : make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < NT; i += nthr) {
+                const uint4 e = e_nx;
+                if (i + nthr < NT) e_nx = Ein.get(i + nthr);
+                const Row<CE> xi = lds_row<CE>(X, i * RB);
+                const Row<CE> gp = lds_row<CE>(GS, i * RB);
+                Row<CE> go;
+#pragma unroll
+                for (int c = 0; c < CE; ++c) go.v[c] = b * gp.v[c];
+                Row<CE> p, t, o;
+                float D, lse;
+                ell_bwd_dst<CE, W>(X, e, xi, go, Mu, p, D, lse, t, o);
+#pragma unroll
+                for (int c = 0; c < CE; ++c) gtau = fmaf(gp.v[c], o.v[c] - xi.v[c], gtau);
+#pragma unroll
+                for (int aa = 0; aa < CE; ++aa)
+#pragma unroll
+                    for (int bb = 0; bb < CE; ++bb) acc[aa * CE + bb] = fmaf(xi.v[aa], t.v[bb], acc[aa * CE + bb]);
+#pragma unroll
+                for (int bb = 0; bb < CE; ++bb) acc[CE * CE + bb] += t.v[bb];
+                const Row<CE> Mt = apply_M<CE>(Mu, t);
+                Row<CE> gs;
+#pragma unroll
+                for (int c = 0; c < CE; ++c) gs.v[c] = fmaf(1.0f - b, gp.v[c], Mt.v[c]);   // Euler: a = 1
+                sts_row<CE>(P, i * RB, p);
+                *reinterpret_cast<float2*>(DL + (size_t)i * 8) = make_float2(D, lse);
+                sts_row<CE>(GO, i * RB, go);
+                sts_row<CE>(GS, i * RB, gs);
+            }
+        }
+        const bool need_src = (l > 0) || (a.g_x0 != nullptr);
+        if (need_src) {
+            __syncthreads();   // P, DL, GO visible; every gather of X done
+            // ---- phase B: source pass -------------------------------------------------------
+            const float* xprev_g = (l > 0) ? a.states + (size_t)(l - 1) * state_stride : nullptr;
+            uint4 e_nx = (tid < NT) ? Eout.get(tid) : make_uint4(0, 0, 0, 0);
+            for (int j = tid; j < NT; j += nthr) {
+                const uint4 e = e_nx;
+                if (j + nthr < NT) e_nx = Eout.get(j + nthr);
+                Row<CE> xprev;
+                if (xprev_g) xprev = load_row_cg<CE>(xprev_g, (int64_t)n0 + j);   // issued early, used last
+                const Row<CE> xj = lds_row<CE>(X, j * RB);
+                const Row<CE> sc = ell_bwd_src<CE, W>(P, GO, DL, e, xj);
+                Row<CE> g = lds_row<CE>(GS, j * RB);
+#pragma unroll
+                for (int c = 0; c < CE; ++c) g.v[c] += sc.v[c];
+                sts_row<CE>(GS, j * RB, g);
+                if (xprev_g) sts_row<CE>(X, j * RB, xprev);
+                else if (a.g_x0) store_row<CE>(a.g_x0, (int64_t)n0 + j, g);
+            }
+            __syncthreads();   // GS / X of the next layer visible; gathers of P / DL / GO done
+        }
+        if (per_layer) {
+            acc[NACC - 1] = gtau;
+            block_reduce<NACC>(acc, red, a.partials + ((size_t)tile * slots + l) * NACC);
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+        } else if (a.tau_partials) {
+            float one[1] = {gtau};
+            block_reduce<1>(one, red, a.tau_partials + (size_t)tile * a.L + l);
+        }
+    }
+    if (!per_layer) block_reduce<NACC>(acc, red, a.partials + (size_t)tile * NACC);
+}
+
+template <int CE, int W, bool ELLS>
+__global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd(const Args a) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const Layout lay = make_layout(CE, KIND_BWD, a.cap_nodes, ELLS, (nthr + 31) >> 5);
+    unsigned char* X = smem + lay.xa;
+    unsigned char* GO = smem + lay.xb;
+    unsigned char* P = smem + lay.p;
+    unsigned char* GS = smem + lay.gs;
+    unsigned char* DL = smem + lay.dl;
+    float* Mu = reinterpret_cast<float*>(smem + lay.mu);
+    float* red = reinterpret_cast<float*>(smem + lay.red);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    uint32_t parity = 0;
+    const size_t state_stride = (size_t)a.N * CE;
+
+    for (int tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
+        const int n0 = a.tile_ptr[tile];
+        const int NT = a.tile_ptr[tile + 1] - n0;
+        __syncthreads();
+        const float* xl = a.states + (size_t)(a.L - 1) * state_stride + (size_t)n0 * CE;
+        const bool bulk_x = ((reinterpret_cast<uintptr_t>(xl) & 15) == 0) && (((uint32_t)NT * RB) % 16 == 0);
+        const uint32_t tx = (ELLS ? 2u * (uint32_t)NT * 16u : 0u) + (bulk_x ? (uint32_t)NT * RB : 0u);
+        if (tid == 0 && tx) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(bar, tx);
+            if (ELLS) {
+                bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
+                bulk_g2s(smem + lay.eout, a.ell_out + n0, (uint32_t)NT * 16u, bar);
+            }
+            if (bulk_x) bulk_g2s(X, xl, (uint32_t)NT * RB, bar);
+        }
+        if (!bulk_x)
+            for (int i = tid; i < NT; i += nthr) sts_row<CE>(X, i * RB, load_row_cg<CE>(xl, i));
+        // cotangent of x_phys = x^L[:, :dim]  ->  dL/dx^L (zero in the other channels)
+        for (int i = tid; i < NT; i += nthr) sts_row<CE>(GS, i * RB, load_dims<CE>(a.g_xphys, (int64_t)n0 + i, a.dim));
+        const int lw = (a.Lw > 1) ? a.L - 1 : 0;
+        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)lw * MUSZ + t];
+        if (tx) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        __syncthreads();
+        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
+        EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + n0};
+        tile_backward<CE, W, ELLS>(a, tile, n0, NT, X, GO, P, DL, GS, Ein, Eout, Mu, red);
+    }
+}
+
+// ============================================================================================
+// train: feature assembly + forward + mesh loss + backward of a tile, one launch
+// ============================================================================================
+// Replaces pack -> forward -> loss -> backward of the training step (src/run_GNN.py:99-131 with
+// loss_type = mesh_loss): x_phys and its cotangent never leave the SM.  The layer states go to
+// `states` (L2-resident scratch) on the way up and are read back by the same thread on the way
+// down; ld.global.cg keeps those reads coherent.
+template <int CE, int W, bool ELLS>
+__global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const Args a) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const Layout lay = make_layout(CE, KIND_BWD, a.cap_nodes, ELLS, (nthr + 31) >> 5);
+    unsigned char* B0 = smem + lay.xa;
+    unsigned char* B1 = smem + lay.xb;
+    unsigned char* P = smem + lay.p;
+    unsigned char* GS = smem + lay.gs;
+    unsigned char* DL = smem + lay.dl;
+    float* Mu = reinterpret_cast<float*>(smem + lay.mu);
+    float* red = reinterpret_cast<float*>(smem + lay.red);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    uint32_t parity = 0;
+    const size_t state_stride = (size_t)a.N * CE;
+
+    for (int tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
+        const int n0 = a.tile_ptr[tile];
+        const int NT = a.tile_ptr[tile + 1] - n0;
+        __syncthreads();
+        if (ELLS && tid == 0) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(bar, 2u * (uint32_t)NT * 16u);
+            bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
+            bulk_g2s(smem + lay.eout, a.ell_out + n0, (uint32_t)NT * 16u, bar);
+        }
+        // features = cat[x_comp, f, uu] + identity (zero-pad) encoder: src/GNN.py:225-239,75-83,270
+        unsigned char* Xc = B0;
+        unsigned char* Xn = B1;
+        {
+            const float fs = (a.f && a.f_scale) ? a.f_scale[0] : 1.0f;
+            const float us = (a.uu && a.uu_scale) ? a.uu_scale[0] : 1.0f;
+            const int cf = a.dim, cu = a.dim + (a.f ? 1 : 0);
+            for (int i = tid; i < NT; i += nthr) {
+                const int64_t gi = (int64_t)n0 + i;
+                Row<CE> x = load_dims<CE>(a.x_comp, gi, a.dim);
+#pragma unroll
+                for (int c = 0; c < CE; ++c) {
+                    if (a.f && c == cf) x.v[c] = a.f_scale ? a.f[gi] / fs : a.f[gi];
+                    if (a.uu && c == cu) x.v[c] = a.uu_scale ? a.uu[gi] / us : a.uu[gi];
+                }
+                sts_row<CE>(Xc, i * RB, x);
+                store_row<CE>(a.states, gi, x);
+            }
+        }
+        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+        if (ELLS) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        __syncthreads();
+        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
+        EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + n0};
+
+        // ---- forward (Euler), loss and cotangent fused into the last layer --------------------
+        float loss_acc = 0.f;
+        for (int l = 0; l < a.L; ++l) {
+            if (a.Lw > 1 && l > 0) {
+                for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+                __syncthreads();
+            }
+            const float h = a.tau[l];
+            const bool last = (l == a.L - 1);
+            float* st_out = last ? nullptr : a.states + (size_t)(l + 1) * state_stride;
+            uint4 e_nx = (tid < NT) ? Ein.get(tid) : make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < NT; i += nthr) {
+                const uint4 e = e_nx;
+                if (i + nthr < NT) e_nx = Ein.get(i + nthr);
+                const Row<CE> y = lds_row<CE>(Xc, i * RB);
+                const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mu);
+                Row<CE> xn;
+#pragma unroll
+                for (int c = 0; c < CE; ++c) xn.v[c] = fmaf(h, k.v[c], y.v[c]);
+                if (!last) {
+                    sts_row<CE>(Xn, i * RB, xn);
+                    store_row<CE>(st_out, (int64_t)n0 + i, xn);
+                } else {
+                    const int64_t gi = (int64_t)n0 + i;
+                    if (a.x_phys) store_dims<CE>(a.x_phys, gi, a.dim, xn);
+                    const Row<CE> tg = load_dims<CE>(a.target, gi, a.dim);
+                    Row<CE> g;
+#pragma unroll
+                    for (int c = 0; c < CE; ++c) {
+                        const float d = (c < a.dim) ? xn.v[c] - tg.v[c] : 0.f;
+                        if (a.loss_kind == 0) {
+                            loss_acc += fabsf(d);
+                            g.v[c] = (d > 0.f) ? a.grad_scale : ((d < 0.f) ? -a.grad_scale : 0.f);   // torch sign()
+                        } else {
+                            loss_acc = fmaf(d, d, loss_acc);
+                            g.v[c] = 2.0f * a.grad_scale * d;
+                        }
+                    }
+                    sts_row<CE>(GS, i * RB, g);
+                }
+            }
+            __syncthreads();
+            if (!last) {
+                unsigned char* t = Xc;
+                Xc = Xn;
+                Xn = t;
+            }
+        }
+        // Xc = x^{L-1} (never overwritten by the last layer), Xn = free -> GO
+        if (a.Lw > 1) {
+            // weights of layer L-1 are already in Mu
+        }
+        {
+            float one[1] = {loss_acc};
+            block_reduce<1>(one, red, a.loss_partials + tile);
+        }
+        tile_backward<CE, W, ELLS>(a, tile, n0, NT, Xc, Xn, P, DL, GS, Ein, Eout, Mu, red);
+    }
+}
+
+// ============================================================================================
+// host-side launchers (instantiated per (CE, W) translation unit by GAD_ELL_INSTANTIATE)
+// ============================================================================================
+template <typename K>
+int prepare_launch(K kernel, int threads, size_t smem_bytes, int T, int* grid) {
+    GAD_CHECK_ARG((int)smem_bytes <= smem_optin_bytes(), "ELL kernel: tile needs %zu B of shared memory (> %d)",
+                  smem_bytes, smem_optin_bytes());
+    GAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    GAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int occ = 0;
+    GAD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem_bytes));
+    GAD_CHECK_ARG(occ >= 1, "ELL kernel: launch of %d threads with %zu B of shared memory does not fit an SM", threads,
+                  smem_bytes);
+    const long long cap = (long long)occ * sm_count();
+    *grid = (int)((long long)T < cap ? T : cap);
+    return GAD_OK;
+}
+
+template <int CE, int W, bool ELLS>
+int launch_fwd_t(const Args& a, int method, int threads, cudaStream_t st) {
+    int grid = 0, rc;
+    if (method == GAD_METHOD_EULER) {
+        const size_t bytes = make_layout(CE, KIND_FWD, a.cap_nodes, ELLS, (threads + 31) / 32).total;
+        if ((rc = prepare_launch(k_ell_fwd<CE, W, ELLS, GAD_METHOD_EULER>, threads, bytes, a.T, &grid))) return rc;
+        k_ell_fwd<CE, W, ELLS, GAD_METHOD_EULER><<<grid, threads, bytes, st>>>(a);
+    } else {
+        const size_t bytes = make_layout(CE, KIND_FWD_RK4, a.cap_nodes, ELLS, (threads + 31) / 32).total;
+        if ((rc = prepare_launch(k_ell_fwd<CE, W, ELLS, GAD_METHOD_RK4>, threads, bytes, a.T, &grid))) return rc;
+        k_ell_fwd<CE, W, ELLS, GAD_METHOD_RK4><<<grid, threads, bytes, st>>>(a);
+    }
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+template <int CE, int W, bool ELLS>
+int launch_bwd_t(const Args& a, int threads, cudaStream_t st) {
+    int grid = 0, rc;
+    const size_t bytes = make_layout(CE, KIND_BWD, a.cap_nodes, ELLS, (threads + 31) / 32).total;
+    if ((rc = prepare_launch(k_ell_bwd<CE, W, ELLS>, threads, bytes, a.T, &grid))) return rc;
+    k_ell_bwd<CE, W, ELLS><<<grid, threads, bytes, st>>>(a);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+template <int CE, int W, bool ELLS>
+int launch_train_t(const Args& a, int threads, cudaStream_t st) {
+    int grid = 0, rc;
+    const size_t bytes = make_layout(CE, KIND_BWD, a.cap_nodes, ELLS, (threads + 31) / 32).total;
+    if ((rc = prepare_launch(k_ell_train<CE, W, ELLS>, threads, bytes, a.T, &grid))) return rc;
+    k_ell_train<CE, W, ELLS><<<grid, threads, bytes, st>>>(a);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// which: 0 forward, 1 backward, 2 train
+#define GAD_ELL_INSTANTIATE(CE_, W_)                                                                         \
+    int ell_launch_c##CE_##w##W_(int which, const Args& a, int method, int ells, int threads, cudaStream_t st) { \
+        if (which == 0)                                                                                      \
+            return ells ? launch_fwd_t<CE_, W_, true>(a, method, threads, st)                                \
+                        : launch_fwd_t<CE_, W_, false>(a, method, threads, st);                              \
+        if (which == 1)                                                                                      \
+            return ells ? launch_bwd_t<CE_, W_, true>(a, threads, st) : launch_bwd_t<CE_, W_, false>(a, threads, st); \
+        return ells ? launch_train_t<CE_, W_, true>(a, threads, st) : launch_train_t<CE_, W_, false>(a, threads, st); \
+    }
+
+#define GAD_ELL_DECLARE(CE_, W_) \
+    int ell_launch_c##CE_##w##W_(int which, const Args& a, int method, int ells, int threads, cudaStream_t st);
+
+}  // namespace ell
+}  // namespace gad

@@ -40,13 +40,27 @@
 
 namespace gad {
 
-__device__ __forceinline__ float gexp(float x) {
-#if GAD_FAST_EXP
-    return __expf(x);
-#else
-    return expf(x);
-#endif
+// All logits are in the log2 domain: gad_prepare_weights folds log2(e) into (M, u), so
+// alpha_e = 2^(s_e - m) / Z and the backward carries ds' = ln2 * alpha (da - D); gad_weight_grads
+// undoes the fold.  ex2.approx / lg2.approx are single MUFU ops with 2^-22 relative error.
+constexpr float LN2_F = 0.69314718055994530942f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gexp(float x) { return ex2_approx(x); }
 
 template <int CE>
 struct Row {
@@ -259,7 +273,7 @@ __device__ __forceinline__ Row<CE> node_bwd_dst(const float* __restrict__ X, con
 #pragma unroll
         for (int q = 0; q < W; ++q) {
             if (q < deg) {
-                const float ds = (s[q] * rZ) * (da[q] - D);
+                const float ds = (s[q] * rZ * LN2_F) * (da[q] - D);
 #pragma unroll
                 for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj[q].v[c], t.v[c]);
             }
@@ -274,7 +288,7 @@ __device__ __forceinline__ Row<CE> node_bwd_dst(const float* __restrict__ X, con
         for (int e = e_begin; e < e_end; ++e) {
             const Row<CE> xj = load_row<CE>(X, (int64_t)col[e]);
             const float alpha = gexp(dot<CE>(p, xj) - m) * rZ;
-            const float ds = alpha * (dot<CE>(go, xj) - D);
+            const float ds = (alpha * LN2_F) * (dot<CE>(go, xj) - D);
 #pragma unroll
             for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj.v[c], t.v[c]);
         }
@@ -291,8 +305,8 @@ __device__ __forceinline__ Row<CE> node_bwd_dst(const float* __restrict__ X, con
     for (int bb = 0; bb < CE; ++bb) acc[CE * CE + bb] += t.v[bb];
     rec->p = p;
     rec->D = D;
-    // alpha_e = exp(s_e - lse);  lse = m + log Z.  Empty row: never read by a source pass.
-    rec->lse = (deg > 0) ? m - logf(rZ) : 0.f;
+    // alpha_e = 2^(s_e - lse);  lse = m + log2 Z.  Empty row: never read by a source pass.
+    rec->lse = (deg > 0) ? m - log2f(rZ) : 0.f;
     const Row<CE> Mt = apply_M<CE>(Mu, t);
     Row<CE> gs;
 #pragma unroll
@@ -315,7 +329,7 @@ __device__ __forceinline__ Row<CE> node_bwd_src(const float* __restrict__ P, con
         const float2 dl = DL[i];
         const float alpha = gexp(dot<CE>(p, xj) - dl.y);
         const float da = b * dot<CE>(gp, xj);
-        const float ds = alpha * (da - dl.x);
+        const float ds = (alpha * LN2_F) * (da - dl.x);
         const float ab = alpha * b;
 #pragma unroll
         for (int c = 0; c < CE; ++c) accv.v[c] = fmaf(ab, gp.v[c], fmaf(ds, p.v[c], accv.v[c]));

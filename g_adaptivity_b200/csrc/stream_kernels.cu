@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(TB) k_alpha(const int32_t* __restrict__ rowptr
     node_feval<CE, int32_t>(x, col, b, e_end, xi, Mu, nullptr, &st, &p);
     for (int e = b; e < e_end; ++e) {
         const Row<CE> xj = load_row<CE>(x, (int64_t)col[e]);
-        alpha[eid[e]] = expf(dot<CE>(p, xj) - st.m) * st.rZ;
+        alpha[eid[e]] = gexp(dot<CE>(p, xj) - st.m) * st.rZ;
     }
 }
 
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(TB) k_bwd_src(const int32_t* __restrict__ t_ro
 #pragma unroll
             for (int c = 0; c < CE; ++c) gp.v[c] = (c < gplus_dim) ? gplus[i * gplus_dim + c] : 0.f;
             const float2 dl = DL[i];
-            const float alpha = expf(dot<CE>(p, xj) - dl.y);
-            const float ds = alpha * (b * dot<CE>(gp, xj) - dl.x);
+            const float alpha = gexp(dot<CE>(p, xj) - dl.y);
+            const float ds = (alpha * LN2_F) * (b * dot<CE>(gp, xj) - dl.x);
             const float ab = alpha * b;
 #pragma unroll
             for (int c = 0; c < CE; ++c) accv.v[c] = fmaf(ab, gp.v[c], fmaf(ds, p.v[c], accv.v[c]));

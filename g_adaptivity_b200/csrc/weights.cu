@@ -15,6 +15,8 @@
 namespace gad {
 namespace {
 
+constexpr double LOG2E = 1.4426950408889634074;
+
 __global__ void k_prepare_weights(const float* __restrict__ Wq, const float* __restrict__ bq,
                                   const float* __restrict__ Wk, int C, int CE, float inv_temp,
                                   float* __restrict__ Mu) {
@@ -23,7 +25,7 @@ __global__ void k_prepare_weights(const float* __restrict__ Wq, const float* __r
     const float* wk = Wk + (size_t)l * C * C;
     const float* b = bq + (size_t)l * C;
     float* out = Mu + (size_t)l * (CE * CE + CE);
-    const double c = (double)inv_temp / sqrt((double)C);
+    const double c = LOG2E * (double)inv_temp / sqrt((double)C);   // logits live in the log2 domain
     const int live = CE < C ? CE : C;
     for (int idx = threadIdx.x; idx < CE * CE + CE; idx += blockDim.x) {
         double acc = 0.0;
@@ -52,7 +54,8 @@ __global__ void k_weight_grads(const float* __restrict__ Wq, const float* __rest
     const float* b = bq + (size_t)l * C;
     const float* GM = gMu + (size_t)l * (CE * CE + CE);
     const float* Gu = GM + CE * CE;
-    const double c = (double)inv_temp / sqrt((double)C);
+    // the kernels return G' = ln2 * G (ds' = ln2 ds) for M' = log2e * M: d/dM = log2e * d/dM'
+    const double c = LOG2E * (double)inv_temp / sqrt((double)C);
     const int live = CE < C ? CE : C;
     for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
         const int o = idx / C, a = idx % C;

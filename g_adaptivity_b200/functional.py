@@ -28,6 +28,12 @@ def live_channels(in_dim: int, hidden_dim: int) -> Tuple[int, int]:
     raise NotImplementedError(f"{live} live channels: the sm_100a kernels are instantiated for <= 8")
 
 
+def use_ell(graph: MeshGraph, CE: int) -> bool:
+    """True when the mesh-resident ELL kernels serve this graph (bounded degree, tiles planned,
+    ELL rows built for this channel width); otherwise the CSR mesh-resident / streaming kernels do."""
+    return graph.ell_in is not None and graph.ell_ce == CE and graph.tile_ptr is not None
+
+
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -103,6 +109,13 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
     assert graph.N == N
     x_phys = torch.empty((N, dim), dtype=torch.float32, device=x0.device)
     use_tiles = graph.tile_ptr is not None and not force_stream
+    if use_tiles and use_ell(graph, CE):
+        with torch.cuda.device(x0.device):
+            _lib.check(lib.gad_deform_fwd_ell(
+                _lib.ptr(graph.ell_in), N, _lib.ptr(graph.tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
+                _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys),
+                _lib.ptr(states), _stream(x0)), "gad_deform_fwd_ell")
+        return x_phys
     ws = None
     ws_bytes = 0
     if not use_tiles:
@@ -131,6 +144,16 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
     g_x0 = torch.empty((N, CE), dtype=torch.float32, device=dev) if want_gx0 else None
     use_tiles = graph.tile_ptr is not None and not force_stream
     T = graph.T if use_tiles else 0
+    if use_tiles and use_ell(graph, CE):
+        ws_bytes = lib.gad_ell_workspace_bytes(CE, T, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gad_deform_bwd_ell(
+                _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.tile_ptr), T,
+                graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw,
+                _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes,
+                _stream(states)), "gad_deform_bwd_ell")
+        return gMu, g_tau, g_x0
     ws_bytes = lib.gad_deform_bwd_workspace_bytes(N, CE, T, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

@@ -64,6 +64,9 @@ class MeshGraph:
         self.col_walk = self.t_dst_walk = None   # per-row ascending copies used by the deformer kernels
         self.max_in_deg = self.max_out_deg = 0
         self.tile_ptr = None        # int32 [T+1] on device, or None -> streaming kernels
+        self.ell_in = self.ell_out = None   # uint16 [N, 8] ELL rows (mesh-resident ELL kernels), or None
+        self.ell_ce = 0             # channel width the ELL byte offsets were built for
+        self.ell_deg = 0            # max(in-degree, out-degree)
         self.T = 0
         self.max_tile_nodes = 0
         self.max_tile_edges = 0
@@ -74,7 +77,7 @@ class MeshGraph:
     def build(edge_index: torch.Tensor, num_nodes: int, masks: Sequence[Optional[torch.Tensor]] = (),
               extra_loops: Optional[torch.Tensor] = None, self_loops: bool = False,
               mesh_sizes: Optional[Sequence[int]] = None, device=None, ce: int = 4,
-              tile_target: Optional[int] = None) -> "MeshGraph":
+              tile_target: Optional[int] = None, use_ell: bool = True) -> "MeshGraph":
         lib = _lib.load()
         if device is None:
             device = edge_index.device
@@ -136,15 +139,16 @@ class MeshGraph:
                 _lib.check(lib.gad_graph_sort_rows(_lib.ptr(g.t_rowptr), _lib.ptr(g.t_dst), N, _lib.ptr(g.t_dst_walk),
                                                    stream), "gad_graph_sort_rows")
         if mesh_sizes is not None:
-            g.plan(mesh_sizes, ce=ce, tile_target=tile_target)
+            g.plan(mesh_sizes, ce=ce, tile_target=tile_target, use_ell=use_ell)
         return g
 
     # ------------------------------------------------------------------------------------
-    def plan(self, mesh_sizes: Sequence[int], ce: int = 4, tile_target: Optional[int] = None):
+    def plan(self, mesh_sizes: Sequence[int], ce: int = 4, tile_target: Optional[int] = None, use_ell: bool = True):
         """Choose tiles for the mesh-resident kernels; falls back to streaming (tile_ptr = None)
         when a mesh does not fit one CTA's shared memory or the batch is not a disjoint union."""
         lib = _lib.load()
         self.tile_ptr, self.T, self.max_tile_nodes, self.max_tile_edges = None, 0, 0, 0
+        self.ell_in = self.ell_out = None
         if int(np.sum(mesh_sizes)) != self.N:
             raise ValueError("mesh_sizes do not add up to the node count")
         tp = plan_tiles(mesh_sizes, target_nodes=tile_target or _DEFAULT_TILE_TARGET)
@@ -171,6 +175,35 @@ class MeshGraph:
         self.tile_ptr, self.T = tile_ptr, T
         self.max_tile_nodes, self.max_tile_edges = max_nodes, max(max_edges, 1)
         self.sm_count = sm.value
+        if use_ell:
+            self._build_ell(ce)
+
+    def _build_ell(self, ce: int):
+        """ELL rows for the mesh-resident ELL kernels (csrc/ell_kernels.cuh): possible when every
+        node has at most 7 in- and out-edges and the tile fits 16-bit row offsets / shared memory."""
+        import os
+        lib = _lib.load()
+        self.ell_in = self.ell_out = None
+        self.ell_ce, self.ell_deg = 0, 0
+        if os.environ.get("GAD_NO_ELL") or ce not in (2, 4) or self.E == 0:
+            return
+        deg = max(self.max_in_deg, self.max_out_deg)
+        if not lib.gad_ell_supported(ce, self.max_tile_nodes, deg, 1):
+            return
+        ell_in = torch.empty((self.N, 8), dtype=torch.int16, device=self.device)
+        ell_out = torch.empty((self.N, 8), dtype=torch.int16, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._info[4:5].zero_()
+            _lib.check(lib.gad_graph_build_ell(_lib.ptr(self.rowptr), _lib.ptr(self.col_walk), self.N,
+                                               _lib.ptr(self.tile_ptr), self.T, ce, _lib.ptr(ell_in),
+                                               _lib.ptr(self._info), stream), "gad_graph_build_ell")
+            _lib.check(lib.gad_graph_build_ell(_lib.ptr(self.t_rowptr), _lib.ptr(self.t_dst_walk), self.N,
+                                               _lib.ptr(self.tile_ptr), self.T, ce, _lib.ptr(ell_out),
+                                               _lib.ptr(self._info), stream), "gad_graph_build_ell")
+        if int(self._info[4].item()) != 0:
+            return
+        self.ell_in, self.ell_out, self.ell_ce, self.ell_deg = ell_in, ell_out, ce, deg
 
 
 def C_int():

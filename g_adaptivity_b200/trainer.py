@@ -128,7 +128,8 @@ class DeformerTrainer:
             s.loss = torch.zeros(1, **f32)
             s.loss_ws = torch.empty(lib.gad_mesh_loss_workspace_bytes(N * self.dim), dtype=torch.uint8, device=dev)
             T = s.graph.T if s.graph.tile_ptr is not None else 0
-            s.bwd_ws_bytes = lib.gad_deform_bwd_workspace_bytes(N, self.CE, T, self.L)
+            s.bwd_ws_bytes = max(lib.gad_deform_bwd_workspace_bytes(N, self.CE, T, self.L),
+                                 lib.gad_ell_workspace_bytes(self.CE, T, self.L))
             s.bwd_ws = torch.empty(s.bwd_ws_bytes, dtype=torch.uint8, device=dev)
             s.fwd_ws_bytes = 0 if T else lib.gad_deform_workspace_bytes(N, self.CE, self.method)
             s.fwd_ws = torch.empty(max(s.fwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
@@ -162,7 +163,21 @@ class DeformerTrainer:
         CE, L, Lw, C, dim = self.CE, self.L, self.Lw, self.C, self.dim
         tiles = g.tile_ptr is not None and not self.opt.get("gad_force_stream", False)
         inv_temp = self.model.inv_temp
-        if stage in ("all", "pre"):
+        ell = tiles and GF.use_ell(g, CE) and not self.opt.get("gad_no_fused_train", False)
+        if stage in ("all", "pre") and ell:
+            # one launch per tile for pack + forward + loss + backward (csrc/ell_kernels.cuh: k_ell_train)
+            count = s.N * dim
+            chk(lib.gad_prepare_weights(P(self.Wq), P(self.bq), P(self.Wk), Lw, C, CE, inv_temp, P(self.Mu), stream_ptr),
+                "gad_prepare_weights")
+            chk(lib.gad_deform_train_ell(P(g.ell_in), P(g.ell_out), s.N, P(g.tile_ptr), g.T, g.max_tile_nodes, g.ell_deg,
+                                         P(s.x_comp), P(s.f), P(s.uu), None, None, P(s.target), dim, CE, P(self.Mu), Lw,
+                                         P(self.tau), L, 0 if self.loss_kind == "l1" else 1,
+                                         1.0 / (count * self.world), 1.0 / count, P(s.states), P(self.gMu), P(self.gtau),
+                                         P(s.loss), P(s.x_phys), P(s.bwd_ws), s.bwd_ws_bytes, stream_ptr),
+                "gad_deform_train_ell")
+            chk(lib.gad_weight_grads(P(self.Wq), P(self.bq), P(self.Wk), P(self.gMu), Lw, C, CE, inv_temp, P(self.gWq),
+                                     P(self.gbq), P(self.gWk), P(self.gbk), stream_ptr), "gad_weight_grads")
+        elif stage in ("all", "pre"):
             chk(lib.gad_prepare_weights(P(self.Wq), P(self.bq), P(self.Wk), Lw, C, CE, inv_temp, P(self.Mu), stream_ptr),
                 "gad_prepare_weights")
             chk(lib.gad_pack_features(P(s.x_comp), P(s.f), P(s.uu), None, None, s.N, dim, CE, P(s.states), stream_ptr),

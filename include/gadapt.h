@@ -47,6 +47,7 @@ extern "C" {
 #define GAD_INFO_MAX_IN_DEG 1
 #define GAD_INFO_MAX_OUT_DEG 2
 #define GAD_INFO_CROSS_TILE 3   /* edges whose endpoints lie in different tiles (gad_graph_check_tiles) */
+#define GAD_INFO_ELL_BAD 4      /* rows that do not fit the ELL form (gad_graph_build_ell)             */
 
 int gad_version(void);
 const char* gad_last_error(void);
@@ -128,6 +129,42 @@ int gad_deform_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_r
                    const float* g_xphys, int dim, int CE, const float* Mu, int Lw, const float* tau,
                    int L, float* gMu, float* g_tau, float* g_x0, void* workspace,
                    size_t workspace_bytes, void* stream);
+
+/* ---- mesh-resident ELL path -------------------------------------------------------------------
+ * The fast path for batches of bounded-degree meshes (every 1-D / 2-D mesh of the reference: in-
+ * and out-degree <= 7 with self-loops).  Topology is one 16-byte row per node and direction:
+ *     ell[i] = { uint16 off_0 .. off_6, uint16 degree },  off_q = (neighbour_q - tile_start) * CE * 4
+ * built once per graph by gad_graph_build_ell from the row-sorted CSR (ptr = rowptr, idx = col) or
+ * CSC (t_rowptr, t_dst) arrays and the tile plan; rows that do not fit (degree > 7, neighbour
+ * outside the tile, offset > 65535) are counted in info[GAD_INFO_ELL_BAD] and the caller must
+ * fall back to gad_deform_fwd / gad_deform_bwd.  max_deg = max(in-degree, out-degree) of the graph.
+ * gad_deform_fwd_ell / gad_deform_bwd_ell: same contract as gad_deform_fwd / gad_deform_bwd
+ * (Euler or RK4 forward, Euler backward), CE in {2, 4}.
+ * gad_deform_train_ell: the training pass of src/run_GNN.py:99-131 with loss_type = mesh_loss in ONE
+ * launch per tile -- feature assembly (GNN.py:225-239), L Euler layers, mean L1 / MSE loss against
+ * `target` [N, dim], and the backward -- followed by the fixed-order reduction:
+ *     gMu [Lw, CE*CE+CE], g_tau [L] (may be NULL), loss[0] = loss_scale * sum |out - target| (or ^2),
+ * with the cotangent grad_scale * d(sum)/d(out).  `states` [L, N, CE] is scratch (layer inputs),
+ * x_phys [N, dim] is optional.  workspace: gad_ell_workspace_bytes(CE, T, L).
+ */
+int gad_graph_build_ell(const int32_t* ptr, const int32_t* idx, int64_t N, const int32_t* tile_ptr, int T,
+                        int CE, void* ell_rows, int32_t* info, void* stream);
+/* 1 when the ELL kernels can run tiles of this size (shared-memory fit), else 0. */
+int gad_ell_supported(int CE, int max_tile_nodes, int max_deg, int train);
+size_t gad_ell_workspace_bytes(int CE, int T, int L);
+int gad_deform_fwd_ell(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T, int max_tile_nodes,
+                       int max_deg, const float* x0, int dim, int CE, const float* Mu, int Lw,
+                       const float* tau, int L, int method, float* x_phys, float* states, void* stream);
+int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
+                       int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
+                       int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,
+                       float* g_x0, void* workspace, size_t workspace_bytes, void* stream);
+int gad_deform_train_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
+                         int max_tile_nodes, int max_deg, const float* x_comp, const float* f,
+                         const float* uu, const float* f_scale, const float* uu_scale, const float* target,
+                         int dim, int CE, const float* Mu, int Lw, const float* tau, int L, int loss_kind,
+                         float grad_scale, float loss_scale, float* states, float* gMu, float* g_tau,
+                         float* loss, float* x_phys, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --
  * res = A(x) x - x  for x [N, CE];  alpha (optional) [E] in filtered edge-list order.

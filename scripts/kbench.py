@@ -54,14 +54,35 @@ def main():
     res = {"tag": a.tag, "mesh": list(md), "batch": a.batch, "nodes": tr.slots[0].N, "tiles": tr.slots[0].graph.T,
            "max_tile_nodes": tr.slots[0].graph.max_tile_nodes}
 
+    from g_adaptivity_b200 import functional as GF
+    ell = GF.use_ell(tr.slots[0].graph, tr.CE)
+    res["ell"] = bool(ell)
+
     def fwd(s):
         g = s.graph
+        if ell:
+            lib.gad_deform_fwd_ell(P(g.ell_in), s.N, P(g.tile_ptr), g.T, g.max_tile_nodes, g.ell_deg, P(s.states),
+                                   model.dim, tr.CE, P(tr.Mu), tr.Lw, P(tr.tau), tr.L, 0, P(s.x_phys), P(s.states), st)
+            return
         lib.gad_deform_fwd(P(g.rowptr), P(g.col_walk), s.N, g.E, P(g.tile_ptr), g.T, g.max_tile_nodes, g.max_tile_edges,
                            P(s.states), model.dim, tr.CE, P(tr.Mu), tr.Lw, P(tr.tau), tr.L, 0, P(s.x_phys), P(s.states),
                            P(s.fwd_ws), s.fwd_ws_bytes, st)
 
+    def train(s):
+        g = s.graph
+        cnt = s.N * model.dim
+        lib.gad_deform_train_ell(P(g.ell_in), P(g.ell_out), s.N, P(g.tile_ptr), g.T, g.max_tile_nodes, g.ell_deg,
+                                 P(s.x_comp), P(s.f), P(s.uu), None, None, P(s.target), model.dim, tr.CE, P(tr.Mu), tr.Lw,
+                                 P(tr.tau), tr.L, 0, 1.0 / cnt, 1.0 / cnt, P(s.states), P(tr.gMu), P(tr.gtau),
+                                 P(s.loss), None, P(s.bwd_ws), s.bwd_ws_bytes, st)
+
     def bwd(s):
         g = s.graph
+        if ell:
+            lib.gad_deform_bwd_ell(P(g.ell_in), P(g.ell_out), s.N, P(g.tile_ptr), g.T, g.max_tile_nodes, g.ell_deg,
+                                   P(s.states), P(s.g_out), model.dim, tr.CE, P(tr.Mu), tr.Lw, P(tr.tau), tr.L,
+                                   P(tr.gMu), P(tr.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, st)
+            return
         lib.gad_deform_bwd(P(g.rowptr), P(g.col_walk), P(g.t_rowptr), P(g.t_dst_walk), s.N, g.E, P(g.tile_ptr), g.T,
                            g.max_tile_nodes, g.max_tile_edges, P(s.states), P(s.g_out), model.dim, tr.CE, P(tr.Mu),
                            tr.Lw, P(tr.tau), tr.L, P(tr.gMu), P(tr.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, st)
@@ -70,7 +91,13 @@ def main():
         for s in tr.slots:                      # one full eager step per slot: states / g_out valid
             tr._issue(s, st, with_optimizer=False)
     tr.synchronize()
-    for name, fn in (("fwd_us", fwd), ("bwd_us", bwd)):
+    if ell:   # g_out for the stand-alone backward timing (the fused train kernel never materialises it)
+        with torch.cuda.stream(tr.stream):
+            for s in tr.slots:
+                lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * model.dim, 0, 1.0 / (s.N * model.dim), P(s.loss),
+                                  P(s.g_out), P(s.loss_ws), st)
+        tr.synchronize()
+    for name, fn in (("fwd_us", fwd), ("bwd_us", bwd)) + ((("train_us", train),) if ell else ()):
         evs = []
         with torch.cuda.stream(tr.stream):
             torch.cuda._sleep(int(2e7))     # let the host run ahead: event pairs then time the device only

@@ -1,0 +1,145 @@
+"""GPU parity of the mesh-resident ELL kernels (csrc/ell_kernels.cuh) and of the one-launch training
+pass `gad_deform_train_ell`, against the CPU oracle and against the CSR mesh-resident kernels.
+
+Bars as in test_gpu_parity.py: coordinates 1e-5 relative, parameter gradients 1e-4 relative.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gad_testutil as util
+from g_adaptivity_b200 import GNN, synth
+from g_adaptivity_b200.trainer import DeformerTrainer
+from oracle import gnn_oracle
+from test_gpu_parity import COORD_TOL, GRAD_TOL, check_grads, cuda_model, grads_of, oracle_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(mesh_dims, B, seed=0, burgers=False, **over):
+    opt = synth.burgers_opt(mesh_dims, **over) if burgers else synth.default_opt(mesh_dims, **over)
+    ds = synth.SyntheticDataset(len(mesh_dims), mesh_dims)
+    data = synth.make_batch(mesh_dims, B, seed=seed, burgers=burgers)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    return opt, ds, data, ref
+
+
+@pytest.mark.parametrize("mesh_dims,B,burgers,over,slots", [
+    ((30, 30), 16, False, {}, 6),                       # cfg2 shape: CE=4, 6 slots
+    ((12, 12), 5, False, {"self_loops": True}, 7),      # +self-loops: 7 slots
+    ((200,), 64, True, {}, 2),                          # 1-D Burgers: CE=2, 2 slots
+    ((40,), 9, True, {"self_loops": True}, 3),          # 1-D + self-loops: 3 slots
+    ((10, 10), 4, False, {"gnn_inc_feat_f": False, "gnn_inc_feat_uu": False}, 6),   # 2-D, CE=2
+    ((50, 50), 4, False, {}, 6),                        # cfg5 shape: ELL rows streamed from L2
+    ((9, 9), 3, False, {"fix_boundary": False}, 6),
+])
+def test_ell_path_matches_oracle_and_csr_path(mesh_dims, B, burgers, over, slots):
+    opt, ds, data, ref = _case(mesh_dims, B, burgers=burgers, **over)
+    ref_out = ref(data)
+    gnn_oracle.mesh_loss(ref_out, data.x_phys).backward()
+    ref_grads = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    g64, floor, scale = util.fp64_grads_and_noise_floor(ds, opt, data, ref, ref_grads)
+    outs = {}
+    for no_ell in (False, True):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_no_ell=no_ell)
+        model.train()
+        out = model(data)
+        g = model.last_graph
+        assert g.tile_ptr is not None
+        assert (g.ell_in is None) == no_ell
+        if not no_ell:
+            assert max(g.max_in_deg, g.max_out_deg) <= slots
+        assert util.rel_err(out, ref_out) <= COORD_TOL
+        tgt = data.x_phys.cuda()
+        F.l1_loss(out, tgt if tgt.dim() == 2 else tgt.unsqueeze(-1)).backward()
+        util.check_grads_conditioned(grads_of(model), g64, floor, scale)
+        outs[no_ell] = out.detach().cpu()
+    assert util.rel_err(outs[False], outs[True]) <= 2e-6
+
+
+def test_ell_rows_encode_the_csr():
+    """ELL rows are a re-encoding of the (row-sorted) CSR / CSC arrays: integer-exact."""
+    opt, ds, data, ref = _case((13, 13), 6)
+    model = cuda_model(ds, opt, ref.state_dict())
+    model(data)
+    g = model.last_graph
+    tp = g.tile_ptr.cpu().numpy()
+    tile_of = np.searchsorted(tp, np.arange(g.N), side="right") - 1
+    for ell, ptr, idx in ((g.ell_in, g.rowptr, g.col_walk), (g.ell_out, g.t_rowptr, g.t_dst_walk)):
+        rows = ell.cpu().numpy().view(np.uint16).astype(np.int64)
+        ptr, idx = ptr.cpu().numpy(), idx.cpu().numpy()
+        deg = np.diff(ptr)
+        assert np.array_equal(rows[:, 7], deg)
+        for i in range(g.N):
+            want = (idx[ptr[i]:ptr[i + 1]] - tp[tile_of[i]]) * (g.ell_ce * 4)
+            assert np.array_equal(rows[i, :deg[i]], want)
+            assert not rows[i, deg[i]:7].any()
+
+
+@pytest.mark.parametrize("loss", ["l1", "mse"])
+@pytest.mark.parametrize("over", [
+    {},
+    {"share_conv": False},
+    {"learn_step": True},
+    {"share_conv": False, "learn_step": True, "num_layers": 3},
+    {"num_layers": 1},
+    {"softmax_temp_type": "fixed", "softmax_temp": 2.0},
+])
+def test_fused_train_step_matches_oracle(loss, over):
+    """One launch per tile for pack + forward + loss + backward: loss value and every parameter
+    gradient against autograd on the oracle."""
+    opt, ds, data, ref = _case((14, 14), 11, seed=4, loss_fn=loss, **over)
+    ref_out = ref(data)
+    ref_loss = gnn_oracle.mesh_loss(ref_out, data.x_phys, loss_fn=loss)
+    ref_loss.backward()
+    ref_grads = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    model = cuda_model(ds, opt, ref.state_dict())
+    tr = DeformerTrainer(model, use_cuda_graph=False, loss_fn=loss)
+    sid = tr.add_batch(data)
+    assert tr.slots[sid].graph.ell_in is not None
+    with torch.cuda.stream(tr.stream):
+        tr._issue(tr.slots[sid], tr.stream.cuda_stream, with_optimizer=False)
+    tr.synchronize()
+    assert abs(tr.slots[sid].loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert util.rel_err(tr.slots[sid].x_phys, ref_out) <= COORD_TOL
+    check_grads(grads_of(model), ref_grads)
+
+
+def test_fused_train_equals_unfused_kernels():
+    opt, ds, data, ref = _case((30, 30), 24, seed=6)
+    res = []
+    for no_fused in (False, True):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_no_fused_train=no_fused)
+        tr = DeformerTrainer(model, use_cuda_graph=False)
+        sid = tr.add_batch(data)
+        with torch.cuda.stream(tr.stream):
+            tr._issue(tr.slots[sid], tr.stream.cuda_stream, with_optimizer=False)
+        tr.synchronize()
+        res.append((tr.slots[sid].loss.item(), tr.gflat.clone().cpu()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[1][0])
+    scale = res[1][1].abs().max().item()
+    assert (res[0][1] - res[1][1]).abs().max().item() <= 1e-5 * scale
+
+
+def test_fused_train_graph_replay_is_deterministic_and_trains():
+    opt, ds, data, ref = _case((30, 30), 32, seed=8)
+    finals = []
+    for _ in range(2):
+        model = cuda_model(ds, opt, ref.state_dict())
+        tr = DeformerTrainer(model, lr=1e-2)
+        sid = tr.add_batch(data)
+        losses = []
+        for _ in range(12):
+            loss = tr.step(sid)
+            with torch.cuda.stream(tr.stream):      # the step runs on the trainer's stream
+                losses.append(loss.clone())
+        tr.synchronize()
+        losses = [float(x.item()) for x in losses]
+        assert losses[-1] < losses[0]
+        finals.append((losses, tr.flat.clone().cpu()))
+    assert finals[0][0] == finals[1][0]
+    assert torch.equal(finals[0][1], finals[1][1])

@@ -181,7 +181,11 @@ def _compare_with_oracle(mesh_dims, B, over=None, burgers=False, backward=True, 
         gnn_oracle.mesh_loss(ref_out, data.x_phys).backward()
         tgt = data.x_phys.cuda()
         F.l1_loss(out, tgt if tgt.dim() == 2 else tgt.unsqueeze(-1)).backward()
-        check_grads(grads_of(model), {n: p.grad for n, p in ref.named_parameters() if p.grad is not None})
+        ref_grads = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+        # bar: 1e-4 against the oracle evaluated in fp64, widened to twice the fp32 oracle's own
+        # deviation from fp64 where that is larger (large batches: sums of 10^5 signed terms)
+        g64, floor, scale = util.fp64_grads_and_noise_floor(ds, opt, data, ref, ref_grads)
+        util.check_grads_conditioned(grads_of(model), g64, floor, scale, tol=GRAD_TOL)
     return model, out, ref_out, data
 
 
