@@ -23,6 +23,29 @@ _i64 = C.c_int64
 _f = C.c_float
 _sz = C.c_size_t
 
+_i32 = C.c_int32
+_fp = C.c_void_p
+
+
+class TrainDesc(C.Structure):
+    """`gad_train_desc` of include/gadapt.h, field by field."""
+    _fields_ = [
+        ("ell_in", _fp), ("ell_out", _fp), ("tile_ptr", _fp), ("N", _i64),
+        ("T", _i32), ("max_tile_nodes", _i32), ("max_deg", _i32),
+        ("x_comp", _fp), ("f", _fp), ("uu", _fp), ("f_scale", _fp), ("uu_scale", _fp), ("target", _fp),
+        ("dim", _i32), ("CE", _i32),
+        ("Mu", _fp), ("tau", _fp), ("Lw", _i32), ("L", _i32), ("C", _i32), ("inv_temp", _f),
+        ("loss_kind", _i32), ("grad_scale", _f), ("loss_scale", _f),
+        ("states", _fp), ("gMu", _fp), ("g_tau", _fp), ("loss", _fp), ("x_phys", _fp),
+        ("workspace", _fp), ("workspace_bytes", _sz),
+        ("tail", _i32), ("counter", _fp),
+        ("Wq", _fp), ("bq", _fp), ("Wk", _fp), ("gWq", _fp), ("gbq", _fp), ("gWk", _fp), ("gbk", _fp),
+        ("params", _fp), ("grads", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("n_params", _i64),
+        ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("weight_decay", _f), ("adam_grad_scale", _f),
+        ("step", _fp),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/gadapt.h declaration by declaration
 SIGNATURES = {
     "gad_version": (_i, []),
@@ -48,6 +71,7 @@ SIGNATURES = {
     "gad_deform_bwd_ell": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "gad_deform_train_ell": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i,
                                   _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gad_train_step_ell": (_i, [C.POINTER(TrainDesc), _p]),
     "gad_conv_fwd": (_i, [_p, _p, _p, _i64, _i64, _p, _i, _p, _p, _p, _p]),
     "gad_conv_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "gad_mesh_loss": (_i, [_p, _p, _i64, _i, _f, _p, _p, _p, _p]),

@@ -57,39 +57,8 @@ __global__ void k_ell_reduce(const float* __restrict__ partials, int T, int slot
                              float* __restrict__ gMu, const float* __restrict__ tau_partials, int L,
                              float* __restrict__ g_tau, const float* __restrict__ loss_partials, float loss_scale,
                              float* __restrict__ loss) {
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    const int ncol = slots * nacc;
-    const float* src = nullptr;
-    int stride = 0;
-    if (w < ncol) {
-        src = partials + w;
-        stride = ncol;
-    } else if (w < ncol + L) {
-        if (!(tau_partials && g_tau)) return;
-        src = tau_partials + (w - ncol);
-        stride = L;
-    } else if (w == ncol + L) {
-        if (!(loss_partials && loss)) return;
-        src = loss_partials;
-        stride = 1;
-    } else {
-        return;
-    }
-    float s = 0.f;
-    for (int t = lane; t < T; t += 32) s += src[(size_t)t * stride];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (lane != 0) return;
-    if (w < ncol) {
-        const int l = w / nacc, a = w % nacc;
-        if (a < musz) gMu[(size_t)l * musz + a] = s;
-        else if (g_tau && slots > 1) g_tau[l] = s;
-    } else if (w < ncol + L) {
-        g_tau[w - ncol] = s;
-    } else {
-        loss[0] = s * loss_scale;
-    }
+    tail::reduce_partials(partials, T, slots, nacc, musz, gMu, tau_partials, L, g_tau, loss_partials, loss_scale, loss,
+                          blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
 }
 
 int env_int(const char* name, int dflt) {
@@ -316,4 +285,83 @@ extern "C" int gad_deform_train_ell(const void* ell_in, const void* ell_out, int
     cudaStream_t st = as_stream(stream);
     if ((rc = dispatch(CE, p, 2, a, GAD_METHOD_EULER, st))) return rc;
     return reduce_partials(CE, T, Lw, L, ws, gMu, g_tau, loss_scale, loss, st);
+}
+
+extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
+    GAD_CHECK_ARG(d, "gad_train_step_ell: null descriptor");
+    GAD_CHECK_ARG(d->ell_in && d->ell_out && d->tile_ptr && d->x_comp && d->target && d->Mu && d->tau && d->states &&
+                      d->gMu && d->loss && d->workspace && d->counter,
+                  "gad_train_step_ell: null pointer");
+    GAD_CHECK_ARG(d->N > 0 && d->T > 0 && d->L > 0 && d->dim >= 1 && d->dim <= d->CE && (d->Lw == 1 || d->Lw == d->L),
+                  "gad_train_step_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)d->N, d->T, d->L, d->dim, d->CE,
+                  d->Lw);
+    GAD_CHECK_ARG(d->dim + (d->f ? 1 : 0) + (d->uu ? 1 : 0) <= d->CE, "gad_train_step_ell: input features exceed CE=%d",
+                  d->CE);
+    GAD_CHECK_ARG(d->loss_kind == 0 || d->loss_kind == 1, "gad_train_step_ell: unknown loss kind %d", d->loss_kind);
+    GAD_CHECK_ARG(d->tail == 1 || d->tail == 2, "gad_train_step_ell: tail must be 1 or 2 (got %d)", d->tail);
+    GAD_CHECK_ARG(d->Wq && d->bq && d->Wk && d->gWq && d->gbq && d->gWk && d->gbk && d->C > 0,
+                  "gad_train_step_ell: the tail needs the Linear parameters and their gradient buffers");
+    GAD_CHECK_ARG(d->tail < 2 || (d->params && d->grads && d->exp_avg && d->exp_avg_sq && d->step && d->n_params > 0),
+                  "gad_train_step_ell: tail == 2 needs the flat parameter vector and the Adam state");
+    GAD_CHECK_ARG(d->workspace_bytes >= ws_floats(d->CE, d->T, d->L) * sizeof(float),
+                  "gad_train_step_ell: workspace too small");
+    Plan p;
+    int rc = make_plan(d->CE, KIND_BWD, d->max_tile_nodes, d->max_deg, &p);
+    if (rc) return rc;
+    const int NACC = d->CE * d->CE + d->CE + 1;
+    float* ws = reinterpret_cast<float*>(d->workspace);
+    Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(d->ell_in);
+    a.ell_out = reinterpret_cast<const uint4*>(d->ell_out);
+    a.tile_ptr = d->tile_ptr;
+    a.T = d->T;
+    a.cap_nodes = d->max_tile_nodes;
+    a.N = d->N;
+    a.Mu = d->Mu;
+    a.tau = d->tau;
+    a.Lw = d->Lw;
+    a.L = d->L;
+    a.dim = d->dim;
+    a.x_phys = d->x_phys;
+    a.states = d->states;
+    a.partials = ws;
+    a.tau_partials = (d->g_tau && d->Lw == 1) ? ws + (size_t)d->T * d->L * NACC : nullptr;
+    a.x_comp = d->x_comp;
+    a.f = d->f;
+    a.uu = d->uu;
+    a.f_scale = d->f_scale;
+    a.uu_scale = d->uu_scale;
+    a.target = d->target;
+    a.loss_kind = d->loss_kind;
+    a.grad_scale = d->grad_scale;
+    a.loss_partials = ws + (size_t)d->T * d->L * NACC + (size_t)d->T * d->L;
+    a.tail = d->tail;
+    a.counter = d->counter;
+    a.gMu = d->gMu;
+    a.g_tau = d->g_tau;
+    a.loss = d->loss;
+    a.loss_scale = d->loss_scale;
+    a.Wq = d->Wq;
+    a.bq = d->bq;
+    a.Wk = d->Wk;
+    a.gWq = d->gWq;
+    a.gbq = d->gbq;
+    a.gWk = d->gWk;
+    a.gbk = d->gbk;
+    a.C = d->C;
+    a.inv_temp = d->inv_temp;
+    a.Mu_next = d->Mu;
+    a.params = d->params;
+    a.grads = d->grads;
+    a.exp_avg = d->exp_avg;
+    a.exp_avg_sq = d->exp_avg_sq;
+    a.n_params = d->n_params;
+    a.lr = d->lr;
+    a.beta1 = d->beta1;
+    a.beta2 = d->beta2;
+    a.eps = d->eps;
+    a.weight_decay = d->weight_decay;
+    a.adam_grad_scale = d->adam_grad_scale;
+    a.step = reinterpret_cast<long long*>(d->step);
+    return dispatch(d->CE, p, 2, a, GAD_METHOD_EULER, as_stream(stream));
 }

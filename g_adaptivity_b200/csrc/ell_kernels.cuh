@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "ell_math.cuh"
+#include "tail_math.cuh"
 
 namespace gad {
 namespace ell {
@@ -99,6 +100,31 @@ struct Args {
     int loss_kind;          // 0: L1, 1: MSE
     float grad_scale;       // cotangent = grad_scale * d|out - target| (or d(out - target)^2)
     float* loss_partials;   // [T] sum over the tile of |d| or d^2
+    // train tail, run by the last CTA to finish (tail = 0: none, the host launches the reduction;
+    // 1: reduction + weight gradients; 2: + Adam + the folded weights of the NEXT step)
+    int tail;
+    unsigned int* counter;  // zero before the first launch; the last CTA resets it
+    float* gMu;             // [Lw, CE*CE+CE]
+    float* g_tau;           // [L] or null
+    float* loss;            // [1]
+    float loss_scale;
+    const float* Wq;        // [Lw, C, C] (views of `params` when tail == 2)
+    const float* bq;
+    const float* Wk;
+    float* gWq;
+    float* gbq;
+    float* gWk;
+    float* gbk;
+    int C;
+    float inv_temp;
+    float* Mu_next;         // = Mu (rewritten in place once every CTA is done with it)
+    float* params;          // flat parameter vector and Adam state (tail == 2)
+    const float* grads;
+    float* exp_avg;
+    float* exp_avg_sq;
+    long long n_params;
+    float lr, beta1, beta2, eps, weight_decay, adam_grad_scale;
+    long long* step;
 };
 
 template <int CE>
@@ -455,11 +481,39 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
         const int n0 = a.tile_ptr[tile];
         const int NT = a.tile_ptr[tile + 1] - n0;
         __syncthreads();
-        if (ELLS && tid == 0) {
+        // Inputs of the tile by 1-D TMA bulk copies: ELL rows to their buffers, x_comp | f | uu to a
+        // staging area in the (not yet used) P buffer, the target mesh to the DL buffer.
+        const uint32_t xc_bytes = (uint32_t)NT * (uint32_t)a.dim * 4u, sc_bytes = (uint32_t)NT * 4u;
+        const float* xc_g = a.x_comp + (size_t)n0 * a.dim;
+        const float* tg_g = a.target + (size_t)n0 * a.dim;
+        const float* f_g = a.f ? a.f + n0 : nullptr;
+        const float* uu_g = a.uu ? a.uu + n0 : nullptr;
+        const bool stage = a.dim <= 2 && (NT % 4 == 0) &&
+                           ((reinterpret_cast<uintptr_t>(xc_g) | reinterpret_cast<uintptr_t>(tg_g) |
+                             reinterpret_cast<uintptr_t>(f_g) | reinterpret_cast<uintptr_t>(uu_g)) & 15) == 0;
+        unsigned char* st_xc = P;
+        unsigned char* st_f = P + xc_bytes;
+        unsigned char* st_uu = st_f + (a.f ? sc_bytes : 0u);
+        const uint32_t tx = (ELLS ? 2u * (uint32_t)NT * 16u : 0u) +
+                            (stage ? 2u * xc_bytes + (a.f ? sc_bytes : 0u) + (a.uu ? sc_bytes : 0u) : 0u);
+        if (tid == 0 && tx) {
             fence_proxy_async_smem();
-            mbar_expect_tx(bar, 2u * (uint32_t)NT * 16u);
-            bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
-            bulk_g2s(smem + lay.eout, a.ell_out + n0, (uint32_t)NT * 16u, bar);
+            mbar_expect_tx(bar, tx);
+            if (ELLS) {
+                bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
+                bulk_g2s(smem + lay.eout, a.ell_out + n0, (uint32_t)NT * 16u, bar);
+            }
+            if (stage) {
+                bulk_g2s(st_xc, xc_g, xc_bytes, bar);
+                if (a.f) bulk_g2s(st_f, f_g, sc_bytes, bar);
+                if (a.uu) bulk_g2s(st_uu, uu_g, sc_bytes, bar);
+                bulk_g2s(DL, tg_g, xc_bytes, bar);
+            }
+        }
+        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+        if (tx) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
         }
         // features = cat[x_comp, f, uu] + identity (zero-pad) encoder: src/GNN.py:225-239,75-83,270
         unsigned char* Xc = B0;
@@ -470,20 +524,27 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
             const int cf = a.dim, cu = a.dim + (a.f ? 1 : 0);
             for (int i = tid; i < NT; i += nthr) {
                 const int64_t gi = (int64_t)n0 + i;
-                Row<CE> x = load_dims<CE>(a.x_comp, gi, a.dim);
+                Row<CE> x;
+                float fv = 0.f, uv = 0.f;
+                if (stage) {
+                    x = load_dims<CE>(reinterpret_cast<const float*>(st_xc), i, a.dim);
+                    if (a.f) fv = reinterpret_cast<const float*>(st_f)[i];
+                    if (a.uu) uv = reinterpret_cast<const float*>(st_uu)[i];
+                } else {
+                    x = load_dims<CE>(a.x_comp, gi, a.dim);
+                    if (a.f) fv = a.f[gi];
+                    if (a.uu) uv = a.uu[gi];
+                }
+                if (a.f_scale) fv = fv / fs;     // the reference divides (f / torch.max(f), GNN.py:232)
+                if (a.uu_scale) uv = uv / us;
 #pragma unroll
                 for (int c = 0; c < CE; ++c) {
-                    if (a.f && c == cf) x.v[c] = a.f_scale ? a.f[gi] / fs : a.f[gi];
-                    if (a.uu && c == cu) x.v[c] = a.uu_scale ? a.uu[gi] / us : a.uu[gi];
+                    if (a.f && c == cf) x.v[c] = fv;
+                    if (a.uu && c == cu) x.v[c] = uv;
                 }
                 sts_row<CE>(Xc, i * RB, x);
                 store_row<CE>(a.states, gi, x);
             }
-        }
-        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
-        if (ELLS) {
-            mbar_wait(bar, parity);
-            parity ^= 1;
         }
         __syncthreads();
         EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
@@ -514,7 +575,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
                 } else {
                     const int64_t gi = (int64_t)n0 + i;
                     if (a.x_phys) store_dims<CE>(a.x_phys, gi, a.dim, xn);
-                    const Row<CE> tg = load_dims<CE>(a.target, gi, a.dim);
+                    const Row<CE> tg = stage ? load_dims<CE>(reinterpret_cast<const float*>(DL), i, a.dim)
+                                             : load_dims<CE>(a.target, gi, a.dim);
                     Row<CE> g;
 #pragma unroll
                     for (int c = 0; c < CE; ++c) {
@@ -546,6 +608,39 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
             block_reduce<1>(one, red, a.loss_partials + tile);
         }
         tile_backward<CE, W, ELLS>(a, tile, n0, NT, Xc, Xn, P, DL, GS, Ein, Eout, Mu, red);
+    }
+
+    // ---- tail: the last CTA to finish reduces the partials (fixed order -> deterministic), applies
+    // the chain rule to the Linear parameters and, single-GPU, takes the Adam step and refolds the
+    // weights for the next launch: the whole training step is this one kernel.
+    if (a.tail == 0) return;
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(a.counter, 1u);
+        s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        constexpr int NACC = MUSZ + 1;
+        const int slots = a.Lw > 1 ? a.L : 1;
+        tail::reduce_partials(a.partials, a.T, slots, NACC, MUSZ, a.gMu, a.tau_partials, a.L, a.g_tau, a.loss_partials,
+                              a.loss_scale, a.loss, tid >> 5, (nthr + 31) >> 5);
+        __syncthreads();
+        tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
+        if (a.tail >= 2) {
+            __syncthreads();
+            const long long t = a.step[0] + 1;
+            tail::adam(a.params, a.grads, a.exp_avg, a.exp_avg_sq, a.n_params, a.lr, a.beta1, a.beta2, a.eps,
+                       a.weight_decay, a.adam_grad_scale, t);
+            __syncthreads();
+            if (tid == 0) a.step[0] = t;
+            tail::prepare_weights(a.Wq, a.bq, a.Wk, a.Lw, a.C, CE, a.inv_temp, a.Mu_next);
+        }
+        if (tid == 0) *a.counter = 0u;
     }
 }
 

@@ -2,6 +2,7 @@
 // semantics of the reference training loop (src/run_GNN.py:88,128,131), as one single-CTA kernel
 // so that the whole training step is CUDA-graph replayable with no host involvement.
 #include "common.cuh"
+#include "tail_math.cuh"
 
 namespace gad {
 namespace {
@@ -11,21 +12,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
                                               float b1, float b2, float eps, float wd, float gscale,
                                               int64_t* __restrict__ step) {
     const int64_t t = step[0] + 1;
-    const double bc1 = 1.0 - pow((double)b1, (double)t);
-    const double bc2 = 1.0 - pow((double)b2, (double)t);
-    const float step_size = (float)((double)lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        float gi = g[i] * gscale;
-        const float pi = p[i];
-        if (wd != 0.f) gi = fmaf(wd, pi, gi);
-        const float mi = m[i] + (1.f - b1) * (gi - m[i]);          // lerp, as torch does
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = pi - step_size * (mi / denom);
-    }
+    tail::adam(p, g, m, v, n, lr, b1, b2, eps, wd, gscale, t);
     __syncthreads();
     if (threadIdx.x == 0) step[0] = t;
 }

@@ -1,0 +1,155 @@
+// CTA-wide device routines for the small dense steps around the deformer kernels: the folded
+// projection (M, u), its chain rule back to the Linear parameters, the fixed-order reduction of the
+// per-tile partials and Adam.  Each is callable from a stand-alone single-CTA kernel (weights.cu,
+// optim.cu, ell_api.cu) or from the tail of the one-launch training kernel (ell_kernels.cuh), where
+// the last CTA to finish runs them back to back so that a whole training step is one launch.
+//
+// The reference computes q = x Wq^T + bq and k = x Wk^T + bk for every node and layer
+// (src/GRAND_plus.py:225-226, two [N,C]x[C,C] addmm calls) and then <q_i, k_j>/sqrt(C) per edge
+// (:279).  Only min(in_dim, C) input channels are ever non-zero (identity encoder,
+// src/GNN.py:75-83), and every term of <q_i, k_j> that does not depend on j cancels in the
+// segment softmax (:333).  What remains is the bilinear form
+//     s_e = x_i^T M x_j + u^T x_j,   M = c Wq^T Wk  (CE x CE),  u = c Wk^T bq,  c = log2(e)/(sqrt(C) T)
+// (log2 domain: the kernels exponentiate with ex2), so the "projection GEMM" shrinks to one
+// CE x CE x C product per weight set and step -- a few hundred FMAs, done in fp64 by one CTA.  That
+// is why no tcgen05 tile is issued for it: a 128 x 8 x 8 tf32 MMA would need a 3xTF32 split for the
+// 1e-5 parity bar (SURVEY hazard 10) plus a TMEM round trip per 32 B of node state, for work that
+// no longer exists per node.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gad {
+namespace tail {
+
+constexpr double LOG2E = 1.4426950408889634074;
+
+// Mu[l] = { M (CE x CE, row-major M[a][b]), u (CE) } for l < Lw.
+__device__ __forceinline__ void prepare_weights(const float* Wq, const float* bq,
+                                                const float* Wk, int Lw, int C, int CE, float inv_temp,
+                                                float* Mu) {
+    const double c = LOG2E * (double)inv_temp / sqrt((double)C);   // logits live in the log2 domain
+    const int live = CE < C ? CE : C;
+    const int musz = CE * CE + CE;
+    for (int idx = threadIdx.x; idx < Lw * musz; idx += blockDim.x) {
+        const int l = idx / musz, r = idx % musz;
+        const float* wq = Wq + (size_t)l * C * C;
+        const float* wk = Wk + (size_t)l * C * C;
+        const float* b = bq + (size_t)l * C;
+        double acc = 0.0;
+        if (r < CE * CE) {
+            const int a = r / CE, bcol = r % CE;
+            if (a < live && bcol < live)
+                for (int o = 0; o < C; ++o) acc += (double)wq[o * C + a] * (double)wk[o * C + bcol];
+        } else {
+            const int bcol = r - CE * CE;
+            if (bcol < live)
+                for (int o = 0; o < C; ++o) acc += (double)b[o] * (double)wk[o * C + bcol];
+        }
+        Mu[idx] = (float)(c * acc);
+    }
+}
+
+// dWq[o,a] = c sum_b Wk[o,b] G_M[a,b];  dWk[o,b] = c (sum_a Wq[o,a] G_M[a,b] + bq[o] G_u[b]);
+// dbq[o] = c sum_b Wk[o,b] G_u[b];  dbk = 0.   (gMu = dL/d(M, u) in the log2 domain: same c.)
+__device__ __forceinline__ void weight_grads(const float* Wq, const float* bq,
+                                             const float* Wk, const float* gMu, int Lw, int C, int CE,
+                                             float inv_temp, float* gWq, float* gbq,
+                                             float* gWk, float* gbk) {
+    const double c = LOG2E * (double)inv_temp / sqrt((double)C);
+    const int live = CE < C ? CE : C;
+    const int musz = CE * CE + CE;
+    for (int idx = threadIdx.x; idx < Lw * C * C; idx += blockDim.x) {
+        const int l = idx / (C * C), r = idx % (C * C);
+        const int o = r / C, a = r % C;
+        const float* wq = Wq + (size_t)l * C * C;
+        const float* wk = Wk + (size_t)l * C * C;
+        const float* b = bq + (size_t)l * C;
+        const float* GM = gMu + (size_t)l * musz;
+        const float* Gu = GM + CE * CE;
+        double dq = 0.0, dk = 0.0;
+        if (a < live) {
+            for (int bb = 0; bb < live; ++bb) dq += (double)wk[o * C + bb] * (double)GM[a * CE + bb];
+            for (int aa = 0; aa < live; ++aa) dk += (double)wq[o * C + aa] * (double)GM[aa * CE + a];
+            dk += (double)b[o] * (double)Gu[a];
+        }
+        gWq[idx] = (float)(c * dq);
+        gWk[idx] = (float)(c * dk);
+    }
+    for (int idx = threadIdx.x; idx < Lw * C; idx += blockDim.x) {
+        const int l = idx / C, o = idx % C;
+        const float* wk = Wk + (size_t)l * C * C;
+        const float* Gu = gMu + (size_t)l * musz + CE * CE;
+        double d = 0.0;
+        for (int bb = 0; bb < live; ++bb) d += (double)wk[o * C + bb] * (double)Gu[bb];
+        gbq[idx] = (float)(c * d);
+        gbk[idx] = 0.0f;
+    }
+}
+
+// torch.optim.Adam semantics (run_GNN.py:88,128,131): L2 weight decay added to the gradient,
+// bias-corrected moments.  `step` is a device counter, incremented by the caller after the sweep.
+__device__ __forceinline__ void adam(float* p, const float* g, float* m,
+                                     float* v, int64_t n, float lr, float b1, float b2, float eps,
+                                     float wd, float gscale, int64_t t) {
+    const double bc1 = 1.0 - pow((double)b1, (double)t);
+    const double bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float gi = g[i] * gscale;
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = m[i] + (1.f - b1) * (gi - m[i]);          // lerp, as torch does
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
+// Fixed-order sum of the per-tile partials, one warp per output column (lanes stride over tiles,
+// then a butterfly): columns [0, slots*nacc) are (G_M, G_u[, g_tau]) per weight slot, then L
+// step-size columns (shared weights) and one loss column.  Reads bypass L1 (written by other CTAs).
+__device__ __forceinline__ void reduce_partials(const float* partials, int T, int slots, int nacc, int musz,
+                                                float* gMu, const float* tau_partials, int L,
+                                                float* g_tau, const float* loss_partials,
+                                                float loss_scale, float* loss, int warp, int nwarps) {
+    const int lane = threadIdx.x & 31;
+    const int ncol = slots * nacc;
+    for (int w = warp; w < ncol + L + 1; w += nwarps) {
+        const float* src;
+        int stride;
+        if (w < ncol) {
+            src = partials + w;
+            stride = ncol;
+        } else if (w < ncol + L) {
+            if (!(tau_partials && g_tau)) continue;
+            src = tau_partials + (w - ncol);
+            stride = L;
+        } else {
+            if (!(loss_partials && loss)) continue;
+            src = loss_partials;
+            stride = 1;
+        }
+        float s = 0.f;
+        for (int t = lane; t < T; t += 32) s += __ldcg(src + (size_t)t * stride);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane != 0) continue;
+        if (w < ncol) {
+            const int l = w / nacc, a = w % nacc;
+            if (a < musz) gMu[(size_t)l * musz + a] = s;
+            else if (g_tau && slots > 1) g_tau[l] = s;
+        } else if (w < ncol + L) {
+            g_tau[w - ncol] = s;
+        } else {
+            loss[0] = s * loss_scale;
+        }
+    }
+}
+
+}  // namespace tail
+}  // namespace gad

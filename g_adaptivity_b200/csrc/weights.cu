@@ -1,79 +1,25 @@
-// Dense per-layer projection, folded.
+// Dense per-layer projection, folded (derivation and device routines: tail_math.cuh).
 //
-// The reference computes q = x Wq^T + bq and k = x Wk^T + bk for every node and layer
-// (src/GRAND_plus.py:225-226, two [N,C]x[C,C] addmm calls) and then <q_i, k_j>/sqrt(C) per edge
-// (:279).  Only min(in_dim, C) input channels are ever non-zero (identity encoder,
-// src/GNN.py:75-83), and every term of <q_i, k_j> that does not depend on j cancels in the
-// segment softmax (:333).  What remains is the bilinear form
-//     s_e = x_i^T M x_j + u^T x_j,   M = c Wq^T Wk  (CE x CE),  u = c Wk^T bq,  c = 1/(sqrt(C) T)
-// so the "projection GEMM" shrinks to one CE x CE x C product per weight set and launch -- a few
-// hundred FMAs, done here in fp64 by a single CTA.  That is why no tcgen05 tile is issued for
-// it: a 128 x 8 x 8 tf32 MMA would need a 3xTF32 split for the 1e-5 parity bar (SURVEY hazard 10)
-// plus a TMEM round trip per 32 B of node state, for work that no longer exists per node.
+// gad_prepare_weights: (Wq, bq, Wk) -> Mu = {M = c Wq^T Wk, u = c Wk^T bq}, c = log2(e)/(sqrt(C) T);
+// gad_weight_grads: the chain rule from dL/d(M, u) back to the Linear parameters of
+// src/GRAND_plus.py:146-147 (d/d lin_key.bias == 0: softmax shift invariance).
 #include "common.cuh"
+#include "tail_math.cuh"
 
 namespace gad {
 namespace {
 
-constexpr double LOG2E = 1.4426950408889634074;
-
 __global__ void k_prepare_weights(const float* __restrict__ Wq, const float* __restrict__ bq,
-                                  const float* __restrict__ Wk, int C, int CE, float inv_temp,
+                                  const float* __restrict__ Wk, int Lw, int C, int CE, float inv_temp,
                                   float* __restrict__ Mu) {
-    const int l = blockIdx.x;
-    const float* wq = Wq + (size_t)l * C * C;
-    const float* wk = Wk + (size_t)l * C * C;
-    const float* b = bq + (size_t)l * C;
-    float* out = Mu + (size_t)l * (CE * CE + CE);
-    const double c = LOG2E * (double)inv_temp / sqrt((double)C);   // logits live in the log2 domain
-    const int live = CE < C ? CE : C;
-    for (int idx = threadIdx.x; idx < CE * CE + CE; idx += blockDim.x) {
-        double acc = 0.0;
-        if (idx < CE * CE) {
-            const int a = idx / CE, bcol = idx % CE;
-            if (a < live && bcol < live)
-                for (int o = 0; o < C; ++o) acc += (double)wq[o * C + a] * (double)wk[o * C + bcol];
-        } else {
-            const int bcol = idx - CE * CE;
-            if (bcol < live)
-                for (int o = 0; o < C; ++o) acc += (double)b[o] * (double)wk[o * C + bcol];
-        }
-        out[idx] = (float)(c * acc);
-    }
+    tail::prepare_weights(Wq, bq, Wk, Lw, C, CE, inv_temp, Mu);
 }
 
-// dWq[o,a] = c sum_b Wk[o,b] G_M[a,b];  dWk[o,b] = c (sum_a Wq[o,a] G_M[a,b] + bq[o] G_u[b]);
-// dbq[o] = c sum_b Wk[o,b] G_u[b];  dbk = 0.
 __global__ void k_weight_grads(const float* __restrict__ Wq, const float* __restrict__ bq,
-                               const float* __restrict__ Wk, const float* __restrict__ gMu, int C, int CE,
+                               const float* __restrict__ Wk, const float* __restrict__ gMu, int Lw, int C, int CE,
                                float inv_temp, float* __restrict__ gWq, float* __restrict__ gbq,
                                float* __restrict__ gWk, float* __restrict__ gbk) {
-    const int l = blockIdx.x;
-    const float* wq = Wq + (size_t)l * C * C;
-    const float* wk = Wk + (size_t)l * C * C;
-    const float* b = bq + (size_t)l * C;
-    const float* GM = gMu + (size_t)l * (CE * CE + CE);
-    const float* Gu = GM + CE * CE;
-    // the kernels return G' = ln2 * G (ds' = ln2 ds) for M' = log2e * M: d/dM = log2e * d/dM'
-    const double c = LOG2E * (double)inv_temp / sqrt((double)C);
-    const int live = CE < C ? CE : C;
-    for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
-        const int o = idx / C, a = idx % C;
-        double dq = 0.0, dk = 0.0;
-        if (a < live) {
-            for (int bb = 0; bb < live; ++bb) dq += (double)wk[o * C + bb] * (double)GM[a * CE + bb];
-            for (int aa = 0; aa < live; ++aa) dk += (double)wq[o * C + aa] * (double)GM[aa * CE + a];
-            dk += (double)b[o] * (double)Gu[a];
-        }
-        gWq[(size_t)l * C * C + idx] = (float)(c * dq);
-        gWk[(size_t)l * C * C + idx] = (float)(c * dk);
-    }
-    for (int o = threadIdx.x; o < C; o += blockDim.x) {
-        double d = 0.0;
-        for (int bb = 0; bb < live; ++bb) d += (double)wk[o * C + bb] * (double)Gu[bb];
-        gbq[(size_t)l * C + o] = (float)(c * d);
-        gbk[(size_t)l * C + o] = 0.0f;
-    }
+    tail::weight_grads(Wq, bq, Wk, gMu, Lw, C, CE, inv_temp, gWq, gbq, gWk, gbk);
 }
 
 }  // namespace
@@ -85,7 +31,7 @@ extern "C" int gad_prepare_weights(const float* Wq, const float* bq, const float
                                    float inv_temp, float* Mu, void* stream) {
     GAD_CHECK_ARG(Wq && bq && Wk && Mu, "gad_prepare_weights: null pointer");
     GAD_CHECK_ARG(Lw > 0 && C > 0 && (CE == 2 || CE == 4 || CE == 8), "gad_prepare_weights: Lw=%d C=%d CE=%d", Lw, C, CE);
-    k_prepare_weights<<<Lw, 128, 0, as_stream(stream)>>>(Wq, bq, Wk, C, CE, inv_temp, Mu);
+    k_prepare_weights<<<1, 128, 0, as_stream(stream)>>>(Wq, bq, Wk, Lw, C, CE, inv_temp, Mu);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
@@ -95,7 +41,7 @@ extern "C" int gad_weight_grads(const float* Wq, const float* bq, const float* W
                                 void* stream) {
     GAD_CHECK_ARG(Wq && bq && Wk && gMu && gWq && gbq && gWk && gbk, "gad_weight_grads: null pointer");
     GAD_CHECK_ARG(Lw > 0 && C > 0 && (CE == 2 || CE == 4 || CE == 8), "gad_weight_grads: Lw=%d C=%d CE=%d", Lw, C, CE);
-    k_weight_grads<<<Lw, 128, 0, as_stream(stream)>>>(Wq, bq, Wk, gMu, C, CE, inv_temp, gWq, gbq, gWk, gbk);
+    k_weight_grads<<<1, 256, 0, as_stream(stream)>>>(Wq, bq, Wk, gMu, Lw, C, CE, inv_temp, gWq, gbq, gWk, gbk);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

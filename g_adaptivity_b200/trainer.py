@@ -7,6 +7,13 @@ replayable CUDA graph per resident batch ("slot"):
     pack features -> fold weights (M, u) -> fused forward -> loss + cotangent -> fused backward
     -> weight gradients -> [gradient all-reduce over NCCL] -> Adam
 
+On bounded-degree mesh batches (every mesh of the reference) all of that is ONE launch,
+`gad_train_step_ell` (csrc/ell_kernels.cuh: k_ell_train): each CTA runs pack + forward + loss +
+backward of its tiles out of shared memory and the last CTA to finish reduces the per-tile
+partials in a fixed order, applies the chain rule to the Linear parameters, takes the Adam step
+and refolds (M, u) for the next step.  With more than one rank the kernel stops after the chain
+rule, NCCL all-reduces the flat gradient, and Adam + refold follow as two tiny kernels.
+
 Sharding: a batch is a disjoint union of meshes, so ranks take contiguous shards of
 whole meshes with no data-path collective; the only exchange is the all-reduce of the flat
 gradient (144 + L floats).  The mesh loss is a mean over ALL nodes of the global batch
@@ -19,6 +26,7 @@ kernels, the all-reduce and Adam all work on contiguous memory and `model.state_
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Optional
 
 import torch
@@ -62,6 +70,8 @@ class DeformerTrainer:
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.lib = _lib.load()
         self.stream = torch.cuda.Stream(device=self.dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)   # last-CTA election of k_ell_train
+        self.sync_weights()
 
     # ------------------------------------------------------------------------------------
     def _flatten_parameters(self):
@@ -105,6 +115,42 @@ class DeformerTrainer:
     def broadcast_parameters(self, src: int = 0):
         if self.world > 1:
             dist.broadcast(self.flat, src=src, group=self.pg)
+        self.sync_weights()
+
+    def sync_weights(self):
+        """Refold (M, u) from the Linear parameters.  The one-launch step keeps `Mu == fold(params)` as an
+        invariant (its tail refolds after Adam); call this after changing the parameters from outside
+        (`load_state_dict`, manual edits)."""
+        with torch.cuda.device(self.dev):
+            torch.cuda.current_stream(self.dev).synchronize()
+            with torch.cuda.stream(self.stream):
+                _lib.check(self.lib.gad_prepare_weights(_lib.ptr(self.Wq), _lib.ptr(self.bq), _lib.ptr(self.Wk), self.Lw,
+                                                        self.C, self.CE, self.model.inv_temp, _lib.ptr(self.Mu),
+                                                        self.stream.cuda_stream), "gad_prepare_weights")
+
+    def _train_desc(self, s: "_Slot", tail: int) -> "_lib.TrainDesc":
+        """Descriptor of one `gad_train_step_ell` launch on slot `s` (include/gadapt.h: gad_train_desc)."""
+        P, g = _lib.ptr, s.graph
+        count = s.N * self.dim
+        b1, b2 = self.betas
+        d = _lib.TrainDesc()
+        d.ell_in, d.ell_out, d.tile_ptr, d.N = P(g.ell_in), P(g.ell_out), P(g.tile_ptr), s.N
+        d.T, d.max_tile_nodes, d.max_deg = g.T, g.max_tile_nodes, g.ell_deg
+        d.x_comp, d.f, d.uu, d.f_scale, d.uu_scale, d.target = P(s.x_comp), P(s.f), P(s.uu), None, None, P(s.target)
+        d.dim, d.CE = self.dim, self.CE
+        d.Mu, d.tau, d.Lw, d.L, d.C, d.inv_temp = P(self.Mu), P(self.tau), self.Lw, self.L, self.C, self.model.inv_temp
+        d.loss_kind = 0 if self.loss_kind == "l1" else 1
+        d.grad_scale, d.loss_scale = 1.0 / (count * self.world), 1.0 / count
+        d.states, d.gMu, d.g_tau, d.loss, d.x_phys = P(s.states), P(self.gMu), P(self.gtau), P(s.loss), P(s.x_phys)
+        d.workspace, d.workspace_bytes = P(s.bwd_ws), s.bwd_ws_bytes
+        d.tail, d.counter = tail, P(self.counter)
+        d.Wq, d.bq, d.Wk = P(self.Wq), P(self.bq), P(self.Wk)
+        d.gWq, d.gbq, d.gWk, d.gbk = P(self.gWq), P(self.gbq), P(self.gWk), P(self.gbk)
+        d.params, d.grads, d.exp_avg, d.exp_avg_sq = P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq)
+        d.n_params = self.flat.numel()
+        d.lr, d.beta1, d.beta2, d.eps, d.weight_decay, d.adam_grad_scale = self.lr, b1, b2, self.eps, self.wd, 1.0
+        d.step = P(self.step_count)
+        return d
 
     # ------------------------------------------------------------------------------------
     def add_batch(self, data) -> int:
@@ -160,25 +206,28 @@ class DeformerTrainer:
         """Enqueue the kernels of one training step on `stream_ptr` (captured or eager)."""
         lib, P, chk = self.lib, _lib.ptr, _lib.check
         g = s.graph
-        CE, L, Lw, C, dim = self.CE, self.L, self.Lw, self.C, self.dim
+        CE, L, Lw, C_, dim = self.CE, self.L, self.Lw, self.C, self.dim
         tiles = g.tile_ptr is not None and not self.opt.get("gad_force_stream", False)
         inv_temp = self.model.inv_temp
         ell = tiles and GF.use_ell(g, CE) and not self.opt.get("gad_no_fused_train", False)
-        if stage in ("all", "pre") and ell:
-            # one launch per tile for pack + forward + loss + backward (csrc/ell_kernels.cuh: k_ell_train)
-            count = s.N * dim
-            chk(lib.gad_prepare_weights(P(self.Wq), P(self.bq), P(self.Wk), Lw, C, CE, inv_temp, P(self.Mu), stream_ptr),
-                "gad_prepare_weights")
-            chk(lib.gad_deform_train_ell(P(g.ell_in), P(g.ell_out), s.N, P(g.tile_ptr), g.T, g.max_tile_nodes, g.ell_deg,
-                                         P(s.x_comp), P(s.f), P(s.uu), None, None, P(s.target), dim, CE, P(self.Mu), Lw,
-                                         P(self.tau), L, 0 if self.loss_kind == "l1" else 1,
-                                         1.0 / (count * self.world), 1.0 / count, P(s.states), P(self.gMu), P(self.gtau),
-                                         P(s.loss), P(s.x_phys), P(s.bwd_ws), s.bwd_ws_bytes, stream_ptr),
-                "gad_deform_train_ell")
-            chk(lib.gad_weight_grads(P(self.Wq), P(self.bq), P(self.Wk), P(self.gMu), Lw, C, CE, inv_temp, P(self.gWq),
-                                     P(self.gbq), P(self.gWk), P(self.gbk), stream_ptr), "gad_weight_grads")
-        elif stage in ("all", "pre"):
-            chk(lib.gad_prepare_weights(P(self.Wq), P(self.bq), P(self.Wk), Lw, C, CE, inv_temp, P(self.Mu), stream_ptr),
+        if ell:
+            # ONE launch per step (csrc/ell_kernels.cuh: k_ell_train): pack + forward + loss + backward per
+            # tile, then the last CTA reduces, applies the chain rule and -- single GPU -- takes the Adam step
+            # and refolds (M, u) for the next step.  Data parallel: all-reduce, Adam and refold follow.
+            if stage in ("all", "pre"):
+                single = self.world == 1 and with_optimizer
+                chk(lib.gad_train_step_ell(C.byref(self._train_desc(s, 2 if single else 1)), stream_ptr),
+                    "gad_train_step_ell")
+            if stage in ("all", "post") and with_optimizer and self.world > 1:
+                b1, b2 = self.betas
+                chk(lib.gad_adam_step(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.flat.numel(),
+                                      self.lr, b1, b2, self.eps, self.wd, 1.0, P(self.step_count), stream_ptr),
+                    "gad_adam_step")
+                chk(lib.gad_prepare_weights(P(self.Wq), P(self.bq), P(self.Wk), Lw, C_, CE, inv_temp, P(self.Mu),
+                                            stream_ptr), "gad_prepare_weights")
+            return
+        if stage in ("all", "pre"):
+            chk(lib.gad_prepare_weights(P(self.Wq), P(self.bq), P(self.Wk), Lw, C_, CE, inv_temp, P(self.Mu), stream_ptr),
                 "gad_prepare_weights")
             chk(lib.gad_pack_features(P(s.x_comp), P(s.f), P(s.uu), None, None, s.N, dim, CE, P(s.states), stream_ptr),
                 "gad_pack_features")
@@ -194,7 +243,7 @@ class DeformerTrainer:
                                    g.max_tile_edges, P(s.states), P(s.g_out), dim, CE, P(self.Mu), Lw, P(self.tau), L,
                                    P(self.gMu), P(self.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, stream_ptr),
                 "gad_deform_bwd")
-            chk(lib.gad_weight_grads(P(self.Wq), P(self.bq), P(self.Wk), P(self.gMu), Lw, C, CE, inv_temp, P(self.gWq),
+            chk(lib.gad_weight_grads(P(self.Wq), P(self.bq), P(self.Wk), P(self.gMu), Lw, C_, CE, inv_temp, P(self.gWq),
                                      P(self.gbq), P(self.gWk), P(self.gbk), stream_ptr), "gad_weight_grads")
         if stage in ("all", "post") and with_optimizer:
             b1, b2 = self.betas
@@ -220,6 +269,8 @@ class DeformerTrainer:
                     self._issue(s, self.stream.cuda_stream, stage="post")
                 for t, v in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_count), saved):
                     t.copy_(v)
+            self.stream.synchronize()
+            self.sync_weights()
             self.stream.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.stream):

@@ -166,6 +166,65 @@ int gad_deform_train_ell(const void* ell_in, const void* ell_out, int64_t N, con
                          float grad_scale, float loss_scale, float* states, float* gMu, float* g_tau,
                          float* loss, float* x_phys, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One WHOLE training step in one launch (src/run_GNN.py:99-131 with loss_type = mesh_loss): the
+ * kernel of gad_deform_train_ell, whose last CTA to finish also runs the fixed-order reduction,
+ * the chain rule to the Linear parameters (tail >= 1: what gad_weight_grads does) and -- tail == 2,
+ * single-GPU training -- the Adam step on the flat parameter vector followed by the refold of
+ * (M, u) for the NEXT step into Mu.  With tail == 1 the caller all-reduces `gWq..gbk` (data
+ * parallel) and then calls gad_adam_step + gad_prepare_weights.  All pointers are device pointers.
+ * `counter` is one zero-initialised uint32 owned by the caller (the kernel leaves it zero).
+ * When tail == 2, Wq / bq / Wk must be views into `params` and gWq.. views into `grads`. */
+typedef struct gad_train_desc {
+    /* topology (gad_graph_build_ell) */
+    const void* ell_in;
+    const void* ell_out;
+    const int32_t* tile_ptr;
+    int64_t N;
+    int32_t T, max_tile_nodes, max_deg;
+    /* inputs: features of src/GNN.py:225-239 and the target mesh */
+    const float* x_comp;
+    const float* f;
+    const float* uu;
+    const float* f_scale;
+    const float* uu_scale;
+    const float* target;
+    int32_t dim, CE;
+    /* model */
+    float* Mu;           /* [Lw, CE*CE+CE], current folded weights; rewritten when tail == 2 */
+    const float* tau;    /* [L] */
+    int32_t Lw, L, C;
+    float inv_temp;
+    /* loss: loss[0] = loss_scale * sum, cotangent = grad_scale * d(sum)/d(out) */
+    int32_t loss_kind;
+    float grad_scale, loss_scale;
+    /* scratch and outputs */
+    float* states;       /* [L, N, CE] */
+    float* gMu;          /* [Lw, CE*CE+CE] */
+    float* g_tau;        /* [L] or NULL */
+    float* loss;         /* [1] */
+    float* x_phys;       /* [N, dim] or NULL */
+    void* workspace;     /* gad_ell_workspace_bytes(CE, T, L) */
+    size_t workspace_bytes;
+    /* tail */
+    int32_t tail;        /* 1: reduce + weight grads, 2: + Adam + refold */
+    uint32_t* counter;
+    const float* Wq;
+    const float* bq;
+    const float* Wk;
+    float* gWq;
+    float* gbq;
+    float* gWk;
+    float* gbk;
+    float* params;
+    const float* grads;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n_params;
+    float lr, beta1, beta2, eps, weight_decay, adam_grad_scale;
+    int64_t* step;
+} gad_train_desc;
+int gad_train_step_ell(const gad_train_desc* desc, void* stream);
+
 /* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --
  * res = A(x) x - x  for x [N, CE];  alpha (optional) [E] in filtered edge-list order.
  */

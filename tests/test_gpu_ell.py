@@ -143,3 +143,25 @@ def test_fused_train_graph_replay_is_deterministic_and_trains():
         finals.append((losses, tr.flat.clone().cpu()))
     assert finals[0][0] == finals[1][0]
     assert torch.equal(finals[0][1], finals[1][1])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_one_launch_step_equals_multi_kernel_step(use_graph):
+    """Adam + refold in the tail of the train kernel == gad_weight_grads / gad_adam_step /
+    gad_prepare_weights as separate launches: same parameters after several steps."""
+    opt, ds, data, ref = _case((20, 20), 12, seed=5, learn_step=True)
+    res = []
+    for no_fused in (False, True):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_no_fused_train=no_fused)
+        tr = DeformerTrainer(model, lr=3e-3, use_cuda_graph=use_graph)
+        sid = tr.add_batch(data)
+        for _ in range(6):
+            tr.step(sid)
+        tr.synchronize()
+        res.append((tr.flat.clone().cpu(), tr.slots[sid].loss.item(), int(tr.step_count.item())))
+    assert res[0][2] == res[1][2] == 6
+    assert abs(res[0][1] - res[1][1]) <= 2e-5 * abs(res[1][1])
+    assert (res[0][0] - res[1][0]).abs().max().item() <= 2e-5 * res[1][0].abs().max().item()
+    # the model's parameters are views of the trainer's flat vector: state_dict sees the update
+    sd = model.state_dict()
+    assert not torch.equal(sd["conv_layers.0.lin_query.weight"].cpu(), ref.state_dict()["conv_layers.0.lin_query.weight"])
