@@ -31,7 +31,7 @@ namespace gad {
 namespace ell {
 
 #ifndef GAD_ELL_MAXT
-#define GAD_ELL_MAXT 640    // largest CTA; with 1 CTA of 640 or 2 CTAs of 320 threads: <= 96 registers
+#define GAD_ELL_MAXT 512    // largest CTA; 1 CTA of 512 or 2 CTAs of 256 threads per SM: <= 128 registers, no spills
 #endif
 #ifndef GAD_ELL_MINB
 #define GAD_ELL_MINB 1

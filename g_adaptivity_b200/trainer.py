@@ -32,7 +32,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, dp
 from . import functional as GF
 from .GNN import GNN
 
@@ -113,8 +113,7 @@ class DeformerTrainer:
         self.gMu = torch.empty_like(self.Mu)
 
     def broadcast_parameters(self, src: int = 0):
-        if self.world > 1:
-            dist.broadcast(self.flat, src=src, group=self.pg)
+        dp.broadcast_flat(self.flat, src=src, group=self.pg)
         self.sync_weights()
 
     def sync_weights(self):
@@ -140,7 +139,7 @@ class DeformerTrainer:
         d.dim, d.CE = self.dim, self.CE
         d.Mu, d.tau, d.Lw, d.L, d.C, d.inv_temp = P(self.Mu), P(self.tau), self.Lw, self.L, self.C, self.model.inv_temp
         d.loss_kind = 0 if self.loss_kind == "l1" else 1
-        d.grad_scale, d.loss_scale = 1.0 / (count * self.world), 1.0 / count
+        d.grad_scale, d.loss_scale = dp.local_grad_scale(count, world=self.world), 1.0 / count
         d.states, d.gMu, d.g_tau, d.loss, d.x_phys = P(s.states), P(self.gMu), P(self.gtau), P(s.loss), P(s.x_phys)
         d.workspace, d.workspace_bytes = P(s.bwd_ws), s.bwd_ws_bytes
         d.tail, d.counter = tail, P(self.counter)
@@ -236,7 +235,8 @@ class DeformerTrainer:
                                    self.method, P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, stream_ptr),
                 "gad_deform_fwd")
             chk(lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * dim, 0 if self.loss_kind == "l1" else 1,
-                                  1.0 / (s.N * dim * self.world), P(s.loss), P(s.g_out), P(s.loss_ws), stream_ptr),
+                                  dp.local_grad_scale(s.N * dim, world=self.world), P(s.loss), P(s.g_out), P(s.loss_ws),
+                                  stream_ptr),
                 "gad_mesh_loss")
             chk(lib.gad_deform_bwd(P(g.rowptr), P(g.col_walk), P(g.t_rowptr), P(g.t_dst_walk), s.N, g.E,
                                    P(g.tile_ptr) if tiles else None, g.T if tiles else 0, g.max_tile_nodes,
@@ -252,8 +252,7 @@ class DeformerTrainer:
                 "gad_adam_step")
 
     def _allreduce(self):
-        if self.world > 1:
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+        dp.allreduce_flat(self.gflat, group=self.pg)
 
     def capture(self, sid: int):
         """Capture the step of slot `sid` into a CUDA graph (gradient all-reduce included)."""
@@ -302,6 +301,53 @@ class DeformerTrainer:
         with torch.cuda.stream(self.stream):
             out = loss.to("cpu", non_blocking=False)
         return float(out)
+
+    def run_from_host(self, host_batches, steps: int) -> torch.Tensor:
+        """Pipelined end-to-end training loop over host-resident (pinned) batches: the inputs of step
+        k + 1 travel host -> device on a copy stream while step k computes, and every step's loss is
+        read back device -> host asynchronously into pinned memory.  Slot k % R receives batch
+        k % len(host_batches); needs R = len(self.slots) >= 2.  Returns the `steps` losses (host)."""
+        R = len(self.slots)
+        if R < 2:
+            raise ValueError("run_from_host needs at least two resident slots (double buffering)")
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._in_ready = [torch.cuda.Event() for _ in range(R)]
+            self._slot_free = [torch.cuda.Event() for _ in range(R)]
+        losses = torch.empty(steps, dtype=torch.float32).pin_memory()
+        cs, ms = self._copy_stream, self.stream
+        cs.wait_stream(ms)
+        nb = len(host_batches)
+
+        def upload(k):
+            sid = k % R
+            s, data = self.slots[sid], host_batches[k % nb]
+            with torch.cuda.stream(cs):
+                if k >= R:
+                    cs.wait_event(self._slot_free[sid])      # step k - R has consumed this slot's inputs
+                xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
+                tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
+                s.x_comp.copy_(xc, non_blocking=True)
+                s.target.copy_(tg, non_blocking=True)
+                if s.f is not None:
+                    s.f.copy_(data.f_tensor, non_blocking=True)
+                if s.uu is not None:
+                    s.uu.copy_(data.uu_tensor, non_blocking=True)
+                self._in_ready[sid].record(cs)
+
+        upload(0)
+        for k in range(steps):
+            sid = k % R
+            if k + 1 < steps:
+                upload(k + 1)
+            with torch.cuda.stream(ms):
+                ms.wait_event(self._in_ready[sid])
+            loss = self.step(sid)
+            with torch.cuda.stream(ms):
+                losses[k:k + 1].copy_(loss, non_blocking=True)
+                self._slot_free[sid].record(ms)
+        ms.synchronize()
+        return losses
 
     def synchronize(self):
         self.stream.synchronize()
