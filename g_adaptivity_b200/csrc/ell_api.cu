@@ -20,32 +20,82 @@ GAD_ELL_DECLARE(4, 7)
 namespace {
 
 // ---- ELL rows from the CSR / CSC walk arrays -----------------------------------------------
-// One CTA per tile.  ell[i] = { (nbr_q - n0) * ROWBYTES as uint16, q < 7 ; degree }.
+// One CTA per tile.  ell[i] = { (row_q - n0) * ROWBYTES as uint16 for q < 7 ; 7-bit validity mask }.
+// Slot choice: the first W distinct neighbour offsets (j - i) met in the tile define the canonical
+// slots; a neighbour goes to the slot of its offset when that slot is free (else to any free slot),
+// and an empty slot is padded with the row the canonical offset points at (clamped into the tile).
+// On a structured mesh slot q then means "the same direction" for every node, boundary nodes
+// included, so the q-th gather of consecutive lanes reads consecutive rows: no bank conflicts.
+// Any assignment is CORRECT (the kernels mask by the validity bits); this one is merely fast.
 __global__ void k_build_ell(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                            const int32_t* __restrict__ tile_ptr, int T, int rowbytes, uint4* __restrict__ ell,
+                            const int32_t* __restrict__ tile_ptr, int T, int rowbytes, int W, uint4* __restrict__ ell,
                             int32_t* __restrict__ bad) {
     const int t = blockIdx.x;
     if (t >= T) return;
+    __shared__ int tab[ELL_SLOTS];
+    __shared__ int ntab_s;
     const int n0 = tile_ptr[t], n1 = tile_ptr[t + 1];
+    if (threadIdx.x == 0) {
+        int nt = 0;
+        for (int i = n0; i < n1 && nt < W; ++i)
+            for (int e = ptr[i]; e < ptr[i + 1] && nt < W; ++e) {
+                const int d = idx[e] - i;
+                bool seen = false;
+                for (int q = 0; q < nt; ++q) seen |= (tab[q] == d);
+                if (!seen) tab[nt++] = d;
+            }
+        ntab_s = nt;
+    }
+    __syncthreads();
+    const int ntab = ntab_s;
     for (int i = n0 + threadIdx.x; i < n1; i += blockDim.x) {
         const int b = ptr[i], e = ptr[i + 1];
         const int deg = e - b;
-        uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        bool ok = (deg <= ELL_SLOTS);
-        for (int q = 0; q < ELL_SLOTS; ++q) {
-            if (q < deg && ok) {
-                const int j = idx[b + q];
-                const long long off = (long long)(j - n0) * rowbytes;
-                if (j < n0 || j >= n1 || off > 0xffff) ok = false;
-                else h[q] = (uint32_t)off;
+        int slot[ELL_SLOTS];
+        for (int q = 0; q < ELL_SLOTS; ++q) slot[q] = -1;
+        bool ok = (deg <= W);
+        unsigned placed = 0;
+        if (ok) {
+            for (int k = 0; k < deg; ++k) {           // canonical slot of the neighbour's offset
+                const int j = idx[b + k];
+                if (j < n0 || j >= n1) ok = false;
+                for (int q = 0; q < ntab; ++q)
+                    if (!(placed >> k & 1u) && slot[q] < 0 && tab[q] == j - i) {
+                        slot[q] = j;
+                        placed |= 1u << k;
+                    }
             }
+            for (int k = 0; k < deg; ++k) {           // leftovers: any free slot
+                if (placed >> k & 1u) continue;
+                for (int q = 0; q < W; ++q)
+                    if (slot[q] < 0) {
+                        slot[q] = idx[b + k];
+                        placed |= 1u << k;
+                        break;
+                    }
+            }
+        }
+        uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t mask = 0;
+        for (int q = 0; q < ELL_SLOTS; ++q) {
+            int j;
+            if (ok && slot[q] >= 0) {
+                j = slot[q];
+                mask |= 1u << q;
+            } else {
+                j = i + ((q < ntab) ? tab[q] : 0);    // padding: a valid row, masked out by the kernels
+                j = j < n0 ? n0 : (j >= n1 ? n1 - 1 : j);
+            }
+            const long long off = (long long)(j - n0) * rowbytes;
+            if (off > 0xffff) ok = false;
+            h[q] = (uint32_t)(off & 0xffff);
         }
         if (!ok) {
             atomicAdd(bad, 1);
             for (int q = 0; q < 8; ++q) h[q] = 0;
-        } else {
-            h[7] = (uint32_t)deg;
+            mask = 0;
         }
+        h[7] = mask;
         ell[i] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
     }
 }
@@ -60,6 +110,9 @@ __global__ void k_ell_reduce(const float* __restrict__ partials, int T, int slot
     tail::reduce_partials(partials, T, slots, nacc, musz, gMu, tau_partials, L, g_tau, loss_partials, loss_scale, loss,
                           blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
 }
+
+// instantiated slot counts: 2, 3, 6, 7
+int slots_for(int max_deg) { return max_deg <= 2 ? 2 : (max_deg <= 3 ? 3 : (max_deg <= 6 ? 6 : 7)); }
 
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -80,7 +133,7 @@ int make_plan(int CE, int kind, int max_tile_nodes, int max_deg, Plan* p) {
     GAD_CHECK_ARG(max_deg >= 0 && max_deg <= ELL_SLOTS, "ELL kernels need degree <= %d (got %d)", ELL_SLOTS, max_deg);
     GAD_CHECK_ARG(max_tile_nodes > 0 && (long long)max_tile_nodes * CE * 4 <= 0x10000,
                   "ELL kernels: tile of %d nodes exceeds the 16-bit row offsets", max_tile_nodes);
-    p->w = max_deg <= 2 ? 2 : (max_deg <= 3 ? 3 : (max_deg <= 6 ? 6 : 7));
+    p->w = slots_for(max_deg);
     const int nw = GAD_ELL_MAXT / 32;
     const size_t with = make_layout(CE, kind, max_tile_nodes, true, nw).total + 1024;
     const size_t without = make_layout(CE, kind, max_tile_nodes, false, nw).total + 1024;
@@ -153,11 +206,13 @@ using namespace gad;
 using namespace gad::ell;
 
 extern "C" int gad_graph_build_ell(const int32_t* ptr, const int32_t* idx, int64_t N, const int32_t* tile_ptr, int T,
-                                   int CE, void* ell_rows, int32_t* info, void* stream) {
+                                   int CE, int max_deg, void* ell_rows, int32_t* info, void* stream) {
     GAD_CHECK_ARG(ptr && idx && tile_ptr && ell_rows && info && N > 0 && T > 0, "gad_graph_build_ell: bad arguments");
     GAD_CHECK_ARG(CE == 2 || CE == 4, "gad_graph_build_ell: CE must be 2 or 4 (got %d)", CE);
-    k_build_ell<<<T, 256, 0, as_stream(stream)>>>(ptr, idx, tile_ptr, T, CE * 4, reinterpret_cast<uint4*>(ell_rows),
-                                                 info + GAD_INFO_ELL_BAD);
+    GAD_CHECK_ARG(max_deg >= 0 && max_deg <= ELL_SLOTS, "gad_graph_build_ell: max_deg=%d exceeds %d slots", max_deg,
+                  ELL_SLOTS);
+    k_build_ell<<<T, 128, 0, as_stream(stream)>>>(ptr, idx, tile_ptr, T, CE * 4, slots_for(max_deg),
+                                                 reinterpret_cast<uint4*>(ell_rows), info + GAD_INFO_ELL_BAD);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

@@ -237,12 +237,15 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
             const bool last = (l == a.L - 1);
             float* st_out = (a.states && !last) ? a.states + (size_t)(l + 1) * state_stride : nullptr;
             if constexpr (METHOD == GAD_METHOD_EULER) {
+                float Mr[MUSZ];   // (M, u) in registers for the whole layer: no broadcast loads per node
+#pragma unroll
+                for (int t = 0; t < MUSZ; ++t) Mr[t] = Mu[t];
                 uint4 e_nx = (tid < NT) ? Ein.get(tid) : make_uint4(0, 0, 0, 0);
                 for (int i = tid; i < NT; i += nthr) {
                     const uint4 e = e_nx;
                     if (i + nthr < NT) e_nx = Ein.get(i + nthr);
                     const Row<CE> y = lds_row<CE>(Xc, i * RB);
-                    const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mu);
+                    const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mr);
                     Row<CE> xn;
 #pragma unroll
                     for (int c = 0; c < CE; ++c) xn.v[c] = fmaf(h, k.v[c], y.v[c]);
@@ -560,12 +563,15 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
             const float h = a.tau[l];
             const bool last = (l == a.L - 1);
             float* st_out = last ? nullptr : a.states + (size_t)(l + 1) * state_stride;
+            float Mr[MUSZ];   // (M, u) in registers for the whole layer: no broadcast loads per node
+#pragma unroll
+            for (int t = 0; t < MUSZ; ++t) Mr[t] = Mu[t];
             uint4 e_nx = (tid < NT) ? Ein.get(tid) : make_uint4(0, 0, 0, 0);
             for (int i = tid; i < NT; i += nthr) {
                 const uint4 e = e_nx;
                 if (i + nthr < NT) e_nx = Ein.get(i + nthr);
                 const Row<CE> y = lds_row<CE>(Xc, i * RB);
-                const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mu);
+                const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mr);
                 Row<CE> xn;
 #pragma unroll
                 for (int c = 0; c < CE; ++c) xn.v[c] = fmaf(h, k.v[c], y.v[c]);
@@ -630,8 +636,11 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
         tail::reduce_partials(a.partials, a.T, slots, NACC, MUSZ, a.gMu, a.tau_partials, a.L, a.g_tau, a.loss_partials,
                               a.loss_scale, a.loss, tid >> 5, (nthr + 31) >> 5);
         __syncthreads();
-        tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
         if (a.tail >= 2) {
+            // Wq / bq / Wk alias `params` and dWq[o,a] reads Wk[o,:] (dWk reads Wq[o,:], bq[o]): every
+            // read of the old weights must precede the first Adam write -> chain rule, barrier, Adam,
+            // barrier, refold.
+            tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
             __syncthreads();
             const long long t = a.step[0] + 1;
             tail::adam(a.params, a.grads, a.exp_avg, a.exp_avg_sq, a.n_params, a.lr, a.beta1, a.beta2, a.eps,
@@ -639,6 +648,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
             __syncthreads();
             if (tid == 0) a.step[0] = t;
             tail::prepare_weights(a.Wq, a.bq, a.Wk, a.Lw, a.C, CE, a.inv_temp, a.Mu_next);
+        } else {
+            tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
         }
         if (tid == 0) *a.counter = 0u;
     }

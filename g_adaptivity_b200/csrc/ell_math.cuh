@@ -2,13 +2,15 @@
 //
 // Mesh graphs have tiny, bounded degree (<= 7 incoming / outgoing edges per node, self-loops
 // included), so a tile's topology is stored as fixed-width rows of eight uint16:
-//     ell[i] = { off_0 .. off_6, deg }      off_q = (tile-local index of the q-th neighbour) * ROWBYTES
+//     ell[i] = { off_0 .. off_6, valid }    off_q = (tile-local index of the row in slot q) * ROWBYTES
 // One 128-bit load fetches a node's whole adjacency; the offsets are pre-multiplied byte offsets
 // into the shared-memory state buffer, so a neighbour gather is `LDS.128 [off + base]` with no
-// address arithmetic.  Unused slots hold offset 0 (a valid row) and are masked out of the softmax
-// by setting their logit to -inf, which makes every per-slot code path branch-free: all W
-// gathers of a row are issued back to back (memory-level parallelism), then max / ex2 / aggregate
-// run from registers.
+// address arithmetic.  Bit q of `valid` says slot q holds a neighbour; the other slots point at a
+// valid row too and are masked out of the softmax by setting their logit to -inf, which makes
+// every per-slot code path branch-free: all W gathers of a row are issued back to back
+// (memory-level parallelism), then max / ex2 / aggregate run from registers.  The builder
+// (ell_api.cu: k_build_ell) gives every neighbour offset its own slot, so the q-th gather of
+// consecutive lanes reads consecutive rows on structured meshes.
 //
 // All logits are in the log2 domain: gad_prepare_weights folds log2(e) into (M, u), the kernels
 // use ex2.approx / lg2.approx / rcp.approx (one MUFU each, relative error 2^-22), and the backward
@@ -24,7 +26,7 @@
 
 namespace gad {
 
-constexpr int ELL_SLOTS = 7;      // neighbour slots per row; the 8th uint16 is the degree
+constexpr int ELL_SLOTS = 7;      // neighbour slots per row; the 8th uint16 is the validity mask
 
 template <int CE>
 struct EllRow {
@@ -35,7 +37,8 @@ __device__ __forceinline__ uint32_t ell_off(const uint4& e, int q) {
     const uint32_t w = (q >> 1) == 0 ? e.x : ((q >> 1) == 1 ? e.y : ((q >> 1) == 2 ? e.z : e.w));
     return (q & 1) ? (w >> 16) : (w & 0xffffu);
 }
-__device__ __forceinline__ int ell_deg(const uint4& e) { return (int)(e.w >> 16); }
+__device__ __forceinline__ uint32_t ell_valid(const uint4& e) { return e.w >> 16; }
+__device__ __forceinline__ bool ell_has(const uint4& e, int q) { return (e.w >> (16 + q)) & 1u; }
 
 template <int CE>
 __device__ __forceinline__ Row<CE> lds_row(const unsigned char* __restrict__ base, uint32_t byte_off) {
@@ -68,7 +71,7 @@ __device__ __forceinline__ void sts_row(unsigned char* __restrict__ base, uint32
 template <int CE, int W>
 __device__ __forceinline__ Row<CE> ell_feval(const unsigned char* __restrict__ Xb, const uint4& ell,
                                              const Row<CE>& y, const float* __restrict__ Mu) {
-    const int deg = ell_deg(ell);
+    const bool any = ell_valid(ell) != 0;
     const Row<CE> p = project<CE>(Mu, y);
     Row<CE> xj[W];
     float s[W];
@@ -77,7 +80,7 @@ __device__ __forceinline__ Row<CE> ell_feval(const unsigned char* __restrict__ X
     for (int q = 0; q < W; ++q) {
         xj[q] = lds_row<CE>(Xb, ell_off(ell, q));
         const float d = dot<CE>(p, xj[q]);
-        s[q] = (q < deg) ? d : -CUDART_INF_F;
+        s[q] = ell_has(ell, q) ? d : -CUDART_INF_F;
         m = fmaxf(m, s[q]);
     }
     float Z = 0.f;
@@ -89,7 +92,7 @@ __device__ __forceinline__ Row<CE> ell_feval(const unsigned char* __restrict__ X
 #pragma unroll
         for (int c = 0; c < CE; ++c) o.v[c] = fmaf(w, xj[q].v[c], o.v[c]);
     }
-    const float rZ = (deg > 0) ? rcp_approx(Z) : 0.f;   // no in-edge: o = 0 (empty scatter row)
+    const float rZ = any ? rcp_approx(Z) : 0.f;   // no in-edge: o = 0 (empty scatter row)
     Row<CE> k;
 #pragma unroll
     for (int c = 0; c < CE; ++c) k.v[c] = fmaf(o.v[c], rZ, -y.v[c]);
@@ -103,7 +106,7 @@ template <int CE, int W>
 __device__ __forceinline__ void ell_bwd_dst(const unsigned char* __restrict__ Xb, const uint4& ell,
                                             const Row<CE>& xi, const Row<CE>& go, const float* __restrict__ Mu,
                                             Row<CE>& p, float& D, float& lse, Row<CE>& t, Row<CE>& o) {
-    const int deg = ell_deg(ell);
+    const bool any = ell_valid(ell) != 0;
     p = project<CE>(Mu, xi);
     Row<CE> xj[W];
     float s[W];
@@ -112,7 +115,7 @@ __device__ __forceinline__ void ell_bwd_dst(const unsigned char* __restrict__ Xb
     for (int q = 0; q < W; ++q) {
         xj[q] = lds_row<CE>(Xb, ell_off(ell, q));
         const float d = dot<CE>(p, xj[q]);
-        s[q] = (q < deg) ? d : -CUDART_INF_F;
+        s[q] = ell_has(ell, q) ? d : -CUDART_INF_F;
         m = fmaxf(m, s[q]);
     }
     float Z = 0.f;
@@ -124,11 +127,11 @@ __device__ __forceinline__ void ell_bwd_dst(const unsigned char* __restrict__ Xb
 #pragma unroll
         for (int c = 0; c < CE; ++c) o.v[c] = fmaf(s[q], xj[q].v[c], o.v[c]);
     }
-    const float rZ = (deg > 0) ? rcp_approx(Z) : 0.f;
+    const float rZ = any ? rcp_approx(Z) : 0.f;
 #pragma unroll
     for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
     D = dot<CE>(go, o);
-    lse = (deg > 0) ? m + lg2_approx(Z) : 0.f;   // empty row: never read by a source pass
+    lse = any ? m + lg2_approx(Z) : 0.f;   // empty row: never read by a source pass
     const float scale = rZ * LN2_F;
     t = zero_row<CE>();
 #pragma unroll
@@ -148,7 +151,6 @@ __device__ __forceinline__ Row<CE> ell_bwd_src(const unsigned char* __restrict__
                                                const unsigned char* __restrict__ Gb,
                                                const unsigned char* __restrict__ DLb, const uint4& ell,
                                                const Row<CE>& xj) {
-    const int deg = ell_deg(ell);
     Row<CE> acc = zero_row<CE>();
 #pragma unroll
     for (int q = 0; q < W; ++q) {
@@ -157,7 +159,7 @@ __device__ __forceinline__ Row<CE> ell_bwd_src(const unsigned char* __restrict__
         const Row<CE> go = lds_row<CE>(Gb, off);
         const float2 dl = *reinterpret_cast<const float2*>(DLb + (CE == 4 ? (off >> 1) : off));
         const float sv = dot<CE>(p, xj) - dl.y;
-        const float alpha = ex2_approx((q < deg) ? sv : -CUDART_INF_F);
+        const float alpha = ex2_approx(ell_has(ell, q) ? sv : -CUDART_INF_F);
         const float c = (dot<CE>(go, xj) - dl.x) * LN2_F;
 #pragma unroll
         for (int ch = 0; ch < CE; ++ch) acc.v[ch] = fmaf(alpha, fmaf(c, p.v[ch], go.v[ch]), acc.v[ch]);

@@ -352,9 +352,9 @@ __device__ __forceinline__ void block_reduce(float (&acc)[NACC], float* __restri
     }
     __syncthreads();
     for (int k = threadIdx.x; k < NACC; k += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nwarp; ++w) s += red[k * nwarp + w];
-        out[k] = s;
+        double s = 0.0;   // the sums cancel heavily (signed gradient terms): keep the cross-warp step exact
+        for (int w = 0; w < nwarp; ++w) s += (double)red[k * nwarp + w];
+        out[k] = (float)s;
     }
     __syncthreads();
 }

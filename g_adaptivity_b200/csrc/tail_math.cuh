@@ -88,26 +88,56 @@ __device__ __forceinline__ void weight_grads(const float* Wq, const float* bq,
     }
 }
 
-// torch.optim.Adam semantics (run_GNN.py:88,128,131): L2 weight decay added to the gradient,
-// bias-corrected moments.  `step` is a device counter, incremented by the caller after the sweep.
-__device__ __forceinline__ void adam(float* p, const float* g, float* m,
-                                     float* v, int64_t n, float lr, float b1, float b2, float eps,
-                                     float wd, float gscale, int64_t t) {
-    const double bc1 = 1.0 - pow((double)b1, (double)t);
-    const double bc2 = 1.0 - pow((double)b2, (double)t);
-    const float step_size = (float)((double)lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        float gi = g[i] * gscale;
-        const float pi = p[i];
-        if (wd != 0.f) gi = fmaf(wd, pi, gi);
-        const float mi = m[i] + (1.f - b1) * (gi - m[i]);          // lerp, as torch does
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = pi - step_size * (mi / denom);
+// b^t for integer t >= 0 by repeated squaring (exact to a few ulp; ~2 log2(t) multiplies instead of
+// a double-precision pow() call on the serial tail of the training kernel).
+__device__ __forceinline__ double ipow(double b, long long t) {
+    double r = 1.0;
+    while (t > 0) {
+        if (t & 1) r *= b;
+        b *= b;
+        t >>= 1;
     }
+    return r;
+}
+
+// torch.optim.Adam semantics (run_GNN.py:88,128,131): L2 weight decay added to the gradient,
+// bias-corrected moments.
+struct AdamCoef {
+    float step_size, bc2_sqrt, b1, b2, eps, wd, gscale;
+};
+
+__device__ __forceinline__ AdamCoef adam_coef(float lr, float b1, float b2, float eps, float wd, float gscale,
+                                              long long t) {
+    const double bc1 = 1.0 - ipow((double)b1, t);
+    const double bc2 = 1.0 - ipow((double)b2, t);
+    AdamCoef c;
+    c.step_size = (float)((double)lr / bc1);
+    c.bc2_sqrt = (float)sqrt(bc2);
+    c.b1 = b1;
+    c.b2 = b2;
+    c.eps = eps;
+    c.wd = wd;
+    c.gscale = gscale;
+    return c;
+}
+
+__device__ __forceinline__ void adam_one(const AdamCoef& c, float* p, float g, float* m, float* v, long long i) {
+    float gi = g * c.gscale;
+    const float pi = p[i];
+    if (c.wd != 0.f) gi = fmaf(c.wd, pi, gi);
+    const float mi = m[i] + (1.f - c.b1) * (gi - m[i]);          // lerp, as torch does
+    const float vi = c.b2 * v[i] + (1.f - c.b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / c.bc2_sqrt + c.eps;
+    p[i] = pi - c.step_size * (mi / denom);
+}
+
+// `t` = step number of THIS update (1-based); the caller stores it back to the device counter.
+__device__ __forceinline__ void adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1,
+                                     float b2, float eps, float wd, float gscale, int64_t t) {
+    const AdamCoef c = adam_coef(lr, b1, b2, eps, wd, gscale, t);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) adam_one(c, p, g[i], m, v, i);
 }
 
 // Fixed-order sum of the per-tile partials, one warp per output column (lanes stride over tiles,
@@ -134,11 +164,12 @@ __device__ __forceinline__ void reduce_partials(const float* partials, int T, in
             src = loss_partials;
             stride = 1;
         }
-        float s = 0.f;
-        for (int t = lane; t < T; t += 32) s += __ldcg(src + (size_t)t * stride);
+        double sd = 0.0;   // fp64: the per-tile partials cancel heavily across meshes
+        for (int t = lane; t < T; t += 32) sd += (double)__ldcg(src + (size_t)t * stride);
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        for (int d = 16; d > 0; d >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, d);
         if (lane != 0) continue;
+        const float s = (float)sd;
         if (w < ncol) {
             const int l = w / nacc, a = w % nacc;
             if (a < musz) gMu[(size_t)l * musz + a] = s;

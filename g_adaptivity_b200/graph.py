@@ -196,10 +196,10 @@ class MeshGraph:
         with torch.cuda.device(self.device):
             self._info[4:5].zero_()
             _lib.check(lib.gad_graph_build_ell(_lib.ptr(self.rowptr), _lib.ptr(self.col_walk), self.N,
-                                               _lib.ptr(self.tile_ptr), self.T, ce, _lib.ptr(ell_in),
+                                               _lib.ptr(self.tile_ptr), self.T, ce, deg, _lib.ptr(ell_in),
                                                _lib.ptr(self._info), stream), "gad_graph_build_ell")
             _lib.check(lib.gad_graph_build_ell(_lib.ptr(self.t_rowptr), _lib.ptr(self.t_dst_walk), self.N,
-                                               _lib.ptr(self.tile_ptr), self.T, ce, _lib.ptr(ell_out),
+                                               _lib.ptr(self.tile_ptr), self.T, ce, deg, _lib.ptr(ell_out),
                                                _lib.ptr(self._info), stream), "gad_graph_build_ell")
         if int(self._info[4].item()) != 0:
             return

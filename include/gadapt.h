@@ -133,9 +133,13 @@ int gad_deform_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_r
 /* ---- mesh-resident ELL path -------------------------------------------------------------------
  * The fast path for batches of bounded-degree meshes (every 1-D / 2-D mesh of the reference: in-
  * and out-degree <= 7 with self-loops).  Topology is one 16-byte row per node and direction:
- *     ell[i] = { uint16 off_0 .. off_6, uint16 degree },  off_q = (neighbour_q - tile_start) * CE * 4
- * built once per graph by gad_graph_build_ell from the row-sorted CSR (ptr = rowptr, idx = col) or
- * CSC (t_rowptr, t_dst) arrays and the tile plan; rows that do not fit (degree > 7, neighbour
+ *     ell[i] = { uint16 off_0 .. off_6, uint16 valid },  off_q = (row_q - tile_start) * CE * 4
+ * where bit q of `valid` says slot q holds a neighbour (the other slots point at some valid row of
+ * the tile and are masked out).  Only the first W = {2,3,6,7} >= max_deg slots are used; WHICH slot
+ * a neighbour sits in is free, and the builder picks one slot per neighbour offset (j - i) so that
+ * on structured meshes consecutive nodes gather consecutive rows (no shared-memory bank conflicts).
+ * Built once per graph by gad_graph_build_ell from the row-sorted CSR (ptr = rowptr, idx = col) or
+ * CSC (t_rowptr, t_dst) arrays and the tile plan; rows that do not fit (degree > max_deg, neighbour
  * outside the tile, offset > 65535) are counted in info[GAD_INFO_ELL_BAD] and the caller must
  * fall back to gad_deform_fwd / gad_deform_bwd.  max_deg = max(in-degree, out-degree) of the graph.
  * gad_deform_fwd_ell / gad_deform_bwd_ell: same contract as gad_deform_fwd / gad_deform_bwd
@@ -148,7 +152,7 @@ int gad_deform_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_r
  * x_phys [N, dim] is optional.  workspace: gad_ell_workspace_bytes(CE, T, L).
  */
 int gad_graph_build_ell(const int32_t* ptr, const int32_t* idx, int64_t N, const int32_t* tile_ptr, int T,
-                        int CE, void* ell_rows, int32_t* info, void* stream);
+                        int CE, int max_deg, void* ell_rows, int32_t* info, void* stream);
 /* 1 when the ELL kernels can run tiles of this size (shared-memory fit), else 0. */
 int gad_ell_supported(int CE, int max_tile_nodes, int max_deg, int train);
 size_t gad_ell_workspace_bytes(int CE, int T, int L);
