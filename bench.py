@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring", type=int, default=16, help="distinct resident batches walked by the timed loop")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-epoch", action="store_true", help="one CUDA graph per step instead of one per pass over the ring")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
@@ -270,15 +271,34 @@ def main():
         clocks.start()
 
     # ---- device-resident timing: W warm-up + exactly K timed steps -------------------------
-    for i in range(W):
-        trainer.step(i % R)
+    # The ring is walked as epochs: one CUDA graph holds the R steps of a pass over the resident
+    # batches (consecutive steps linked by programmatic dependent launch); a remainder of K mod R
+    # steps runs as single-step graphs.
+    ring = list(range(R))
+
+    def run_steps(n, first=0):
+        i = first
+        while n > 0:
+            if not args.no_graph and not args.no_epoch and i % R == 0 and n >= R:
+                trainer.run_epoch(ring)
+                i += R
+                n -= R
+            else:
+                trainer.step(i % R)
+                i += 1
+                n -= 1
+        return i
+
+    if not args.no_graph and not args.no_epoch:
+        trainer.capture_epoch(ring)
+    nxt = run_steps(W)
+    nxt = (nxt + R - 1) // R * R      # start the timed region on an epoch boundary
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.gad_launch_count()
     clocks.mark(True)
     ev0.record(trainer.stream)
-    for i in range(K):
-        trainer.step(i % R)
+    run_steps(K, nxt)
     ev1.record(trainer.stream)
     barrier()
     clocks.mark(False)
@@ -402,7 +422,9 @@ def main():
                             + (", NCCL grad all-reduce" if world > 1 else "") + ")",
                 "nodes_per_step_per_gpu": n_nodes, "edges_per_step_per_gpu": n_edges, "live_channels": model.live,
                 "l2": f"ring of {R} distinct resident batches, {ro_bytes / 1e6:.0f} MB read-only inputs (> 126 MB L2)",
-                "launch": "eager" if args.no_graph else "cuda-graph replay",
+                "launch": "eager" if args.no_graph else ("cuda-graph replay, one graph per step" if args.no_epoch else
+                                                         f"cuda-graph replay, one graph per pass over the ring ({R} steps, "
+                                                         "programmatic dependent launch between steps)"),
                 "tiles": s0.graph.T, "max_tile_nodes": s0.graph.max_tile_nodes,
             },
             "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": int(launches_per_step),

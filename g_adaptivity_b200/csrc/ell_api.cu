@@ -418,5 +418,6 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     a.weight_decay = d->weight_decay;
     a.adam_grad_scale = d->adam_grad_scale;
     a.step = reinterpret_cast<long long*>(d->step);
+    a.pdl = (d->flags & GAD_TRAIN_PDL) ? 1 : 0;
     return dispatch(d->CE, p, 2, a, GAD_METHOD_EULER, as_stream(stream));
 }

@@ -125,6 +125,7 @@ struct Args {
     long long n_params;
     float lr, beta1, beta2, eps, weight_decay, adam_grad_scale;
     long long* step;
+    int pdl;                // host side: launch with the programmatic-stream-serialization attribute
 };
 
 template <int CE>
@@ -451,6 +452,12 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd(const Ar
     }
 }
 
+// Programmatic dependent launch (sm_90+): `launch_dependents` lets the NEXT kernel of the stream start
+// its CTAs while this one still runs; `wait` blocks until every prerequisite grid has completed and
+// its memory is visible.  Both are no-ops when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ============================================================================================
 // train: feature assembly + forward + mesh loss + backward of a tile, one launch
 // ============================================================================================
@@ -473,6 +480,10 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
     float* Mu = reinterpret_cast<float*>(smem + lay.mu);
     float* red = reinterpret_cast<float*>(smem + lay.red);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
+    // The next training step (same stream, programmatic dependency) may start its CTAs now: its
+    // input staging below touches only data no kernel writes, so it overlaps this step's compute;
+    // everything this step produces is consumed after pdl_wait().
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -513,6 +524,9 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
                 bulk_g2s(DL, tg_g, xc_bytes, bar);
             }
         }
+        // previous step done (weights refolded, its reads of `states` finished): from here on this
+        // step may read Mu / tau and write global memory
+        pdl_wait();
         for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
         if (tx) {
             mbar_wait(bar, parity);
@@ -704,6 +718,23 @@ int launch_train_t(const Args& a, int threads, cudaStream_t st) {
     int grid = 0, rc;
     const size_t bytes = make_layout(CE, KIND_BWD, a.cap_nodes, ELLS, (threads + 31) / 32).total;
     if ((rc = prepare_launch(k_ell_train<CE, W, ELLS>, threads, bytes, a.T, &grid))) return rc;
+    if (a.pdl) {
+        // programmatic dependent launch: this kernel may start while its predecessor in the stream is
+        // still running (it synchronises itself with griddepcontrol.wait)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GAD_CUDA(cudaLaunchKernelEx(&cfg, k_ell_train<CE, W, ELLS>, a));
+        count_launch(1);
+        return GAD_OK;
+    }
     k_ell_train<CE, W, ELLS><<<grid, threads, bytes, st>>>(a);
     GAD_LAUNCH_CHECK();
     return GAD_OK;

@@ -68,6 +68,9 @@ class DeformerTrainer:
         self._flatten_parameters()
         self.slots: List[_Slot] = []
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.epoch_graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        # programmatic dependent launch between the train kernels of consecutive steps (single GPU)
+        self.use_pdl = bool(opt.get("gad_pdl", True)) and self.world == 1
         self.lib = _lib.load()
         self.stream = torch.cuda.Stream(device=self.dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)   # last-CTA election of k_ell_train
@@ -149,6 +152,7 @@ class DeformerTrainer:
         d.n_params = self.flat.numel()
         d.lr, d.beta1, d.beta2, d.eps, d.weight_decay, d.adam_grad_scale = self.lr, b1, b2, self.eps, self.wd, 1.0
         d.step = P(self.step_count)
+        d.flags = 1 if (self.use_pdl and tail == 2) else 0      # GAD_TRAIN_PDL
         return d
 
     # ------------------------------------------------------------------------------------
@@ -278,6 +282,39 @@ class DeformerTrainer:
                 self._allreduce()
                 self._issue(s, cs, stage="post")
             self.graphs[sid] = g
+
+    def capture_epoch(self, sids) -> tuple:
+        """Capture the steps of the resident batches `sids`, in order, into ONE CUDA graph.  On a single
+        GPU every step is one kernel and consecutive kernels are linked by programmatic dependent
+        launch: step k + 1 stages its inputs (TMA) while step k still computes, then waits for it."""
+        key = tuple(int(s) for s in sids)
+        if key in self.epoch_graphs:
+            return key
+        for sid in set(key):             # warm-up / attribute set-up happens in the single-step capture
+            if sid not in self.graphs:
+                self.capture(sid)
+        with torch.cuda.device(self.dev):
+            self.stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                cs = torch.cuda.current_stream(self.dev).cuda_stream
+                for sid in key:
+                    s = self.slots[sid]
+                    self._issue(s, cs, stage="pre")
+                    self._allreduce()
+                    self._issue(s, cs, stage="post")
+            self.epoch_graphs[key] = g
+        return key
+
+    def run_epoch(self, sids):
+        """One pass over the resident batches `sids` (one training step each) as a single graph replay.
+        Returns the per-slot loss tensors (device; each holds the loss of that slot's LAST step)."""
+        if not self.use_graph:
+            return [self.step(sid) for sid in sids]
+        key = self.capture_epoch(sids)
+        with torch.cuda.stream(self.stream):
+            self.epoch_graphs[key].replay()
+        return [self.slots[sid].loss for sid in key]
 
     def step(self, sid: int):
         """One training step on the resident batch `sid` (asynchronous; loss stays on the device)."""

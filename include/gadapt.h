@@ -226,7 +226,13 @@ typedef struct gad_train_desc {
     int64_t n_params;
     float lr, beta1, beta2, eps, weight_decay, adam_grad_scale;
     int64_t* step;
+    /* launch flags: bit 0 = programmatic dependent launch (the kernel may start while the previous
+     * kernel of the stream is still running; it stages its inputs, then waits for it before touching
+     * anything a kernel writes).  The inputs (x_comp, f, uu, target, ELL rows) must then not be
+     * written by the preceding kernel of the stream. */
+    int32_t flags;
 } gad_train_desc;
+#define GAD_TRAIN_PDL 1
 int gad_train_step_ell(const gad_train_desc* desc, void* stream);
 
 /* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --

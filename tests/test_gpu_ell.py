@@ -174,3 +174,27 @@ def test_one_launch_step_equals_multi_kernel_step(use_graph):
     # the model's parameters are views of the trainer's flat vector: state_dict sees the update
     sd = model.state_dict()
     assert not torch.equal(sd["conv_layers.0.lin_query.weight"].cpu(), ref.state_dict()["conv_layers.0.lin_query.weight"])
+
+
+@pytest.mark.parametrize("pdl", [True, False])
+def test_epoch_graph_equals_step_by_step(pdl):
+    """One CUDA graph for a pass over the ring (programmatic dependent launch between the steps)
+    trains exactly like one graph replay per step."""
+    opt, ds, _, ref = _case((30, 30), 8, seed=1)
+    batches = [synth.make_batch((30, 30), 40, seed=20 + r) for r in range(3)]
+    res = []
+    for epoch_mode in (True, False):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_pdl=pdl)
+        tr = DeformerTrainer(model, lr=5e-3)
+        sids = [tr.add_batch(b) for b in batches]
+        for _ in range(4):
+            if epoch_mode:
+                tr.run_epoch(sids)
+            else:
+                for sid in sids:
+                    tr.step(sid)
+        tr.synchronize()
+        res.append((tr.flat.clone().cpu(), [tr.slots[s].loss.item() for s in sids], int(tr.step_count.item())))
+    assert res[0][2] == res[1][2] == 12
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1]
