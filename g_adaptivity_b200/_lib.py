@@ -42,7 +42,7 @@ class TrainDesc(C.Structure):
         ("Wq", _fp), ("bq", _fp), ("Wk", _fp), ("gWq", _fp), ("gbq", _fp), ("gWk", _fp), ("gbk", _fp),
         ("params", _fp), ("grads", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("n_params", _i64),
         ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("weight_decay", _f), ("adam_grad_scale", _f),
-        ("step", _fp), ("flags", _i32),
+        ("step", _fp), ("flags", _i32), ("trace", _fp),
     ]
 
 

@@ -419,5 +419,6 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     a.adam_grad_scale = d->adam_grad_scale;
     a.step = reinterpret_cast<long long*>(d->step);
     a.pdl = (d->flags & GAD_TRAIN_PDL) ? 1 : 0;
+    a.trace = reinterpret_cast<long long*>(d->trace);
     return dispatch(d->CE, p, 2, a, GAD_METHOD_EULER, as_stream(stream));
 }

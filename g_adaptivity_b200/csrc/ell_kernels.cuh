@@ -126,6 +126,21 @@ struct Args {
     float lr, beta1, beta2, eps, weight_decay, adam_grad_scale;
     long long* step;
     int pdl;                // host side: launch with the programmatic-stream-serialization attribute
+    long long* trace;       // optional [gridDim, 64] globaltimer marks of the train kernel (profiling aid)
+};
+
+// Phase timeline of the train kernel: thread 0 of every CTA stamps %globaltimer (ns) at the phase
+// boundaries when Args::trace is set (scripts/ktrace.py); compiled out of the hot loops otherwise.
+struct Tracer {
+    long long* p;
+    int n;
+    __device__ __forceinline__ void mark() {
+        if (p && threadIdx.x == 0 && n < 64) {
+            long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p[n++] = t;
+        }
+    }
 };
 
 template <int CE>
@@ -484,6 +499,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
     // input staging below touches only data no kernel writes, so it overlaps this step's compute;
     // everything this step produces is consumed after pdl_wait().
     pdl_launch_dependents();
+    Tracer tr{a.trace ? a.trace + (size_t)blockIdx.x * 64 : nullptr, 0};
+    tr.mark();   // 0: kernel entry
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -527,11 +544,13 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
         // previous step done (weights refolded, its reads of `states` finished): from here on this
         // step may read Mu / tau and write global memory
         pdl_wait();
+        tr.mark();   // 1: predecessor done
         for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
         if (tx) {
             mbar_wait(bar, parity);
             parity ^= 1;
         }
+        tr.mark();   // 2: inputs landed
         // features = cat[x_comp, f, uu] + identity (zero-pad) encoder: src/GNN.py:225-239,75-83,270
         unsigned char* Xc = B0;
         unsigned char* Xn = B1;
@@ -613,6 +632,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
                 }
             }
             __syncthreads();
+            tr.mark();   // 3 .. 2+L: forward layers
             if (!last) {
                 unsigned char* t = Xc;
                 Xc = Xn;
@@ -627,7 +647,9 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
             float one[1] = {loss_acc};
             block_reduce<1>(one, red, a.loss_partials + tile);
         }
+        tr.mark();   // loss reduced
         tile_backward<CE, W, ELLS>(a, tile, n0, NT, Xc, Xn, P, DL, GS, Ein, Eout, Mu, red);
+        tr.mark();   // backward + block reduction done
     }
 
     // ---- tail: the last CTA to finish reduces the partials (fixed order -> deterministic), applies
@@ -643,6 +665,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
     }
     __syncthreads();
     if (!s_last) return;
+    tr.mark();   // elected
     __threadfence();
     {
         constexpr int NACC = MUSZ + 1;
@@ -650,22 +673,26 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
         tail::reduce_partials(a.partials, a.T, slots, NACC, MUSZ, a.gMu, a.tau_partials, a.L, a.g_tau, a.loss_partials,
                               a.loss_scale, a.loss, tid >> 5, (nthr + 31) >> 5);
         __syncthreads();
+        tr.mark();   // partials reduced
         if (a.tail >= 2) {
             // Wq / bq / Wk alias `params` and dWq[o,a] reads Wk[o,:] (dWk reads Wq[o,:], bq[o]): every
             // read of the old weights must precede the first Adam write -> chain rule, barrier, Adam,
             // barrier, refold.
             tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
             __syncthreads();
+            tr.mark();   // chain rule
             const long long t = a.step[0] + 1;
             tail::adam(a.params, a.grads, a.exp_avg, a.exp_avg_sq, a.n_params, a.lr, a.beta1, a.beta2, a.eps,
                        a.weight_decay, a.adam_grad_scale, t);
             __syncthreads();
+            tr.mark();   // Adam
             if (tid == 0) a.step[0] = t;
             tail::prepare_weights(a.Wq, a.bq, a.Wk, a.Lw, a.C, CE, a.inv_temp, a.Mu_next);
         } else {
             tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
         }
         if (tid == 0) *a.counter = 0u;
+        tr.mark();   // tail done (last CTA only)
     }
 }
 

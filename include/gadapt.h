@@ -231,6 +231,9 @@ typedef struct gad_train_desc {
      * anything a kernel writes).  The inputs (x_comp, f, uu, target, ELL rows) must then not be
      * written by the preceding kernel of the stream. */
     int32_t flags;
+    /* optional profiling aid: int64 [grid, 64] buffer receiving %globaltimer marks at the phase
+     * boundaries of every CTA (NULL = off) */
+    int64_t* trace;
 } gad_train_desc;
 #define GAD_TRAIN_PDL 1
 int gad_train_step_ell(const gad_train_desc* desc, void* stream);
