@@ -405,6 +405,7 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     a.gbk = d->gbk;
     a.C = d->C;
     a.inv_temp = d->inv_temp;
+    a.cfold = tail::fold_scale(d->inv_temp, d->C);
     a.Mu_next = d->Mu;
     a.params = d->params;
     a.grads = d->grads;
@@ -420,5 +421,35 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     a.step = reinterpret_cast<long long*>(d->step);
     a.pdl = (d->flags & GAD_TRAIN_PDL) ? 1 : 0;
     a.trace = reinterpret_cast<long long*>(d->trace);
-    return dispatch(d->CE, p, 2, a, GAD_METHOD_EULER, as_stream(stream));
+    cudaStream_t st = as_stream(stream);
+    // The in-kernel tail keeps mirrors of the flat parameter / gradient vectors in shared memory: it
+    // needs Wq / bq / Wk to be views of `params` (tail 2) and its scratch plan to fit the CTA.
+    auto within = [](const float* q, const float* base, long long n) { return q >= base && q < base + n; };
+    const long long np = d->tail >= 2 ? d->n_params : 0;
+    const Layout lay = make_layout(d->CE, KIND_BWD, d->max_tile_nodes, p.ells != 0, (p.threads + 31) / 32);
+    bool fused_tail = plan_tail(d->CE, d->Lw, d->L, d->C, a.tau_partials && a.g_tau, true, np, d->T, (p.threads + 31) / 32,
+                                lay.bar).ok;
+    if (d->tail >= 2) {
+        const float* views[] = {d->Wq, d->bq, d->Wk};
+        const float* gviews[] = {d->gWq, d->gbq, d->gWk, d->gbk};
+        for (const float* v : views) fused_tail = fused_tail && within(v, d->params, np);
+        for (const float* v : gviews) fused_tail = fused_tail && within(v, d->grads, np);
+        if (d->g_tau) fused_tail = fused_tail && within(d->g_tau, d->grads, np);
+    }
+    if (fused_tail) return dispatch(d->CE, p, 2, a, GAD_METHOD_EULER, st);
+    // generic path: the same step as separate launches
+    a.tail = 0;
+    a.pdl = 0;
+    if ((rc = dispatch(d->CE, p, 2, a, GAD_METHOD_EULER, st))) return rc;
+    if ((rc = reduce_partials(d->CE, d->T, d->Lw, d->L, ws, d->gMu, d->g_tau, d->loss_scale, d->loss, st))) return rc;
+    if ((rc = gad_weight_grads(d->Wq, d->bq, d->Wk, d->gMu, d->Lw, d->C, d->CE, d->inv_temp, d->gWq, d->gbq, d->gWk, d->gbk,
+                               stream)))
+        return rc;
+    if (d->tail >= 2) {
+        if ((rc = gad_adam_step(d->params, d->grads, d->exp_avg, d->exp_avg_sq, d->n_params, d->lr, d->beta1, d->beta2,
+                                d->eps, d->weight_decay, d->adam_grad_scale, d->step, stream)))
+            return rc;
+        if ((rc = gad_prepare_weights(d->Wq, d->bq, d->Wk, d->Lw, d->C, d->CE, d->inv_temp, d->Mu, stream))) return rc;
+    }
+    return GAD_OK;
 }

@@ -23,6 +23,8 @@
 // partials summed by a second tiny kernel.  No floating-point atomics: bit-reproducible.
 #pragma once
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ell_math.cuh"
 #include "tail_math.cuh"
@@ -38,6 +40,8 @@ namespace ell {
 #endif
 
 enum Kind { KIND_FWD = 0, KIND_FWD_RK4 = 1, KIND_BWD = 2 };
+
+constexpr size_t TAIL_SCRATCH_MIN = 24 * 1024;
 
 struct Layout {
     uint32_t xa, xb, p, gs, dl, ein, eout, mu, red, bar, total;
@@ -65,6 +69,7 @@ __host__ __device__ inline Layout make_layout(int CE, int kind, int cap_nodes, b
     }
     s.mu = bump((size_t)(CE * CE + CE) * sizeof(float));
     if (kind == KIND_BWD) s.red = bump((size_t)(CE * CE + CE + 1) * nwarps * sizeof(float));
+    if (kind == KIND_BWD && o < TAIL_SCRATCH_MIN) o = TAIL_SCRATCH_MIN;   // train tail: [0, bar) is its scratch
     s.bar = bump(16);
     s.total = (uint32_t)o;
     return s;
@@ -117,6 +122,7 @@ struct Args {
     float* gbk;
     int C;
     float inv_temp;
+    double cfold;           // tail::fold_scale(inv_temp, C), computed on the host
     float* Mu_next;         // = Mu (rewritten in place once every CTA is done with it)
     float* params;          // flat parameter vector and Adam state (tail == 2)
     const float* grads;
@@ -126,6 +132,7 @@ struct Args {
     float lr, beta1, beta2, eps, weight_decay, adam_grad_scale;
     long long* step;
     int pdl;                // host side: launch with the programmatic-stream-serialization attribute
+    int tail_cta;           // 1: the last CTA of the grid (an extra one, without tiles) runs the tail
     long long* trace;       // optional [gridDim, 64] globaltimer marks of the train kernel (profiling aid)
 };
 
@@ -474,6 +481,266 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ============================================================================================
+// tail of the training step: reduction of the per-tile partials, chain rule, Adam, refold
+// ============================================================================================
+// Run by ONE CTA per launch.  What it costs is the length of its dependent instruction stream
+// (every stage is a few hundred mostly-serial instructions of one warp), not bandwidth, so it is
+// split in two:
+//   tail_prepare  everything that does not depend on this step's partials -- shared-memory mirrors
+//                 of the flat parameter / gradient vectors (cp.async), the Adam moments of the
+//                 thread's parameter in registers, the structurally-zero gradient entries;
+//   tail_finish   partials -> fixed-order fp64 column sums -> chain rule to the Linear parameters
+//                 (src/GRAND_plus.py:225-226 folded, tail_math.cuh) -> Adam (src/run_GNN.py:88,128,131)
+//                 on the mirror -> refold of (M, u) for the next launch, all through shared memory
+//                 with 32-bit offsets: one L2 round trip (the partials) and four barriers.
+// When the whole grid is resident at once the training kernel adds a reducer CTA that owns no tile:
+// it runs tail_prepare while the tiles are being processed, waits until every tile CTA has checked
+// in, and runs tail_finish.  Otherwise the last tile CTA to finish runs both parts.  The host checks
+// plan_tail().ok (and that Wq / bq / Wk, gWq / gbq / gWk / gbk are views of params / grads) and
+// otherwise launches with tail = 0 followed by the stand-alone kernels.
+struct TailPlan {
+    uint32_t colsum, wp, gmu, ps, gs, stage;   // byte offsets into the scratch
+    int ncol, ntau, nloss, ncolT, TC;          // columns of the three partial arrays; tiles per chunk
+    int nps;                                   // floats mirrored in `ps`
+    bool ok;
+};
+
+__host__ __device__ inline TailPlan plan_tail(int CE, int Lw, int L, int C, bool tau_cols, bool loss_col,
+                                              long long n_params, int T, int nwarps, size_t scratch_bytes) {
+    const int MUSZ = CE * CE + CE, NACC = MUSZ + 1;
+    TailPlan p{};
+    p.ncol = (Lw > 1 ? L : 1) * NACC;
+    p.ntau = tau_cols ? L : 0;
+    p.nloss = loss_col ? 1 : 0;
+    p.ncolT = p.ncol + p.ntau + p.nloss;
+    // Adam (n_params > 0): mirror of the whole flat vector; else [Wq | bq | Wk]
+    const long long nps = n_params > 0 ? n_params : (long long)Lw * (2 * C * C + C);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o = (o + bytes + 15) & ~size_t(15);
+        return (uint32_t)at;
+    };
+    p.colsum = take((size_t)p.ncolT * sizeof(double));
+    p.wp = take((size_t)p.ncolT * nwarps * sizeof(double));
+    p.gmu = take((size_t)Lw * MUSZ * sizeof(float));
+    p.ps = take((size_t)nps * sizeof(float));
+    p.gs = take((size_t)n_params * sizeof(float));
+    p.stage = (uint32_t)o;
+    p.nps = (int)nps;
+    p.ok = nps < (1 << 24) && o + (size_t)p.ncolT * sizeof(float) <= scratch_bytes;
+    if (!p.ok) return p;
+    long long tc = (long long)((scratch_bytes - o) / sizeof(float)) / p.ncolT;
+    if (tc > T) tc = T;
+    if (tc > 32) tc &= ~31LL;
+    p.TC = (int)tc;
+    return p;
+}
+
+struct TailCtx {
+    TailPlan tp;
+    uint32_t oWq, obq, oWk;        // float offsets of the weights in the `ps` mirror
+    uint32_t ogWq, ogbq, ogWk;     // float offsets of their gradients in the `gs` mirror (Adam)
+    float m0, v0;                  // Adam moments of parameter `tid`
+};
+
+template <int CE>
+__device__ __forceinline__ void tail_prepare(const Args& a, unsigned char* scratch, uint32_t scratch_bytes, TailCtx& cx) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const bool adam = a.tail >= 2;
+    const int np = adam ? (int)a.n_params : 0;
+    const int C = a.C, rows = a.Lw * C;
+    cx.tp = plan_tail(CE, a.Lw, a.L, C, a.tau_partials && a.g_tau, a.loss_partials && a.loss, np, a.T,
+                      (nthr + 31) >> 5, scratch_bytes);
+    float* Ps = reinterpret_cast<float*>(scratch + cx.tp.ps);
+    float* Gs = reinterpret_cast<float*>(scratch + cx.tp.gs);
+    double* colsum = reinterpret_cast<double*>(scratch + cx.tp.colsum);
+    cx.m0 = cx.v0 = 0.f;
+    if (adam) {
+        cx.oWq = (uint32_t)(a.Wq - a.params);
+        cx.obq = (uint32_t)(a.bq - a.params);
+        cx.oWk = (uint32_t)(a.Wk - a.params);
+        cx.ogWq = (uint32_t)(a.gWq - a.grads);
+        cx.ogbq = (uint32_t)(a.gbq - a.grads);
+        cx.ogWk = (uint32_t)(a.gWk - a.grads);
+        if (tid < np) {
+            cx.m0 = __ldcg(a.exp_avg + tid);
+            cx.v0 = __ldcg(a.exp_avg_sq + tid);
+        }
+        tail::stage_async(Ps, a.params, np);
+        tail::stage_async(Gs, a.grads, np);   // entries the tail does not produce keep their value
+    } else {
+        cx.oWq = 0;
+        cx.obq = (uint32_t)(rows * C);
+        cx.oWk = cx.obq + (uint32_t)rows;
+        cx.ogWq = cx.ogbq = cx.ogWk = 0;
+        tail::stage_async(Ps + cx.oWq, a.Wq, rows * C);
+        tail::stage_async(Ps + cx.obq, a.bq, rows);
+        tail::stage_async(Ps + cx.oWk, a.Wk, rows * C);
+    }
+    for (int c = tid; c < cx.tp.ncolT; c += nthr) colsum[c] = 0.0;
+    tail::stage_wait();
+    __syncthreads();
+    // structurally zero gradients: d/d lin_key.bias (softmax shift invariance) and the columns of
+    // Wq / Wk that only ever multiply dead channels
+    const int gbk_off = adam ? (int)(a.gbk - a.grads) : 0;
+#pragma unroll 1
+    for (int lo = tid; lo < rows; lo += nthr) {
+        a.gbk[lo] = 0.0f;
+        if (adam) Gs[gbk_off + lo] = 0.0f;
+    }
+    if (C > CE) {
+        const int dead = C - CE;
+#pragma unroll 1
+        for (int idx = tid; idx < rows * dead; idx += nthr) {
+            const int lo = idx / dead, o = lo * C + CE + (idx - lo * dead);
+            a.gWq[o] = 0.0f;
+            a.gWk[o] = 0.0f;
+            if (adam) {
+                Gs[cx.ogWq + o] = 0.0f;
+                Gs[cx.ogWk + o] = 0.0f;
+            }
+        }
+    }
+}
+
+template <int CE>
+__device__ __forceinline__ void tail_finish(const Args& a, unsigned char* scratch, const TailCtx& cx,
+                                            const tail::AdamCoef& coef, long long t_step, Tracer& tr) {
+    constexpr int MUSZ = CE * CE + CE;
+    constexpr int NACC = MUSZ + 1;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = (nthr + 31) >> 5;
+    const bool adam = a.tail >= 2;
+    const int np = adam ? (int)a.n_params : 0;
+    const int slots = a.Lw > 1 ? a.L : 1;
+    const TailPlan& tp = cx.tp;
+    const int ncol = tp.ncol, ntau = tp.ntau, nloss = tp.nloss, ncolT = tp.ncolT, TC = tp.TC;
+    double* colsum = reinterpret_cast<double*>(scratch + tp.colsum);
+    double* wp = reinterpret_cast<double*>(scratch + tp.wp);
+    float* gMu_s = reinterpret_cast<float*>(scratch + tp.gmu);
+    float* Ps = reinterpret_cast<float*>(scratch + tp.ps);
+    float* Gs = reinterpret_cast<float*>(scratch + tp.gs);
+    float* S = reinterpret_cast<float*>(scratch + tp.stage);
+
+    // ---- (1) fixed-order column sums: lane = column, warp = contiguous range of tiles (two
+    // interleaved fp64 chains), then the warps' sums in warp order; chunk by chunk
+#pragma unroll 1
+    for (int t0 = 0; t0 < a.T; t0 += TC) {
+        const int nt = (a.T - t0 < TC) ? a.T - t0 : TC;
+        float* S0 = S;
+        float* S1 = S0 + nt * ncol;
+        float* S2 = S1 + nt * ntau;
+        tail::stage_async(S0, a.partials + (size_t)t0 * ncol, nt * ncol);
+        if (ntau) tail::stage_async(S1, a.tau_partials + (size_t)t0 * a.L, nt * ntau);
+        if (nloss) tail::stage_async(S2, a.loss_partials + t0, nt);
+        tail::stage_wait();
+        __syncthreads();
+        const int tpw = (nt + nwarps - 1) / nwarps;
+        const int tb = warp * tpw, te = (tb + tpw < nt) ? tb + tpw : nt;
+#pragma unroll 1
+        for (int c = lane; c < ncolT; c += 32) {
+            const float* src = (c < ncol) ? S0 + c : ((c < ncol + ntau) ? S1 + (c - ncol) : S2);
+            const int stride = (c < ncol) ? ncol : ((c < ncol + ntau) ? ntau : 1);
+            double s0 = 0.0, s1 = 0.0;   // fp64: the per-tile partials cancel heavily across meshes
+            int t = tb;
+#pragma unroll 4
+            for (; t + 1 < te; t += 2) {
+                s0 += (double)src[t * stride];
+                s1 += (double)src[(t + 1) * stride];
+            }
+            if (t < te) s0 += (double)src[t * stride];
+            wp[warp * ncolT + c] = s0 + s1;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int c = tid; c < ncolT; c += nthr) {
+            double sd = colsum[c];
+            for (int w = 0; w < nwarps; ++w) sd += wp[w * ncolT + c];
+            colsum[c] = sd;
+            if (t0 + TC >= a.T) {   // last chunk: the column is complete
+                const float sv = (float)sd;
+                if (c < ncol) {
+                    const int l = c / NACC, k = c - l * NACC;
+                    if (k < MUSZ) {
+                        gMu_s[l * MUSZ + k] = sv;
+                        a.gMu[l * MUSZ + k] = sv;
+                    } else if (a.g_tau && slots > 1) {
+                        a.g_tau[l] = sv;
+                        if (adam) Gs[(a.g_tau - a.grads) + l] = sv;
+                    }
+                } else if (c < ncol + ntau) {
+                    a.g_tau[c - ncol] = sv;
+                    if (adam) Gs[(a.g_tau - a.grads) + (c - ncol)] = sv;
+                } else {
+                    a.loss[0] = sv * a.loss_scale;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    tr.mark();   // partials reduced
+
+    // ---- (2) chain rule: rows lo = l * C + o of Wq / Wk viewed as [Lw * C, C], live columns only
+    // (same arithmetic, same order as tail::weight_grads); the bias rows go to the high threads
+    const int C = a.C, rows = a.Lw * C;
+    const int live = CE < C ? CE : C;
+    const double cfold = a.cfold;
+#pragma unroll 1
+    for (int idx = tid; idx < rows * CE; idx += nthr) {
+        const int aa = idx % CE, lo = idx / CE;
+        if (aa >= live) continue;
+        const int l = (a.Lw > 1) ? lo / C : 0;
+        float dq, dk;
+        tail::weight_grad_entry<CE>(Ps + cx.oWq + lo * C, Ps + cx.oWk + lo * C, Ps[cx.obq + lo], gMu_s + l * MUSZ, live, aa,
+                                    cfold, dq, dk);
+        const int o = lo * C + aa;
+        a.gWq[o] = dq;
+        a.gWk[o] = dk;
+        if (adam) {
+            Gs[cx.ogWq + o] = dq;
+            Gs[cx.ogWk + o] = dk;
+        }
+    }
+#pragma unroll 1
+    for (int lo = nthr - 1 - tid; lo < rows; lo += nthr) {
+        const int l = (a.Lw > 1) ? lo / C : 0;
+        const float* wk = Ps + cx.oWk + lo * C;
+        const float* Gu = gMu_s + l * MUSZ + CE * CE;
+        double d = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < CE; ++bb)
+            if (bb < live) d += (double)wk[bb] * (double)Gu[bb];
+        const float g = (float)(cfold * d);
+        a.gbq[lo] = g;
+        if (adam) Gs[cx.ogbq + lo] = g;
+    }
+    if (!adam) return;
+    __syncthreads();
+    tr.mark();   // chain rule
+
+    // ---- (3) Adam on the mirror ------------------------------------------------------------------
+#pragma unroll 1
+    for (int i = tid; i < np; i += nthr) {
+        float m = cx.m0, v = cx.v0;
+        if (i >= nthr) {
+            m = __ldcg(a.exp_avg + i);
+            v = __ldcg(a.exp_avg_sq + i);
+        }
+        const float pn = tail::adam_update(coef, Ps[i], Gs[i], m, v);
+        Ps[i] = pn;
+        a.params[i] = pn;
+        a.exp_avg[i] = m;
+        a.exp_avg_sq[i] = v;
+    }
+    if (tid == 0) a.step[0] = t_step;
+    __syncthreads();
+    tr.mark();   // Adam
+
+    // ---- (4) refold (M, u) of the next step from the mirror ---------------------------------------
+    tail::prepare_weights_t<CE>(Ps + cx.oWq, Ps + cx.obq, Ps + cx.oWk, a.Lw, C, cfold, a.Mu_next);
+}
+
+// ============================================================================================
 // train: feature assembly + forward + mesh loss + backward of a tile, one launch
 // ============================================================================================
 // Replaces pack -> forward -> loss -> backward of the training step (src/run_GNN.py:99-131 with
@@ -495,6 +762,9 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
     float* Mu = reinterpret_cast<float*>(smem + lay.mu);
     float* red = reinterpret_cast<float*>(smem + lay.red);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
+    __shared__ int s_last;
+    __shared__ long long s_step;
+    __shared__ tail::AdamCoef s_coef;
     // The next training step (same stream, programmatic dependency) may start its CTAs now: its
     // input staging below touches only data no kernel writes, so it overlaps this step's compute;
     // everything this step produces is consumed after pdl_wait().
@@ -507,8 +777,13 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
     }
     uint32_t parity = 0;
     const size_t state_stride = (size_t)a.N * CE;
+    // With a whole grid resident at once (T + 1 <= CTA slots) an EXTRA CTA, the last of the grid, is
+    // the reducer: it owns no tile, prepares the tail while the tiles are processed, waits until every tile CTA
+    // has checked in and then runs the tail.  Otherwise the last tile CTA to finish runs it.
+    const int tile_ctas = a.tail_cta ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const bool reducer = a.tail_cta && (int)blockIdx.x == tile_ctas;
 
-    for (int tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
+    for (int tile = reducer ? a.T : (int)blockIdx.x; tile < a.T; tile += tile_ctas) {
         const int n0 = a.tile_ptr[tile];
         const int NT = a.tile_ptr[tile + 1] - n0;
         __syncthreads();
@@ -545,7 +820,13 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
         // step may read Mu / tau and write global memory
         pdl_wait();
         tr.mark();   // 1: predecessor done
-        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+        // Adam's bias corrections of THIS step (a serial fp64 chain) are worked out now by one thread
+        // of every CTA, hidden behind the tile's work, so that whichever CTA runs the tail has them
+        if (a.tail >= 2 && !a.tail_cta && tile == (int)blockIdx.x && tid == nthr - 1) {
+            s_step = __ldcg(a.step) + 1;
+            s_coef = tail::adam_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.adam_grad_scale, s_step);
+        }
+        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = __ldcg(a.Mu + t);
         if (tx) {
             mbar_wait(bar, parity);
             parity ^= 1;
@@ -656,44 +937,44 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
     // the chain rule to the Linear parameters and, single-GPU, takes the Adam step and refolds the
     // weights for the next launch: the whole training step is this one kernel.
     if (a.tail == 0) return;
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int prev = atomicAdd(a.counter, 1u);
-        s_last = (prev == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    tr.mark();   // elected
-    __threadfence();
-    {
-        constexpr int NACC = MUSZ + 1;
-        const int slots = a.Lw > 1 ? a.L : 1;
-        tail::reduce_partials(a.partials, a.T, slots, NACC, MUSZ, a.gMu, a.tau_partials, a.L, a.g_tau, a.loss_partials,
-                              a.loss_scale, a.loss, tid >> 5, (nthr + 31) >> 5);
-        __syncthreads();
-        tr.mark();   // partials reduced
-        if (a.tail >= 2) {
-            // Wq / bq / Wk alias `params` and dWq[o,a] reads Wk[o,:] (dWk reads Wq[o,:], bq[o]): every
-            // read of the old weights must precede the first Adam write -> chain rule, barrier, Adam,
-            // barrier, refold.
-            tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
-            __syncthreads();
-            tr.mark();   // chain rule
-            const long long t = a.step[0] + 1;
-            tail::adam(a.params, a.grads, a.exp_avg, a.exp_avg_sq, a.n_params, a.lr, a.beta1, a.beta2, a.eps,
-                       a.weight_decay, a.adam_grad_scale, t);
-            __syncthreads();
-            tr.mark();   // Adam
-            if (tid == 0) a.step[0] = t;
-            tail::prepare_weights(a.Wq, a.bq, a.Wk, a.Lw, a.C, CE, a.inv_temp, a.Mu_next);
-        } else {
-            tail::weight_grads(a.Wq, a.bq, a.Wk, a.gMu, a.Lw, a.C, CE, a.inv_temp, a.gWq, a.gbq, a.gWk, a.gbk);
+    if (!reducer) {
+        // every global value the tail reads (partials, loss / step-size partials) was written by warp 0
+        // (block_reduce): release them with one fence, then count this CTA in
+        if (tid < 32) {
+            __threadfence();
+            __syncwarp();
+            if (tid == 0) {
+                const unsigned int prev = atomicAdd(a.counter, 1u);
+                s_last = (prev == gridDim.x - 1) ? 1 : 0;
+            }
         }
-        if (tid == 0) *a.counter = 0u;
-        tr.mark();   // tail done (last CTA only)
+        if (a.tail_cta) return;
+        __syncthreads();
+        if (!s_last) return;
+        tr.mark();   // elected
     }
+    TailCtx cx;
+    if (reducer) pdl_wait();   // previous step complete: its step counter, moments and weights are final
+    tail_prepare<CE>(a, smem, lay.bar, cx);
+    if (reducer) {
+        tr.mark();   // prepared
+        if (a.tail >= 2 && tid == nthr - 1) {
+            s_step = __ldcg(a.step) + 1;
+            s_coef = tail::adam_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.adam_grad_scale, s_step);
+        }
+        if (tid == 0) {
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counter) : "memory");
+            } while (seen < (unsigned)tile_ctas);
+        }
+        __syncthreads();
+        tr.mark();   // every tile CTA has checked in
+    }
+    __threadfence();
+    tail_finish<CE>(a, smem, cx, s_coef, s_step, tr);
+    if (tid == 0) *a.counter = 0u;
+    tr.mark();   // tail done
 }
 
 // ============================================================================================
@@ -741,10 +1022,15 @@ int launch_bwd_t(const Args& a, int threads, cudaStream_t st) {
 }
 
 template <int CE, int W, bool ELLS>
-int launch_train_t(const Args& a, int threads, cudaStream_t st) {
+int launch_train_t(const Args& a_in, int threads, cudaStream_t st) {
     int grid = 0, rc;
-    const size_t bytes = make_layout(CE, KIND_BWD, a.cap_nodes, ELLS, (threads + 31) / 32).total;
-    if ((rc = prepare_launch(k_ell_train<CE, W, ELLS>, threads, bytes, a.T, &grid))) return rc;
+    const size_t bytes = make_layout(CE, KIND_BWD, a_in.cap_nodes, ELLS, (threads + 31) / 32).total;
+    if ((rc = prepare_launch(k_ell_train<CE, W, ELLS>, threads, bytes, a_in.T + 1, &grid))) return rc;
+    Args a = a_in;
+    // grid == T + 1: every tile has its own CTA and one more fits -> that one is the reducer
+    static const bool allow_reducer = !(getenv("GAD_TAIL_CTA") && atoi(getenv("GAD_TAIL_CTA")) == 0);
+    a.tail_cta = (allow_reducer && a.tail != 0 && grid == a.T + 1) ? 1 : 0;
+    if (!a.tail_cta && grid > a.T) grid = a.T;
     if (a.pdl) {
         // programmatic dependent launch: this kernel may start while its predecessor in the stream is
         // still running (it synchronises itself with griddepcontrol.wait)

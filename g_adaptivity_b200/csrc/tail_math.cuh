@@ -26,10 +26,13 @@ namespace tail {
 constexpr double LOG2E = 1.4426950408889634074;
 
 // Mu[l] = { M (CE x CE, row-major M[a][b]), u (CE) } for l < Lw.
+__host__ __device__ __forceinline__ double fold_scale(float inv_temp, int C) {
+    return LOG2E * (double)inv_temp / sqrt((double)C);   // logits live in the log2 domain
+}
+
 __device__ __forceinline__ void prepare_weights(const float* Wq, const float* bq,
-                                                const float* Wk, int Lw, int C, int CE, float inv_temp,
+                                                const float* Wk, int Lw, int C, int CE, double c,
                                                 float* Mu) {
-    const double c = LOG2E * (double)inv_temp / sqrt((double)C);   // logits live in the log2 domain
     const int live = CE < C ? CE : C;
     const int musz = CE * CE + CE;
     for (int idx = threadIdx.x; idx < Lw * musz; idx += blockDim.x) {
@@ -55,9 +58,8 @@ __device__ __forceinline__ void prepare_weights(const float* Wq, const float* bq
 // dbq[o] = c sum_b Wk[o,b] G_u[b];  dbk = 0.   (gMu = dL/d(M, u) in the log2 domain: same c.)
 __device__ __forceinline__ void weight_grads(const float* Wq, const float* bq,
                                              const float* Wk, const float* gMu, int Lw, int C, int CE,
-                                             float inv_temp, float* gWq, float* gbq,
+                                             double c, float* gWq, float* gbq,
                                              float* gWk, float* gbk) {
-    const double c = LOG2E * (double)inv_temp / sqrt((double)C);
     const int live = CE < C ? CE : C;
     const int musz = CE * CE + CE;
     for (int idx = threadIdx.x; idx < Lw * C * C; idx += blockDim.x) {
@@ -121,16 +123,23 @@ __device__ __forceinline__ AdamCoef adam_coef(float lr, float b1, float b2, floa
     return c;
 }
 
-__device__ __forceinline__ void adam_one(const AdamCoef& c, float* p, float g, float* m, float* v, long long i) {
+// one element; returns the new parameter, updates (m, v) in place
+__device__ __forceinline__ float adam_update(const AdamCoef& c, float pi, float g, float& m, float& v) {
     float gi = g * c.gscale;
-    const float pi = p[i];
     if (c.wd != 0.f) gi = fmaf(c.wd, pi, gi);
-    const float mi = m[i] + (1.f - c.b1) * (gi - m[i]);          // lerp, as torch does
-    const float vi = c.b2 * v[i] + (1.f - c.b2) * gi * gi;
+    const float mi = m + (1.f - c.b1) * (gi - m);          // lerp, as torch does
+    const float vi = c.b2 * v + (1.f - c.b2) * gi * gi;
+    m = mi;
+    v = vi;
+    const float denom = sqrtf(vi) / c.bc2_sqrt + c.eps;
+    return pi - c.step_size * (mi / denom);
+}
+
+__device__ __forceinline__ void adam_one(const AdamCoef& c, float* p, float g, float* m, float* v, long long i) {
+    float mi = m[i], vi = v[i];
+    p[i] = adam_update(c, p[i], g, mi, vi);
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / c.bc2_sqrt + c.eps;
-    p[i] = pi - c.step_size * (mi / denom);
 }
 
 // `t` = step number of THIS update (1-based); the caller stores it back to the device counter.
@@ -179,6 +188,86 @@ __device__ __forceinline__ void reduce_partials(const float* partials, int T, in
         } else {
             loss[0] = s * loss_scale;
         }
+    }
+}
+
+
+// ---- pieces of the single-pass tail of the training kernel (ell_kernels.cuh: train_tail) -------
+// Asynchronous coalesced copy of n floats global -> shared (cp.async.cg: 16-byte lines straight
+// from L2, no register round trip), so that SEVERAL arrays can be in flight at once and the whole
+// staging costs one L2 latency; finish with stage_wait() + __syncthreads().  The (< 4 float)
+// remainder and unaligned arrays go through registers with ld.global.cg.
+// (The tail runs once per launch on cold instruction-cache lines, so its cost is dominated by code
+// size: one out-of-line copy, loops not unrolled.)
+static __device__ __noinline__ void stage_async(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        const int n4 = n >> 2;
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+        const size_t g0 = __cvta_generic_to_global(src);
+#pragma unroll 1
+        for (int i = tid; i < n4; i += nthr)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * (uint32_t)i), "l"(g0 + 16ull * (size_t)i)
+                         : "memory");
+#pragma unroll 1
+        for (int i = (n4 << 2) + tid; i < n; i += nthr) dst[i] = __ldcg(src + i);
+    } else {
+#pragma unroll 1
+        for (int i = tid; i < n; i += nthr) dst[i] = __ldcg(src + i);
+    }
+}
+__device__ __forceinline__ void stage_wait() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Chain rule of the fold for ONE entry (row lo = l * C + o, column a < live) of Wq / Wk: same
+// arithmetic, same order as weight_grads above, with the live-channel loops unrolled so that every
+// operand load is issued up front.  wq / wk point at the row, bo = bq[lo], GM at the layer's (G_M, G_u).
+template <int CE>
+__device__ __forceinline__ void weight_grad_entry(const float* wq, const float* wk, float bo, const float* GM,
+                                                  int live, int a, double c, float& dWq, float& dWk) {
+    float wkv[CE], wqv[CE], gq[CE], gk[CE];
+#pragma unroll
+    for (int bb = 0; bb < CE; ++bb) {
+        const bool on = bb < live;
+        wkv[bb] = on ? wk[bb] : 0.f;
+        wqv[bb] = on ? wq[bb] : 0.f;
+        gq[bb] = on ? GM[a * CE + bb] : 0.f;
+        gk[bb] = on ? GM[bb * CE + a] : 0.f;
+    }
+    const float gu = GM[CE * CE + a];
+    double dq = 0.0, dk = 0.0;
+#pragma unroll
+    for (int bb = 0; bb < CE; ++bb)
+        if (bb < live) dq += (double)wkv[bb] * (double)gq[bb];
+#pragma unroll
+    for (int aa = 0; aa < CE; ++aa)
+        if (aa < live) dk += (double)wqv[aa] * (double)gk[aa];
+    dk += (double)bo * (double)gu;
+    dWq = (float)(c * dq);
+    dWk = (float)(c * dk);
+}
+
+// prepare_weights with CE known at compile time and a rolled reduction loop (small code).
+template <int CE>
+__device__ __forceinline__ void prepare_weights_t(const float* Wq, const float* bq, const float* Wk, int Lw, int C,
+                                                  double c, float* Mu) {
+    constexpr int MUSZ = CE * CE + CE;
+    const int live = CE < C ? CE : C;
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < Lw * MUSZ; idx += blockDim.x) {
+        const int l = idx / MUSZ, r = idx % MUSZ;
+        const bool isM = r < CE * CE;
+        const int acol = isM ? r / CE : 0, bcol = isM ? r % CE : r - CE * CE;
+        const float* wk = Wk + (size_t)l * C * C + bcol;
+        const float* lhs = isM ? Wq + (size_t)l * C * C + acol : bq + (size_t)l * C;   // Wq[o, a] or bq[o]
+        const int ls = isM ? C : 1;
+        double acc = 0.0;
+        if (acol < live && bcol < live) {
+#pragma unroll 2
+            for (int o = 0; o < C; ++o) acc += (double)lhs[(size_t)o * ls] * (double)wk[(size_t)o * C];
+        }
+        Mu[idx] = (float)(c * acc);
     }
 }
 

@@ -12,14 +12,14 @@ namespace {
 __global__ void k_prepare_weights(const float* __restrict__ Wq, const float* __restrict__ bq,
                                   const float* __restrict__ Wk, int Lw, int C, int CE, float inv_temp,
                                   float* __restrict__ Mu) {
-    tail::prepare_weights(Wq, bq, Wk, Lw, C, CE, inv_temp, Mu);
+    tail::prepare_weights(Wq, bq, Wk, Lw, C, CE, tail::fold_scale(inv_temp, C), Mu);
 }
 
 __global__ void k_weight_grads(const float* __restrict__ Wq, const float* __restrict__ bq,
                                const float* __restrict__ Wk, const float* __restrict__ gMu, int Lw, int C, int CE,
                                float inv_temp, float* __restrict__ gWq, float* __restrict__ gbq,
                                float* __restrict__ gWk, float* __restrict__ gbk) {
-    tail::weight_grads(Wq, bq, Wk, gMu, Lw, C, CE, inv_temp, gWq, gbq, gWk, gbk);
+    tail::weight_grads(Wq, bq, Wk, gMu, Lw, C, CE, tail::fold_scale(inv_temp, C), gWq, gbq, gWk, gbk);
 }
 
 }  // namespace

@@ -45,21 +45,30 @@ def main():
     grid = int((t[:, 0] > 0).sum())
     t = t[:grid]
     L = a.layers
+    red = None
+    if grid == T + 1:            # reducer CTA (owns no tile): entry, dry pass, all tiles in, reduced, chain rule, Adam, done
+        red, t = t[grid - 1], t[:grid - 1]
     names = ["entry->pdl_wait", "pdl_wait->inputs"] + [f"fwd{l}" for l in range(L)] + ["loss reduce", "backward+reduce"]
     t0 = t[:, 0].min()
     nm = 2 + L + 2 + 1
     d = np.diff(t[:, :nm], axis=1) / 1e3
-    print(f"grid {grid} CTAs, {T} tiles; kernel span {(t[:, :nm + 1].max() - t0) / 1e3:.2f} us")
+    print(f"grid {grid} CTAs, {T} tiles; tile CTAs span {(t[:, :nm].max() - t0) / 1e3:.2f} us")
     print("entry spread (us): min %.2f med %.2f max %.2f" % tuple(np.percentile((t[:, 0] - t0) / 1e3, [0, 50, 100])))
     for k, n in enumerate(names):
         print(f"  {n:20s} med {np.median(d[:, k]):7.2f}  p10 {np.percentile(d[:, k], 10):7.2f}  p90 {np.percentile(d[:, k], 90):7.2f} us")
     end = t[:, nm - 1]
     print("CTA end (us after first entry): med %.2f max %.2f" % (np.median(end - t0) / 1e3, (end.max() - t0) / 1e3))
-    k = int(np.argmax(t[:, nm + 4]))
-    if t[k, nm + 4] > 0:
-        tl = t[k, nm - 1:nm + 5]
-        print("tail CTA %d: own end %.2f | elected +%.2f | reduced +%.2f | chain rule +%.2f | adam +%.2f | refold +%.2f -> done at %.2f us" %
-              ((k, (tl[0] - t0) / 1e3) + tuple(np.diff(tl) / 1e3) + ((tl[-1] - t0) / 1e3,)))
+    if red is not None:
+        r = (red[:7] - t0) / 1e3
+        print("reducer CTA: entry %.2f | dry pass done %.2f | all tiles in %.2f (last tile CTA end %.2f) | reduced +%.2f | "
+              "chain rule +%.2f | adam +%.2f | refold +%.2f -> done at %.2f us" %
+              (r[0], r[1], r[2], (end.max() - t0) / 1e3, r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[6]))
+    else:
+        k = int(np.argmax(t[:, nm + 4]))
+        if t[k, nm + 4] > 0:
+            tl = t[k, nm - 1:nm + 5]
+            print("tail CTA %d: own end %.2f | elected +%.2f | reduced +%.2f | chain rule +%.2f | adam +%.2f | refold +%.2f -> done at %.2f us" %
+                  ((k, (tl[0] - t0) / 1e3) + tuple(np.diff(tl) / 1e3) + ((tl[-1] - t0) / 1e3,)))
 
 
 if __name__ == "__main__":
