@@ -229,6 +229,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -419,7 +421,8 @@ def main():
             "config": {
                 "workload": f"cfg2: {MESHES_PER_GPU} x {MESH_DIMS[0]}x{MESH_DIMS[1]} meshes per GPU, fwd+bwd train step "
                             f"(L={NUM_LAYERS} Euler layers, hidden 8, L1 mesh loss, Adam"
-                            + (", NCCL grad all-reduce" if world > 1 else "") + ")",
+                            + ("" if world == 1 else (", gradient all-reduce inside the kernel over NVLink peer memory"
+                                                      if trainer.fused_dp else ", NCCL grad all-reduce")) + ")",
                 "nodes_per_step_per_gpu": n_nodes, "edges_per_step_per_gpu": n_edges, "live_channels": model.live,
                 "l2": f"ring of {R} distinct resident batches, {ro_bytes / 1e6:.0f} MB read-only inputs (> 126 MB L2)",
                 "launch": "eager" if args.no_graph else ("cuda-graph replay, one graph per step" if args.no_epoch else
@@ -432,7 +435,15 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: the captured graphs hold collectives and
+        # destroy_process_group() can wait on them forever.  Everything is flushed; the ranks agree
+        # that they are done, then exit hard.
+        trainer.close()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -43,6 +43,7 @@ class TrainDesc(C.Structure):
         ("params", _fp), ("grads", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("n_params", _i64),
         ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("weight_decay", _f), ("adam_grad_scale", _f),
         ("step", _fp), ("flags", _i32), ("trace", _fp),
+        ("rank", _i32), ("world", _i32), ("peers", _fp), ("peer_seq", _fp),
     ]
 
 
@@ -77,6 +78,11 @@ SIGNATURES = {
     "gad_mesh_loss": (_i, [_p, _p, _i64, _i, _f, _p, _p, _p, _p]),
     "gad_mesh_loss_workspace_bytes": (_sz, [_i64]),
     "gad_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p, _p]),
+    "gad_peer_exchange_bytes": (_sz, [_i, _i64]),
+    "gad_peer_alloc": (_i, [_sz, C.POINTER(_p), _p]),
+    "gad_peer_open": (_i, [_p, C.POINTER(_p)]),
+    "gad_peer_close": (_i, [_p]),
+    "gad_peer_free": (_i, [_p]),
 }
 
 

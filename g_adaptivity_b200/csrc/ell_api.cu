@@ -420,6 +420,10 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     a.adam_grad_scale = d->adam_grad_scale;
     a.step = reinterpret_cast<long long*>(d->step);
     a.pdl = (d->flags & GAD_TRAIN_PDL) ? 1 : 0;
+    a.rank = d->rank;
+    a.world = d->world;
+    a.peers = d->peers;
+    a.peer_seq = d->peer_seq;
     a.trace = reinterpret_cast<long long*>(d->trace);
     cudaStream_t st = as_stream(stream);
     // The in-kernel tail keeps mirrors of the flat parameter / gradient vectors in shared memory: it
@@ -435,6 +439,14 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
         for (const float* v : views) fused_tail = fused_tail && within(v, d->params, np);
         for (const float* v : gviews) fused_tail = fused_tail && within(v, d->grads, np);
         if (d->g_tau) fused_tail = fused_tail && within(d->g_tau, d->grads, np);
+    }
+    const bool exchange = d->world > 1 && d->peers;
+    if (exchange) {
+        GAD_CHECK_ARG(d->tail == 2 && d->peer_seq && d->rank >= 0 && d->rank < d->world && d->world <= GAD_MAX_PEERS,
+                      "gad_train_step_ell: the peer exchange needs tail == 2, a sequence counter and rank < world <= %d",
+                      GAD_MAX_PEERS);
+        GAD_CHECK_ARG(fused_tail, "gad_train_step_ell: the peer exchange needs the in-kernel tail (flat parameter views, "
+                                  "scratch of %u B)", lay.bar);
     }
     if (fused_tail) return dispatch(d->CE, p, 2, a, GAD_METHOD_EULER, st);
     // generic path: the same step as separate launches

@@ -133,6 +133,10 @@ struct Args {
     long long* step;
     int pdl;                // host side: launch with the programmatic-stream-serialization attribute
     int tail_cta;           // 1: the last CTA of the grid (an extra one, without tiles) runs the tail
+    // data parallel over peer memory (tail == 2): receive buffers of all ranks, see peer.cu
+    int rank, world;
+    void* const* peers;
+    unsigned int* peer_seq;
     long long* trace;       // optional [gridDim, 64] globaltimer marks of the train kernel (profiling aid)
 };
 
@@ -542,7 +546,54 @@ struct TailCtx {
     uint32_t oWq, obq, oWk;        // float offsets of the weights in the `ps` mirror
     uint32_t ogWq, ogbq, ogWk;     // float offsets of their gradients in the `gs` mirror (Adam)
     float m0, v0;                  // Adam moments of parameter `tid`
+    uint32_t seq;                  // sequence number of this launch's peer exchange (world > 1)
 };
+
+// ---- gradient all-reduce over peer memory, inside the tail ----------------------------------------
+// Every rank stores { value, seq } words (8 bytes: single-copy atomic, so the tag travels with the
+// data and no fence is needed -- the LL protocol of NCCL) into slot [seq & 1][rank] of EVERY
+// rank's receive buffer, then sums slots [seq & 1][0 .. world) of its own buffer in rank order
+// once their tags match.  Same order on every rank: the reduced gradient, hence the parameters,
+// stay bit-identical across ranks.  Two parities make the buffers safe to reuse: a peer can only
+// overwrite parity p two exchanges later, which needs this rank's contribution to the exchange
+// in between, which this rank sends only after it has finished reading parity p.
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void peer_allreduce(const Args& a, float* Gs, int n, uint32_t seq,
+                                               unsigned long long* const* s_peers) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const size_t slot = (size_t)(seq & 1u) * a.world;
+#pragma unroll 1
+    for (int i = tid; i < n; i += nthr) {
+        const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(Gs[i]);
+#pragma unroll 1
+        for (int r = 0; r < a.world; ++r) st_sys_u64(s_peers[r] + (slot + a.rank) * n + i, word);
+    }
+    const unsigned long long* own = s_peers[a.rank];
+    float* grads_out = const_cast<float*>(a.grads);
+#pragma unroll 1
+    for (int i = tid; i < n; i += nthr) {
+        float sum = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < a.world; ++r) {
+            const unsigned long long* src = own + (slot + r) * n + i;
+            unsigned long long w;
+            do {
+                w = ld_sys_u64(src);
+            } while ((uint32_t)(w >> 32) != seq);
+            sum += __uint_as_float((uint32_t)w);
+        }
+        Gs[i] = sum;
+        grads_out[i] = sum;
+    }
+}
 
 template <int CE>
 __device__ __forceinline__ void tail_prepare(const Args& a, unsigned char* scratch, uint32_t scratch_bytes, TailCtx& cx) {
@@ -556,6 +607,7 @@ __device__ __forceinline__ void tail_prepare(const Args& a, unsigned char* scrat
     float* Gs = reinterpret_cast<float*>(scratch + cx.tp.gs);
     double* colsum = reinterpret_cast<double*>(scratch + cx.tp.colsum);
     cx.m0 = cx.v0 = 0.f;
+    cx.seq = (adam && a.world > 1 && a.peers) ? __ldcg(a.peer_seq) + 1u : 0u;
     if (adam) {
         cx.oWq = (uint32_t)(a.Wq - a.params);
         cx.obq = (uint32_t)(a.bq - a.params);
@@ -716,7 +768,16 @@ __device__ __forceinline__ void tail_finish(const Args& a, unsigned char* scratc
     }
     if (!adam) return;
     __syncthreads();
-    tr.mark();   // chain rule
+    if (cx.seq) {
+        // data parallel: SUM all-reduce of the flat gradient over peer memory (NVLink), in place
+        __shared__ unsigned long long* s_peers[GAD_MAX_PEERS];
+        if (tid < a.world) s_peers[tid] = reinterpret_cast<unsigned long long*>(a.peers[tid]);
+        __syncthreads();
+        peer_allreduce(a, Gs, np, cx.seq, s_peers);
+        if (tid == 0) *a.peer_seq = cx.seq;
+        __syncthreads();
+    }
+    tr.mark();   // chain rule (+ gradient exchange)
 
     // ---- (3) Adam on the mirror ------------------------------------------------------------------
 #pragma unroll 1

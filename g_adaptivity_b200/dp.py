@@ -9,9 +9,18 @@ gradient exactly (for equal shard sizes; ragged shards weight by their node coun
 
 Pure host logic (works on CPU tensors with the gloo backend: tests/test_dp_gloo.py); the trainer
 uses it with NCCL over NVLink.
+
+`PeerExchange` sets up the faster route used on one NVLink / NVSwitch node: every rank allocates a
+small receive buffer in the CUDA library, the ranks all-gather the CUDA IPC handles over
+`torch.distributed` and map each other's buffers; the training kernel then performs the gradient
+all-reduce itself, by peer stores and loads inside its tail (csrc/ell_kernels.cuh:
+peer_allreduce), so a data-parallel step stays ONE launch.  NCCL remains the set-up plumbing and
+the fallback (other nodes, IPC unavailable).
 """
 from __future__ import annotations
 
+import ctypes as C
+import socket
 from typing import Optional, Tuple
 
 import torch
@@ -51,3 +60,77 @@ def broadcast_flat(flat: torch.Tensor, src: int = 0, group=None) -> torch.Tensor
     if world_size(group) > 1:
         dist.broadcast(flat, src=src, group=group)
     return flat
+
+
+class PeerExchange:
+    """Receive buffers of all ranks of `group`, mapped into this process (CUDA IPC), for the
+    in-kernel gradient all-reduce.  `ok` is the same on every rank: the set-up ends with a MIN
+    all-reduce of the local outcome, so either all ranks use the peer path or none does."""
+
+    MAX_PEERS = 16     # GAD_MAX_PEERS (include/gadapt.h)
+
+    def __init__(self, lib, n_params: int, device: torch.device, group=None):
+        self.lib, self.dev, self.group = lib, device, group
+        self.world = world_size(group)
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.own = C.c_void_p()
+        self.opened = []
+        self.ptrs = None            # int64 [world] device array of receive-buffer pointers
+        self.seq = None             # uint32 launch sequence, advanced by the kernel
+        self.ok = False
+        self.why = ""
+        if self.world <= 1:
+            self.why = "single rank"
+            return
+        good, addrs = 1, [0] * self.world
+        handle = C.create_string_buffer(64)
+        try:
+            if self.world > self.MAX_PEERS:
+                raise RuntimeError(f"world {self.world} > {self.MAX_PEERS}")
+            with torch.cuda.device(device):
+                nbytes = lib.gad_peer_exchange_bytes(self.world, int(n_params))
+                if lib.gad_peer_alloc(nbytes, C.byref(self.own), handle) != 0:
+                    raise RuntimeError(lib.gad_last_error().decode())
+        except Exception as e:   # noqa: BLE001 -- any local failure must still reach the collective below
+            good, self.why = 0, f"alloc: {e}"
+        mine = (socket.gethostname(), bytes(handle.raw), good)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        if good and any(h[0] != mine[0] for h in everyone):
+            good, self.why = 0, "ranks on different hosts"
+        if good and not all(h[2] for h in everyone):
+            good, self.why = 0, "a peer failed to allocate"
+        if good:
+            try:
+                with torch.cuda.device(device):
+                    for r, (_, raw, _) in enumerate(everyone):
+                        if r == self.rank:
+                            addrs[r] = self.own.value
+                            continue
+                        p = C.c_void_p()
+                        if lib.gad_peer_open(C.create_string_buffer(raw, 64), C.byref(p)) != 0:
+                            raise RuntimeError(lib.gad_last_error().decode())
+                        self.opened.append(p)
+                        addrs[r] = p.value
+            except Exception as e:   # noqa: BLE001
+                good, self.why = 0, f"open: {e}"
+        flag = torch.tensor([good], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(flag.item())
+        if self.ok:
+            self.ptrs = torch.tensor(addrs, dtype=torch.int64, device=device)
+            self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        else:
+            self.why = self.why or "a peer could not map the buffers"
+            self.close()
+
+    def close(self):
+        """Unmap the peers' buffers and free the own one (all ranks must be past their last step)."""
+        with torch.cuda.device(self.dev):
+            for p in self.opened:
+                self.lib.gad_peer_close(p)
+            self.opened = []
+            if self.own.value:
+                self.lib.gad_peer_free(self.own)
+                self.own = C.c_void_p()
+        self.ok = False

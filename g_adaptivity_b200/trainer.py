@@ -69,9 +69,16 @@ class DeformerTrainer:
         self.slots: List[_Slot] = []
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.epoch_graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        # programmatic dependent launch between the train kernels of consecutive steps (single GPU)
-        self.use_pdl = bool(opt.get("gad_pdl", True)) and self.world == 1
         self.lib = _lib.load()
+        # data parallel on one NVLink node: the training kernel all-reduces the gradient itself over
+        # peer memory (dp.PeerExchange); otherwise NCCL between the train kernel and Adam
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.peer = None
+        if self.world > 1 and bool(opt.get("gad_peer_allreduce", True)) and self.dev.type == "cuda":
+            self.peer = dp.PeerExchange(self.lib, self.flat.numel(), self.dev, group=process_group)
+        self.fused_dp = self.peer is not None and self.peer.ok
+        # programmatic dependent launch between the train kernels of consecutive steps (one launch per step)
+        self.use_pdl = bool(opt.get("gad_pdl", True)) and (self.world == 1 or self.fused_dp)
         self.stream = torch.cuda.Stream(device=self.dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)   # last-CTA election of k_ell_train
         self.sync_weights()
@@ -153,6 +160,8 @@ class DeformerTrainer:
         d.lr, d.beta1, d.beta2, d.eps, d.weight_decay, d.adam_grad_scale = self.lr, b1, b2, self.eps, self.wd, 1.0
         d.step = P(self.step_count)
         d.flags = 1 if (self.use_pdl and tail == 2) else 0      # GAD_TRAIN_PDL
+        if self.fused_dp and tail == 2:
+            d.rank, d.world, d.peers, d.peer_seq = self.rank, self.world, P(self.peer.ptrs), P(self.peer.seq)
         return d
 
     # ------------------------------------------------------------------------------------
@@ -217,11 +226,11 @@ class DeformerTrainer:
             # ONE launch per step (csrc/ell_kernels.cuh: k_ell_train): pack + forward + loss + backward per
             # tile, then the last CTA reduces, applies the chain rule and -- single GPU -- takes the Adam step
             # and refolds (M, u) for the next step.  Data parallel: all-reduce, Adam and refold follow.
+            single = (self.world == 1 or self.fused_dp) and with_optimizer
             if stage in ("all", "pre"):
-                single = self.world == 1 and with_optimizer
                 chk(lib.gad_train_step_ell(C.byref(self._train_desc(s, 2 if single else 1)), stream_ptr),
                     "gad_train_step_ell")
-            if stage in ("all", "post") and with_optimizer and self.world > 1:
+            if stage in ("all", "post") and with_optimizer and not single:
                 b1, b2 = self.betas
                 chk(lib.gad_adam_step(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.flat.numel(),
                                       self.lr, b1, b2, self.eps, self.wd, 1.0, P(self.step_count), stream_ptr),
@@ -255,8 +264,29 @@ class DeformerTrainer:
                                   self.lr, b1, b2, self.eps, self.wd, 1.0, P(self.step_count), stream_ptr),
                 "gad_adam_step")
 
-    def _allreduce(self):
+    def _allreduce(self, s: Optional[_Slot] = None):
+        """NCCL all-reduce of the flat gradient -- unless the train kernel of this slot does the
+        exchange itself over peer memory (fused_dp on the one-launch path)."""
+        if self.fused_dp and s is not None and self._one_launch(s):
+            return
         dp.allreduce_flat(self.gflat, group=self.pg)
+
+    def _one_launch(self, s: _Slot) -> bool:
+        g = s.graph
+        tiles = g.tile_ptr is not None and not self.opt.get("gad_force_stream", False)
+        return bool(tiles and GF.use_ell(g, self.CE) and not self.opt.get("gad_no_fused_train", False))
+
+    def close(self):
+        """Drop the captured graphs and the peer mappings (call on every rank, after the last step)."""
+        self.stream.synchronize()
+        self.graphs.clear()
+        self.epoch_graphs.clear()
+        if self.peer is not None:
+            if self.world > 1:
+                dist.barrier(group=self.pg)
+            self.peer.close()
+            self.peer = None
+            self.fused_dp = False
 
     def capture(self, sid: int):
         """Capture the step of slot `sid` into a CUDA graph (gradient all-reduce included)."""
@@ -268,7 +298,7 @@ class DeformerTrainer:
                 saved = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_count)]
                 for _ in range(2):
                     self._issue(s, self.stream.cuda_stream, stage="pre")
-                    self._allreduce()
+                    self._allreduce(s)
                     self._issue(s, self.stream.cuda_stream, stage="post")
                 for t, v in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_count), saved):
                     t.copy_(v)
@@ -279,7 +309,7 @@ class DeformerTrainer:
             with torch.cuda.graph(g, stream=self.stream):
                 cs = torch.cuda.current_stream(self.dev).cuda_stream
                 self._issue(s, cs, stage="pre")
-                self._allreduce()
+                self._allreduce(s)
                 self._issue(s, cs, stage="post")
             self.graphs[sid] = g
 
@@ -301,7 +331,7 @@ class DeformerTrainer:
                 for sid in key:
                     s = self.slots[sid]
                     self._issue(s, cs, stage="pre")
-                    self._allreduce()
+                    self._allreduce(s)
                     self._issue(s, cs, stage="post")
             self.epoch_graphs[key] = g
         return key
@@ -327,7 +357,7 @@ class DeformerTrainer:
             with torch.cuda.stream(self.stream):
                 s = self.slots[sid]
                 self._issue(s, self.stream.cuda_stream, stage="pre")
-                self._allreduce()
+                self._allreduce(s)
                 self._issue(s, self.stream.cuda_stream, stage="post")
         return self.slots[sid].loss
 

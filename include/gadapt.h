@@ -177,6 +177,8 @@ int gad_deform_train_ell(const void* ell_in, const void* ell_out, int64_t N, con
  * (M, u) for the NEXT step into Mu.  With tail == 1 the caller all-reduces `gWq..gbk` (data
  * parallel) and then calls gad_adam_step + gad_prepare_weights.  All pointers are device pointers.
  * `counter` is one zero-initialised uint32 owned by the caller (the kernel leaves it zero).
+ * When the whole grid plus one CTA is resident at once, that extra CTA ("reducer") runs the tail:
+ * it prepares while the tiles are processed and finishes once every tile CTA has checked in.
  * When tail == 2, Wq / bq / Wk must be views into `params` and gWq.. views into `grads`. */
 typedef struct gad_train_desc {
     /* topology (gad_graph_build_ell) */
@@ -234,8 +236,19 @@ typedef struct gad_train_desc {
     /* optional profiling aid: int64 [grid, 64] buffer receiving %globaltimer marks at the phase
      * boundaries of every CTA (NULL = off) */
     int64_t* trace;
+    /* data parallel over peer memory (tail == 2, world > 1; see gad_peer_alloc): between the chain
+     * rule and Adam the kernel stores its flat gradient into every rank's receive buffer over
+     * NVLink and sums, in rank order, what the peers stored into its own -- the SUM all-reduce of
+     * src/run_GNN.py's (single-process) gradient, fused into the step.  `peers` is a DEVICE array of
+     * `world` receive-buffer pointers (entry `rank` = this rank's own buffer), `peer_seq` one
+     * zero-initialised device uint32 that the kernel advances by one per launch; every rank must
+     * issue the same sequence of launches.  world <= 1 or peers == NULL: no exchange. */
+    int32_t rank, world;
+    void* const* peers;
+    uint32_t* peer_seq;
 } gad_train_desc;
 #define GAD_TRAIN_PDL 1
+#define GAD_MAX_PEERS 16
 int gad_train_step_ell(const gad_train_desc* desc, void* stream);
 
 /* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --
@@ -261,6 +274,19 @@ size_t gad_mesh_loss_workspace_bytes(int64_t count);
 int gad_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                   int64_t* step, void* stream);
+
+/* ---- peer memory for the data-parallel gradient exchange (one process per GPU, one node) -------
+ * The reference trains single-process (src/run_GNN.py:95-131); sharding a batch by whole meshes
+ * needs exactly one exchange per step, the SUM of the flat gradient.  gad_peer_alloc returns a
+ * zeroed device buffer of gad_peer_exchange_bytes(world, n_params) and its CUDA IPC handle
+ * (GAD_IPC_HANDLE_BYTES bytes, to be all-gathered by the host side); gad_peer_open maps a peer's
+ * buffer from its handle.  gad_train_step_ell does the exchange inside the training kernel. */
+#define GAD_IPC_HANDLE_BYTES 64
+size_t gad_peer_exchange_bytes(int world, int64_t n_params);
+int gad_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out);
+int gad_peer_open(const void* handle, void** dev_ptr);
+int gad_peer_close(void* dev_ptr);
+int gad_peer_free(void* dev_ptr);
 
 #ifdef __cplusplus
 }
