@@ -877,22 +877,13 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
                 bulk_g2s(DL, tg_g, xc_bytes, bar);
             }
         }
-        // previous step done (weights refolded, its reads of `states` finished): from here on this
-        // step may read Mu / tau and write global memory
-        pdl_wait();
-        tr.mark();   // 1: predecessor done
-        // Adam's bias corrections of THIS step (a serial fp64 chain) are worked out now by one thread
-        // of every CTA, hidden behind the tile's work, so that whichever CTA runs the tail has them
-        if (a.tail >= 2 && !a.tail_cta && tile == (int)blockIdx.x && tid == nthr - 1) {
-            s_step = __ldcg(a.step) + 1;
-            s_coef = tail::adam_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.adam_grad_scale, s_step);
-        }
-        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = __ldcg(a.Mu + t);
+        // Everything that only needs the step's INPUTS happens before the wait on the previous step, i.e.
+        // in its shadow when the launches are chained by programmatic dependent launch.
         if (tx) {
             mbar_wait(bar, parity);
             parity ^= 1;
         }
-        tr.mark();   // 2: inputs landed
+        tr.mark();   // 1: inputs landed
         // features = cat[x_comp, f, uu] + identity (zero-pad) encoder: src/GNN.py:225-239,75-83,270
         unsigned char* Xc = B0;
         unsigned char* Xn = B1;
@@ -920,10 +911,23 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
                     if (a.f && c == cf) x.v[c] = fv;
                     if (a.uu && c == cu) x.v[c] = uv;
                 }
-                sts_row<CE>(Xc, i * RB, x);
-                store_row<CE>(a.states, gi, x);
+                sts_row<CE>(Xc, i * RB, x);   // x^0 reaches `states` from the first layer's loop, after the wait
             }
         }
+        __syncthreads();
+        // previous step done (weights refolded, its reads of `states` finished): from here on this
+        // step may read Mu / tau and write global memory
+        pdl_wait();
+        tr.mark();   // 2: predecessor done
+        // Adam's bias corrections of THIS step (a serial fp64 chain) are worked out now by one thread
+        // of every CTA, hidden behind the tile's work, so that whichever CTA runs the tail has them
+        if (a.tail >= 2 && !a.tail_cta && tile == (int)blockIdx.x && tid == nthr - 1) {
+            s_step = __ldcg(a.step) + 1;
+            s_coef = tail::adam_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.adam_grad_scale, s_step);
+        }
+        // (M, u): one L2 request per CTA (every thread loading it would hammer a single L2 line from
+        // 2000 warps at once), then through shared memory
+        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = __ldcg(a.Mu + t);
         __syncthreads();
         EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
         EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + n0};
@@ -935,7 +939,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
                 for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
                 __syncthreads();
             }
-            const float h = a.tau[l];
+            const float h = __ldcg(a.tau + l);
             const bool last = (l == a.L - 1);
             float* st_out = last ? nullptr : a.states + (size_t)(l + 1) * state_stride;
             float Mr[MUSZ];   // (M, u) in registers for the whole layer: no broadcast loads per node
@@ -946,6 +950,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
                 const uint4 e = e_nx;
                 if (i + nthr < NT) e_nx = Ein.get(i + nthr);
                 const Row<CE> y = lds_row<CE>(Xc, i * RB);
+                if (l == 0) store_row<CE>(a.states, (int64_t)n0 + i, y);
                 const Row<CE> k = ell_feval<CE, W>(Xc, e, y, Mr);
                 Row<CE> xn;
 #pragma unroll

@@ -48,7 +48,7 @@ def main():
     red = None
     if grid == T + 1:            # reducer CTA (owns no tile): entry, dry pass, all tiles in, reduced, chain rule, Adam, done
         red, t = t[grid - 1], t[:grid - 1]
-    names = ["entry->pdl_wait", "pdl_wait->inputs"] + [f"fwd{l}" for l in range(L)] + ["loss reduce", "backward+reduce"]
+    names = ["entry->inputs", "assemble->pdl_wait"] + [f"fwd{l}" for l in range(L)] + ["loss reduce", "backward+reduce"]
     t0 = t[:, 0].min()
     nm = 2 + L + 2 + 1
     d = np.diff(t[:, :nm], axis=1) / 1e3
@@ -60,7 +60,7 @@ def main():
     print("CTA end (us after first entry): med %.2f max %.2f" % (np.median(end - t0) / 1e3, (end.max() - t0) / 1e3))
     if red is not None:
         r = (red[:7] - t0) / 1e3
-        print("reducer CTA: entry %.2f | dry pass done %.2f | all tiles in %.2f (last tile CTA end %.2f) | reduced +%.2f | "
+        print("reducer CTA: entry %.2f | prepared %.2f | all tiles in %.2f (last tile CTA end %.2f) | reduced +%.2f | "
               "chain rule +%.2f | adam +%.2f | refold +%.2f -> done at %.2f us" %
               (r[0], r[1], r[2], (end.max() - t0) / 1e3, r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[6]))
     else:
