@@ -176,8 +176,25 @@ class GNN(nn.Module):
         self._graphs.put(key, g, keep)
         return g
 
+    def _folded_weights(self, dev):
+        """(M, u) of the current Linear parameters (csrc/weights.cu), cached until a parameter changes:
+        keyed on storage and version counter of every parameter plus `_param_epoch`, which the
+        trainer bumps because its kernels update the parameters without touching the counters."""
+        convs = [self.conv_layers[0]] if self.opt["share_conv"] else list(self.conv_layers)
+        ps = [p for c in convs for p in (c.lin_query.weight, c.lin_query.bias, c.lin_key.weight)]
+        key = (tuple((p.data_ptr(), p._version) for p in ps), getattr(self, "_param_epoch", 0), self.inv_temp, str(dev))
+        if getattr(self, "_mu_key", None) != key:
+            Wq, bq, Wk, _ = self._weights()
+            self._mu = GF.prepare_weights(Wq.detach(), bq.detach(), Wk.detach(), self.CE, self.inv_temp)
+            self._mu_key = key
+        return self._mu
+
     def _weights(self):
         convs = [self.conv_layers[0]] if self.opt["share_conv"] else list(self.conv_layers)
+        if len(convs) == 1:      # views: no kernels, no copies
+            c = convs[0]
+            return (c.lin_query.weight.unsqueeze(0), c.lin_query.bias.unsqueeze(0), c.lin_key.weight.unsqueeze(0),
+                    c.lin_key.bias.unsqueeze(0))
         Wq = torch.stack([c.lin_query.weight for c in convs])
         bq = torch.stack([c.lin_query.bias for c in convs])
         Wk = torch.stack([c.lin_key.weight for c in convs])
@@ -206,14 +223,27 @@ class GNN(nn.Module):
             uu_scale = torch.max(uu).reshape(1).float() if uu is not None else None
         if x_comp.dim() == 1:
             x_comp = x_comp.unsqueeze(-1)
-        Wq, bq, Wk, bk = self._weights()
         tau = self._tau(dev)
         keep_alpha = isinstance(opt.get("show_mesh_evol_plots"), bool) or opt["conv_type"] == "GRAND"
         keep_alpha = keep_alpha and bool(opt.get("gad_store_alpha", True))
-        aux = {"keep_states": keep_alpha}
-        x_phys = GF.DeformFunction.apply(
-            x_comp, f, uu, f_scale, uu_scale, Wq, bq, Wk, bk, tau, graph, self.dim, self.CE, self.inv_temp,
-            GF.METHODS[opt.get("ode_method", "euler")], bool(opt.get("gad_force_stream", False)), aux)
+        Mu_in = self._folded_weights(dev)
+        aux = {"keep_states": keep_alpha, "Mu_in": Mu_in}
+        method = GF.METHODS[opt.get("ode_method", "euler")]
+        force_stream = bool(opt.get("gad_force_stream", False))
+        if not torch.is_grad_enabled():
+            # inference: no autograd node; on mesh-resident graphs the whole call is one kernel launch
+            N = x_comp.shape[0]
+            L = int(tau.numel())
+            states = torch.empty((L, N, self.CE), dtype=torch.float32, device=dev) if keep_alpha else None
+            x_phys = GF.deform_forward_raw(graph, x_comp, f, uu, f_scale, uu_scale, self.dim, self.CE, Mu_in,
+                                           GF._f32(tau.detach().reshape(-1)), method, states=states,
+                                           force_stream=force_stream)
+            aux["states"], aux["Mu"] = states, Mu_in
+        else:
+            Wq, bq, Wk, bk = self._weights()
+            x_phys = GF.DeformFunction.apply(
+                x_comp, f, uu, f_scale, uu_scale, Wq, bq, Wk, bk, tau, graph, self.dim, self.CE, self.inv_temp,
+                method, force_stream, aux)
         if keep_alpha and aux.get("states") is not None:
             states, Mu = aux["states"], aux["Mu"]
             L = opt["num_layers"]
@@ -227,3 +257,70 @@ class GNN(nn.Module):
             torch.cuda.current_stream(dev).synchronize()
         self.end_MLmodel = time.time()
         return x_phys
+
+    def inference_session(self, data) -> "InferenceSession":
+        """Replayable deformer call on a fixed topology (extension; the Burgers roll-out of
+        src/utils_eval_Burgers.py:269,297 calls the model on the same mesh with a new `uu` every time
+        step): static device copies of the inputs, one captured CUDA graph holding the single
+        forward launch; `session(uu=...)` refreshes inputs and replays."""
+        return InferenceSession(self, data)
+
+
+class InferenceSession:
+    """`GNN.forward(data)` in inference mode as one CUDA-graph replay (see GNN.inference_session).
+
+    The output tensor is static: it is overwritten by the next call.  Parameters are read when the
+    session is created (and again by `refresh_weights()`)."""
+
+    def __init__(self, model: GNN, data):
+        opt = model.opt
+        self.model, self.dev = model, model._device()
+        dev = self.dev
+        if opt["gnn_normalize"]:
+            raise NotImplementedError("inference_session with gnn_normalize=True is not implemented")
+        self.graph = model._graph(data, dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
+        self.x_comp = xc.to(**f32).contiguous().clone()
+        self.f = data.f_tensor.to(**f32).contiguous().clone() if opt["gnn_inc_feat_f"] else None
+        self.uu = data.uu_tensor.to(**f32).contiguous().clone() if opt["gnn_inc_feat_uu"] else None
+        self.tau = GF._f32(model._tau(dev).detach().reshape(-1)).clone()
+        self.Mu = model._folded_weights(dev).clone()
+        self.method = GF.METHODS[opt.get("ode_method", "euler")]
+        self.force_stream = bool(opt.get("gad_force_stream", False))
+        self.stream = torch.cuda.Stream(device=dev)
+        self.out = None
+        with torch.cuda.device(dev):
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self.stream):
+                self._call()                       # warm-up: attribute set-up, allocations
+            self.stream.synchronize()
+            self.cuda_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.cuda_graph, stream=self.stream):
+                self.out = self._call()
+
+    def _call(self):
+        m = self.model
+        return GF.deform_forward_raw(self.graph, self.x_comp, self.f, self.uu, None, None, m.dim, m.CE, self.Mu, self.tau,
+                                     self.method, states=None, force_stream=self.force_stream)
+
+    def refresh_weights(self):
+        with torch.cuda.stream(self.stream):
+            self.Mu.copy_(self.model._folded_weights(self.dev))
+            self.tau.copy_(GF._f32(self.model._tau(self.dev).detach().reshape(-1)))
+
+    def __call__(self, x_comp=None, f=None, uu=None) -> torch.Tensor:
+        """Replay with (optionally) new node inputs; returns the static output tensor [N, dim].  The
+        replay is ordered after the caller's current stream and the caller's stream after it."""
+        cur = torch.cuda.current_stream(self.dev)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            if x_comp is not None:
+                self.x_comp.copy_(x_comp if x_comp.dim() == 2 else x_comp.unsqueeze(-1), non_blocking=True)
+            if f is not None and self.f is not None:
+                self.f.copy_(f, non_blocking=True)
+            if uu is not None and self.uu is not None:
+                self.uu.copy_(uu, non_blocking=True)
+            self.cuda_graph.replay()
+        cur.wait_stream(self.stream)
+        return self.out

@@ -256,6 +256,43 @@ extern "C" int gad_deform_fwd_ell(const void* ell_in, int64_t N, const int32_t* 
     return dispatch(CE, p, 0, a, method, as_stream(stream));
 }
 
+extern "C" int gad_deform_fwd_ell_raw(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T,
+                                      int max_tile_nodes, int max_deg, const float* x_comp, const float* f,
+                                      const float* uu, const float* f_scale, const float* uu_scale, int dim, int CE,
+                                      const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
+                                      float* states, void* stream) {
+    GAD_CHECK_ARG(ell_in && tile_ptr && x_comp && Mu && tau && x_phys, "gad_deform_fwd_ell_raw: null pointer");
+    GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
+                  "gad_deform_fwd_ell_raw: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
+    GAD_CHECK_ARG(dim + (f ? 1 : 0) + (uu ? 1 : 0) <= CE, "gad_deform_fwd_ell_raw: %d input features exceed CE=%d",
+                  dim + (f ? 1 : 0) + (uu ? 1 : 0), CE);
+    GAD_CHECK_ARG(method == GAD_METHOD_EULER || method == GAD_METHOD_RK4, "gad_deform_fwd_ell_raw: unknown method %d",
+                  method);
+    Plan p;
+    int rc = make_plan(CE, method == GAD_METHOD_RK4 ? KIND_FWD_RK4 : KIND_FWD, max_tile_nodes, max_deg, &p);
+    if (rc) return rc;
+    Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(ell_in);
+    a.tile_ptr = tile_ptr;
+    a.T = T;
+    a.cap_nodes = max_tile_nodes;
+    a.N = N;
+    a.Mu = Mu;
+    a.tau = tau;
+    a.Lw = Lw;
+    a.L = L;
+    a.dim = dim;
+    a.x0 = nullptr;          // selects the fused feature assembly
+    a.x_comp = x_comp;
+    a.f = f;
+    a.uu = uu;
+    a.f_scale = f_scale;
+    a.uu_scale = uu_scale;
+    a.x_phys = x_phys;
+    a.states = states;
+    return dispatch(CE, p, 0, a, method, as_stream(stream));
+}
+
 extern "C" int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                                   int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
                                   int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,

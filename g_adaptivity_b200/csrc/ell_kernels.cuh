@@ -208,6 +208,43 @@ struct EllView {
     }
 };
 
+// features = cat[x_comp, f, uu] (optionally f / max f, uu / max uu) + identity (zero-pad) encoder:
+// src/GNN.py:225-239,75-83,270.  Inputs come from the TMA staging areas (`stage`) or from global
+// memory; rows go to the shared-memory state buffer and, when `states0` is given, to states[0].
+template <int CE>
+__device__ __forceinline__ void assemble_rows(const Args& a, int n0, int NT, bool stage, const unsigned char* st_xc,
+                                              const unsigned char* st_f, const unsigned char* st_uu, unsigned char* Xc,
+                                              float* states0) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const float fs = (a.f && a.f_scale) ? a.f_scale[0] : 1.0f;
+    const float us = (a.uu && a.uu_scale) ? a.uu_scale[0] : 1.0f;
+    const int cf = a.dim, cu = a.dim + (a.f ? 1 : 0);
+    for (int i = tid; i < NT; i += nthr) {
+        const int64_t gi = (int64_t)n0 + i;
+        Row<CE> x;
+        float fv = 0.f, uv = 0.f;
+        if (stage) {
+            x = load_dims<CE>(reinterpret_cast<const float*>(st_xc), i, a.dim);
+            if (a.f) fv = reinterpret_cast<const float*>(st_f)[i];
+            if (a.uu) uv = reinterpret_cast<const float*>(st_uu)[i];
+        } else {
+            x = load_dims<CE>(a.x_comp, gi, a.dim);
+            if (a.f) fv = a.f[gi];
+            if (a.uu) uv = a.uu[gi];
+        }
+        if (a.f_scale) fv = fv / fs;     // the reference divides (f / torch.max(f), GNN.py:232)
+        if (a.uu_scale) uv = uv / us;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) {
+            if (a.f && c == cf) x.v[c] = fv;
+            if (a.uu && c == cu) x.v[c] = uv;
+        }
+        sts_row<CE>(Xc, i * RB, x);
+        if (states0) store_row<CE>(states0, gi, x);
+    }
+}
+
 // ============================================================================================
 // forward
 // ============================================================================================
@@ -236,6 +273,38 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
         const int n0 = a.tile_ptr[tile];
         const int NT = a.tile_ptr[tile + 1] - n0;
         __syncthreads();   // previous tile fully consumed (and the mbarrier initialised)
+        if (a.x0 == nullptr) {
+            // fused feature assembly (gad_deform_fwd_ell with raw inputs): x_comp | f | uu staged by TMA
+            // into the not-yet-used Xn buffer (dim + 2 <= CE floats per node), rows assembled into Xc
+            const uint32_t xc_bytes = (uint32_t)NT * (uint32_t)a.dim * 4u, sc_bytes = (uint32_t)NT * 4u;
+            const float* xc_g = a.x_comp + (size_t)n0 * a.dim;
+            const float* f_g = a.f ? a.f + n0 : nullptr;
+            const float* uu_g = a.uu ? a.uu + n0 : nullptr;
+            const bool stage = (NT % 4 == 0) && ((reinterpret_cast<uintptr_t>(xc_g) | reinterpret_cast<uintptr_t>(f_g) |
+                                                   reinterpret_cast<uintptr_t>(uu_g)) & 15) == 0 &&
+                               (xc_bytes % 16 == 0);
+            unsigned char* st_xc = Xn;
+            unsigned char* st_f = st_xc + xc_bytes;
+            unsigned char* st_uu = st_f + (a.f ? sc_bytes : 0u);
+            const uint32_t tx = (ELLS ? (uint32_t)NT * 16u : 0u) +
+                                (stage ? xc_bytes + (a.f ? sc_bytes : 0u) + (a.uu ? sc_bytes : 0u) : 0u);
+            if (tid == 0 && tx) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(bar, tx);
+                if (ELLS) bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
+                if (stage) {
+                    bulk_g2s(st_xc, xc_g, xc_bytes, bar);
+                    if (a.f) bulk_g2s(st_f, f_g, sc_bytes, bar);
+                    if (a.uu) bulk_g2s(st_uu, uu_g, sc_bytes, bar);
+                }
+            }
+            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+            if (tx) {
+                mbar_wait(bar, parity);
+                parity ^= 1;
+            }
+            assemble_rows<CE>(a, n0, NT, stage, st_xc, st_f, st_uu, Xc, a.states);
+        } else {
         const float* x0t = a.x0 + (size_t)n0 * CE;
         const bool bulk_x = ((reinterpret_cast<uintptr_t>(x0t) & 15) == 0) && (((uint32_t)NT * RB) % 16 == 0);
         const uint32_t tx = (ELLS ? (uint32_t)NT * 16u : 0u) + (bulk_x ? (uint32_t)NT * RB : 0u);
@@ -251,6 +320,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
         if (tx) {
             mbar_wait(bar, parity);
             parity ^= 1;
+        }
         }
         __syncthreads();
         EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
@@ -887,33 +957,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
         // features = cat[x_comp, f, uu] + identity (zero-pad) encoder: src/GNN.py:225-239,75-83,270
         unsigned char* Xc = B0;
         unsigned char* Xn = B1;
-        {
-            const float fs = (a.f && a.f_scale) ? a.f_scale[0] : 1.0f;
-            const float us = (a.uu && a.uu_scale) ? a.uu_scale[0] : 1.0f;
-            const int cf = a.dim, cu = a.dim + (a.f ? 1 : 0);
-            for (int i = tid; i < NT; i += nthr) {
-                const int64_t gi = (int64_t)n0 + i;
-                Row<CE> x;
-                float fv = 0.f, uv = 0.f;
-                if (stage) {
-                    x = load_dims<CE>(reinterpret_cast<const float*>(st_xc), i, a.dim);
-                    if (a.f) fv = reinterpret_cast<const float*>(st_f)[i];
-                    if (a.uu) uv = reinterpret_cast<const float*>(st_uu)[i];
-                } else {
-                    x = load_dims<CE>(a.x_comp, gi, a.dim);
-                    if (a.f) fv = a.f[gi];
-                    if (a.uu) uv = a.uu[gi];
-                }
-                if (a.f_scale) fv = fv / fs;     // the reference divides (f / torch.max(f), GNN.py:232)
-                if (a.uu_scale) uv = uv / us;
-#pragma unroll
-                for (int c = 0; c < CE; ++c) {
-                    if (a.f && c == cf) x.v[c] = fv;
-                    if (a.uu && c == cu) x.v[c] = uv;
-                }
-                sts_row<CE>(Xc, i * RB, x);   // x^0 reaches `states` from the first layer's loop, after the wait
-            }
-        }
+        assemble_rows<CE>(a, n0, NT, stage, st_xc, st_f, st_uu, Xc, nullptr);   // x^0 reaches `states` from the first layer's loop, after the wait
         __syncthreads();
         // previous step done (weights refolded, its reads of `states` finished): from here on this
         // step may read Mu / tau and write global memory

@@ -130,6 +130,38 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
     return x_phys
 
 
+def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: int, CE: int, Mu: torch.Tensor,
+                       tau: torch.Tensor, method: int = METHOD_EULER, states: Optional[torch.Tensor] = None,
+                       force_stream: bool = False) -> torch.Tensor:
+    """Raw inputs -> x_phys [N, dim]: on mesh-resident ELL graphs ONE launch (feature assembly fused
+    into the forward kernel's input staging, csrc/ell_kernels.cuh); otherwise pack + forward."""
+    _need_cuda(x_comp, f, uu, Mu, tau)
+    x_comp = _f32(x_comp)
+    if x_comp.dim() == 1:
+        x_comp = x_comp.unsqueeze(-1)
+    N = x_comp.shape[0]
+    if not (graph.tile_ptr is not None and not force_stream and use_ell(graph, CE)):
+        x0 = states[0] if states is not None else torch.empty((N, CE), dtype=torch.float32, device=x_comp.device)
+        pack_features(x_comp, f, uu, f_scale, uu_scale, CE, out=x0)
+        return deform_forward(graph, x0, dim, Mu, tau, method, states=states, force_stream=force_stream)
+    lib = _lib.load()
+    # identity encoder with hidden < in_dim truncates (src/GNN.py:84-90): features beyond CE are dropped
+    if f is not None and dim >= CE:
+        f = None
+    if uu is not None and dim + (1 if f is not None else 0) >= CE:
+        uu = None
+    f, uu = _f32(f), _f32(uu)
+    L, Lw = int(tau.numel()), int(Mu.shape[0])
+    assert graph.N == N
+    x_phys = torch.empty((N, dim), dtype=torch.float32, device=x_comp.device)
+    with torch.cuda.device(x_comp.device):
+        _lib.check(lib.gad_deform_fwd_ell_raw(
+            _lib.ptr(graph.ell_in), N, _lib.ptr(graph.tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
+            _lib.ptr(x_comp), _lib.ptr(f), _lib.ptr(uu), _lib.ptr(f_scale), _lib.ptr(uu_scale), dim, CE, _lib.ptr(Mu),
+            Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys), _lib.ptr(states), _stream(x_comp)), "gad_deform_fwd_ell_raw")
+    return x_phys
+
+
 def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tensor, dim: int, Mu: torch.Tensor,
                     tau: torch.Tensor, want_gtau: bool = False, want_gx0: bool = False, force_stream: bool = False):
     """Cotangent of x_phys -> (gMu [Lw, CE*CE+CE], g_tau [L] | None, g_x0 [N, CE] | None)."""
@@ -230,17 +262,14 @@ class DeformFunction(torch.autograd.Function):
         N = x_comp.shape[0]
         needs = any(ctx.needs_input_grad)
         tau_d = _f32(tau.detach().reshape(-1))
-        Mu = prepare_weights(Wq.detach(), bq.detach(), Wk.detach(), CE, inv_temp)
+        Mu = aux.get("Mu_in") if aux is not None else None     # folded weights cached by the module
+        if Mu is None:
+            Mu = prepare_weights(Wq.detach(), bq.detach(), Wk.detach(), CE, inv_temp)
         keep_states = aux is not None and aux.get('keep_states', False)
-        save = needs or keep_states
-        if save:
-            states = torch.empty((L, N, CE), dtype=torch.float32, device=x_comp.device)
-            x0 = states[0]
-        else:
-            states, x0 = None, torch.empty((N, CE), dtype=torch.float32, device=x_comp.device)
-        pack_features(x_comp.detach(), None if f is None else f.detach(), None if uu is None else uu.detach(),
-                      f_scale, uu_scale, CE, out=x0)
-        x_phys = deform_forward(graph, x0, dim, Mu, tau_d, method, states=states, force_stream=force_stream)
+        states = torch.empty((L, N, CE), dtype=torch.float32, device=x_comp.device) if (needs or keep_states) else None
+        x_phys = deform_forward_raw(graph, x_comp.detach(), None if f is None else f.detach(),
+                                    None if uu is None else uu.detach(), f_scale, uu_scale, dim, CE, Mu, tau_d, method,
+                                    states=states, force_stream=force_stream)
         ctx.method = method
         ctx.graph, ctx.dim, ctx.CE, ctx.inv_temp, ctx.force_stream = graph, dim, CE, inv_temp, force_stream
         ctx.has_f, ctx.has_uu = f is not None, uu is not None

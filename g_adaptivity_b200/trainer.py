@@ -336,18 +336,24 @@ class DeformerTrainer:
             self.epoch_graphs[key] = g
         return key
 
+    def _touch_params(self):
+        # the kernels update the parameters in place without bumping tensor version counters
+        self.model._param_epoch = getattr(self.model, "_param_epoch", 0) + 1
+
     def run_epoch(self, sids):
         """One pass over the resident batches `sids` (one training step each) as a single graph replay.
         Returns the per-slot loss tensors (device; each holds the loss of that slot's LAST step)."""
         if not self.use_graph:
             return [self.step(sid) for sid in sids]
         key = self.capture_epoch(sids)
+        self._touch_params()
         with torch.cuda.stream(self.stream):
             self.epoch_graphs[key].replay()
         return [self.slots[sid].loss for sid in key]
 
     def step(self, sid: int):
         """One training step on the resident batch `sid` (asynchronous; loss stays on the device)."""
+        self._touch_params()
         if self.use_graph:
             if sid not in self.graphs:
                 self.capture(sid)

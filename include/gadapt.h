@@ -159,6 +159,15 @@ size_t gad_ell_workspace_bytes(int CE, int T, int L);
 int gad_deform_fwd_ell(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T, int max_tile_nodes,
                        int max_deg, const float* x0, int dim, int CE, const float* Mu, int Lw,
                        const float* tau, int L, int method, float* x_phys, float* states, void* stream);
+/* The same forward from the RAW inputs of src/GNN.py:225-239 (x_comp [N, dim], f [N] | NULL, uu [N] |
+ * NULL, optional batch-wide maxima f_scale / uu_scale): feature assembly + identity encoder are
+ * fused into the kernel's input staging, so a deformer call is ONE launch.  `states` (optional,
+ * [L, N, CE]) receives the layer inputs x^0 .. x^{L-1} for gad_deform_bwd_ell. */
+int gad_deform_fwd_ell_raw(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T, int max_tile_nodes,
+                           int max_deg, const float* x_comp, const float* f, const float* uu,
+                           const float* f_scale, const float* uu_scale, int dim, int CE, const float* Mu,
+                           int Lw, const float* tau, int L, int method, float* x_phys, float* states,
+                           void* stream);
 int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                        int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
                        int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,

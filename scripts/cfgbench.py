@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Throughput of the BASELINE.json configs that are NOT the bench line (parity-test cases), for
+DESIGN.md section 6: module-seam forward (cfg 1, 3, 4) and trainer step (cfg 2, 5 slice), CUDA
+events on the launching stream, inputs device-resident.   python scripts/cfgbench.py [--quick]"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+PEAK = 6539.9
+
+
+def fwd_bytes(N, E, ce, fevals, in_dim, dim):
+    return fevals * (8 * ce + 4 * E / N + 4) + 4 * in_dim + 4 * dim
+
+
+def time_forward(md, B, over, burgers, iters):
+    from g_adaptivity_b200 import GNN, synth
+    dev = torch.device("cuda", 0)
+    opt = synth.burgers_opt(md) if burgers else synth.default_opt(md)
+    opt.update(device="cuda:0", gad_store_alpha=False, **over)
+    ds = synth.SyntheticDataset(len(md), md)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev).eval()
+    data = synth.make_batch(md, B, seed=0, burgers=burgers).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model(data)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model(data)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        sess = model.inference_session(data)
+        for _ in range(3):
+            sess()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            sess(uu=data.uu_tensor)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_sess = e0.elapsed_time(e1) / 50
+    g = model.last_graph
+    ms = statistics.median(ts)
+    fevals = opt["num_layers"] * (4 if opt.get("ode_method", "euler") == "rk4" else 1)
+    bpn = fwd_bytes(g.N, g.E, model.live, fevals, sum(model.in_dims), model.dim)
+    return {"nodes": g.N, "edges": g.E, "ms_per_call": round(ms, 4), "gnodes_per_s": round(g.N / ms / 1e6, 4),
+            "bytes_per_node": round(bpn, 1), "roofline_frac": round(g.N * bpn / (ms * 1e-3) / 1e9 / PEAK, 4),
+            "tiles": g.T if g.tile_ptr is not None else 0, "ms_per_call_session": round(ms_sess, 4),
+            "gnodes_per_s_session": round(g.N / ms_sess / 1e6, 4),
+            "roofline_frac_session": round(g.N * bpn / (ms_sess * 1e-3) / 1e9 / PEAK, 4)}
+
+
+def time_train(md, B, ring, iters):
+    from g_adaptivity_b200 import GNN, synth
+    from g_adaptivity_b200.trainer import DeformerTrainer
+    dev = torch.device("cuda", 0)
+    opt = synth.default_opt(md)
+    opt.update(device="cuda:0", gad_store_alpha=False)
+    ds = synth.SyntheticDataset(len(md), md)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev)
+    tr = DeformerTrainer(model)
+    sids = [tr.add_batch(synth.make_batch(md, B, seed=100 + r)) for r in range(ring)]
+    tr.capture_epoch(sids)
+    for _ in range(3):
+        tr.run_epoch(sids)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tr.stream)
+    for _ in range(iters):
+        tr.run_epoch(sids)
+    e1.record(tr.stream)
+    tr.synchronize()
+    ms = e0.elapsed_time(e1) / (iters * ring)
+    s = tr.slots[0]
+    N, E = s.N, s.graph.E
+    d = E / N
+    bpn = 4 * ((8 * 4 + 4 * d + 4) + (12 * 4 + 2 * (4 * d + 4))) + 4 * 4 + 8 * 2
+    return {"nodes": N, "edges": E, "ms_per_step": round(ms, 4), "gnodes_per_s": round(N / ms / 1e6, 4),
+            "bytes_per_node": round(bpn, 1), "roofline_frac": round(N * bpn / (ms * 1e-3) / 1e9 / PEAK, 4),
+            "tiles": s.graph.T}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    it = 5 if a.quick else 20
+    res = {}
+    res["cfg1_15x15_fwd"] = time_forward((15, 15), 1, {}, False, it)
+    res["cfg3_burgers200_b4096_fwd"] = time_forward((200,), 4096, {}, True, it)
+    res["cfg4_200x200_rk4x64_fwd"] = time_forward((200, 200), 1, {"ode_method": "rk4", "num_layers": 64}, False, it)
+    res["cfg2_30x30_b256_train"] = time_train((30, 30), 256, 8, it)
+    res["cfg5_50x50_b1024_train"] = time_train((50, 50), 1024, 2, max(2, it // 4))
+    for k, v in res.items():
+        print(k, json.dumps(v), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -234,6 +234,28 @@ def test_config3_burgers_1d_200_repeated_calls():
     assert model._graphs.misses == 1 and model._graphs.hits == 3     # topology cached across calls
 
 
+def test_inference_session_replays_burgers_rollout():
+    """CUDA-graph replay of the deformer call (GNN.inference_session) == the module call, for a
+    sequence of uu fields on a fixed 1-D mesh batch."""
+    mesh_dims, B = (200,), 256
+    opt = synth.burgers_opt(mesh_dims)
+    ds = synth.SyntheticDataset(1, mesh_dims)
+    data = synth.make_batch(mesh_dims, B, seed=3, burgers=True)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    model = cuda_model(ds, opt, ref.state_dict())
+    model.eval()
+    sess = model.inference_session(data)
+    x = data.x_comp.view(B, 200).numpy()
+    with torch.no_grad():
+        for call in range(3):
+            data.uu_tensor = torch.from_numpy((0.2 * np.exp(-((x - 0.3 - 0.1 * call) ** 2) / 0.01)).astype(np.float32).reshape(-1))
+            got = sess(uu=data.uu_tensor.cuda()).clone()
+            want = model(data)
+            assert torch.equal(got, want)
+            assert util.rel_err(got, ref(data)) <= COORD_TOL
+
+
 def test_config4_200x200_rk4_64_steps_forward():
     over = {"ode_method": "rk4", "num_layers": 64}
     model, out, ref_out, data = _compare_with_oracle((200, 200), 1, over=over, backward=False)
