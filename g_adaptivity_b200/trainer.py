@@ -176,10 +176,20 @@ class DeformerTrainer:
             s.N = N
             f32 = dict(dtype=torch.float32, device=dev)
             xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
-            s.x_comp = torch.empty((N, self.dim), **f32)
-            s.f = torch.empty(N, **f32) if self.opt["gnn_inc_feat_f"] else None
-            s.uu = torch.empty(N, **f32) if self.opt["gnn_inc_feat_uu"] else None
-            s.target = torch.empty((N, self.dim), **f32)
+            # node inputs of a step live in ONE device buffer [x_comp | target | f | uu] (segments padded to
+            # 16 bytes, the TMA staging granularity), so that a packed host batch travels in one copy
+            has_f, has_uu = bool(self.opt["gnn_inc_feat_f"]), bool(self.opt["gnn_inc_feat_uu"])
+            seg = [N * self.dim, N * self.dim, N if has_f else 0, N if has_uu else 0]
+            offs, o = [], 0
+            for n in seg:
+                offs.append(o)
+                o += (n + 3) // 4 * 4
+            s.in_offs, s.in_sizes = offs, seg
+            s.inbuf = torch.zeros(o, **f32)
+            s.x_comp = s.inbuf[offs[0]:offs[0] + seg[0]].view(N, self.dim)
+            s.target = s.inbuf[offs[1]:offs[1] + seg[1]].view(N, self.dim)
+            s.f = s.inbuf[offs[2]:offs[2] + seg[2]] if has_f else None
+            s.uu = s.inbuf[offs[3]:offs[3] + seg[3]] if has_uu else None
             s.states = torch.empty((self.L, N, self.CE), **f32)
             s.x_phys = torch.empty((N, self.dim), **f32)
             s.g_out = torch.empty((N, self.dim), **f32)
@@ -197,21 +207,45 @@ class DeformerTrainer:
         self.load_inputs(sid, data)
         return sid
 
-    def load_inputs(self, sid: int, data, non_blocking: bool = True):
-        """Copy one batch's node features and target mesh (host, ideally pinned) into the slot."""
+    def pack_host(self, sid: int, data) -> torch.Tensor:
+        """One pinned host buffer holding `data`'s node inputs in the layout of slot `sid`
+        ([x_comp | target | f | uu]): `load_inputs` / `run_from_host` then move a batch host -> device
+        with a single copy."""
         s = self.slots[sid]
+        buf = torch.zeros(s.inbuf.numel(), dtype=torch.float32).pin_memory()
+        xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
+        tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
+        parts = [xc, tg, data.f_tensor if s.f is not None else None, data.uu_tensor if s.uu is not None else None]
+        for off, n, t in zip(s.in_offs, s.in_sizes, parts):
+            if t is not None and n:
+                buf[off:off + n].copy_(t.reshape(-1))
+        return buf
+
+    def _copy_inputs(self, s: "_Slot", data) -> int:
+        """Enqueue the host -> device copies of one batch on the current stream; returns the bytes."""
+        if torch.is_tensor(data):                       # packed (pack_host): one copy
+            s.inbuf.copy_(data, non_blocking=True)
+            return data.numel() * 4
         xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
         tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
         nbytes = 0
-        with torch.cuda.stream(self.stream):
-            s.x_comp.copy_(xc, non_blocking=non_blocking); nbytes += xc.numel() * 4
-            s.target.copy_(tg, non_blocking=non_blocking); nbytes += tg.numel() * 4
-            if s.f is not None:
-                s.f.copy_(data.f_tensor, non_blocking=non_blocking); nbytes += data.f_tensor.numel() * 4
-            if s.uu is not None:
-                s.uu.copy_(data.uu_tensor, non_blocking=non_blocking); nbytes += data.uu_tensor.numel() * 4
-        s.h2d_bytes = nbytes
+        s.x_comp.copy_(xc, non_blocking=True); nbytes += xc.numel() * 4
+        s.target.copy_(tg, non_blocking=True); nbytes += tg.numel() * 4
+        if s.f is not None:
+            s.f.copy_(data.f_tensor, non_blocking=True); nbytes += data.f_tensor.numel() * 4
+        if s.uu is not None:
+            s.uu.copy_(data.uu_tensor, non_blocking=True); nbytes += data.uu_tensor.numel() * 4
         return nbytes
+
+    def load_inputs(self, sid: int, data, non_blocking: bool = True):
+        """Copy one batch's node features and target mesh (host, ideally pinned; a `Batch` or a buffer
+        packed by `pack_host`) into the slot."""
+        s = self.slots[sid]
+        with torch.cuda.stream(self.stream):
+            s.h2d_bytes = self._copy_inputs(s, data)
+            if not non_blocking:
+                self.stream.synchronize()
+        return s.h2d_bytes
 
     # ------------------------------------------------------------------------------------
     def _issue(self, s: _Slot, stream_ptr: int, with_optimizer: bool = True, stage: str = "all"):
@@ -398,14 +432,7 @@ class DeformerTrainer:
             with torch.cuda.stream(cs):
                 if k >= R:
                     cs.wait_event(self._slot_free[sid])      # step k - R has consumed this slot's inputs
-                xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
-                tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
-                s.x_comp.copy_(xc, non_blocking=True)
-                s.target.copy_(tg, non_blocking=True)
-                if s.f is not None:
-                    s.f.copy_(data.f_tensor, non_blocking=True)
-                if s.uu is not None:
-                    s.uu.copy_(data.uu_tensor, non_blocking=True)
+                s.h2d_bytes = self._copy_inputs(s, data)
                 self._in_ready[sid].record(cs)
 
         upload(0)
