@@ -163,17 +163,30 @@ class GNN(nn.Module):
         g = self._graphs.get(key)
         if g is not None:
             return g
+        # Identity miss (a fresh Batch from the loader): look the topology up by CONTENT before building
+        ckey, dev_copies = None, {}
+        if opt.get("gad_content_cache", True):
+            ckey, dev_copies = GraphCache.content_key_of(data, flags, dev, use_masks=bool(opt["fix_boundary"]))
+            g = self._graphs.get(ckey)
+            if g is not None:
+                self._graphs.misses_identity = getattr(self._graphs, "misses_identity", 0) + 1
+                self._graphs.alias(key, g, tuple(getattr(data, n, None) for n in GraphCache.TOPOLOGY_FIELDS))
+                return g
         sizes = self._mesh_sizes(data)
         N = int(data.x_comp.shape[0])
         masks, loops = (), None
         if opt["fix_boundary"]:
-            masks = (data.to_boundary_edge_mask, data.to_corner_nodes_mask, data.diff_boundary_edges_mask)
+            masks = tuple(dev_copies.get(n, getattr(data, n)) for n in
+                          ("to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask"))
             loops = corner_loops(data, self.dim, opt["mesh_dims"], sizes)
-        g = MeshGraph.build(data.edge_index, N, masks=masks, extra_loops=loops, self_loops=bool(opt["self_loops"]),
+        g = MeshGraph.build(dev_copies.get("edge_index", data.edge_index), N, masks=masks, extra_loops=loops,
+                            self_loops=bool(opt["self_loops"]),
                             mesh_sizes=sizes, device=dev, ce=self.CE, tile_target=opt.get("gad_tile_nodes"),
                             use_ell=not opt.get("gad_no_ell", False))
-        keep = (data.edge_index, data.batch) + tuple(m for m in masks)
+        keep = (data.edge_index, data.batch) + tuple(getattr(data, n, None) for n in GraphCache.TOPOLOGY_FIELDS)
         self._graphs.put(key, g, keep)
+        if ckey is not None:
+            self._graphs._d[ckey] = g
         return g
 
     def _folded_weights(self, dev):

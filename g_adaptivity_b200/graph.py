@@ -249,6 +249,58 @@ class GraphCache:
             parts += [None if t is None else (t.data_ptr(), t._version)]
         return tuple(parts) + tuple(flags)
 
+    TOPOLOGY_FIELDS = ("edge_index", "to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask", "batch")
+
+    @staticmethod
+    def content_key_of(data, flags, device, use_masks: bool = True):
+        """(key, device copies): key = 128-bit device fingerprint (csrc/graph_build.cu: k_fingerprint)
+        of edge_index / masks / batch + a host hash of the corner-node lists + `flags`.  Costs the
+        host -> device copies the graph build needs anyway, one pass over them at HBM speed and one
+        16-byte read-back."""
+        import hashlib
+        lib = _lib.load()
+        dev = torch.device(device)
+        out = torch.zeros(2, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        copies, shapes = {}, []
+        with torch.cuda.device(dev):
+            for k, name in enumerate(GraphCache.TOPOLOGY_FIELDS):
+                t = getattr(data, name, None)
+                if t is None or (not use_masks and name.endswith("_mask")):
+                    shapes.append(None)
+                    continue
+                td = t.to(dev, non_blocking=True).contiguous()
+                if td.data_ptr() % 8:
+                    td = td.clone()
+                copies[name] = td
+                shapes.append((tuple(td.shape), str(td.dtype)))
+                _lib.check(lib.gad_fingerprint(_lib.ptr(td), td.numel() * td.element_size(), 0x1234 + 7919 * k,
+                                               _lib.ptr(out), stream), "gad_fingerprint")
+        h = hashlib.blake2b(digest_size=16)
+        for c in (getattr(data, "corner_nodes", None) or []):
+            h.update(np.ascontiguousarray(np.asarray(c, dtype=np.int64)).tobytes())
+            h.update(b"|")
+        sizes = getattr(data, "mesh_sizes", None)
+        if sizes is not None:
+            h.update(np.asarray(list(sizes), dtype=np.int64).tobytes())
+        fp = tuple(out.tolist())     # the one synchronisation
+        return ("content", fp, tuple(shapes), h.hexdigest()) + tuple(flags), copies
+
+    def alias(self, key, graph, keepalive):
+        """Register another identity key for an existing graph (kept alive like any entry)."""
+        self._d[key] = graph
+        self._alias_keep = getattr(self, "_alias_keep", collections.OrderedDict())
+        self._alias_keep[key] = keepalive
+        while len(self._alias_keep) > 4 * self.capacity:
+            self._alias_keep.popitem(last=False)
+        self._trim()
+
+    def _trim(self):
+        while len(self._d) > 3 * self.capacity:
+            k, _ = self._d.popitem(last=False)
+            if hasattr(self, "_alias_keep"):
+                self._alias_keep.pop(k, None)
+
     def get(self, key):
         g = self._d.get(key)
         if g is not None:
@@ -260,8 +312,7 @@ class GraphCache:
         self.misses += 1
         graph._keepalive = keepalive
         self._d[key] = graph
-        while len(self._d) > self.capacity:
-            self._d.popitem(last=False)
+        self._trim()
 
     def clear(self):
         self._d.clear()

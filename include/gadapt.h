@@ -83,6 +83,12 @@ int gad_graph_sort_rows(const int32_t* ptr, const int32_t* idx, int64_t N, int32
 int gad_graph_check_tiles(const int32_t* rowptr, const int32_t* col, int64_t N,
                           const int32_t* tile_ptr, int T, int32_t* info, void* stream);
 
+/* Content fingerprint of a (contiguous, 8-byte aligned) device buffer: out[0..1] += a 128-bit
+ * position-sensitive hash of its bytes under `seed`.  The host keys its graph cache on the
+ * fingerprints of edge_index / masks / batch, so that the FRESH Batch object the reference's loader
+ * yields every iteration (src/run_GNN.py:97-105) finds the topology built for an earlier one. */
+int gad_fingerprint(const void* data, size_t bytes, uint64_t seed, uint64_t* out, void* stream);
+
 /* ---- weights ----------------------------------------------------------------------------
  * Mu[l] = { M (CE x CE, row-major, M[a][b]), u (CE) } for each of the Lw weight sets
  * (Lw = 1 when share_conv, src/GNN.py:131-137).  Wq/Wk are [Lw, C, C] ([out, in] like

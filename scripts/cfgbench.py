@@ -7,6 +7,7 @@ import json
 import os
 import statistics
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -92,6 +93,44 @@ def time_train(md, B, ring, iters):
             "tiles": s.graph.T}
 
 
+def time_module_train_fresh(md, B, iters, content_cache):
+    """The reference's loop shape: a FRESH Batch object per iteration, model(data) -> L1 loss ->
+    backward -> torch.optim.Adam.step(), all through the module seam (host tensors in)."""
+    import torch.nn.functional as F
+    from g_adaptivity_b200 import GNN, synth
+    dev = torch.device("cuda", 0)
+    opt = synth.default_opt(md)
+    opt.update(device="cuda:0", gad_store_alpha=False, gad_content_cache=content_cache)
+    ds = synth.SyntheticDataset(len(md), md)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev).train()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-3)
+    base = synth.make_batch(md, B, seed=0)
+    base.pin_memory()
+
+    def fresh():
+        b = base.clone()
+        b.pin_memory()
+        return b
+
+    batches = [fresh() for _ in range(iters + 3)]
+    ts = []
+    for it, data in enumerate(batches):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        optim.zero_grad(set_to_none=True)
+        out = model(data)
+        F.l1_loss(out, data.x_phys.to(dev, non_blocking=True)).backward()
+        optim.step()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(time.perf_counter() - t0)
+    ms = 1e3 * statistics.median(ts)
+    N = base.x_comp.shape[0]
+    return {"nodes": N, "ms_per_step": round(ms, 4), "gnodes_per_s": round(N / ms / 1e6, 4),
+            "graph_builds": model._graphs.misses, "content_hits": getattr(model._graphs, "misses_identity", 0)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -103,6 +142,8 @@ def main():
     res["cfg4_200x200_rk4x64_fwd"] = time_forward((200, 200), 1, {"ode_method": "rk4", "num_layers": 64}, False, it)
     res["cfg2_30x30_b256_train"] = time_train((30, 30), 256, 8, it)
     res["cfg5_50x50_b1024_train"] = time_train((50, 50), 1024, 2, max(2, it // 4))
+    res["cfg2_module_seam_train_fresh_batches_content_cache"] = time_module_train_fresh((30, 30), 256, it, True)
+    res["cfg2_module_seam_train_fresh_batches_identity_cache_only"] = time_module_train_fresh((30, 30), 256, it, False)
     for k, v in res.items():
         print(k, json.dumps(v), flush=True)
 

@@ -234,6 +234,38 @@ def test_config3_burgers_1d_200_repeated_calls():
     assert model._graphs.misses == 1 and model._graphs.hits == 3     # topology cached across calls
 
 
+def test_graph_cache_finds_fresh_batch_objects_by_content():
+    """The loader of the reference yields a new Batch object per iteration (src/run_GNN.py:97-105):
+    the graph cache must recognise the topology by content (device fingerprint), and must NOT confuse
+    batches whose topology differs."""
+    mesh_dims, B = (12, 12), 6
+    opt = synth.default_opt(mesh_dims)
+    ds = synth.SyntheticDataset(2, mesh_dims)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    model = cuda_model(ds, opt, ref.state_dict())
+    model.eval()
+    outs = []
+    with torch.no_grad():
+        for it in range(3):
+            data = synth.make_batch(mesh_dims, B, seed=5)         # fresh tensors, same content
+            outs.append(model(data))
+    assert model._graphs.misses == 1 and getattr(model._graphs, "misses_identity", 0) == 2
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert util.rel_err(outs[0], ref(synth.make_batch(mesh_dims, B, seed=5))) <= COORD_TOL
+    # one edge redirected -> different fingerprint -> rebuilt, and the result follows the new topology
+    data = synth.make_batch(mesh_dims, B, seed=5)
+    keep = ~(data.to_boundary_edge_mask | data.to_corner_nodes_mask | data.diff_boundary_edges_mask)
+    e = int(torch.nonzero(keep)[0])
+    data.edge_index = data.edge_index.clone()
+    data.edge_index[0, e] = data.edge_index[1, e]                  # becomes a self-loop
+    with torch.no_grad():
+        out2 = model(data)
+        assert model._graphs.misses == 2
+        assert util.rel_err(out2, ref(data)) <= COORD_TOL
+    assert not torch.equal(out2, outs[0])
+
+
 def test_inference_session_replays_burgers_rollout():
     """CUDA-graph replay of the deformer call (GNN.inference_session) == the module call, for a
     sequence of uu fields on a fixed 1-D mesh batch."""
