@@ -1,0 +1,422 @@
+// Streaming ELL kernels: the deformer on meshes too large for one CTA's shared memory (a 60x60 mesh
+// already is), one launch per F-evaluation / backward pass, one thread per node, state in global
+// memory (L2-resident for the sizes in question).
+//
+// Same arithmetic as the mesh-resident ELL kernels (ell_math.cuh) -- branch-free rows of W slots,
+// all gathers of a row issued back to back, log2-domain softmax with ex2 / lg2 / rcp -- but the
+// topology is a "wide" row per node and direction,
+//     wide[i] = { int32 j_0 .. j_6, int32 valid }        (32 bytes, two 128-bit loads)
+// holding ABSOLUTE neighbour ids (unused slots hold i itself and are masked out), and the
+// neighbour rows are gathered from global memory through the read-only path.  Against the CSR
+// streaming kernels (stream_kernels.cu: two to three passes over col[] per node, each a dependent
+// index load + gather) a node is one pass with no dependent index loads.
+//
+// Replaces, per layer, `layer(x, edge_index)` + the Euler update (src/GNN.py:273-296) and its
+// autograd (src/run_GNN.py:127,130) for graphs of degree <= 7.
+#include "common.cuh"
+#include "node_math.cuh"
+
+namespace gad {
+namespace {
+
+constexpr int TB = 256;
+constexpr int WIDE_SLOTS = 7;
+
+inline unsigned nblocks(int64_t n, int t = TB) { return (unsigned)((n + t - 1) / t); }
+
+struct Wide {
+    int nb[8];   // nb[7] = validity mask
+    __device__ __forceinline__ bool has(int q) const { return (nb[7] >> q) & 1; }
+};
+
+__device__ __forceinline__ Wide load_wide(const int4* __restrict__ rows, int64_t i) {
+    const int4 a = __ldg(rows + 2 * i), b = __ldg(rows + 2 * i + 1);
+    Wide w;
+    w.nb[0] = a.x; w.nb[1] = a.y; w.nb[2] = a.z; w.nb[3] = a.w;
+    w.nb[4] = b.x; w.nb[5] = b.y; w.nb[6] = b.z; w.nb[7] = b.w;
+    return w;
+}
+
+template <int CE>
+__device__ __forceinline__ Row<CE> ldg_row(const float* __restrict__ base, int64_t i) {
+    Row<CE> r;
+    if constexpr (CE == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(base) + i);
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+    } else {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base) + i);
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+        r.v[2] = t.z;
+        r.v[3] = t.w;
+    }
+    return r;
+}
+
+// cotangent rows: [N, CE], or [N, dim] (dim < CE) for the layer next to the loss
+template <int CE>
+__device__ __forceinline__ Row<CE> load_gplus(const float* __restrict__ g, int64_t i, int gdim) {
+    if (gdim >= CE) return ldg_row<CE>(g, i);
+    Row<CE> r;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) r.v[c] = (c < gdim) ? __ldg(g + i * gdim + c) : 0.f;
+    return r;
+}
+
+// ---- wide rows from the (row-sorted) CSR / CSC walk arrays ---------------------------------------
+__global__ void __launch_bounds__(TB) k_build_wide(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                   int64_t N, int4* __restrict__ rows, int32_t* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int b = ptr[i], deg = ptr[i + 1] - b;
+    int v[8];
+#pragma unroll
+    for (int q = 0; q < WIDE_SLOTS; ++q) v[q] = (q < deg) ? idx[b + q] : (int)i;
+    v[7] = (deg >= WIDE_SLOTS) ? 0x7f : ((1 << deg) - 1);
+    if (deg > WIDE_SLOTS) {
+        atomicAdd(bad, 1);
+        v[7] = 0;
+    }
+    rows[2 * i] = make_int4(v[0], v[1], v[2], v[3]);
+    rows[2 * i + 1] = make_int4(v[4], v[5], v[6], v[7]);
+}
+
+// ---- forward stage (same contract as k_stage of stream_kernels.cu) -------------------------------
+//     k = F(y);  v = final ? acc_in + k : k;  out1 = base + c1 v;  out2 = acc_in + c2 k
+template <int CE, int W>
+__global__ void __launch_bounds__(TB) k_wide_stage(const int4* __restrict__ rows, int64_t N, const float* __restrict__ y,
+                                                   const float* __restrict__ base, const float* __restrict__ acc_in,
+                                                   const float* __restrict__ Mu_g, const float* __restrict__ tau,
+                                                   float c1_scale, float c2, int final_stage, float* __restrict__ out1,
+                                                   float* __restrict__ out2, float* __restrict__ xphys, int dim) {
+    __shared__ float Mu[CE * CE + CE];
+    for (int t = threadIdx.x; t < CE * CE + CE; t += blockDim.x) Mu[t] = Mu_g[t];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const Wide w = load_wide(rows, i);
+    const Row<CE> yi = ldg_row<CE>(y, i);
+    // ---- F(y) at node i: project, gather, softmax, aggregate (ell_math.cuh: ell_feval) ----
+    const Row<CE> p = project<CE>(Mu, yi);
+    Row<CE> xj[W];
+    float s[W];
+    float m = -3.0e38f;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        xj[q] = ldg_row<CE>(y, (int64_t)w.nb[q]);
+        const float d = dot<CE>(p, xj[q]);
+        s[q] = w.has(q) ? d : -CUDART_INF_F;
+        m = fmaxf(m, s[q]);
+    }
+    float Z = 0.f;
+    Row<CE> o = zero_row<CE>();
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const float e = ex2_approx(s[q] - m);
+        Z += e;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) o.v[c] = fmaf(e, xj[q].v[c], o.v[c]);
+    }
+    const float rZ = (w.nb[7] != 0) ? rcp_approx(Z) : 0.f;
+    Row<CE> k;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) k.v[c] = fmaf(o.v[c], rZ, -yi.v[c]);
+    // ---- stage combination ----
+    const float c1 = (tau ? tau[0] : 1.0f) * c1_scale;
+    Row<CE> a_in = zero_row<CE>(), b_in = zero_row<CE>();
+    if (acc_in) a_in = ldg_row<CE>(acc_in, i);
+    if (base) b_in = (base == y) ? yi : ldg_row<CE>(base, i);
+    Row<CE> o1;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) {
+        const float v = final_stage ? a_in.v[c] + k.v[c] : k.v[c];
+        o1.v[c] = fmaf(c1, v, b_in.v[c]);
+    }
+    if (out1) store_row<CE>(out1, i, o1);
+    if (out2) {
+        Row<CE> o2;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) o2.v[c] = fmaf(c2, k.v[c], a_in.v[c]);
+        store_row<CE>(out2, i, o2);
+    }
+    if (xphys) {
+        for (int d = 0; d < dim && d < CE; ++d) xphys[i * dim + d] = o1.v[d];
+    }
+}
+
+// ---- backward, destination pass (contract of k_bwd_dst; math of ell_bwd_dst) ----------------------
+// grid-stride over nodes so that the number of weight-gradient partials is bounded.
+template <int CE, int W>
+__global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ rows, int64_t N, const float* __restrict__ x,
+                                                     const float* __restrict__ gplus, int gplus_dim,
+                                                     const float* __restrict__ Mu_g, const float* __restrict__ tau,
+                                                     float a_coef, float* __restrict__ P, float2* __restrict__ DL,
+                                                     float* __restrict__ gself, float* __restrict__ partials) {
+    constexpr int NACC = CE * CE + CE + 1;
+    __shared__ float Mu[CE * CE + CE];
+    __shared__ float red[NACC * (TB / 32)];
+    for (int t = threadIdx.x; t < CE * CE + CE; t += blockDim.x) Mu[t] = Mu_g[t];
+    __syncthreads();
+    const float b = tau ? tau[0] : 1.0f;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const Wide w = load_wide(rows, i);
+        const Row<CE> xi = ldg_row<CE>(x, i);
+        const Row<CE> gp = load_gplus<CE>(gplus, i, gplus_dim);
+        Row<CE> go;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) go.v[c] = b * gp.v[c];
+        const bool any = w.nb[7] != 0;
+        const Row<CE> p = project<CE>(Mu, xi);
+        Row<CE> xj[W];
+        float s[W];
+        float m = -3.0e38f;
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            xj[q] = ldg_row<CE>(x, (int64_t)w.nb[q]);
+            const float d = dot<CE>(p, xj[q]);
+            s[q] = w.has(q) ? d : -CUDART_INF_F;
+            m = fmaxf(m, s[q]);
+        }
+        float Z = 0.f;
+        Row<CE> o = zero_row<CE>();
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            s[q] = ex2_approx(s[q] - m);   // w_q
+            Z += s[q];
+#pragma unroll
+            for (int c = 0; c < CE; ++c) o.v[c] = fmaf(s[q], xj[q].v[c], o.v[c]);
+        }
+        const float rZ = any ? rcp_approx(Z) : 0.f;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
+        const float D = dot<CE>(go, o);
+        const float lse = any ? m + lg2_approx(Z) : 0.f;
+        const float scale = rZ * LN2_F;
+        Row<CE> t = zero_row<CE>();
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const float ds = (s[q] * scale) * (dot<CE>(go, xj[q]) - D);
+#pragma unroll
+            for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj[q].v[c], t.v[c]);
+        }
+        float gb = 0.f;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) gb = fmaf(gp.v[c], o.v[c] - xi.v[c], gb);
+        acc[NACC - 1] += gb;
+#pragma unroll
+        for (int aa = 0; aa < CE; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < CE; ++bb) acc[aa * CE + bb] = fmaf(xi.v[aa], t.v[bb], acc[aa * CE + bb]);
+#pragma unroll
+        for (int bb = 0; bb < CE; ++bb) acc[CE * CE + bb] += t.v[bb];
+        const Row<CE> Mt = apply_M<CE>(Mu, t);
+        Row<CE> gs;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) gs.v[c] = fmaf(a_coef - b, gp.v[c], Mt.v[c]);
+        store_row<CE>(P, i, p);
+        DL[i] = make_float2(D, lse);
+        store_row<CE>(gself, i, gs);
+    }
+    block_reduce<NACC>(acc, red, partials + (size_t)blockIdx.x * NACC);
+}
+
+// ---- backward, source pass (contract of k_bwd_src; math of ell_bwd_src) -----------------------------
+template <int CE, int W>
+__global__ void __launch_bounds__(TB) k_wide_bwd_src(const int4* __restrict__ rows_out, int64_t N,
+                                                     const float* __restrict__ x, const float* __restrict__ gplus,
+                                                     int gplus_dim, const float* __restrict__ tau,
+                                                     const float* __restrict__ P, const float2* __restrict__ DL,
+                                                     const float* __restrict__ gself, float* __restrict__ gout) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const float b = tau ? tau[0] : 1.0f;
+    const Wide w = load_wide(rows_out, j);
+    const Row<CE> xj = ldg_row<CE>(x, j);
+    Row<CE> p[W], gp[W];
+    float2 dl[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const int64_t i = (int64_t)w.nb[q];
+        p[q] = ldg_row<CE>(P, i);
+        gp[q] = load_gplus<CE>(gplus, i, gplus_dim);
+        dl[q] = __ldg(DL + i);
+    }
+    Row<CE> accv = ldg_row<CE>(gself, j);
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const float sv = dot<CE>(p[q], xj) - dl[q].y;
+        const float alpha = ex2_approx(w.has(q) ? sv : -CUDART_INF_F);
+        const float ds = (alpha * LN2_F) * (b * dot<CE>(gp[q], xj) - dl[q].x);
+        const float ab = alpha * b;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) accv.v[c] = fmaf(ab, gp[q].v[c], fmaf(ds, p[q].v[c], accv.v[c]));
+    }
+    store_row<CE>(gout, j, accv);
+}
+
+// Fixed-order reduction of the per-block partials (one warp per accumulator): out[k] (+)= sum_r part[r, k].
+__global__ void k_wide_reduce(const float* __restrict__ partials, int rows, int nacc, int stride, float* __restrict__ out,
+                              int accumulate) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= nacc) return;
+    double s = 0.0;
+    for (int r = lane; r < rows; r += 32) s += (double)partials[(size_t)r * stride + k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) out[k] = accumulate ? out[k] + (float)s : (float)s;
+}
+
+int grid_for_partials(int64_t N) {
+    const int64_t want = (N + TB - 1) / TB;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+int slots_for(int max_deg) { return max_deg <= 2 ? 2 : (max_deg <= 3 ? 3 : (max_deg <= 6 ? 6 : 7)); }
+
+template <int CE, int W>
+int wide_forward_t(const int4* rows, int64_t N, const float* x0, int dim, const float* Mu, int Lw, const float* tau, int L,
+                   int method, float* x_phys, float* states, float* ws, cudaStream_t st) {
+    const size_t row = (size_t)N * CE;
+    const int MUSZ = CE * CE + CE;
+    const size_t rowa = align_up(row, 64);
+    float* ping[2] = {ws, ws + rowa};
+    float* ybuf = ws + 2 * rowa;    // RK4: stage inputs y2 / y4
+    float* abuf = ws + 3 * rowa;    // RK4: k1 + 2 k2 + 2 k3
+    float* y3buf = ws + 4 * rowa;   // RK4: stage input y3
+    const float* cur = x0;
+    const unsigned G = nblocks(N);
+    for (int l = 0; l < L; ++l) {
+        const float* Mul = Mu + (size_t)(Lw > 1 ? l : 0) * MUSZ;
+        const float* tl = tau + l;
+        const bool last = (l == L - 1);
+        float* nxt = last ? nullptr : (states ? states + (size_t)(l + 1) * row : ping[l & 1]);
+        float* xp = last ? x_phys : nullptr;
+        if (method == GAD_METHOD_EULER) {
+            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, cur, cur, nullptr, Mul, tl, 1.0f, 0.f, 0, nxt, nullptr, xp, dim);
+            GAD_LAUNCH_CHECK();
+        } else {
+            // classical RK4 on F(y) = A(y) y - y (stream_kernels.cu: stream_forward)
+            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, cur, cur, nullptr, Mul, tl, 0.5f, 1.0f, 0, ybuf, abuf, nullptr, dim);
+            GAD_LAUNCH_CHECK();
+            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, ybuf, cur, abuf, Mul, tl, 0.5f, 2.0f, 0, y3buf, abuf, nullptr, dim);
+            GAD_LAUNCH_CHECK();
+            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, y3buf, cur, abuf, Mul, tl, 1.0f, 2.0f, 0, ybuf, abuf, nullptr, dim);
+            GAD_LAUNCH_CHECK();
+            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, ybuf, cur, abuf, Mul, tl, 1.0f / 6.0f, 0.f, 1, nxt, nullptr, xp, dim);
+            GAD_LAUNCH_CHECK();
+        }
+        cur = nxt;
+    }
+    return GAD_OK;
+}
+
+template <int CE, int W>
+int wide_backward_t(const int4* rows_in, const int4* rows_out, int64_t N, const float* states, const float* g_xphys,
+                    int dim, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau, float* g_x0,
+                    float* ws, cudaStream_t st) {
+    constexpr int NACC = CE * CE + CE + 1;
+    const int MUSZ = CE * CE + CE;
+    const size_t row = (size_t)N * CE;
+    const int G = grid_for_partials(N);
+    const size_t rowa = align_up(row, 64);
+    float* P = ws;
+    float* gself = ws + rowa;
+    float* gping[2] = {ws + 2 * rowa, ws + 3 * rowa};
+    float2* DL = reinterpret_cast<float2*>(ws + 4 * rowa);
+    float* partials = ws + 4 * rowa + align_up(2 * (size_t)N, 64);
+    GAD_CUDA(cudaMemsetAsync(gMu, 0, (size_t)Lw * MUSZ * sizeof(float), st));
+    const float* gcur = g_xphys;
+    int gdim = dim;
+    for (int l = L - 1; l >= 0; --l) {
+        const float* Mul = Mu + (size_t)(Lw > 1 ? l : 0) * MUSZ;
+        const float* xl = states + (size_t)l * row;
+        const float* tl = tau + l;
+        float* gout = (l == 0 && g_x0) ? g_x0 : gping[l & 1];
+        k_wide_bwd_dst<CE, W><<<G, TB, 0, st>>>(rows_in, N, xl, gcur, gdim, Mul, tl, 1.0f, P, DL, gself, partials);
+        GAD_LAUNCH_CHECK();
+        if (l > 0 || g_x0) {
+            k_wide_bwd_src<CE, W><<<nblocks(N), TB, 0, st>>>(rows_out, N, xl, gcur, gdim, tl, P, DL, gself, gout);
+            GAD_LAUNCH_CHECK();
+        }
+        k_wide_reduce<<<(MUSZ + 7) / 8, 256, 0, st>>>(partials, G, MUSZ, NACC, gMu + (size_t)(Lw > 1 ? l : 0) * MUSZ, 1);
+        GAD_LAUNCH_CHECK();
+        if (g_tau) {
+            k_wide_reduce<<<1, 32, 0, st>>>(partials + MUSZ, G, 1, NACC, g_tau + l, 0);
+            GAD_LAUNCH_CHECK();
+        }
+        gcur = gout;
+        gdim = CE;
+    }
+    return GAD_OK;
+}
+
+}  // namespace
+
+size_t stream_fwd_ws_floats(int64_t N, int CE, int method);
+size_t stream_bwd_ws_floats(int64_t N, int CE);
+
+}  // namespace gad
+
+using namespace gad;
+
+#define GAD_WIDE_DISPATCH(FN, ...)                                                     \
+    do {                                                                               \
+        const int w__ = slots_for(max_deg);                                            \
+        if (CE == 2 && w__ == 2) return FN<2, 2>(__VA_ARGS__);                         \
+        if (CE == 2 && w__ == 3) return FN<2, 3>(__VA_ARGS__);                         \
+        if (CE == 2 && w__ == 6) return FN<2, 6>(__VA_ARGS__);                         \
+        if (CE == 2 && w__ == 7) return FN<2, 7>(__VA_ARGS__);                         \
+        if (CE == 4 && w__ == 2) return FN<4, 2>(__VA_ARGS__);                         \
+        if (CE == 4 && w__ == 3) return FN<4, 3>(__VA_ARGS__);                         \
+        if (CE == 4 && w__ == 6) return FN<4, 6>(__VA_ARGS__);                         \
+        if (CE == 4 && w__ == 7) return FN<4, 7>(__VA_ARGS__);                         \
+        set_error("wide kernels: no instantiation for CE=%d max_deg=%d", CE, max_deg); \
+        return GAD_ERR_UNSUPPORTED;                                                    \
+    } while (0)
+
+extern "C" int gad_graph_build_wide(const int32_t* ptr, const int32_t* idx, int64_t N, void* wide_rows, int32_t* info,
+                                    void* stream) {
+    GAD_CHECK_ARG(ptr && idx && wide_rows && info && N > 0, "gad_graph_build_wide: bad arguments");
+    k_build_wide<<<nblocks(N), TB, 0, as_stream(stream)>>>(ptr, idx, N, reinterpret_cast<int4*>(wide_rows),
+                                                          info + GAD_INFO_ELL_BAD);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+extern "C" int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, const float* x0, int dim, int CE,
+                                   const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
+                                   float* states, void* workspace, size_t workspace_bytes, void* stream) {
+    GAD_CHECK_ARG(wide_in && x0 && Mu && tau && x_phys && workspace, "gad_deform_fwd_wide: null pointer");
+    GAD_CHECK_ARG(N > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L) && max_deg >= 0 && max_deg <= WIDE_SLOTS,
+                  "gad_deform_fwd_wide: N=%lld L=%d dim=%d CE=%d Lw=%d max_deg=%d", (long long)N, L, dim, CE, Lw, max_deg);
+    GAD_CHECK_ARG(method == GAD_METHOD_EULER || method == GAD_METHOD_RK4, "gad_deform_fwd_wide: unknown method %d", method);
+    GAD_CHECK_ARG(!states || states == x0, "gad_deform_fwd_wide: when states is given, x0 must alias states[0]");
+    GAD_CHECK_ARG(workspace_bytes >= stream_fwd_ws_floats(N, CE, method) * sizeof(float),
+                  "gad_deform_fwd_wide: workspace too small");
+    const int4* rows = reinterpret_cast<const int4*>(wide_in);
+    float* ws = reinterpret_cast<float*>(workspace);
+    cudaStream_t st = as_stream(stream);
+    GAD_WIDE_DISPATCH(wide_forward_t, rows, N, x0, dim, Mu, Lw, tau, L, method, x_phys, states, ws, st);
+}
+
+extern "C" int gad_deform_bwd_wide(const void* wide_in, const void* wide_out, int64_t N, int max_deg,
+                                   const float* states, const float* g_xphys, int dim, int CE, const float* Mu, int Lw,
+                                   const float* tau, int L, float* gMu, float* g_tau, float* g_x0, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    GAD_CHECK_ARG(wide_in && wide_out && states && g_xphys && Mu && tau && gMu && workspace,
+                  "gad_deform_bwd_wide: null pointer");
+    GAD_CHECK_ARG(N > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L) && max_deg >= 0 && max_deg <= WIDE_SLOTS,
+                  "gad_deform_bwd_wide: N=%lld L=%d dim=%d CE=%d Lw=%d max_deg=%d", (long long)N, L, dim, CE, Lw, max_deg);
+    GAD_CHECK_ARG(workspace_bytes >= stream_bwd_ws_floats(N, CE) * sizeof(float), "gad_deform_bwd_wide: workspace too small");
+    const int4* rin = reinterpret_cast<const int4*>(wide_in);
+    const int4* rout = reinterpret_cast<const int4*>(wide_out);
+    float* ws = reinterpret_cast<float*>(workspace);
+    cudaStream_t st = as_stream(stream);
+    GAD_WIDE_DISPATCH(wide_backward_t, rin, rout, N, states, g_xphys, dim, Mu, Lw, tau, L, gMu, g_tau, g_x0, ws, st);
+}

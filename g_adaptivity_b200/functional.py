@@ -121,6 +121,12 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
     if not use_tiles:
         ws_bytes = lib.gad_deform_workspace_bytes(N, CE, method)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
+        if graph.ensure_wide(CE):      # streaming ELL kernels (csrc/stream_ell.cu)
+            with torch.cuda.device(x0.device):
+                _lib.check(lib.gad_deform_fwd_wide(
+                    _lib.ptr(graph.wide_in), N, graph.wide_deg, _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L,
+                    method, _lib.ptr(x_phys), _lib.ptr(states), _lib.ptr(ws), ws_bytes, _stream(x0)), "gad_deform_fwd_wide")
+            return x_phys
     with torch.cuda.device(x0.device):
         _lib.check(lib.gad_deform_fwd(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col_walk), N, graph.E,
@@ -188,6 +194,13 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
         return gMu, g_tau, g_x0
     ws_bytes = lib.gad_deform_bwd_workspace_bytes(N, CE, T, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if not use_tiles and graph.ensure_wide(CE):
+        with torch.cuda.device(dev):
+            _lib.check(lib.gad_deform_bwd_wide(
+                _lib.ptr(graph.wide_in), _lib.ptr(graph.wide_out), N, graph.wide_deg, _lib.ptr(states), _lib.ptr(g_xphys),
+                dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws),
+                ws_bytes, _stream(states)), "gad_deform_bwd_wide")
+        return gMu, g_tau, g_x0
     with torch.cuda.device(dev):
         _lib.check(lib.gad_deform_bwd(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col_walk), _lib.ptr(graph.t_rowptr), _lib.ptr(graph.t_dst_walk), N, graph.E,

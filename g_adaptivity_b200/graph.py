@@ -65,6 +65,8 @@ class MeshGraph:
         self.max_in_deg = self.max_out_deg = 0
         self.tile_ptr = None        # int32 [T+1] on device, or None -> streaming kernels
         self.ell_in = self.ell_out = None   # uint16 [N, 8] ELL rows (mesh-resident ELL kernels), or None
+        self.wide_in = self.wide_out = None  # int32 [N, 8] wide rows (streaming ELL kernels), built on demand
+        self._wide_tried = False
         self.ell_ce = 0             # channel width the ELL byte offsets were built for
         self.ell_deg = 0            # max(in-degree, out-degree)
         self.T = 0
@@ -204,6 +206,37 @@ class MeshGraph:
         if int(self._info[4].item()) != 0:
             return
         self.ell_in, self.ell_out, self.ell_ce, self.ell_deg = ell_in, ell_out, ce, deg
+
+
+def _ensure_wide(self, ce: int) -> bool:
+    """Wide rows {j_0..j_6, valid} for the streaming ELL kernels (csrc/stream_ell.cu): degree <= 7,
+    CE in {2, 4}.  Built once, on first use of the streaming path."""
+    if self._wide_tried:
+        return self.wide_in is not None
+    self._wide_tried = True
+    if ce not in (2, 4) or self.E == 0 or max(self.max_in_deg, self.max_out_deg) > 7:
+        return False
+    import os
+    if os.environ.get("GAD_NO_WIDE"):
+        return False
+    lib = _lib.load()
+    wi = torch.empty((self.N, 8), dtype=torch.int32, device=self.device)
+    wo = torch.empty((self.N, 8), dtype=torch.int32, device=self.device)
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    with torch.cuda.device(self.device):
+        self._info[4:5].zero_()
+        _lib.check(lib.gad_graph_build_wide(_lib.ptr(self.rowptr), _lib.ptr(self.col_walk), self.N, _lib.ptr(wi),
+                                            _lib.ptr(self._info), stream), "gad_graph_build_wide")
+        _lib.check(lib.gad_graph_build_wide(_lib.ptr(self.t_rowptr), _lib.ptr(self.t_dst_walk), self.N, _lib.ptr(wo),
+                                            _lib.ptr(self._info), stream), "gad_graph_build_wide")
+    if int(self._info[4].item()) != 0:
+        return False
+    self.wide_in, self.wide_out = wi, wo
+    self.wide_deg = max(self.max_in_deg, self.max_out_deg)
+    return True
+
+
+MeshGraph.ensure_wide = _ensure_wide
 
 
 def C_int():

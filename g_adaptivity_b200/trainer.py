@@ -199,7 +199,10 @@ class DeformerTrainer:
             s.bwd_ws_bytes = max(lib.gad_deform_bwd_workspace_bytes(N, self.CE, T, self.L),
                                  lib.gad_ell_workspace_bytes(self.CE, T, self.L))
             s.bwd_ws = torch.empty(s.bwd_ws_bytes, dtype=torch.uint8, device=dev)
-            s.fwd_ws_bytes = 0 if T else lib.gad_deform_workspace_bytes(N, self.CE, self.method)
+            streaming = T == 0 or self.opt.get("gad_force_stream", False)
+            if streaming:
+                s.graph.ensure_wide(self.CE)     # wide rows for the streaming ELL kernels, built outside any capture
+            s.fwd_ws_bytes = lib.gad_deform_workspace_bytes(N, self.CE, self.method) if streaming else 0
             s.fwd_ws = torch.empty(max(s.fwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
             s.h2d_bytes = 0
         self.slots.append(s)
@@ -277,19 +280,31 @@ class DeformerTrainer:
                 "gad_prepare_weights")
             chk(lib.gad_pack_features(P(s.x_comp), P(s.f), P(s.uu), None, None, s.N, dim, CE, P(s.states), stream_ptr),
                 "gad_pack_features")
-            chk(lib.gad_deform_fwd(P(g.rowptr), P(g.col_walk), s.N, g.E, P(g.tile_ptr) if tiles else None, g.T if tiles else 0,
-                                   g.max_tile_nodes, g.max_tile_edges, P(s.states), dim, CE, P(self.Mu), Lw, P(self.tau), L,
-                                   self.method, P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, stream_ptr),
-                "gad_deform_fwd")
+            wide = (not tiles) and g.ensure_wide(CE)      # streaming ELL kernels (csrc/stream_ell.cu)
+            if wide:
+                chk(lib.gad_deform_fwd_wide(P(g.wide_in), s.N, g.wide_deg, P(s.states), dim, CE, P(self.Mu), Lw, P(self.tau), L,
+                                            self.method, P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, stream_ptr),
+                    "gad_deform_fwd_wide")
+            else:
+                chk(lib.gad_deform_fwd(P(g.rowptr), P(g.col_walk), s.N, g.E, P(g.tile_ptr) if tiles else None,
+                                       g.T if tiles else 0, g.max_tile_nodes, g.max_tile_edges, P(s.states), dim, CE,
+                                       P(self.Mu), Lw, P(self.tau), L, self.method, P(s.x_phys), P(s.states), P(s.fwd_ws),
+                                       s.fwd_ws_bytes, stream_ptr),
+                    "gad_deform_fwd")
             chk(lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * dim, 0 if self.loss_kind == "l1" else 1,
                                   dp.local_grad_scale(s.N * dim, world=self.world), P(s.loss), P(s.g_out), P(s.loss_ws),
                                   stream_ptr),
                 "gad_mesh_loss")
-            chk(lib.gad_deform_bwd(P(g.rowptr), P(g.col_walk), P(g.t_rowptr), P(g.t_dst_walk), s.N, g.E,
-                                   P(g.tile_ptr) if tiles else None, g.T if tiles else 0, g.max_tile_nodes,
-                                   g.max_tile_edges, P(s.states), P(s.g_out), dim, CE, P(self.Mu), Lw, P(self.tau), L,
-                                   P(self.gMu), P(self.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, stream_ptr),
-                "gad_deform_bwd")
+            if wide:
+                chk(lib.gad_deform_bwd_wide(P(g.wide_in), P(g.wide_out), s.N, g.wide_deg, P(s.states), P(s.g_out), dim, CE,
+                                            P(self.Mu), Lw, P(self.tau), L, P(self.gMu), P(self.gtau), None, P(s.bwd_ws),
+                                            s.bwd_ws_bytes, stream_ptr), "gad_deform_bwd_wide")
+            else:
+                chk(lib.gad_deform_bwd(P(g.rowptr), P(g.col_walk), P(g.t_rowptr), P(g.t_dst_walk), s.N, g.E,
+                                       P(g.tile_ptr) if tiles else None, g.T if tiles else 0, g.max_tile_nodes,
+                                       g.max_tile_edges, P(s.states), P(s.g_out), dim, CE, P(self.Mu), Lw, P(self.tau), L,
+                                       P(self.gMu), P(self.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, stream_ptr),
+                    "gad_deform_bwd")
             chk(lib.gad_weight_grads(P(self.Wq), P(self.bq), P(self.Wk), P(self.gMu), Lw, C_, CE, inv_temp, P(self.gWq),
                                      P(self.gbq), P(self.gWk), P(self.gbk), stream_ptr), "gad_weight_grads")
         if stage in ("all", "post") and with_optimizer:

@@ -136,6 +136,22 @@ int gad_deform_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_r
                    int L, float* gMu, float* g_tau, float* g_x0, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ---- streaming ELL ("wide") path: meshes too large for one CTA's shared memory, degree <= 7 ------
+ * One launch per F-evaluation / backward pass like gad_deform_fwd / gad_deform_bwd without tiles, but
+ * over rows  wide[i] = { int32 j_0 .. j_6, int32 valid }  (32 bytes; absolute neighbour ids, unused
+ * slots = i, masked by `valid`): a node is ONE branch-free pass with no dependent index loads.
+ * gad_graph_build_wide converts a (row-sorted) CSR or CSC; rows with more than 7 entries are counted
+ * into info[GAD_INFO_ELL_BAD].  Workspaces: gad_deform_workspace_bytes / gad_deform_bwd_workspace_bytes. */
+int gad_graph_build_wide(const int32_t* ptr, const int32_t* idx, int64_t N, void* wide_rows, int32_t* info,
+                         void* stream);
+int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, const float* x0, int dim, int CE,
+                        const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
+                        float* states, void* workspace, size_t workspace_bytes, void* stream);
+int gad_deform_bwd_wide(const void* wide_in, const void* wide_out, int64_t N, int max_deg, const float* states,
+                        const float* g_xphys, int dim, int CE, const float* Mu, int Lw, const float* tau, int L,
+                        float* gMu, float* g_tau, float* g_x0, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* ---- mesh-resident ELL path -------------------------------------------------------------------
  * The fast path for batches of bounded-degree meshes (every 1-D / 2-D mesh of the reference: in-
  * and out-degree <= 7 with self-loops).  Topology is one 16-byte row per node and direction:

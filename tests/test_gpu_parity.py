@@ -193,10 +193,22 @@ def test_config1_15x15_single_mesh():
     _compare_with_oracle((15, 15), 1)
 
 
-@pytest.mark.parametrize("force_stream", [False, True])
+@pytest.mark.parametrize("force_stream", [False, True, "csr"])
 def test_config2_30x30_batch256_fwd_bwd(force_stream):
-    model, out, ref_out, data = _compare_with_oracle((30, 30), 256, gad_force_stream=force_stream)
+    """mesh-resident ELL kernels / streaming ELL ("wide") kernels / CSR streaming kernels."""
+    extra = {"gad_force_stream": bool(force_stream)}
+    if force_stream == "csr":
+        extra["gad_no_wide"] = True
+    model, out, ref_out, data = _compare_with_oracle((30, 30), 256, **extra)
     assert model.last_graph.tile_ptr is not None      # the plan exists; force_stream only bypasses it
+    assert (model.last_graph.wide_in is not None) == (force_stream is True)
+
+
+def test_large_mesh_streams_through_wide_rows():
+    """A 64x64 mesh does not fit one CTA: forward + backward run on the streaming ELL kernels."""
+    model, *_ = _compare_with_oracle((64, 64), 3)
+    g = model.last_graph
+    assert g.tile_ptr is None and g.wide_in is not None and g.wide_deg <= 7
     # size-independent properties on the full batch
     n = 30
     o = out.detach().cpu().view(256, n, n, 2)
