@@ -92,7 +92,7 @@ __device__ __forceinline__ Row<CE> ell_feval(const unsigned char* __restrict__ X
 #pragma unroll
         for (int c = 0; c < CE; ++c) o.v[c] = fmaf(w, xj[q].v[c], o.v[c]);
     }
-    const float rZ = any ? rcp_approx(Z) : 0.f;   // no in-edge: o = 0 (empty scatter row)
+    const float rZ = any ? rcp_refined(Z) : 0.f;   // no in-edge: o = 0 (empty scatter row)
     Row<CE> k;
 #pragma unroll
     for (int c = 0; c < CE; ++c) k.v[c] = fmaf(o.v[c], rZ, -y.v[c]);
@@ -127,7 +127,7 @@ __device__ __forceinline__ void ell_bwd_dst(const unsigned char* __restrict__ Xb
 #pragma unroll
         for (int c = 0; c < CE; ++c) o.v[c] = fmaf(s[q], xj[q].v[c], o.v[c]);
     }
-    const float rZ = any ? rcp_approx(Z) : 0.f;
+    const float rZ = any ? rcp_refined(Z) : 0.f;
 #pragma unroll
     for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
     D = dot<CE>(go, o);

@@ -60,6 +60,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// rcp.approx + one Newton step.  The raw MUFU result is off by up to 2^-22 with a SYSTEMATIC sign, so
+// the attention weights of a row would sum to 1 + eps with the same eps at every node; in the
+// backward that leaves sum_e ds_e = -ln2 eps D_i instead of 0, a bias that does not average out in
+// G_u = sum_i t_i (the gradient of lin_query.bias), whose true value is a heavily cancelling sum.
+// Two FMAs bring the weights' sum to 1 within rounding (random sign).
+__device__ __forceinline__ float rcp_refined(float x) {
+    const float r = rcp_approx(x);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
 __device__ __forceinline__ float gexp(float x) { return ex2_approx(x); }
 
 template <int CE>

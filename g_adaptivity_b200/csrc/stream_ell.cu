@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(TB) k_wide_stage(const int4* __restrict__ rows
 #pragma unroll
         for (int c = 0; c < CE; ++c) o.v[c] = fmaf(e, xj[q].v[c], o.v[c]);
     }
-    const float rZ = (w.nb[7] != 0) ? rcp_approx(Z) : 0.f;
+    const float rZ = (w.nb[7] != 0) ? rcp_refined(Z) : 0.f;
     Row<CE> k;
 #pragma unroll
     for (int c = 0; c < CE; ++c) k.v[c] = fmaf(o.v[c], rZ, -yi.v[c]);
@@ -152,10 +152,12 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ ro
                                                      const float* __restrict__ gplus, int gplus_dim,
                                                      const float* __restrict__ Mu_g, const float* __restrict__ tau,
                                                      float a_coef, float* __restrict__ P, float2* __restrict__ DL,
-                                                     float* __restrict__ gself, float* __restrict__ partials) {
+                                                     float* __restrict__ gself, float* __restrict__ partials,
+                                                     int accumulate) {
     constexpr int NACC = CE * CE + CE + 1;
     __shared__ float Mu[CE * CE + CE];
     __shared__ float red[NACC * (TB / 32)];
+    __shared__ float blk[NACC];
     for (int t = threadIdx.x; t < CE * CE + CE; t += blockDim.x) Mu[t] = Mu_g[t];
     __syncthreads();
     const float b = tau ? tau[0] : 1.0f;
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ ro
 #pragma unroll
             for (int c = 0; c < CE; ++c) o.v[c] = fmaf(s[q], xj[q].v[c], o.v[c]);
         }
-        const float rZ = any ? rcp_approx(Z) : 0.f;
+        const float rZ = any ? rcp_refined(Z) : 0.f;
 #pragma unroll
         for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
         const float D = dot<CE>(go, o);
@@ -221,7 +223,13 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ ro
         DL[i] = make_float2(D, lse);
         store_row<CE>(gself, i, gs);
     }
-    block_reduce<NACC>(acc, red, partials + (size_t)blockIdx.x * NACC);
+    // per-block partial row: (G_M, G_u) accumulate over the layers of a shared weight set (same block,
+    // same order every time: deterministic), the step-size column is per layer
+    block_reduce<NACC>(acc, red, blk);
+    if (threadIdx.x < NACC) {
+        float* dst = partials + (size_t)blockIdx.x * NACC + threadIdx.x;
+        *dst = (accumulate && threadIdx.x < NACC - 1) ? *dst + blk[threadIdx.x] : blk[threadIdx.x];
+    }
 }
 
 // ---- backward, source pass (contract of k_bwd_src; math of ell_bwd_src) -----------------------------
@@ -338,14 +346,18 @@ int wide_backward_t(const int4* rows_in, const int4* rows_out, int64_t N, const 
         const float* xl = states + (size_t)l * row;
         const float* tl = tau + l;
         float* gout = (l == 0 && g_x0) ? g_x0 : gping[l & 1];
-        k_wide_bwd_dst<CE, W><<<G, TB, 0, st>>>(rows_in, N, xl, gcur, gdim, Mul, tl, 1.0f, P, DL, gself, partials);
+        const bool shared_w = (Lw == 1);
+        k_wide_bwd_dst<CE, W><<<G, TB, 0, st>>>(rows_in, N, xl, gcur, gdim, Mul, tl, 1.0f, P, DL, gself, partials,
+                                                (shared_w && l < L - 1) ? 1 : 0);
         GAD_LAUNCH_CHECK();
         if (l > 0 || g_x0) {
             k_wide_bwd_src<CE, W><<<nblocks(N), TB, 0, st>>>(rows_out, N, xl, gcur, gdim, tl, P, DL, gself, gout);
             GAD_LAUNCH_CHECK();
         }
-        k_wide_reduce<<<(MUSZ + 7) / 8, 256, 0, st>>>(partials, G, MUSZ, NACC, gMu + (size_t)(Lw > 1 ? l : 0) * MUSZ, 1);
-        GAD_LAUNCH_CHECK();
+        if (!shared_w || l == 0) {   // shared weights: one reduction of the accumulated partials at the end
+            k_wide_reduce<<<(MUSZ + 7) / 8, 256, 0, st>>>(partials, G, MUSZ, NACC, gMu + (size_t)(shared_w ? 0 : l) * MUSZ, 1);
+            GAD_LAUNCH_CHECK();
+        }
         if (g_tau) {
             k_wide_reduce<<<1, 32, 0, st>>>(partials + MUSZ, G, 1, NACC, g_tau + l, 0);
             GAD_LAUNCH_CHECK();

@@ -203,12 +203,6 @@ def test_config2_30x30_batch256_fwd_bwd(force_stream):
     assert model.last_graph.tile_ptr is not None      # the plan exists; force_stream only bypasses it
     assert (model.last_graph.wide_in is not None) == (force_stream is True)
 
-
-def test_large_mesh_streams_through_wide_rows():
-    """A 64x64 mesh does not fit one CTA: forward + backward run on the streaming ELL kernels."""
-    model, *_ = _compare_with_oracle((64, 64), 3)
-    g = model.last_graph
-    assert g.tile_ptr is None and g.wide_in is not None and g.wide_deg <= 7
     # size-independent properties on the full batch
     n = 30
     o = out.detach().cpu().view(256, n, n, 2)
@@ -217,6 +211,13 @@ def test_large_mesh_streams_through_wide_rows():
         assert torch.equal(o[:, iy, ix], x[:, iy, ix])
     assert o[:, :, 0, 0].abs().max() <= 1e-6 and (o[:, :, -1, 0] - 1).abs().max() <= 1e-6   # sides stay on sides
     assert o[:, 0, :, 1].abs().max() <= 1e-6 and (o[:, -1, :, 1] - 1).abs().max() <= 1e-6
+
+
+def test_large_mesh_streams_through_wide_rows():
+    """A 64x64 mesh does not fit one CTA: forward + backward run on the streaming ELL kernels."""
+    model, *_ = _compare_with_oracle((64, 64), 3)
+    g = model.last_graph
+    assert g.tile_ptr is None and g.wide_in is not None and g.wide_deg <= 7
 
 
 def test_config3_burgers_1d_200_repeated_calls():
