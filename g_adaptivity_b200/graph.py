@@ -67,6 +67,11 @@ class MeshGraph:
         self.ell_in = self.ell_out = None   # uint16 [N, 8] ELL rows (mesh-resident ELL kernels), or None
         self.wide_in = self.wide_out = None  # int32 [N, 8] wide rows (streaming ELL kernels), built on demand
         self._wide_tried = False
+        self.cl_in = self.cl_out = None      # int32 [N, 8] cluster rows (cluster-resident training kernel)
+        self.cl_C = self.cl_S = 0            # cluster size, slab size
+        self.mesh_ptr = None                 # int32 [M + 1] on device
+        self.mesh_sizes = None
+        self._cl_tried = False
         self.ell_ce = 0             # channel width the ELL byte offsets were built for
         self.ell_deg = 0            # max(in-degree, out-degree)
         self.T = 0
@@ -153,6 +158,7 @@ class MeshGraph:
         self.ell_in = self.ell_out = None
         if int(np.sum(mesh_sizes)) != self.N:
             raise ValueError("mesh_sizes do not add up to the node count")
+        self.mesh_sizes = [int(n) for n in mesh_sizes]
         tp = plan_tiles(mesh_sizes, target_nodes=tile_target or _DEFAULT_TILE_TARGET)
         if tp is None:
             return
@@ -237,6 +243,44 @@ def _ensure_wide(self, ce: int) -> bool:
 
 
 MeshGraph.ensure_wide = _ensure_wide
+
+
+def _ensure_cluster(self, ce: int) -> bool:
+    """Cluster rows for the cluster-resident training kernel (csrc/cl_kernels.cu): meshes that do not
+    fit one CTA but fit a thread-block cluster of up to 16 (degree <= 7, CE in {2, 4}, every mesh a
+    connected component of the batch).  Built once, on first use."""
+    if self._cl_tried:
+        return self.cl_in is not None
+    self._cl_tried = True
+    import ctypes
+    import os
+    if (os.environ.get("GAD_NO_CLUSTER") or ce not in (2, 4) or self.E == 0 or self.mesh_sizes is None
+            or self.tile_ptr is not None or max(self.max_in_deg, self.max_out_deg) > 7):
+        return False
+    lib = _lib.load()
+    Cc, Sc = ctypes.c_int(0), ctypes.c_int(0)
+    if lib.gad_cluster_plan(ce, max(self.mesh_sizes), ctypes.byref(Cc), ctypes.byref(Sc)) != 0:
+        return False
+    M = len(self.mesh_sizes)
+    mp = np.concatenate([[0], np.cumsum(np.asarray(self.mesh_sizes, dtype=np.int64))]).astype(np.int32)
+    mesh_ptr = torch.from_numpy(mp).to(self.device)
+    ci = torch.empty((self.N, 8), dtype=torch.int32, device=self.device)
+    co = torch.empty((self.N, 8), dtype=torch.int32, device=self.device)
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    with torch.cuda.device(self.device):
+        self._info[4:5].zero_()
+        for ptr, idx, out in ((self.rowptr, self.col_walk, ci), (self.t_rowptr, self.t_dst_walk, co)):
+            _lib.check(lib.gad_graph_build_cluster(_lib.ptr(ptr), _lib.ptr(idx), _lib.ptr(mesh_ptr), M, max(self.mesh_sizes),
+                                                   ce, Cc.value, _lib.ptr(out), _lib.ptr(self._info), stream),
+                       "gad_graph_build_cluster")
+    if int(self._info[4].item()) != 0:      # an edge leaves its mesh or a row is too long
+        return False
+    self.cl_in, self.cl_out, self.cl_C, self.cl_S, self.mesh_ptr = ci, co, Cc.value, Sc.value, mesh_ptr
+    self.cl_deg = max(self.max_in_deg, self.max_out_deg)
+    return True
+
+
+MeshGraph.ensure_cluster = _ensure_cluster
 
 
 def C_int():

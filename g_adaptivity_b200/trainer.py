@@ -143,8 +143,12 @@ class DeformerTrainer:
         count = s.N * self.dim
         b1, b2 = self.betas
         d = _lib.TrainDesc()
-        d.ell_in, d.ell_out, d.tile_ptr, d.N = P(g.ell_in), P(g.ell_out), P(g.tile_ptr), s.N
-        d.T, d.max_tile_nodes, d.max_deg = g.T, g.max_tile_nodes, g.ell_deg
+        if g.tile_ptr is None:      # cluster-resident meshes (gad_train_step_cluster)
+            d.ell_in, d.ell_out, d.tile_ptr, d.N = P(g.cl_in), P(g.cl_out), P(g.mesh_ptr), s.N
+            d.T, d.max_tile_nodes, d.max_deg = len(g.mesh_sizes), max(g.mesh_sizes), g.cl_deg
+        else:
+            d.ell_in, d.ell_out, d.tile_ptr, d.N = P(g.ell_in), P(g.ell_out), P(g.tile_ptr), s.N
+            d.T, d.max_tile_nodes, d.max_deg = g.T, g.max_tile_nodes, g.ell_deg
         d.x_comp, d.f, d.uu, d.f_scale, d.uu_scale, d.target = P(s.x_comp), P(s.f), P(s.uu), None, None, P(s.target)
         d.dim, d.CE = self.dim, self.CE
         d.Mu, d.tau, d.Lw, d.L, d.C, d.inv_temp = P(self.Mu), P(self.tau), self.Lw, self.L, self.C, self.model.inv_temp
@@ -202,6 +206,11 @@ class DeformerTrainer:
             streaming = T == 0 or self.opt.get("gad_force_stream", False)
             if streaming:
                 s.graph.ensure_wide(self.CE)     # wide rows for the streaming ELL kernels, built outside any capture
+            if T == 0 and not self.opt.get("gad_no_cluster", False) and s.graph.ensure_cluster(self.CE):
+                need = lib.gad_cluster_workspace_bytes(self.CE, len(s.graph.mesh_sizes), s.graph.cl_C, self.L)
+                if need > s.bwd_ws_bytes:
+                    s.bwd_ws_bytes = need
+                    s.bwd_ws = torch.zeros(need, dtype=torch.uint8, device=dev)
             s.fwd_ws_bytes = lib.gad_deform_workspace_bytes(N, self.CE, self.method) if streaming else 0
             s.fwd_ws = torch.empty(max(s.fwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
             s.h2d_bytes = 0
@@ -259,12 +268,16 @@ class DeformerTrainer:
         tiles = g.tile_ptr is not None and not self.opt.get("gad_force_stream", False)
         inv_temp = self.model.inv_temp
         ell = tiles and GF.use_ell(g, CE) and not self.opt.get("gad_no_fused_train", False)
-        if ell:
+        cluster = (not ell) and self._cluster(s)
+        if ell or cluster:
             # ONE launch per step (csrc/ell_kernels.cuh: k_ell_train): pack + forward + loss + backward per
             # tile, then the last CTA reduces, applies the chain rule and -- single GPU -- takes the Adam step
             # and refolds (M, u) for the next step.  Data parallel: all-reduce, Adam and refold follow.
             single = (self.world == 1 or self.fused_dp) and with_optimizer
-            if stage in ("all", "pre"):
+            if stage in ("all", "pre") and cluster:
+                chk(lib.gad_train_step_cluster(C.byref(self._train_desc(s, 2 if single else 1)), g.cl_C, stream_ptr),
+                    "gad_train_step_cluster")
+            elif stage in ("all", "pre"):
                 chk(lib.gad_train_step_ell(C.byref(self._train_desc(s, 2 if single else 1)), stream_ptr),
                     "gad_train_step_ell")
             if stage in ("all", "post") and with_optimizer and not single:
@@ -320,10 +333,16 @@ class DeformerTrainer:
             return
         dp.allreduce_flat(self.gflat, group=self.pg)
 
+    def _cluster(self, s: _Slot) -> bool:
+        """Meshes too large for one CTA run on the cluster-resident kernel (csrc/cl_kernels.cu)."""
+        g = s.graph
+        return bool(g.tile_ptr is None and g.cl_in is not None and not self.opt.get("gad_no_cluster", False)
+                    and not self.opt.get("gad_force_stream", False))
+
     def _one_launch(self, s: _Slot) -> bool:
         g = s.graph
         tiles = g.tile_ptr is not None and not self.opt.get("gad_force_stream", False)
-        return bool(tiles and GF.use_ell(g, self.CE) and not self.opt.get("gad_no_fused_train", False))
+        return bool(tiles and GF.use_ell(g, self.CE) and not self.opt.get("gad_no_fused_train", False)) or self._cluster(s)
 
     def close(self):
         """Drop the captured graphs and the peer mappings (call on every rank, after the last step)."""

@@ -282,6 +282,22 @@ typedef struct gad_train_desc {
 #define GAD_MAX_PEERS 16
 int gad_train_step_ell(const gad_train_desc* desc, void* stream);
 
+/* ---- cluster-resident training step: meshes beyond one CTA's shared memory (60x60 .. ~220x220) -------
+ * One thread-block CLUSTER per mesh: the mesh is cut into `cluster_size` contiguous slabs, each kept
+ * in one CTA's shared memory for the whole pass; rows of other slabs are read through distributed
+ * shared memory.  gad_cluster_plan chooses the cluster size (2..16) and slab size for the largest
+ * mesh; gad_graph_build_cluster converts a (row-sorted) CSR / CSC into cluster rows
+ *     crow[i] = { u32 e_0 .. e_6, u32 valid },  e_q = (owner rank << 24) | (row offset in bytes)
+ * (32 bytes per node); gad_train_step_cluster has gad_train_step_ell's contract with ell_in / ell_out
+ * = cluster rows, tile_ptr = mesh_ptr [T + 1], T = meshes, max_tile_nodes = largest mesh, workspace of
+ * gad_cluster_workspace_bytes.  Replaces src/run_GNN.py:99-131 for such meshes in one launch. */
+int gad_cluster_plan(int CE, int max_mesh_nodes, int* cluster_size, int* slab_nodes);
+int gad_graph_build_cluster(const int32_t* ptr, const int32_t* idx, const int32_t* mesh_ptr, int M,
+                            int max_mesh_nodes, int CE, int cluster_size, void* rows, int32_t* info,
+                            void* stream);
+size_t gad_cluster_workspace_bytes(int CE, int M, int cluster_size, int L);
+int gad_train_step_cluster(const gad_train_desc* desc, int cluster_size, void* stream);
+
 /* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --
  * res = A(x) x - x  for x [N, CE];  alpha (optional) [E] in filtered edge-list order.
  */

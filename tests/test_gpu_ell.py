@@ -198,3 +198,60 @@ def test_epoch_graph_equals_step_by_step(pdl):
     assert res[0][2] == res[1][2] == 12
     assert torch.equal(res[0][0], res[1][0])
     assert res[0][1] == res[1][1]
+
+
+# ------------------------------------------------------------------------------------------
+# cluster-resident kernel (csrc/cl_kernels.cu): meshes beyond one CTA, one thread-block cluster each
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mesh_dims,B,over", [
+    ((64, 64), 3, {}),                                        # 4096 nodes: cluster of 2
+    ((81, 81), 2, {"loss_fn": "mse"}),                         # 6561 nodes: cluster of 4, ragged last slab
+    ((64, 64), 2, {"share_conv": False, "learn_step": True, "num_layers": 3}),
+])
+def test_cluster_train_step_matches_oracle_and_streaming_path(mesh_dims, B, over):
+    loss = over.get("loss_fn", "l1")
+    opt, ds, data, ref = _case(mesh_dims, B, seed=9, **over)
+    ref_out = ref(data)
+    ref_loss = gnn_oracle.mesh_loss(ref_out, data.x_phys, loss_fn=loss)
+    ref_loss.backward()
+    ref_grads = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    res = []
+    for no_cluster in (False, True):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_no_cluster=no_cluster)
+        tr = DeformerTrainer(model, use_cuda_graph=False, loss_fn=loss)
+        sid = tr.add_batch(data)
+        g = tr.slots[sid].graph
+        assert g.tile_ptr is None and (g.cl_in is not None) == (not no_cluster)
+        with torch.cuda.stream(tr.stream):
+            tr._issue(tr.slots[sid], tr.stream.cuda_stream, with_optimizer=False)
+        tr.synchronize()
+        assert abs(tr.slots[sid].loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+        assert util.rel_err(tr.slots[sid].x_phys, ref_out) <= COORD_TOL
+        res.append(tr.gflat.clone().cpu())
+        if not no_cluster:
+            assert g.cl_C >= 2
+            g64, floor, scale = util.fp64_grads_and_noise_floor(ds, opt, data, ref, ref_grads)
+            util.check_grads_conditioned(grads_of(model), g64, floor, scale)
+    scale = res[1].abs().max().item()
+    assert (res[0] - res[1]).abs().max().item() <= 2e-5 * scale      # cluster kernel vs streaming ELL kernels
+
+
+def test_cluster_training_is_deterministic_and_matches_streaming_steps():
+    """Several Adam steps (tail of the cluster kernel, PDL-chained graph replay) == the same steps on
+    the streaming kernels with stand-alone weight-gradient / Adam / refold launches."""
+    opt, ds, data, ref = _case((64, 64), 3, seed=10)
+    finals = []
+    for mode in ("cluster", "cluster", "stream"):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_no_cluster=(mode == "stream"))
+        tr = DeformerTrainer(model, lr=1e-2)
+        sids = [tr.add_batch(data), tr.add_batch(data)]
+        losses = []
+        for _ in range(4):
+            for l in tr.run_epoch(sids):
+                with torch.cuda.stream(tr.stream):
+                    losses.append(l.clone())
+        tr.synchronize()
+        finals.append(([float(x.item()) for x in losses], tr.flat.clone().cpu()))
+    assert finals[0][0] == finals[1][0] and torch.equal(finals[0][1], finals[1][1])     # bit-reproducible
+    assert finals[0][0][-1] < finals[0][0][0]
+    assert (finals[0][1] - finals[2][1]).abs().max().item() <= 2e-4 * finals[2][1].abs().max().item()
