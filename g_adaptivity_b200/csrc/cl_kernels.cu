@@ -55,8 +55,18 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
+// Phase boundary of a cluster.  What has to cross it is SHARED memory only (every global value a
+// thread reads back was written by itself): a CTA-scope fence orders this thread's shared-memory
+// stores before its arrival, and a slab's rows are physically in its SM's shared memory by the time
+// every thread of the cluster has arrived.  The default .release / .acquire forms would add a
+// GPU-scope MEMBAR (waiting for the outstanding `states` stores to reach L2) and an L1 invalidation
+// to each of the 13 barriers of a pass.  GAD_CLUSTER_STRICT_SYNC=1 at build time restores them.
 __device__ __forceinline__ void cluster_sync() {
+#if defined(GAD_CLUSTER_STRICT_SYNC) && GAD_CLUSTER_STRICT_SYNC
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+    asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
 }
 
 // row of CE floats at a shared::cluster address (own or a peer CTA's shared memory)
