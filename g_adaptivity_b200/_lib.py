@@ -81,6 +81,7 @@ SIGNATURES = {
     "gad_cluster_plan": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "gad_graph_build_cluster": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "gad_cluster_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "gad_cluster_occupancy": (_i, [_i, _i, _i, _i, C.POINTER(_i)]),
     "gad_train_step_cluster": (_i, [C.POINTER(TrainDesc), _i, _p]),
     "gad_conv_fwd": (_i, [_p, _p, _p, _i64, _i64, _p, _i, _p, _p, _p, _p]),
     "gad_conv_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),

@@ -30,6 +30,7 @@ constexpr int MAXT = 512;
 struct CRow {
     uint32_t e[8];   // e[7] = validity mask
     __device__ __forceinline__ bool has(int q) const { return (e[7] >> q) & 1u; }
+    __device__ __forceinline__ bool remote() const { return (e[7] >> 15) & 1u; }   // a neighbour lives in another slab
 };
 
 __device__ __forceinline__ CRow load_crow(const uint4* __restrict__ rows, int64_t i) {
@@ -211,14 +212,20 @@ __global__ void __launch_bounds__(MAXT, 1) k_cl_train(const Args a) {
             const Row<CE> y = lds_row<CE>(Xc, i * RB);
             if (l == 0) store_row<CE>(a.states, (int64_t)n0 + i, y);
             // F(y) at node i (ell_math.cuh: ell_feval), neighbour rows through shared::cluster addresses
-            const bool any = e.e[7] != 0;
+            const bool any = (e.e[7] & 0x7fu) != 0;
             const Row<CE> p = project<CE>(Mr, y);
             Row<CE> xj[W];
             float s[W];
             float m = -3.0e38f;
+            if (__any_sync(__activemask(), e.remote())) {   // some row of this warp lives in another slab
+#pragma unroll
+                for (int q = 0; q < W; ++q) xj[q] = ldc_row<CE>(s_base[e.e[q] >> 24] + offXc + (e.e[q] & 0xffffffu));
+            } else {                                        // interior warp: plain shared-memory loads
+#pragma unroll
+                for (int q = 0; q < W; ++q) xj[q] = lds_row<CE>(Xc, e.e[q] & 0xffffffu);
+            }
 #pragma unroll
             for (int q = 0; q < W; ++q) {
-                xj[q] = ldc_row<CE>(s_base[e.e[q] >> 24] + offXc + (e.e[q] & 0xffffffu));
                 const float d = dot<CE>(p, xj[q]);
                 s[q] = e.has(q) ? d : -CUDART_INF_F;
                 m = fmaxf(m, s[q]);
@@ -296,14 +303,20 @@ __global__ void __launch_bounds__(MAXT, 1) k_cl_train(const Args a) {
                 Row<CE> go;
 #pragma unroll
                 for (int c = 0; c < CE; ++c) go.v[c] = b * gp.v[c];
-                const bool any = e.e[7] != 0;
+                const bool any = (e.e[7] & 0x7fu) != 0;
                 const Row<CE> p = project<CE>(Mu, xi);
                 Row<CE> xj[W];
                 float s[W];
                 float m = -3.0e38f;
+                if (__any_sync(__activemask(), e.remote())) {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) xj[q] = ldc_row<CE>(s_base[e.e[q] >> 24] + offX + (e.e[q] & 0xffffffu));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) xj[q] = lds_row<CE>(X, e.e[q] & 0xffffffu);
+                }
 #pragma unroll
                 for (int q = 0; q < W; ++q) {
-                    xj[q] = ldc_row<CE>(s_base[e.e[q] >> 24] + offX + (e.e[q] & 0xffffffu));
                     const float d = dot<CE>(p, xj[q]);
                     s[q] = e.has(q) ? d : -CUDART_INF_F;
                     m = fmaxf(m, s[q]);
@@ -356,12 +369,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_cl_train(const Args a) {
                     const Row<CE> xprev = ell::load_row_cg<CE>(xprev_g, (int64_t)n0 + j);
                     const Row<CE> xj = lds_row<CE>(X, j * RB);
                     Row<CE> g = lds_row<CE>(GS, j * RB);
+                    const bool warp_remote = __any_sync(__activemask(), e.remote());
 #pragma unroll
                     for (int q = 0; q < W; ++q) {
-                        const uint32_t base = s_base[e.e[q] >> 24], off = e.e[q] & 0xffffffu;
-                        const Row<CE> p = ldc_row<CE>(base + offP + off);
-                        const Row<CE> go = ldc_row<CE>(base + offGO + off);
-                        const float2 dl = ldc_f2(base + offDL + (CE == 4 ? (off >> 1) : off));
+                        const uint32_t off = e.e[q] & 0xffffffu;
+                        Row<CE> p, go;
+                        float2 dl;
+                        if (warp_remote) {
+                            const uint32_t base = s_base[e.e[q] >> 24];
+                            p = ldc_row<CE>(base + offP + off);
+                            go = ldc_row<CE>(base + offGO + off);
+                            dl = ldc_f2(base + offDL + (CE == 4 ? (off >> 1) : off));
+                        } else {
+                            p = lds_row<CE>(P, off);
+                            go = lds_row<CE>(GO, off);
+                            dl = *reinterpret_cast<const float2*>(DL + (CE == 4 ? (off >> 1) : off));
+                        }
                         const float sv = dot<CE>(p, xj) - dl.y;
                         const float alpha = ex2_approx(e.has(q) ? sv : -CUDART_INF_F);
                         const float c = (dot<CE>(go, xj) - dl.x) * LN2_F;
@@ -420,7 +443,7 @@ __global__ void __launch_bounds__(256) k_build_crows(const int32_t* __restrict__
         const int i = m0 + li;
         const int b = ptr[i], deg = ptr[i + 1] - b;
         uint32_t v[8];
-        bool ok = deg <= 7;
+        bool ok = deg <= 7, remote = false;
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
             int j = (ok && q < deg) ? idx[b + q] : i;
@@ -430,8 +453,9 @@ __global__ void __launch_bounds__(256) k_build_crows(const int32_t* __restrict__
             }
             const int lj = j - m0, r = lj / S;
             v[q] = ((uint32_t)r << 24) | (uint32_t)((lj - r * S) * rowbytes);
+            remote |= (r != li / S);
         }
-        v[7] = ok ? ((deg >= 7) ? 0x7fu : ((1u << deg) - 1u)) : 0u;
+        v[7] = ok ? (((deg >= 7) ? 0x7fu : ((1u << deg) - 1u)) | (remote ? 0x8000u : 0u)) : 0u;
         if (!ok) atomicAdd(bad, 1);
         rows[2 * (size_t)i] = make_uint4(v[0], v[1], v[2], v[3]);
         rows[2 * (size_t)i + 1] = make_uint4(v[4], v[5], v[6], v[7]);
@@ -516,6 +540,28 @@ extern "C" int gad_graph_build_cluster(const int32_t* ptr, const int32_t* idx, c
     return GAD_OK;
 }
 
+/* How many clusters of `cluster_size` CTAs (slabs of `slab_nodes`) the device can hold at once. */
+extern "C" int gad_cluster_occupancy(int CE, int cluster_size, int slab_nodes, int threads, int* max_active_clusters) {
+    GAD_CHECK_ARG((CE == 2 || CE == 4) && max_active_clusters, "gad_cluster_occupancy: bad arguments");
+    const size_t bytes = cl::make_layout(CE, slab_nodes, (threads + 31) / 32).total;
+    auto kernel = (CE == 4) ? (const void*)cl::k_cl_train<4, 6> : (const void*)cl::k_cl_train<2, 2>;
+    GAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (cluster_size > 8) GAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cluster_size * 64);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GAD_CUDA(cudaOccupancyMaxActiveClusters(max_active_clusters, kernel, &cfg));
+    return GAD_OK;
+}
+
 extern "C" size_t gad_cluster_workspace_bytes(int CE, int M, int cluster_size, int L) {
     return gad_ell_workspace_bytes(CE, M * cluster_size, L);
 }
@@ -547,6 +593,9 @@ extern "C" int gad_train_step_cluster(const gad_train_desc* d, int cluster_size,
     int threads = ((S + 3) / 4 + 31) / 32 * 32;   // about four rounds of nodes per thread
     if (threads < 128) threads = 128;
     if (threads > cl::MAXT) threads = cl::MAXT;
+    // two slabs per SM when their shared memory allows it: 256 threads x 125 registers each
+    if (2 * (cl::make_layout(d->CE, S, 8).total + 1024) <= 233472 && threads > 256) threads = 256;
+    if (getenv("GAD_CLUSTER_THREADS")) threads = atoi(getenv("GAD_CLUSTER_THREADS"));
     const int NACC = d->CE * d->CE + d->CE + 1;
     float* ws = reinterpret_cast<float*>(d->workspace);
     ell::Args a{};

@@ -296,6 +296,8 @@ int gad_graph_build_cluster(const int32_t* ptr, const int32_t* idx, const int32_
                             int max_mesh_nodes, int CE, int cluster_size, void* rows, int32_t* info,
                             void* stream);
 size_t gad_cluster_workspace_bytes(int CE, int M, int cluster_size, int L);
+/* Planning aid: clusters of this shape the device can hold at once (cudaOccupancyMaxActiveClusters). */
+int gad_cluster_occupancy(int CE, int cluster_size, int slab_nodes, int threads, int* max_active_clusters);
 int gad_train_step_cluster(const gad_train_desc* desc, int cluster_size, void* stream);
 
 /* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --
