@@ -57,6 +57,7 @@ SIGNATURES = {
     "gad_graph_build": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gad_graph_sort_rows": (_i, [_p, _p, _i64, _p, _p]),
     "gad_graph_check_tiles": (_i, [_p, _p, _i64, _p, _i, _p, _p]),
+    "gad_edge_masks": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p]),
     "gad_fingerprint": (_i, [_p, _sz, C.c_uint64, _p, _p]),
     "gad_prepare_weights": (_i, [_p, _p, _p, _i, _i, _i, _f, _p, _p]),
     "gad_weight_grads": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p]),

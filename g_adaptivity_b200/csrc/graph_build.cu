@@ -453,3 +453,46 @@ extern "C" int gad_fingerprint(const void* data, size_t bytes, uint64_t seed, ui
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
+
+// ---- edge masks of firedrake_mesh_to_PyG (src/data.py:465-494) on the device -----------------------
+// side_bits[v]: bit k set when node v lies on boundary marker k + 1 (the per-marker DirichletBC node
+// lists of :451-455, as a bit set).  Boundary = any bit; corner = more than one bit (:457-462).
+//   to_boundary  = dst on the boundary and src not                               (:465)
+//   to_corner    = dst is a corner                                                (:468)
+//   diff_boundary= both on the boundary, different marker lists, neither a corner (:479-494)
+// One thread per edge, coalesced; replaces three Python loops over the edge list.
+namespace gad {
+namespace {
+
+__global__ void __launch_bounds__(256) k_edge_masks(const int64_t* __restrict__ ei, int64_t E, const uint8_t* __restrict__ side_bits,
+                                                   int64_t N, uint8_t* __restrict__ to_boundary, uint8_t* __restrict__ to_corner,
+                                                   uint8_t* __restrict__ diff_boundary, int32_t* __restrict__ bad) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int64_t s = ei[e], d = ei[E + e];
+    if (s < 0 || s >= N || d < 0 || d >= N) {
+        atomicAdd(bad, 1);
+        to_boundary[e] = to_corner[e] = diff_boundary[e] = 0;
+        return;
+    }
+    const unsigned bs = side_bits[s], bd = side_bits[d];
+    const bool s_corner = __popc(bs) > 1, d_corner = __popc(bd) > 1;
+    to_boundary[e] = (bd != 0 && bs == 0) ? 1 : 0;
+    to_corner[e] = d_corner ? 1 : 0;
+    diff_boundary[e] = (bs != 0 && bd != 0 && bs != bd && !s_corner && !d_corner) ? 1 : 0;
+}
+
+}  // namespace
+}  // namespace gad
+
+extern "C" int gad_edge_masks(const int64_t* edge_index, int64_t E, const uint8_t* side_bits, int64_t N,
+                              uint8_t* to_boundary, uint8_t* to_corner, uint8_t* diff_boundary, int32_t* info,
+                              void* stream) {
+    GAD_CHECK_ARG(edge_index && side_bits && to_boundary && to_corner && diff_boundary && info && E >= 0 && N > 0,
+                  "gad_edge_masks: bad arguments");
+    if (E == 0) return GAD_OK;
+    gad::k_edge_masks<<<(unsigned)((E + 255) / 256), 256, 0, gad::as_stream(stream)>>>(edge_index, E, side_bits, N, to_boundary,
+                                                                                     to_corner, diff_boundary, info + 7);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}

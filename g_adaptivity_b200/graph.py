@@ -283,6 +283,27 @@ def _ensure_cluster(self, ce: int) -> bool:
 MeshGraph.ensure_cluster = _ensure_cluster
 
 
+def edge_masks(edge_index: torch.Tensor, side_bits: torch.Tensor):
+    """Device version of the three edge masks of `firedrake_mesh_to_PyG` (`src/data.py:465-494`):
+    `side_bits` uint8 [N] has bit k set when the node lies on boundary marker k + 1.  Returns bool
+    tensors (to_boundary_edge_mask, to_corner_nodes_mask, diff_boundary_edges_mask)."""
+    lib = _lib.load()
+    if edge_index.device.type != "cuda":
+        raise RuntimeError("edge_masks needs CUDA tensors (there is no CPU fallback)")
+    dev = edge_index.device
+    ei = edge_index.to(torch.int64).contiguous()
+    sb = side_bits.to(device=dev, dtype=torch.uint8).contiguous()
+    E, N = int(ei.shape[1]), int(sb.numel())
+    out = [torch.empty(E, dtype=torch.uint8, device=dev) for _ in range(3)]
+    info = torch.zeros(8, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gad_edge_masks(_lib.ptr(ei), E, _lib.ptr(sb), N, _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+                                      _lib.ptr(info), torch.cuda.current_stream(dev).cuda_stream), "gad_edge_masks")
+    if int(info[7].item()) != 0:
+        raise ValueError(f"edge_index holds {int(info[7])} node ids outside [0, {N})")
+    return tuple(o.bool() for o in out)
+
+
 def C_int():
     import ctypes
     return ctypes.c_int(0)

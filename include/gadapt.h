@@ -83,6 +83,14 @@ int gad_graph_sort_rows(const int32_t* ptr, const int32_t* idx, int64_t N, int32
 int gad_graph_check_tiles(const int32_t* rowptr, const int32_t* col, int64_t N,
                           const int32_t* tile_ptr, int T, int32_t* info, void* stream);
 
+/* Edge masks of firedrake_mesh_to_PyG (src/data.py:465-494) on the device.  edge_index int64 [2, E];
+ * side_bits uint8 [N], bit k set when node v is on boundary marker k + 1 (src/data.py:451-455); outputs
+ * uint8 [E]: to_boundary_edge_mask, to_corner_nodes_mask, diff_boundary_edges_mask.  Node ids outside
+ * [0, N) are counted into info[7]. */
+int gad_edge_masks(const int64_t* edge_index, int64_t E, const uint8_t* side_bits, int64_t N,
+                   uint8_t* to_boundary, uint8_t* to_corner, uint8_t* diff_boundary, int32_t* info,
+                   void* stream);
+
 /* Content fingerprint of a (contiguous, 8-byte aligned) device buffer: out[0..1] += a 128-bit
  * position-sensitive hash of its bytes under `seed`.  The host keys its graph cache on the
  * fingerprints of edge_index / masks / batch, so that the FRESH Batch object the reference's loader

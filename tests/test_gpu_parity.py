@@ -247,6 +247,33 @@ def test_config3_burgers_1d_200_repeated_calls():
     assert model._graphs.misses == 1 and model._graphs.hits == 3     # topology cached across calls
 
 
+@pytest.mark.parametrize("mesh_dims", [(15, 15), (7, 7), (200,), (2, 2)])
+def test_device_edge_masks_match_reference_semantics(mesh_dims):
+    """gad_edge_masks == the three Python loops of firedrake_mesh_to_PyG (src/data.py:465-494), as
+    restated by synth._masks_from_sides (the generator of every fixture), bit for bit."""
+    from g_adaptivity_b200 import graph as G
+    topo = synth.MeshTopology(mesh_dims)
+    n = topo.num_nodes
+    side_bits = np.zeros(n, dtype=np.uint8)
+    if len(mesh_dims) == 2:
+        m = mesh_dims[0]
+        ids = np.arange(n).reshape(m, m)
+        for k, nodes in enumerate((ids[:, 0], ids[:, -1], ids[0, :], ids[-1, :])):     # markers 1..4
+            side_bits[nodes] |= np.uint8(1 << k)
+    else:
+        side_bits[0] |= 1
+        side_bits[n - 1] |= 2
+    ei = torch.from_numpy(topo.edge_index).cuda()
+    tb, tc, db = G.edge_masks(ei, torch.from_numpy(side_bits))
+    assert torch.equal(tb.cpu(), torch.from_numpy(topo.to_boundary_edge_mask))
+    assert torch.equal(tc.cpu(), torch.from_numpy(topo.to_corner_nodes_mask))
+    assert torch.equal(db.cpu(), torch.from_numpy(topo.diff_boundary_edges_mask))
+    with pytest.raises(ValueError):
+        bad = ei.clone()
+        bad[0, 0] = n + 5
+        G.edge_masks(bad, torch.from_numpy(side_bits))
+
+
 def test_graph_cache_finds_fresh_batch_objects_by_content():
     """The loader of the reference yields a new Batch object per iteration (src/run_GNN.py:97-105):
     the graph cache must recognise the topology by content (device fingerprint), and must NOT confuse
