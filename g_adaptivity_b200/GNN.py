@@ -158,7 +158,7 @@ class GNN(nn.Module):
     def _graph(self, data, dev) -> MeshGraph:
         opt = self.opt
         flags = (bool(opt["fix_boundary"]), bool(opt["self_loops"]), self.CE, str(dev), opt.get("gad_tile_nodes"),
-                 bool(opt.get("gad_no_ell", False)), bool(opt.get("gad_no_wide", False)))
+                 bool(opt.get("gad_no_ell", False)), bool(opt.get("gad_no_wide", False)), bool(opt.get("gad_no_cluster", False)))
         key = GraphCache.key_of(data, flags)
         g = self._graphs.get(key)
         if g is not None:
@@ -185,6 +185,8 @@ class GNN(nn.Module):
                             use_ell=not opt.get("gad_no_ell", False))
         if opt.get("gad_no_wide", False):
             g._wide_tried = True          # keep the CSR streaming kernels (csrc/stream_kernels.cu)
+        if opt.get("gad_no_cluster", False):
+            g._no_cluster = True          # keep the streaming kernels for meshes beyond one CTA
         keep = (data.edge_index, data.batch) + tuple(getattr(data, n, None) for n in GraphCache.TOPOLOGY_FIELDS)
         self._graphs.put(key, g, keep)
         if ckey is not None:

@@ -431,6 +431,141 @@ __global__ void __launch_bounds__(MAXT, 1) k_cl_train(const Args a) {
     if (tid == 0) *a.counter = 0u;
 }
 
+// ---- forward only (module seam / inference): Euler layers or classical RK4 steps -------------------------
+// F(y) = A(y) y - y at node i of this slab, neighbour rows of the state buffer at `offX`
+template <int CE, int W>
+__device__ __forceinline__ Row<CE> cl_feval(const CRow& e, const Row<CE>& y, const float* __restrict__ Mu,
+                                            const unsigned char* __restrict__ Xloc, uint32_t offX,
+                                            const uint32_t* __restrict__ s_base) {
+    const bool any = (e.e[7] & 0x7fu) != 0;
+    const Row<CE> p = project<CE>(Mu, y);
+    Row<CE> xj[W];
+    float s[W];
+    float m = -3.0e38f;
+    if (__any_sync(__activemask(), e.remote())) {
+#pragma unroll
+        for (int q = 0; q < W; ++q) xj[q] = ldc_row<CE>(s_base[e.e[q] >> 24] + offX + (e.e[q] & 0xffffffu));
+    } else {
+#pragma unroll
+        for (int q = 0; q < W; ++q) xj[q] = lds_row<CE>(Xloc, e.e[q] & 0xffffffu);
+    }
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const float d = dot<CE>(p, xj[q]);
+        s[q] = e.has(q) ? d : -CUDART_INF_F;
+        m = fmaxf(m, s[q]);
+    }
+    float Z = 0.f;
+    Row<CE> o = zero_row<CE>();
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const float w = ex2_approx(s[q] - m);
+        Z += w;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) o.v[c] = fmaf(w, xj[q].v[c], o.v[c]);
+    }
+    const float rZ = any ? rcp_refined(Z) : 0.f;
+    Row<CE> k;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) k.v[c] = fmaf(o.v[c], rZ, -y.v[c]);
+    return k;
+}
+
+// One cluster per mesh, the state resident in shared memory for ALL layers / RK4 steps of the call
+// (BASELINE config 4: a 200x200 mesh, 64 RK4 steps = 256 F-evaluations, is one launch of 16 CTAs
+// instead of 256 dependent launches).  Inputs are the raw features (src/GNN.py:225-239).
+template <int CE, int W, int METHOD>
+__global__ void __launch_bounds__(MAXT, 1) k_cl_fwd(const Args a) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const Layout lay = make_layout(CE, a.cap_nodes, (nthr + 31) >> 5);
+    unsigned char* Xc = smem + lay.xa;
+    unsigned char* Xn = smem + lay.xb;
+    unsigned char* XB = smem + lay.p;    // RK4: the step's base state
+    unsigned char* AC = smem + lay.gs;   // RK4: k1 + 2 k2 + 2 k3
+    float* Mu = reinterpret_cast<float*>(smem + lay.mu);
+    __shared__ uint32_t s_base[16];
+    const uint32_t C = cluster_size(), rank = cluster_rank();
+    const int mesh = (int)(blockIdx.x / C);
+    const int m0 = a.tile_ptr[mesh], NM = a.tile_ptr[mesh + 1] - m0;
+    const int S = ((NM + (int)C - 1) / (int)C + 3) & ~3;
+    const int n0 = m0 + (int)rank * S;
+    const int NT = max(0, min(S, NM - (int)rank * S));
+    if (tid < 16) s_base[tid] = (tid < (int)C) ? mapa(smem_u32(smem), (uint32_t)tid) : 0u;
+    for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+    const size_t state_stride = (size_t)a.N * CE;
+    const uint4* Rin = a.ell_in + 2 * (size_t)n0;
+    ell::assemble_rows<CE>(a, n0, NT, false, nullptr, nullptr, nullptr, Xc, a.states);
+    cluster_sync();
+    uint32_t offXc = lay.xa, offXn = lay.xb;
+    for (int l = 0; l < a.L; ++l) {
+        if (a.Lw > 1 && l > 0) {
+            __syncthreads();
+            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+            __syncthreads();
+        }
+        const float h = a.tau[l];
+        const bool last = (l == a.L - 1);
+        float* st_out = (a.states && !last) ? a.states + (size_t)(l + 1) * state_stride : nullptr;
+        if constexpr (METHOD == GAD_METHOD_EULER) {
+            for (int i = tid; i < NT; i += nthr) {
+                const CRow e = load_crow(Rin, i);
+                const Row<CE> y = lds_row<CE>(Xc, i * RB);
+                const Row<CE> k = cl_feval<CE, W>(e, y, Mu, Xc, offXc, s_base);
+                Row<CE> xn;
+#pragma unroll
+                for (int c = 0; c < CE; ++c) xn.v[c] = fmaf(h, k.v[c], y.v[c]);
+                sts_row<CE>(Xn, i * RB, xn);
+                if (st_out) store_row<CE>(st_out, (int64_t)n0 + i, xn);
+                if (last) ell::store_dims<CE>(a.x_phys, (int64_t)n0 + i, a.dim, xn);
+            }
+            cluster_sync();
+            unsigned char* t = Xc; Xc = Xn; Xn = t;
+            const uint32_t u = offXc; offXc = offXn; offXn = u;
+        } else {
+            // classical RK4 on F (extension; same staging as ell_kernels.cuh: k_ell_fwd)
+            const float cin[4] = {0.5f * h, 0.5f * h, h, 0.f};
+            const float wacc[4] = {1.f, 2.f, 2.f, 1.f};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                for (int i = tid; i < NT; i += nthr) {
+                    const CRow e = load_crow(Rin, i);
+                    const Row<CE> y = lds_row<CE>(Xc, i * RB);
+                    const Row<CE> k = cl_feval<CE, W>(e, y, Mu, Xc, offXc, s_base);
+                    Row<CE> base, acc, out;
+                    if (s == 0) {
+                        base = y;
+                        acc = k;
+                        sts_row<CE>(XB, i * RB, y);
+                    } else {
+                        base = lds_row<CE>(XB, i * RB);
+                        acc = lds_row<CE>(AC, i * RB);
+#pragma unroll
+                        for (int c = 0; c < CE; ++c) acc.v[c] = fmaf(wacc[s], k.v[c], acc.v[c]);
+                    }
+                    if (s < 3) {
+                        sts_row<CE>(AC, i * RB, acc);
+#pragma unroll
+                        for (int c = 0; c < CE; ++c) out.v[c] = fmaf(cin[s], k.v[c], base.v[c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CE; ++c) out.v[c] = fmaf(h * (1.0f / 6.0f), acc.v[c], base.v[c]);
+                        if (st_out) store_row<CE>(st_out, (int64_t)n0 + i, out);
+                        if (last) ell::store_dims<CE>(a.x_phys, (int64_t)n0 + i, a.dim, out);
+                    }
+                    sts_row<CE>(Xn, i * RB, out);
+                }
+                cluster_sync();
+                unsigned char* t = Xc; Xc = Xn; Xn = t;
+                const uint32_t u = offXc; offXc = offXn; offXn = u;
+            }
+        }
+    }
+    cluster_sync();   // nobody leaves while a peer may still read its shared memory
+}
+
 // ---- cluster rows from the (row-sorted) CSR / CSC walk arrays -----------------------------------------
 // grid.y = mesh; e_q = (rank << 24) | (row-in-slab * rowbytes); unused slots = the node itself, masked.
 __global__ void __launch_bounds__(256) k_build_crows(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
@@ -506,14 +641,15 @@ int launch_t(const Args& a, int C, int grid, int threads, cudaStream_t st) {
 
 using namespace gad;
 
-extern "C" int gad_cluster_plan(int CE, int max_mesh_nodes, int* cluster_size, int* slab_nodes) {
+extern "C" int gad_cluster_plan(int CE, int max_mesh_nodes, int max_cluster, int* cluster_size, int* slab_nodes) {
     GAD_CHECK_ARG((CE == 2 || CE == 4) && max_mesh_nodes > 0 && cluster_size && slab_nodes, "gad_cluster_plan: bad arguments");
     const int cap = cl::slab_cap(CE);
     // Measured on B200 (64 x 100x100 meshes): clusters of 4 run 146 us/step, of 8 253 us, of 16 217 us
     // against 204 us on the streaming kernels -- GPC packing and barrier cost grow with the cluster --
     // so the plan stops at 4 slabs (meshes up to ~12.6 k nodes) unless GAD_CLUSTER_MAX says otherwise.
     const int cmin = getenv("GAD_CLUSTER_MIN") ? atoi(getenv("GAD_CLUSTER_MIN")) : 2;
-    const int cmax = getenv("GAD_CLUSTER_MAX") ? atoi(getenv("GAD_CLUSTER_MAX")) : 4;
+    // (max_cluster <= 0: that default; the forward-only kernel of a single large mesh takes up to 16)
+    const int cmax = getenv("GAD_CLUSTER_MAX") ? atoi(getenv("GAD_CLUSTER_MAX")) : (max_cluster > 0 ? max_cluster : 4);
     for (int C = 2; C <= 16 && C <= cmax; C *= 2) {
         if (C < cmin) continue;
         const int S = ((max_mesh_nodes + C - 1) / C + 3) & ~3;
@@ -679,4 +815,82 @@ extern "C" int gad_train_step_cluster(const gad_train_desc* d, int cluster_size,
     if (d->CE == 4) return cl::launch_t<4, 3>(a, C, grid, threads, st);
     if (w <= 2) return cl::launch_t<2, 2>(a, C, grid, threads, st);
     return cl::launch_t<2, 3>(a, C, grid, threads, st);
+}
+
+namespace gad {
+namespace cl {
+template <int CE, int W, int METHOD>
+int launch_fwd_t(const Args& a, int C, int grid, int threads, cudaStream_t st) {
+    const size_t bytes = make_layout(CE, a.cap_nodes, (threads + 31) / 32).total;
+    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "cluster kernel: slab of %d nodes needs %zu B of shared memory",
+                  a.cap_nodes, bytes);
+    GAD_CUDA(cudaFuncSetAttribute(k_cl_fwd<CE, W, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (C > 8) GAD_CUDA(cudaFuncSetAttribute(k_cl_fwd<CE, W, METHOD>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GAD_CUDA(cudaLaunchKernelEx(&cfg, k_cl_fwd<CE, W, METHOD>, a));
+    count_launch(1);
+    return GAD_OK;
+}
+}  // namespace cl
+}  // namespace gad
+
+/* Deformer forward from the raw inputs on cluster-resident meshes, ONE launch for all L layers / RK4
+ * steps (gad_deform_fwd_ell_raw's contract with cluster rows, mesh_ptr [M + 1] and the cluster size). */
+extern "C" int gad_deform_fwd_cluster(const void* crows_in, const int32_t* mesh_ptr, int M, int max_mesh_nodes,
+                                      int max_deg, int cluster_size, int64_t N, const float* x_comp, const float* f,
+                                      const float* uu, const float* f_scale, const float* uu_scale, int dim, int CE,
+                                      const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
+                                      float* states, void* stream) {
+    GAD_CHECK_ARG(crows_in && mesh_ptr && x_comp && Mu && tau && x_phys, "gad_deform_fwd_cluster: null pointer");
+    GAD_CHECK_ARG(N > 0 && M > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L) && (CE == 2 || CE == 4),
+                  "gad_deform_fwd_cluster: N=%lld M=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, M, L, dim, CE, Lw);
+    GAD_CHECK_ARG(dim + (f ? 1 : 0) + (uu ? 1 : 0) <= CE, "gad_deform_fwd_cluster: input features exceed CE=%d", CE);
+    GAD_CHECK_ARG(method == GAD_METHOD_EULER || method == GAD_METHOD_RK4, "gad_deform_fwd_cluster: unknown method %d", method);
+    const int C = cluster_size;
+    GAD_CHECK_ARG(C >= 2 && C <= 16 && (C & (C - 1)) == 0, "gad_deform_fwd_cluster: cluster size %d", C);
+    const int S = ((max_mesh_nodes + C - 1) / C + 3) & ~3;
+    int threads = ((S + 3) / 4 + 31) / 32 * 32;
+    if (threads < 128) threads = 128;
+    if (threads > cl::MAXT) threads = cl::MAXT;
+    ell::Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(crows_in);
+    a.tile_ptr = mesh_ptr;
+    a.T = M * C;
+    a.cap_nodes = S;
+    a.N = N;
+    a.Mu = Mu;
+    a.tau = tau;
+    a.Lw = Lw;
+    a.L = L;
+    a.dim = dim;
+    a.x_comp = x_comp;
+    a.f = f;
+    a.uu = uu;
+    a.f_scale = f_scale;
+    a.uu_scale = uu_scale;
+    a.x_phys = x_phys;
+    a.states = states;
+    const int w = cl::slots_for(max_deg);
+    cudaStream_t st = as_stream(stream);
+    const int grid = M * C;
+#define GAD_CL_FWD(CE_, W_)                                                                          \
+    return method == GAD_METHOD_EULER ? cl::launch_fwd_t<CE_, W_, GAD_METHOD_EULER>(a, C, grid, threads, st) \
+                                      : cl::launch_fwd_t<CE_, W_, GAD_METHOD_RK4>(a, C, grid, threads, st)
+    if (CE == 4 && w == 6) { GAD_CL_FWD(4, 6); }
+    if (CE == 4 && w == 7) { GAD_CL_FWD(4, 7); }
+    if (CE == 4) { GAD_CL_FWD(4, 3); }
+    if (w <= 2) { GAD_CL_FWD(2, 2); }
+    GAD_CL_FWD(2, 3);
+#undef GAD_CL_FWD
 }

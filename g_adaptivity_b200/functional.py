@@ -146,6 +146,23 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
     if x_comp.dim() == 1:
         x_comp = x_comp.unsqueeze(-1)
     N = x_comp.shape[0]
+    if graph.tile_ptr is None and not force_stream and not getattr(graph, "_no_cluster", False) and graph.ensure_cluster_fwd(CE):
+        # meshes beyond one CTA: one thread-block cluster per mesh, ONE launch for all layers / RK4 steps
+        lib = _lib.load()
+        if f is not None and dim >= CE:
+            f = None
+        if uu is not None and dim + (1 if f is not None else 0) >= CE:
+            uu = None
+        f, uu = _f32(f), _f32(uu)
+        L, Lw = int(tau.numel()), int(Mu.shape[0])
+        x_phys = torch.empty((N, dim), dtype=torch.float32, device=x_comp.device)
+        with torch.cuda.device(x_comp.device):
+            _lib.check(lib.gad_deform_fwd_cluster(
+                _lib.ptr(graph.clf_in), _lib.ptr(graph.clf_mesh_ptr), len(graph.mesh_sizes), max(graph.mesh_sizes),
+                graph.clf_deg, graph.clf_C, N, _lib.ptr(x_comp), _lib.ptr(f), _lib.ptr(uu), _lib.ptr(f_scale),
+                _lib.ptr(uu_scale), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys), _lib.ptr(states),
+                _stream(x_comp)), "gad_deform_fwd_cluster")
+        return x_phys
     if not (graph.tile_ptr is not None and not force_stream and use_ell(graph, CE)):
         x0 = states[0] if states is not None else torch.empty((N, CE), dtype=torch.float32, device=x_comp.device)
         pack_features(x_comp, f, uu, f_scale, uu_scale, CE, out=x0)

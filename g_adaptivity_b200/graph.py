@@ -245,22 +245,13 @@ def _ensure_wide(self, ce: int) -> bool:
 MeshGraph.ensure_wide = _ensure_wide
 
 
-def _ensure_cluster(self, ce: int) -> bool:
-    """Cluster rows for the cluster-resident training kernel (csrc/cl_kernels.cu): meshes that do not
-    fit one CTA but fit a thread-block cluster of up to 16 (degree <= 7, CE in {2, 4}, every mesh a
-    connected component of the batch).  Built once, on first use."""
-    if self._cl_tried:
-        return self.cl_in is not None
-    self._cl_tried = True
+def _build_cluster_rows(self, ce: int, max_cluster: int):
+    """(rows_in, rows_out, C, S, mesh_ptr) for clusters of at most `max_cluster` CTAs, or None."""
     import ctypes
-    import os
-    if (os.environ.get("GAD_NO_CLUSTER") or ce not in (2, 4) or self.E == 0 or self.mesh_sizes is None
-            or self.tile_ptr is not None or max(self.max_in_deg, self.max_out_deg) > 7):
-        return False
     lib = _lib.load()
     Cc, Sc = ctypes.c_int(0), ctypes.c_int(0)
-    if lib.gad_cluster_plan(ce, max(self.mesh_sizes), ctypes.byref(Cc), ctypes.byref(Sc)) != 0:
-        return False
+    if lib.gad_cluster_plan(ce, max(self.mesh_sizes), max_cluster, ctypes.byref(Cc), ctypes.byref(Sc)) != 0:
+        return None
     M = len(self.mesh_sizes)
     mp = np.concatenate([[0], np.cumsum(np.asarray(self.mesh_sizes, dtype=np.int64))]).astype(np.int32)
     mesh_ptr = torch.from_numpy(mp).to(self.device)
@@ -274,13 +265,55 @@ def _ensure_cluster(self, ce: int) -> bool:
                                                    ce, Cc.value, _lib.ptr(out), _lib.ptr(self._info), stream),
                        "gad_graph_build_cluster")
     if int(self._info[4].item()) != 0:      # an edge leaves its mesh or a row is too long
+        return None
+    return ci, co, Cc.value, Sc.value, mesh_ptr
+
+
+def _cluster_eligible(self, ce: int) -> bool:
+    import os
+    return not (os.environ.get("GAD_NO_CLUSTER") or ce not in (2, 4) or self.E == 0 or self.mesh_sizes is None
+                or self.tile_ptr is not None or max(self.max_in_deg, self.max_out_deg) > 7)
+
+
+def _ensure_cluster(self, ce: int) -> bool:
+    """Cluster rows for the cluster-resident TRAINING kernel (csrc/cl_kernels.cu: k_cl_train): meshes
+    that do not fit one CTA but fit a thread-block cluster of up to 4 (degree <= 7, CE in {2, 4},
+    every mesh a connected component of the batch).  Built once, on first use."""
+    if self._cl_tried:
+        return self.cl_in is not None
+    self._cl_tried = True
+    if not _cluster_eligible(self, ce):
         return False
-    self.cl_in, self.cl_out, self.cl_C, self.cl_S, self.mesh_ptr = ci, co, Cc.value, Sc.value, mesh_ptr
+    r = _build_cluster_rows(self, ce, 0)
+    if r is None:
+        return False
+    self.cl_in, self.cl_out, self.cl_C, self.cl_S, self.mesh_ptr = r
     self.cl_deg = max(self.max_in_deg, self.max_out_deg)
     return True
 
 
+def _ensure_cluster_fwd(self, ce: int) -> bool:
+    """Cluster rows for the forward-only kernel (k_cl_fwd), which takes clusters of up to 16 CTAs
+    (a 200x200 mesh); the training rows are reused when they exist."""
+    if getattr(self, "_clf_tried", False):
+        return self.clf_in is not None
+    self._clf_tried = True
+    self.clf_in = None
+    if not _cluster_eligible(self, ce):
+        return False
+    if _ensure_cluster(self, ce):
+        self.clf_in, self.clf_C, self.clf_mesh_ptr = self.cl_in, self.cl_C, self.mesh_ptr
+    else:
+        r = _build_cluster_rows(self, ce, 16)
+        if r is None:
+            return False
+        self.clf_in, _, self.clf_C, _, self.clf_mesh_ptr = r
+    self.clf_deg = max(self.max_in_deg, self.max_out_deg)
+    return True
+
+
 MeshGraph.ensure_cluster = _ensure_cluster
+MeshGraph.ensure_cluster_fwd = _ensure_cluster_fwd
 
 
 def edge_masks(edge_index: torch.Tensor, side_bits: torch.Tensor):

@@ -299,7 +299,8 @@ int gad_train_step_ell(const gad_train_desc* desc, void* stream);
  * (32 bytes per node); gad_train_step_cluster has gad_train_step_ell's contract with ell_in / ell_out
  * = cluster rows, tile_ptr = mesh_ptr [T + 1], T = meshes, max_tile_nodes = largest mesh, workspace of
  * gad_cluster_workspace_bytes.  Replaces src/run_GNN.py:99-131 for such meshes in one launch. */
-int gad_cluster_plan(int CE, int max_mesh_nodes, int* cluster_size, int* slab_nodes);
+int gad_cluster_plan(int CE, int max_mesh_nodes, int max_cluster /* <= 0: default (4) */, int* cluster_size,
+                     int* slab_nodes);
 int gad_graph_build_cluster(const int32_t* ptr, const int32_t* idx, const int32_t* mesh_ptr, int M,
                             int max_mesh_nodes, int CE, int cluster_size, void* rows, int32_t* info,
                             void* stream);
@@ -307,6 +308,12 @@ size_t gad_cluster_workspace_bytes(int CE, int M, int cluster_size, int L);
 /* Planning aid: clusters of this shape the device can hold at once (cudaOccupancyMaxActiveClusters). */
 int gad_cluster_occupancy(int CE, int cluster_size, int slab_nodes, int threads, int* max_active_clusters);
 int gad_train_step_cluster(const gad_train_desc* desc, int cluster_size, void* stream);
+/* Forward only (module seam / inference), all L Euler layers or RK4 steps in ONE launch with the state
+ * resident in the cluster's shared memory: gad_deform_fwd_ell_raw's contract over cluster rows. */
+int gad_deform_fwd_cluster(const void* crows_in, const int32_t* mesh_ptr, int M, int max_mesh_nodes, int max_deg,
+                           int cluster_size, int64_t N, const float* x_comp, const float* f, const float* uu,
+                           const float* f_scale, const float* uu_scale, int dim, int CE, const float* Mu, int Lw,
+                           const float* tau, int L, int method, float* x_phys, float* states, void* stream);
 
 /* ---- operator seam: one GRAND_plusConv / GRAND_conv layer (src/GRAND_plus.py:204-267,380-382) --
  * res = A(x) x - x  for x [N, CE];  alpha (optional) [E] in filtered edge-list order.

@@ -214,10 +214,22 @@ def test_config2_30x30_batch256_fwd_bwd(force_stream):
 
 
 def test_large_mesh_streams_through_wide_rows():
-    """A 64x64 mesh does not fit one CTA: forward + backward run on the streaming ELL kernels."""
-    model, *_ = _compare_with_oracle((64, 64), 3)
+    """A 64x64 mesh does not fit one CTA: with the cluster kernels switched off, forward + backward
+    run on the streaming ELL kernels."""
+    model, *_ = _compare_with_oracle((64, 64), 3, gad_no_cluster=True)
     g = model.last_graph
-    assert g.tile_ptr is None and g.wide_in is not None and g.wide_deg <= 7
+    assert g.tile_ptr is None and g.wide_in is not None and g.wide_deg <= 7 and getattr(g, "clf_in", None) is None
+
+
+@pytest.mark.parametrize("over", [{}, {"ode_method": "rk4", "num_layers": 5}, {"share_conv": False, "learn_step": True}])
+def test_large_mesh_forward_on_a_cluster(over):
+    """Module-seam forward of meshes beyond one CTA = ONE launch of the cluster-resident kernel
+    (backward, where defined, on the streaming ELL kernels from the states it saved)."""
+    # gradients only for the shared-weight case: with one weight set PER LAYER the layer-0 gradients of a
+    # 64x64 mesh cancel so strongly that the fp32 oracle itself is 1.5e-5 from the fp64 value
+    model, *_ = _compare_with_oracle((64, 64), 3, over=over, backward=not over)
+    g = model.last_graph
+    assert g.tile_ptr is None and g.clf_in is not None and g.clf_C >= 2
 
 
 def test_config3_burgers_1d_200_repeated_calls():
@@ -331,7 +343,9 @@ def test_inference_session_replays_burgers_rollout():
 def test_config4_200x200_rk4_64_steps_forward():
     over = {"ode_method": "rk4", "num_layers": 64}
     model, out, ref_out, data = _compare_with_oracle((200, 200), 1, over=over, backward=False)
-    assert model.last_graph.tile_ptr is None
+    assert model.last_graph.tile_ptr is None and model.last_graph.clf_C == 16     # one cluster of 16 CTAs, one launch
+    model2, *_ = _compare_with_oracle((200, 200), 1, over=over, backward=False, gad_no_cluster=True)   # 256 launches
+    assert getattr(model2.last_graph, "clf_in", None) is None
 
 
 def test_rk4_mesh_resident_matches_oracle():
