@@ -255,3 +255,32 @@ def test_cluster_training_is_deterministic_and_matches_streaming_steps():
     assert finals[0][0] == finals[1][0] and torch.equal(finals[0][1], finals[1][1])     # bit-reproducible
     assert finals[0][0][-1] < finals[0][0][0]
     assert (finals[0][1] - finals[2][1]).abs().max().item() <= 2e-4 * finals[2][1].abs().max().item()
+
+
+def test_host_fed_loop_packed_buffers_equal_per_tensor_copies():
+    """run_from_host over pack_host buffers (one H2D copy per step) == over Batch objects (one copy per
+    tensor) == resident-batch steps: same losses, same parameters."""
+    opt, ds, _, ref = _case((20, 20), 16, seed=11)
+    batches = [synth.make_batch((20, 20), 16, seed=20 + r) for r in range(3)]
+    for b in batches:
+        b.pin_memory()
+    outs = []
+    for mode in ("resident", "batches", "packed"):
+        model = cuda_model(ds, opt, ref.state_dict())
+        tr = DeformerTrainer(model, lr=1e-2)
+        sids = [tr.add_batch(b) for b in batches]
+        if mode == "resident":
+            losses = []
+            for k in range(9):
+                l = tr.step(sids[k % 3])
+                with torch.cuda.stream(tr.stream):
+                    losses.append(l.clone())
+            tr.synchronize()
+            losses = torch.stack([x.cpu() for x in losses]).reshape(-1)
+        else:
+            src = batches if mode == "batches" else [tr.pack_host(sid, b) for sid, b in zip(sids, batches)]
+            losses = tr.run_from_host(src, 9).clone()
+        outs.append((losses, tr.flat.clone().cpu()))
+    for losses, flat in outs[1:]:
+        assert torch.equal(losses, outs[0][0])
+        assert torch.equal(flat, outs[0][1])
