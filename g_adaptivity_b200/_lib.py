@@ -80,6 +80,7 @@ SIGNATURES = {
                                   _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gad_train_step_ell": (_i, [C.POINTER(TrainDesc), _p]),
     "gad_cluster_plan": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "gad_deform_bwd_cluster": (_i, [_p, _p, _p, _i, _i, _i, _i, _i64, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "gad_deform_fwd_cluster": (_i, [_p, _p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
     "gad_graph_build_cluster": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "gad_cluster_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -116,13 +116,155 @@ __host__ __device__ inline Layout make_layout(int CE, int cap_nodes, int nwarps)
     return s;
 }
 
+// ---- backward of one slab (shared by the train and the backward kernels) ---------------------------------
+// On entry: X = x^{L-1} rows of the slab (buffer at cluster offset offX), GS = dL/dx^L rows, Mu = weights of
+// layer L-1; GO (offset offGO) is free.  Per-CTA partial rows go to a.partials[blockIdx.x].
+template <int CE, int W>
+__device__ __forceinline__ void cl_backward(const Args& a, const Layout& lay, int n0, int NT, unsigned char* X,
+                                            unsigned char* GO, uint32_t offX, uint32_t offGO, unsigned char* P,
+                                            unsigned char* DL, unsigned char* GS, const uint4* __restrict__ Rin,
+                                            const uint4* __restrict__ Rout, float* Mu, float* red,
+                                            const uint32_t* __restrict__ s_base) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    constexpr int NACC = MUSZ + 1;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const size_t state_stride = (size_t)a.N * CE;
+    const uint32_t offP = lay.p, offDL = lay.dl;
+    const bool per_layer = (a.Lw > 1);
+    const int slots = per_layer ? a.L : 1;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    for (int l = a.L - 1; l >= 0; --l) {
+        if (per_layer && l < a.L - 1) {
+            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+            __syncthreads();
+        }
+        const float b = __ldcg(a.tau + l);
+        float gtau = 0.f;
+        // phase A: destination pass (ell_math.cuh: ell_bwd_dst)
+        for (int i = tid; i < NT; i += nthr) {
+            const CRow e = load_crow(Rin, i);
+            const Row<CE> xi = lds_row<CE>(X, i * RB);
+            const Row<CE> gp = lds_row<CE>(GS, i * RB);
+            Row<CE> go;
+#pragma unroll
+            for (int c = 0; c < CE; ++c) go.v[c] = b * gp.v[c];
+            const bool any = (e.e[7] & 0x7fu) != 0;
+            const Row<CE> p = project<CE>(Mu, xi);
+            Row<CE> xj[W];
+            float s[W];
+            float m = -3.0e38f;
+            if (__any_sync(__activemask(), e.remote())) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) xj[q] = ldc_row<CE>(s_base[e.e[q] >> 24] + offX + (e.e[q] & 0xffffffu));
+            } else {
+#pragma unroll
+                for (int q = 0; q < W; ++q) xj[q] = lds_row<CE>(X, e.e[q] & 0xffffffu);
+            }
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const float d = dot<CE>(p, xj[q]);
+                s[q] = e.has(q) ? d : -CUDART_INF_F;
+                m = fmaxf(m, s[q]);
+            }
+            float Z = 0.f;
+            Row<CE> o = zero_row<CE>();
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                s[q] = ex2_approx(s[q] - m);
+                Z += s[q];
+#pragma unroll
+                for (int c = 0; c < CE; ++c) o.v[c] = fmaf(s[q], xj[q].v[c], o.v[c]);
+            }
+            const float rZ = any ? rcp_refined(Z) : 0.f;
+#pragma unroll
+            for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
+            const float D = dot<CE>(go, o);
+            const float lse = any ? m + lg2_approx(Z) : 0.f;
+            const float scale = rZ * LN2_F;
+            Row<CE> t = zero_row<CE>();
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const float ds = (s[q] * scale) * (dot<CE>(go, xj[q]) - D);
+#pragma unroll
+                for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj[q].v[c], t.v[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < CE; ++c) gtau = fmaf(gp.v[c], o.v[c] - xi.v[c], gtau);
+#pragma unroll
+            for (int aa = 0; aa < CE; ++aa)
+#pragma unroll
+                for (int bb = 0; bb < CE; ++bb) acc[aa * CE + bb] = fmaf(xi.v[aa], t.v[bb], acc[aa * CE + bb]);
+#pragma unroll
+            for (int bb = 0; bb < CE; ++bb) acc[CE * CE + bb] += t.v[bb];
+            const Row<CE> Mt = apply_M<CE>(Mu, t);
+            Row<CE> gs;
+#pragma unroll
+            for (int c = 0; c < CE; ++c) gs.v[c] = fmaf(1.0f - b, gp.v[c], Mt.v[c]);
+            sts_row<CE>(P, i * RB, p);
+            *reinterpret_cast<float2*>(DL + (size_t)i * 8) = make_float2(D, lse);
+            sts_row<CE>(GO, i * RB, go);
+            sts_row<CE>(GS, i * RB, gs);
+        }
+        if (l > 0 || a.g_x0) {
+            cluster_sync();   // P, DL, GO of every slab visible; every gather of X done
+            // phase B: source pass (ell_math.cuh: ell_bwd_src), then X <- x^{l-1}
+            const float* xprev_g = (l > 0) ? a.states + (size_t)(l - 1) * state_stride : nullptr;
+            for (int j = tid; j < NT; j += nthr) {
+                const CRow e = load_crow(Rout, j);
+                Row<CE> xprev = zero_row<CE>();
+                if (xprev_g) xprev = ell::load_row_cg<CE>(xprev_g, (int64_t)n0 + j);
+                const Row<CE> xj = lds_row<CE>(X, j * RB);
+                Row<CE> g = lds_row<CE>(GS, j * RB);
+                const bool warp_remote = __any_sync(__activemask(), e.remote());
+#pragma unroll
+                for (int q = 0; q < W; ++q) {
+                    const uint32_t off = e.e[q] & 0xffffffu;
+                    Row<CE> p, go;
+                    float2 dl;
+                    if (warp_remote) {
+                        const uint32_t base = s_base[e.e[q] >> 24];
+                        p = ldc_row<CE>(base + offP + off);
+                        go = ldc_row<CE>(base + offGO + off);
+                        dl = ldc_f2(base + offDL + (CE == 4 ? (off >> 1) : off));
+                    } else {
+                        p = lds_row<CE>(P, off);
+                        go = lds_row<CE>(GO, off);
+                        dl = *reinterpret_cast<const float2*>(DL + (CE == 4 ? (off >> 1) : off));
+                    }
+                    const float sv = dot<CE>(p, xj) - dl.y;
+                    const float alpha = ex2_approx(e.has(q) ? sv : -CUDART_INF_F);
+                    const float c = (dot<CE>(go, xj) - dl.x) * LN2_F;
+#pragma unroll
+                    for (int ch = 0; ch < CE; ++ch) g.v[ch] = fmaf(alpha, fmaf(c, p.v[ch], go.v[ch]), g.v[ch]);
+                }
+                sts_row<CE>(GS, j * RB, g);
+                if (xprev_g) sts_row<CE>(X, j * RB, xprev);
+                else store_row<CE>(a.g_x0, (int64_t)n0 + j, g);
+            }
+            cluster_sync();   // X of the next layer complete; gathers of P / DL / GO done
+        }
+        if (per_layer) {
+            acc[NACC - 1] = gtau;
+            block_reduce<NACC>(acc, red, a.partials + ((size_t)blockIdx.x * slots + l) * NACC);
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+        } else if (a.tau_partials) {
+            float one[1] = {gtau};
+            block_reduce<1>(one, red, a.tau_partials + (size_t)blockIdx.x * a.L + l);
+        }
+    }
+    if (!per_layer) block_reduce<NACC>(acc, red, a.partials + (size_t)blockIdx.x * NACC);
+}
+
 // a.tile_ptr = mesh_ptr [M + 1]; a.T = number of per-CTA partial rows (= grid); a.cap_nodes = slab capacity;
 // a.ell_in / a.ell_out = cluster rows (2 x uint4 per node)
 template <int CE, int W>
 __global__ void __launch_bounds__(MAXT, 1) k_cl_train(const Args a) {
     constexpr uint32_t RB = CE * sizeof(float);
     constexpr int MUSZ = CE * CE + CE;
-    constexpr int NACC = MUSZ + 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const Layout lay = make_layout(CE, a.cap_nodes, (nthr + 31) >> 5);
@@ -279,135 +421,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_cl_train(const Args a) {
     tr.mark();
 
     // ---- backward: Xc = x^{L-1}, Xn = free -> GO ---------------------------------------------------
-    {
-        unsigned char* X = Xc;
-        unsigned char* GO = Xn;
-        const uint32_t offX = offXc, offGO = offXn, offP = lay.p, offDL = lay.dl;
-        const bool per_layer = (a.Lw > 1);
-        const int slots = per_layer ? a.L : 1;
-        float acc[NACC];
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-        for (int l = a.L - 1; l >= 0; --l) {
-            if (per_layer && l < a.L - 1) {
-                for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
-                __syncthreads();
-            }
-            const float b = __ldcg(a.tau + l);
-            float gtau = 0.f;
-            // phase A: destination pass (ell_math.cuh: ell_bwd_dst)
-            for (int i = tid; i < NT; i += nthr) {
-                const CRow e = load_crow(Rin, i);
-                const Row<CE> xi = lds_row<CE>(X, i * RB);
-                const Row<CE> gp = lds_row<CE>(GS, i * RB);
-                Row<CE> go;
-#pragma unroll
-                for (int c = 0; c < CE; ++c) go.v[c] = b * gp.v[c];
-                const bool any = (e.e[7] & 0x7fu) != 0;
-                const Row<CE> p = project<CE>(Mu, xi);
-                Row<CE> xj[W];
-                float s[W];
-                float m = -3.0e38f;
-                if (__any_sync(__activemask(), e.remote())) {
-#pragma unroll
-                    for (int q = 0; q < W; ++q) xj[q] = ldc_row<CE>(s_base[e.e[q] >> 24] + offX + (e.e[q] & 0xffffffu));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < W; ++q) xj[q] = lds_row<CE>(X, e.e[q] & 0xffffffu);
-                }
-#pragma unroll
-                for (int q = 0; q < W; ++q) {
-                    const float d = dot<CE>(p, xj[q]);
-                    s[q] = e.has(q) ? d : -CUDART_INF_F;
-                    m = fmaxf(m, s[q]);
-                }
-                float Z = 0.f;
-                Row<CE> o = zero_row<CE>();
-#pragma unroll
-                for (int q = 0; q < W; ++q) {
-                    s[q] = ex2_approx(s[q] - m);
-                    Z += s[q];
-#pragma unroll
-                    for (int c = 0; c < CE; ++c) o.v[c] = fmaf(s[q], xj[q].v[c], o.v[c]);
-                }
-                const float rZ = any ? rcp_refined(Z) : 0.f;
-#pragma unroll
-                for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
-                const float D = dot<CE>(go, o);
-                const float lse = any ? m + lg2_approx(Z) : 0.f;
-                const float scale = rZ * LN2_F;
-                Row<CE> t = zero_row<CE>();
-#pragma unroll
-                for (int q = 0; q < W; ++q) {
-                    const float ds = (s[q] * scale) * (dot<CE>(go, xj[q]) - D);
-#pragma unroll
-                    for (int c = 0; c < CE; ++c) t.v[c] = fmaf(ds, xj[q].v[c], t.v[c]);
-                }
-#pragma unroll
-                for (int c = 0; c < CE; ++c) gtau = fmaf(gp.v[c], o.v[c] - xi.v[c], gtau);
-#pragma unroll
-                for (int aa = 0; aa < CE; ++aa)
-#pragma unroll
-                    for (int bb = 0; bb < CE; ++bb) acc[aa * CE + bb] = fmaf(xi.v[aa], t.v[bb], acc[aa * CE + bb]);
-#pragma unroll
-                for (int bb = 0; bb < CE; ++bb) acc[CE * CE + bb] += t.v[bb];
-                const Row<CE> Mt = apply_M<CE>(Mu, t);
-                Row<CE> gs;
-#pragma unroll
-                for (int c = 0; c < CE; ++c) gs.v[c] = fmaf(1.0f - b, gp.v[c], Mt.v[c]);
-                sts_row<CE>(P, i * RB, p);
-                *reinterpret_cast<float2*>(DL + (size_t)i * 8) = make_float2(D, lse);
-                sts_row<CE>(GO, i * RB, go);
-                sts_row<CE>(GS, i * RB, gs);
-            }
-            if (l > 0) {
-                cluster_sync();   // P, DL, GO of every slab visible; every gather of X done
-                // phase B: source pass (ell_math.cuh: ell_bwd_src), then X <- x^{l-1}
-                const float* xprev_g = a.states + (size_t)(l - 1) * state_stride;
-                for (int j = tid; j < NT; j += nthr) {
-                    const CRow e = load_crow(Rout, j);
-                    const Row<CE> xprev = ell::load_row_cg<CE>(xprev_g, (int64_t)n0 + j);
-                    const Row<CE> xj = lds_row<CE>(X, j * RB);
-                    Row<CE> g = lds_row<CE>(GS, j * RB);
-                    const bool warp_remote = __any_sync(__activemask(), e.remote());
-#pragma unroll
-                    for (int q = 0; q < W; ++q) {
-                        const uint32_t off = e.e[q] & 0xffffffu;
-                        Row<CE> p, go;
-                        float2 dl;
-                        if (warp_remote) {
-                            const uint32_t base = s_base[e.e[q] >> 24];
-                            p = ldc_row<CE>(base + offP + off);
-                            go = ldc_row<CE>(base + offGO + off);
-                            dl = ldc_f2(base + offDL + (CE == 4 ? (off >> 1) : off));
-                        } else {
-                            p = lds_row<CE>(P, off);
-                            go = lds_row<CE>(GO, off);
-                            dl = *reinterpret_cast<const float2*>(DL + (CE == 4 ? (off >> 1) : off));
-                        }
-                        const float sv = dot<CE>(p, xj) - dl.y;
-                        const float alpha = ex2_approx(e.has(q) ? sv : -CUDART_INF_F);
-                        const float c = (dot<CE>(go, xj) - dl.x) * LN2_F;
-#pragma unroll
-                        for (int ch = 0; ch < CE; ++ch) g.v[ch] = fmaf(alpha, fmaf(c, p.v[ch], go.v[ch]), g.v[ch]);
-                    }
-                    sts_row<CE>(GS, j * RB, g);
-                    sts_row<CE>(X, j * RB, xprev);
-                }
-                cluster_sync();   // X of the next layer complete; gathers of P / DL / GO done
-            }
-            if (per_layer) {
-                acc[NACC - 1] = gtau;
-                block_reduce<NACC>(acc, red, a.partials + ((size_t)blockIdx.x * slots + l) * NACC);
-#pragma unroll
-                for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-            } else if (a.tau_partials) {
-                float one[1] = {gtau};
-                block_reduce<1>(one, red, a.tau_partials + (size_t)blockIdx.x * a.L + l);
-            }
-        }
-        if (!per_layer) block_reduce<NACC>(acc, red, a.partials + (size_t)blockIdx.x * NACC);
-    }
+    cl_backward<CE, W>(a, lay, n0, NT, Xc, Xn, offXc, offXn, P, DL, GS, Rin, Rout, Mu, red, s_base);
     tr.mark();
     // no CTA may leave while a peer can still read its shared memory
     cluster_sync();
@@ -429,6 +443,50 @@ __global__ void __launch_bounds__(MAXT, 1) k_cl_train(const Args a) {
     __threadfence();
     ell::tail_finish<CE>(a, smem, cx, s_coef, s_step, tr);
     if (tid == 0) *a.counter = 0u;
+}
+
+// ---- backward only (autograd of the module seam): from the saved layer inputs ---------------------------
+template <int CE, int W>
+__global__ void __launch_bounds__(MAXT, 1) k_cl_bwd(const Args a) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const Layout lay = make_layout(CE, a.cap_nodes, (nthr + 31) >> 5);
+    unsigned char* X = smem + lay.xa;
+    unsigned char* GO = smem + lay.xb;
+    unsigned char* P = smem + lay.p;
+    unsigned char* GS = smem + lay.gs;
+    unsigned char* DL = smem + lay.dl;
+    float* Mu = reinterpret_cast<float*>(smem + lay.mu);
+    float* red = reinterpret_cast<float*>(smem + lay.red);
+    __shared__ uint32_t s_base[16];
+    const uint32_t C = cluster_size(), rank = cluster_rank();
+    const int mesh = (int)(blockIdx.x / C);
+    const int m0 = a.tile_ptr[mesh], NM = a.tile_ptr[mesh + 1] - m0;
+    const int S = ((NM + (int)C - 1) / (int)C + 3) & ~3;
+    const int n0 = m0 + (int)rank * S;
+    const int NT = max(0, min(S, NM - (int)rank * S));
+    if (tid < 16) s_base[tid] = (tid < (int)C) ? mapa(smem_u32(smem), (uint32_t)tid) : 0u;
+    const size_t state_stride = (size_t)a.N * CE;
+    const float* xl = a.states + (size_t)(a.L - 1) * state_stride;
+    for (int i = tid; i < NT; i += nthr) {
+        sts_row<CE>(X, i * RB, ell::load_row_cg<CE>(xl, (int64_t)n0 + i));
+        sts_row<CE>(GS, i * RB, ell::load_dims<CE>(a.g_xphys, (int64_t)n0 + i, a.dim));   // cotangent of x^L[:, :dim]
+    }
+    const int lw = (a.Lw > 1) ? a.L - 1 : 0;
+    for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)lw * MUSZ + t];
+    cluster_sync();
+    cl_backward<CE, W>(a, lay, n0, NT, X, GO, lay.xa, lay.xb, P, DL, GS, a.ell_in + 2 * (size_t)n0,
+                       a.ell_out + 2 * (size_t)n0, Mu, red, s_base);
+    cluster_sync();   // nobody leaves while a peer may still read its shared memory
+}
+
+// fixed-order fp64 sums of the per-CTA partial rows: one warp per output column (ell_api.cu: k_ell_reduce)
+__global__ void k_cl_reduce(const float* __restrict__ partials, int T, int slots, int nacc, int musz, float* __restrict__ gMu,
+                            const float* __restrict__ tau_partials, int L, float* __restrict__ g_tau) {
+    tail::reduce_partials(partials, T, slots, nacc, musz, gMu, tau_partials, L, g_tau, nullptr, 0.f, nullptr,
+                          blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
 }
 
 // ---- forward only (module seam / inference): Euler layers or classical RK4 steps -------------------------
@@ -893,4 +951,87 @@ extern "C" int gad_deform_fwd_cluster(const void* crows_in, const int32_t* mesh_
     if (w <= 2) { GAD_CL_FWD(2, 2); }
     GAD_CL_FWD(2, 3);
 #undef GAD_CL_FWD
+}
+
+namespace gad {
+namespace cl {
+template <int CE, int W>
+int launch_bwd_t(const Args& a, int C, int grid, int threads, cudaStream_t st) {
+    const size_t bytes = make_layout(CE, a.cap_nodes, (threads + 31) / 32).total;
+    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "cluster kernel: slab of %d nodes needs %zu B of shared memory",
+                  a.cap_nodes, bytes);
+    GAD_CUDA(cudaFuncSetAttribute(k_cl_bwd<CE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (C > 8) GAD_CUDA(cudaFuncSetAttribute(k_cl_bwd<CE, W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GAD_CUDA(cudaLaunchKernelEx(&cfg, k_cl_bwd<CE, W>, a));
+    count_launch(1);
+    return GAD_OK;
+}
+}  // namespace cl
+}  // namespace gad
+
+/* Deformer backward on cluster-resident meshes (gad_deform_bwd_ell's contract over cluster rows):
+ * cotangent g_xphys [N, dim] + saved states [L, N, CE] -> gMu, g_tau (may be NULL), g_x0 (may be NULL).
+ * workspace: gad_cluster_workspace_bytes(CE, M, cluster_size, L). */
+extern "C" int gad_deform_bwd_cluster(const void* crows_in, const void* crows_out, const int32_t* mesh_ptr, int M,
+                                      int max_mesh_nodes, int max_deg, int cluster_size, int64_t N, const float* states,
+                                      const float* g_xphys, int dim, int CE, const float* Mu, int Lw, const float* tau,
+                                      int L, float* gMu, float* g_tau, float* g_x0, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    GAD_CHECK_ARG(crows_in && crows_out && mesh_ptr && states && g_xphys && Mu && tau && gMu && workspace,
+                  "gad_deform_bwd_cluster: null pointer");
+    GAD_CHECK_ARG(N > 0 && M > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L) && (CE == 2 || CE == 4),
+                  "gad_deform_bwd_cluster: N=%lld M=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, M, L, dim, CE, Lw);
+    const int C = cluster_size;
+    GAD_CHECK_ARG(C >= 2 && C <= 16 && (C & (C - 1)) == 0, "gad_deform_bwd_cluster: cluster size %d", C);
+    const int grid = M * C;
+    GAD_CHECK_ARG(workspace_bytes >= gad_ell_workspace_bytes(CE, grid, L), "gad_deform_bwd_cluster: workspace too small");
+    const int S = ((max_mesh_nodes + C - 1) / C + 3) & ~3;
+    int threads = ((S + 3) / 4 + 31) / 32 * 32;
+    if (threads < 128) threads = 128;
+    if (threads > cl::MAXT) threads = cl::MAXT;
+    const int NACC = CE * CE + CE + 1, MUSZ = CE * CE + CE;
+    float* ws = reinterpret_cast<float*>(workspace);
+    ell::Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(crows_in);
+    a.ell_out = reinterpret_cast<const uint4*>(crows_out);
+    a.tile_ptr = mesh_ptr;
+    a.T = grid;
+    a.cap_nodes = S;
+    a.N = N;
+    a.Mu = Mu;
+    a.tau = tau;
+    a.Lw = Lw;
+    a.L = L;
+    a.dim = dim;
+    a.states = const_cast<float*>(states);
+    a.g_xphys = g_xphys;
+    a.partials = ws;
+    a.tau_partials = (g_tau && Lw == 1) ? ws + (size_t)grid * L * NACC : nullptr;
+    a.g_x0 = g_x0;
+    const int w = cl::slots_for(max_deg);
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if (CE == 4 && w == 6) rc = cl::launch_bwd_t<4, 6>(a, C, grid, threads, st);
+    else if (CE == 4 && w == 7) rc = cl::launch_bwd_t<4, 7>(a, C, grid, threads, st);
+    else if (CE == 4) rc = cl::launch_bwd_t<4, 3>(a, C, grid, threads, st);
+    else if (w <= 2) rc = cl::launch_bwd_t<2, 2>(a, C, grid, threads, st);
+    else rc = cl::launch_bwd_t<2, 3>(a, C, grid, threads, st);
+    if (rc) return rc;
+    const int slots = Lw > 1 ? L : 1;
+    const int ncol = slots * NACC + L + 1;
+    cl::k_cl_reduce<<<(ncol + 7) / 8, 256, 0, st>>>(a.partials, grid, slots, NACC, MUSZ, gMu, a.tau_partials, L, g_tau);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
 }

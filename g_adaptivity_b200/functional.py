@@ -209,6 +209,19 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
                 _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes,
                 _stream(states)), "gad_deform_bwd_ell")
         return gMu, g_tau, g_x0
+    if (graph.tile_ptr is None and not force_stream and not getattr(graph, "_no_cluster", False)
+            and graph.ensure_cluster(CE)):
+        # meshes beyond one CTA (up to 4 slabs): cluster-resident backward, one launch + the reduction
+        M = len(graph.mesh_sizes)
+        ws_bytes = lib.gad_cluster_workspace_bytes(CE, M, graph.cl_C, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gad_deform_bwd_cluster(
+                _lib.ptr(graph.cl_in), _lib.ptr(graph.cl_out), _lib.ptr(graph.mesh_ptr), M, max(graph.mesh_sizes),
+                graph.cl_deg, graph.cl_C, N, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau),
+                L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes, _stream(states)),
+                "gad_deform_bwd_cluster")
+        return gMu, g_tau, g_x0
     ws_bytes = lib.gad_deform_bwd_workspace_bytes(N, CE, T, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if not use_tiles and graph.ensure_wide(CE):

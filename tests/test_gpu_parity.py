@@ -230,6 +230,36 @@ def test_large_mesh_forward_on_a_cluster(over):
     model, *_ = _compare_with_oracle((64, 64), 3, over=over, backward=not over)
     g = model.last_graph
     assert g.tile_ptr is None and g.clf_in is not None and g.clf_C >= 2
+    if not over:
+        assert g.cl_in is not None       # the backward ran on the cluster-resident kernel too
+
+
+def test_cluster_backward_equals_streaming_backward():
+    """autograd through the module on 64x64 meshes: cluster-resident backward (one launch) against the
+    streaming ELL kernels, including the gradient of a learnable step size and of the inputs."""
+    import torch.nn.functional as F
+    mesh_dims, B = (64, 64), 2
+    over = {"learn_step": True}
+    opt = synth.default_opt(mesh_dims, **over)
+    ds = synth.SyntheticDataset(2, mesh_dims)
+    data = synth.make_batch(mesh_dims, B, seed=12)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    res = []
+    for no_cluster in (False, True):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_no_cluster=no_cluster)
+        model.train()
+        d = data.clone().to("cuda:0")
+        d.x_comp.requires_grad_(True)
+        out = model(d)
+        F.l1_loss(out, d.x_phys).backward()
+        g = model.last_graph
+        assert (g.cl_in is not None) == (not no_cluster)
+        res.append(({n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}, d.x_comp.grad.clone()))
+    for n in res[0][0]:
+        a, b = res[0][0][n], res[1][0][n]
+        assert (a - b).abs().max().item() <= 2e-5 * max(b.abs().max().item(), 1e-12), n
+    assert util.rel_err(res[0][1], res[1][1]) <= 1e-5
 
 
 def test_config3_burgers_1d_200_repeated_calls():
