@@ -91,6 +91,8 @@ SIGNATURES = {
     "gad_mesh_loss": (_i, [_p, _p, _i64, _i, _f, _p, _p, _p, _p]),
     "gad_mesh_loss_workspace_bytes": (_sz, [_i64]),
     "gad_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p, _p]),
+    "gad_fem1d_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "gad_fem1d_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "gad_peer_exchange_bytes": (_sz, [_i, _i64]),
     "gad_peer_alloc": (_i, [_sz, C.POINTER(_p), _p]),
     "gad_peer_open": (_i, [_p, C.POINTER(_p)]),

@@ -1,0 +1,282 @@
+// Batched differentiable 1-D FEM solve (scope row f1 of SURVEY section 8): what follows the deformer
+// when loss_type = 'pde_loss' on 1-D meshes.  The reference runs `torch_FEM_1D`
+// (firedrake_difFEM/difFEM_1d.py:211-238) once PER MESH in a Python loop (src/GNN.py:307-342): P1
+// stiffness matrix (:83-120), load vector by trapezoid quadrature of f = u''_true times the hat
+// functions (:134-155, 101 points per interval), Dirichlet values u_true(x_0), u_true(x_{n-1}), a
+// dense torch.linalg.solve, and piecewise-linear interpolation at the evaluation points (:62-79);
+// autograd differentiates all of it with respect to the mesh points.
+//
+// Here: one CTA per mesh, everything in shared memory.  The matrix is tridiagonal with closed-form
+// entries (diag_i = -(1/h_{i-1} + 1/h_i), off_i = 1/h_i), solved by the Thomas algorithm; the backward
+// is the hand-derived adjoint (oracle/fem1d_oracle.py: fem1d_adjoint, checked against autograd to
+// 1e-11 in fp64): one more tridiagonal solve for lambda = A^-1 dL/du, entry derivatives with respect
+// to h, the quadrature differentiated through its moving sample points (needs f' = u'''_true), and the
+// interpolation weights.  Arithmetic is fp64 (B200 has the units; the fp32 reference is 2 % .. 30 % away
+// from its own fp64 value on 50 .. 200-node meshes), inputs and outputs are fp32.  As in the reference
+// (:221-222, `torch.tensor([mesh_points[0]])`), no gradient flows through the Dirichlet values.
+#include "common.cuh"
+
+namespace gad {
+namespace {
+
+constexpr int FEM_THREADS = 128;
+
+__device__ __forceinline__ double f_forcing(double x, const double* c, const double* s, int G) {   // :32-36
+    double r = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double d = x - c[g], s2 = s[g] * s[g];
+        r += -2.0 * exp(-d * d / s2) * (s2 - 2.0 * d * d) / (s2 * s2);
+    }
+    return r;
+}
+__device__ __forceinline__ double df_forcing(double x, const double* c, const double* s, int G) {  // f' = u'''
+    double r = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double d = x - c[g], s2 = s[g] * s[g];
+        r += exp(-d * d / s2) * (12.0 * d / (s2 * s2) - 8.0 * d * d * d / (s2 * s2 * s2));
+    }
+    return r;
+}
+__device__ __forceinline__ double u_true(double x, const double* c, const double* s, int G) {      // :38-48
+    double r = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double d = x - c[g];
+        r += exp(-d * d / (s[g] * s[g]));
+    }
+    return r;
+}
+
+// Thomas algorithm for the internal system (size m = n - 2): diag_i = -(1/h_{i-1} + 1/h_i), off_i = 1/h_i
+// (i = internal node 1 .. n-2, stored at i).  rhs / sol / cp are indexed by node; one thread.
+__device__ void thomas(const double* h, int n, const double* rhs, double* cp, double* sol) {
+    // forward sweep (sol doubles as the modified right-hand side)
+    double cprev = 0.0, dprev = 0.0;
+    for (int i = 1; i <= n - 2; ++i) {
+        const double diag = -(1.0 / h[i - 1] + 1.0 / h[i]);
+        const double lower = (i > 1) ? 1.0 / h[i - 1] : 0.0;
+        const double upper = (i < n - 2) ? 1.0 / h[i] : 0.0;
+        const double den = diag - lower * cprev;
+        cprev = upper / den;
+        dprev = (rhs[i] - lower * dprev) / den;
+        cp[i] = cprev;
+        sol[i] = dprev;
+    }
+    for (int i = n - 3; i >= 1; --i) sol[i] -= cp[i] * sol[i + 1];
+}
+
+struct FemSmem {
+    double *x, *h, *rhs, *cp, *u, *lam, *gu, *gxl, *gxr, *c, *s;
+    int* idx;
+};
+
+__device__ __forceinline__ FemSmem carve(unsigned char* smem, int n, int Q, int G) {
+    FemSmem f;
+    double* p = reinterpret_cast<double*>(smem);
+    f.x = p; p += n;
+    f.h = p; p += n;
+    f.rhs = p; p += n;
+    f.cp = p; p += n;
+    f.u = p; p += n;
+    f.lam = p; p += n;
+    f.gu = p; p += n;
+    f.gxl = p; p += n;
+    f.gxr = p; p += n;
+    f.c = p; p += G;
+    f.s = p; p += G;
+    f.idx = reinterpret_cast<int*>(p);
+    return f;
+}
+
+// assembly + solve of one mesh: fills x, h, u (u_0 = BC1, u_{n-1} = BC2)
+__device__ void fem_solve(const FemSmem& f, const float* __restrict__ xg, const float* __restrict__ cg,
+                          const float* __restrict__ sg, int n, int G, int K) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int i = tid; i < n; i += nthr) f.x[i] = (double)xg[i];
+    for (int g = tid; g < G; g += nthr) {
+        f.c[g] = (double)cg[g];
+        f.s[g] = (double)sg[g];
+    }
+    __syncthreads();
+    for (int k = tid; k < n - 1; k += nthr) f.h[k] = f.x[k + 1] - f.x[k];
+    for (int i = tid; i < n; i += nthr) f.rhs[i] = 0.0;
+    __syncthreads();
+    // load vector (:134-155): left_k = int f phi_{k+1}, right_k = int f phi_k over interval k, trapezoid on
+    // K equispaced points; gxl / gxr hold them until they are scattered to the nodes
+    const double inv = 1.0 / (double)(K - 1);
+    for (int k = tid; k < n - 1; k += nthr) {
+        double sl = 0.0, sr = 0.0;
+        for (int m = 0; m < K; ++m) {
+            const double t = m * inv, w = (m == 0 || m == K - 1) ? 0.5 : 1.0;
+            const double fv = w * f_forcing(f.x[k] + f.h[k] * t, f.c, f.s, G);
+            sl += fv * t;
+            sr += fv * (1.0 - t);
+        }
+        f.gxl[k] = f.h[k] * inv * sl;
+        f.gxr[k] = f.h[k] * inv * sr;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) f.rhs[i] = (i > 0 ? f.gxl[i - 1] : 0.0) + (i < n - 1 ? f.gxr[i] : 0.0);
+    __syncthreads();
+    if (tid == 0) {
+        const double bc1 = u_true(f.x[0], f.c, f.s, G), bc2 = u_true(f.x[n - 1], f.c, f.s, G);
+        f.u[0] = bc1;
+        f.u[n - 1] = bc2;
+        if (n > 2) {
+            f.rhs[1] += -bc1 / f.h[0];               // BC1 * A[0, 1]      (:229-232)
+            f.rhs[n - 2] += -bc2 / f.h[n - 2];       // A[-1, -2] * BC2
+            thomas(f.h, n, f.rhs, f.cp, f.u);
+            f.u[0] = bc1;
+            f.u[n - 1] = bc2;
+        }
+    }
+    __syncthreads();
+}
+
+// interval of every evaluation point (:69-71): searchsorted(mesh, q, right=False) - 1, clamped
+__device__ void fem_locate(const FemSmem& f, const float* __restrict__ quad, int n, int Q) {
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        const double xq = (double)quad[q];
+        int lo = 0, hi = n;                      // first i with x[i] >= xq
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (f.x[mid] < xq) lo = mid + 1;
+            else hi = mid;
+        }
+        int k = lo - 1;
+        k = k < 0 ? 0 : (k > n - 2 ? n - 2 : k);   // (the reference clamps to n-1, never reached for q <= x[n-1])
+        f.idx[q] = k;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FEM_THREADS) k_fem1d_fwd(const float* __restrict__ x, const float* __restrict__ centers,
+                                                         const float* __restrict__ scales, const float* __restrict__ quad,
+                                                         int n, int G, int K, int Q, float* __restrict__ sol,
+                                                         float* __restrict__ coeffs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x;
+    const FemSmem f = carve(smem, n, Q, G);
+    fem_solve(f, x + (size_t)b * n, centers + (size_t)b * G, scales + (size_t)b * G, n, G, K);
+    fem_locate(f, quad, n, Q);
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        const int k = f.idx[q];
+        const double r = ((double)quad[q] - f.x[k]) / f.h[k];
+        sol[(size_t)b * Q + q] = (float)(f.u[k] + (f.u[k + 1] - f.u[k]) * r);
+    }
+    if (coeffs)
+        for (int i = threadIdx.x; i < n - 2; i += blockDim.x) coeffs[(size_t)b * (n - 2) + i] = (float)f.u[i + 1];
+}
+
+__global__ void __launch_bounds__(FEM_THREADS) k_fem1d_bwd(const float* __restrict__ x, const float* __restrict__ centers,
+                                                         const float* __restrict__ scales, const float* __restrict__ quad,
+                                                         const float* __restrict__ g_sol, int n, int G, int K, int Q,
+                                                         float* __restrict__ g_x) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const FemSmem f = carve(smem, n, Q, G);
+    fem_solve(f, x + (size_t)b * n, centers + (size_t)b * G, scales + (size_t)b * G, n, G, K);
+    fem_locate(f, quad, n, Q);
+    const float* gs = g_sol + (size_t)b * Q;
+    // interpolation (:62-79): per interval, over its (contiguous) evaluation points -- fixed order, no atomics
+    for (int k = tid; k < n - 1; k += nthr) {
+        int lo = 0, hi = Q;                       // first q with idx[q] >= k
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (f.idx[mid] < k) lo = mid + 1;
+            else hi = mid;
+        }
+        double gu0 = 0.0, gu1 = 0.0, gx0 = 0.0, gx1 = 0.0;
+        const double du = f.u[k + 1] - f.u[k], ih = 1.0 / f.h[k];
+        for (int q = lo; q < Q && f.idx[q] == k; ++q) {
+            const double g = (double)gs[q], r = ((double)quad[q] - f.x[k]) * ih;
+            gu0 += g * (1.0 - r);
+            gu1 += g * r;
+            gx0 += g * du * (r - 1.0) * ih;
+            gx1 += -g * du * r * ih;
+        }
+        f.rhs[k] = gu0;      // contribution of interval k to g_u[k]      (rhs / cp reused as scratch)
+        f.cp[k] = gu1;       //                              to g_u[k + 1]
+        f.gxl[k] = gx0;      //                              to g_x[k]
+        f.gxr[k] = gx1;      //                              to g_x[k + 1]
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) f.gu[i] = (i < n - 1 ? f.rhs[i] : 0.0) + (i > 0 ? f.cp[i - 1] : 0.0);
+    __syncthreads();
+    // lambda = A_int^-1 g_u (the internal matrix is symmetric); zero at the two ends
+    if (tid == 0) {
+        f.lam[0] = 0.0;
+        f.lam[n - 1] = 0.0;
+        if (n > 2) {
+            thomas(f.h, n, f.gu, f.cp, f.lam);
+            f.lam[0] = 0.0;
+            f.lam[n - 1] = 0.0;
+        }
+    }
+    __syncthreads();
+    // per interval: d/dh of the matrix entries and of the boundary terms, and the differentiated quadrature
+    const double inv = 1.0 / (double)(K - 1);
+    for (int k = tid; k < n - 1; k += nthr) {
+        const double hk = f.h[k], inv2 = 1.0 / (hk * hk);
+        const double uk = (k == 0) ? 0.0 : f.u[k], uk1 = (k + 1 == n - 1) ? 0.0 : f.u[k + 1];   // internal coefficients
+        const double lk = f.lam[k], lk1 = f.lam[k + 1];
+        double gh = (-lk * uk) * inv2 + (-lk1 * uk1) * inv2 + (-lk * uk1 - lk1 * uk) * (-inv2);
+        if (k == 0 && n > 2) gh += f.lam[1] * f.u[0] * inv2;
+        if (k == n - 2 && n > 2) gh += f.lam[n - 2] * f.u[n - 1] * inv2;
+        double s0l = 0.0, s0r = 0.0, s1la = 0.0, s1lb = 0.0, s1ra = 0.0, s1rb = 0.0;
+        for (int m = 0; m < K; ++m) {
+            const double t = m * inv, w = (m == 0 || m == K - 1) ? 0.5 : 1.0, p = f.x[k] + hk * t;
+            const double fv = w * f_forcing(p, f.c, f.s, G), dfv = w * df_forcing(p, f.c, f.s, G);
+            s0l += fv * t;
+            s0r += fv * (1.0 - t);
+            s1la += dfv * t * (1.0 - t);
+            s1lb += dfv * t * t;
+            s1ra += dfv * (1.0 - t) * (1.0 - t);
+            s1rb += dfv * (1.0 - t) * t;
+        }
+        const double gl = lk1, gr = lk;            // d loss / d left_k (node k+1), d loss / d right_k (node k)
+        const double to_xk = gl * (-inv * s0l + hk * inv * s1la) + gr * (-inv * s0r + hk * inv * s1ra) - gh;
+        const double to_xk1 = gl * (inv * s0l + hk * inv * s1lb) + gr * (inv * s0r + hk * inv * s1rb) + gh;
+        f.gxl[k] += to_xk;
+        f.gxr[k] += to_xk1;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr)
+        g_x[(size_t)b * n + i] = (float)((i < n - 1 ? f.gxl[i] : 0.0) + (i > 0 ? f.gxr[i - 1] : 0.0));
+}
+
+size_t fem_smem_bytes(int n, int Q, int G) { return (size_t)(9 * n + 2 * G) * sizeof(double) + (size_t)Q * sizeof(int) + 16; }
+
+}  // namespace
+}  // namespace gad
+
+using namespace gad;
+
+/* x [B, n] sorted mesh points per mesh, centers / scales [B, G], quad [Q] (ascending) ->
+ * sol [B, Q] (the P1 solution at the evaluation points), coeffs [B, n-2] (optional). */
+extern "C" int gad_fem1d_fwd(const float* x, const float* centers, const float* scales, const float* quad, int B, int n,
+                             int G, int load_quad_points, int Q, float* sol, float* coeffs, void* stream) {
+    GAD_CHECK_ARG(x && centers && scales && quad && sol, "gad_fem1d_fwd: null pointer");
+    GAD_CHECK_ARG(B > 0 && n >= 3 && G >= 1 && load_quad_points >= 2 && Q >= 1, "gad_fem1d_fwd: B=%d n=%d G=%d K=%d Q=%d", B, n,
+                  G, load_quad_points, Q);
+    const size_t bytes = fem_smem_bytes(n, Q, G);
+    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "gad_fem1d_fwd: a mesh of %d nodes needs %zu B of shared memory", n, bytes);
+    GAD_CUDA(cudaFuncSetAttribute(k_fem1d_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    k_fem1d_fwd<<<B, FEM_THREADS, bytes, as_stream(stream)>>>(x, centers, scales, quad, n, G, load_quad_points, Q, sol, coeffs);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+/* g_sol [B, Q] = d loss / d sol  ->  g_x [B, n] = d loss / d mesh points (forward recomputed). */
+extern "C" int gad_fem1d_bwd(const float* x, const float* centers, const float* scales, const float* quad,
+                             const float* g_sol, int B, int n, int G, int load_quad_points, int Q, float* g_x,
+                             void* stream) {
+    GAD_CHECK_ARG(x && centers && scales && quad && g_sol && g_x, "gad_fem1d_bwd: null pointer");
+    GAD_CHECK_ARG(B > 0 && n >= 3 && G >= 1 && load_quad_points >= 2 && Q >= 1, "gad_fem1d_bwd: B=%d n=%d G=%d K=%d Q=%d", B, n,
+                  G, load_quad_points, Q);
+    const size_t bytes = fem_smem_bytes(n, Q, G);
+    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "gad_fem1d_bwd: a mesh of %d nodes needs %zu B of shared memory", n, bytes);
+    GAD_CUDA(cudaFuncSetAttribute(k_fem1d_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    k_fem1d_bwd<<<B, FEM_THREADS, bytes, as_stream(stream)>>>(x, centers, scales, quad, g_sol, n, G, load_quad_points, Q, g_x);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}

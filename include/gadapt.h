@@ -346,6 +346,19 @@ int gad_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                   int64_t* step, void* stream);
 
+/* ---- next row f1 (1-D): batched differentiable FEM solve after the deformer (loss_type = 'pde_loss') ----
+ * Replaces the per-mesh Python loop of src/GNN.py:307-342 over torch_FEM_1D
+ * (firedrake_difFEM/difFEM_1d.py:211-238: P1 stiffness matrix, load vector by `load_quad_points`-point
+ * trapezoid quadrature of f = u''_true, Dirichlet values u_true(x_0), u_true(x_{n-1}), linear solve,
+ * piecewise-linear interpolation at the Q evaluation points) and its autograd with respect to the mesh
+ * points.  x [B, n] ascending mesh points per mesh, centers / scales [B, G] (Gaussians of u_true),
+ * quad [Q] ascending.  fwd: sol [B, Q], coeffs [B, n-2] (may be NULL).  bwd: g_sol [B, Q] -> g_x [B, n]
+ * (no gradient through the Dirichlet values, as difFEM_1d.py:221-222).  fp64 inside, fp32 outside. */
+int gad_fem1d_fwd(const float* x, const float* centers, const float* scales, const float* quad, int B, int n, int G,
+                  int load_quad_points, int Q, float* sol, float* coeffs, void* stream);
+int gad_fem1d_bwd(const float* x, const float* centers, const float* scales, const float* quad, const float* g_sol,
+                  int B, int n, int G, int load_quad_points, int Q, float* g_x, void* stream);
+
 /* ---- peer memory for the data-parallel gradient exchange (one process per GPU, one node) -------
  * The reference trains single-process (src/run_GNN.py:95-131); sharding a batch by whole meshes
  * needs exactly one exchange per step, the SUM of the flat gradient.  gad_peer_alloc returns a

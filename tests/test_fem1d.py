@@ -1,0 +1,103 @@
+"""1-D differentiable FEM solve (scope row f1): the oracle restatement against the fixtures minted from
+the reference's own difFEM_1d.py (CPU, bit for bit), the hand-derived adjoint against autograd (CPU,
+fp64), and the CUDA kernels against the oracle (GPU)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fem1d_oracle as F1
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_fem1d", "fem1d_*.pt")))
+
+
+def _case(fx, dtype=torch.float32):
+    x = fx["mesh"].to(dtype).clone().requires_grad_(True)
+    quad = torch.linspace(0, 1, fx["eval_quad_points"], dtype=torch.float32).to(dtype)
+    cs = [c.to(dtype) for c in fx["centers"]]
+    ss = [s.to(dtype) for s in fx["scales"]]
+    return x, quad, cs, ss, fx["load_quad_points"]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-3] for p in GOLDEN])
+def test_oracle_reproduces_reference_fem1d_bit_for_bit(path):
+    fx = torch.load(path, weights_only=True)
+    x, quad, cs, ss, K = _case(fx)
+    coeffs, sol, *_ = F1.torch_fem_1d(x, quad, cs, ss, load_quad_points=K)
+    loss = F.mse_loss(sol, F1.u_true(quad, cs, ss))
+    loss.backward()
+    assert torch.equal(sol.detach(), fx["sol"]) and torch.equal(coeffs.detach().reshape(-1), fx["coeffs"])
+    assert loss.item() == fx["loss"]
+    assert torch.equal(x.grad, fx["grad_mesh"])      # including the detached Dirichlet values (difFEM_1d.py:221-222)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-3] for p in GOLDEN])
+def test_hand_adjoint_equals_autograd_fp64(path):
+    fx = torch.load(path, weights_only=True)
+    x, quad, cs, ss, K = _case(fx, torch.float64)
+    _, sol, *_ = F1.torch_fem_1d(x, quad, cs, ss, load_quad_points=K)
+    ut = F1.u_true(quad, cs, ss)
+    F.mse_loss(sol, ut).backward()
+    gx, fw = F1.fem1d_adjoint(x.detach(), quad, cs, ss, K, (2 * (sol - ut) / sol.numel()).detach())
+    assert (fw["sol"] - sol.detach()).abs().max().item() <= 1e-12
+    assert (gx - x.grad).abs().max().item() <= 1e-9 * x.grad.abs().max().item()
+
+
+def _oracle64(mesh, centers, scales, K, Q):
+    x = mesh.double().clone().requires_grad_(True)
+    quad = torch.linspace(0, 1, Q, dtype=torch.float32).double()
+    cs, ss = [c.double() for c in centers], [s.double() for s in scales]
+    coeffs, sol, *_ = F1.torch_fem_1d(x, quad, cs, ss, load_quad_points=K)
+    ut = F1.u_true(quad, cs, ss)
+    loss = F.mse_loss(sol, ut)
+    loss.backward()
+    return coeffs.detach().reshape(-1), sol.detach(), ut, loss.item(), x.grad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-3] for p in GOLDEN])
+def test_cuda_fem1d_matches_oracle(path):
+    """The kernels compute in fp64: compared with the fp64 oracle (solution 1e-6, gradient 1e-5 of its
+    largest entry), and never further from it than the fp32 reference itself is."""
+    from g_adaptivity_b200 import fem1d
+    fx = torch.load(path, weights_only=True)
+    n, K, Q = fx["mesh"].numel(), fx["load_quad_points"], fx["eval_quad_points"]
+    coeffs64, sol64, ut, loss64, g64 = _oracle64(fx["mesh"], fx["centers"], fx["scales"], K, Q)
+    x = fx["mesh"].cuda().clone().requires_grad_(True)
+    quad = torch.linspace(0, 1, Q)
+    coeffs, sol = fem1d.fem1d_solve(x, fx["centers"].view(1, -1), fx["scales"].view(1, -1), quad, n, K)
+    loss = F.mse_loss(sol, ut.float().cuda())
+    loss.backward()
+    assert (sol.detach().cpu().double() - sol64).abs().max().item() <= 2e-6 * sol64.abs().max().item()
+    assert (coeffs.detach().cpu().double().reshape(-1) - coeffs64).abs().max().item() <= 2e-6 * coeffs64.abs().max().item()
+    gscale = g64.abs().max().item()
+    err = (x.grad.cpu().double() - g64).abs().max().item() / gscale
+    ref_err = (fx["grad_mesh"].double() - g64).abs().max().item() / gscale
+    assert err <= max(1e-5, 0.05 * ref_err), (err, ref_err)
+
+
+@pytest.mark.gpu
+def test_cuda_fem1d_batched_and_deterministic():
+    from g_adaptivity_b200 import fem1d
+    rng = np.random.default_rng(0)
+    B, n, G, K, Q = 37, 64, 2, 101, 101
+    xs = np.tile(np.linspace(0, 1, n), (B, 1))
+    xs[:, 1:-1] += (rng.random((B, n - 2)) - 0.5) * 0.3 / (n - 1)
+    centers = torch.from_numpy(rng.uniform(0.25, 0.75, (B, G)).astype(np.float32))
+    scales = torch.from_numpy(rng.uniform(0.1, 0.4, (B, G)).astype(np.float32))
+    x = torch.from_numpy(xs.astype(np.float32)).reshape(-1).cuda().requires_grad_(True)
+    quad = torch.linspace(0, 1, Q)
+    outs = []
+    for _ in range(2):
+        x.grad = None
+        coeffs, sol = fem1d.fem1d_solve(x, centers, scales, quad, n, K)
+        sol.square().mean().backward()
+        outs.append((sol.detach().clone(), x.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert sol.shape == (B * Q,) and coeffs.shape == (B * (n - 2), 1)
+    for b in (0, 17, 36):          # every mesh of the batch against the oracle on that mesh alone
+        _, sol64, _, _, _ = _oracle64(torch.from_numpy(xs[b].astype(np.float32)), centers[b], scales[b], K, Q)
+        assert (outs[0][0][b * Q:(b + 1) * Q].cpu().double() - sol64).abs().max().item() <= 2e-6 * sol64.abs().max().item()
