@@ -134,10 +134,12 @@ class GNN(nn.Module):
             raise NotImplementedError("GRAND with a non-identity non_lin (src/GNN.py:286) is not implemented")
         if opt.get("ode_method", "euler") not in GF.METHODS:
             raise ValueError(f"ode_method must be one of {sorted(GF.METHODS)}")
-        if opt["loss_type"] not in ("mesh_loss", "modular"):
+        if opt["loss_type"] == "pde_loss" and self.dim != 1:
             raise NotImplementedError(
-                "loss_type='pde_loss' appends a per-mesh differentiable FEM solve (src/GNN.py:307-342): "
-                "'next' row 8f1 of the scope table, not part of this build")
+                "loss_type='pde_loss' on 2-D meshes appends a per-mesh differentiable FEM solve (torch_FEM_2D, "
+                "src/GNN.py:329-336): 'next' row 8f1 of the scope table; only the 1-D solve (csrc/fem1d.cu) is built")
+        if opt["loss_type"] not in ("mesh_loss", "modular", "pde_loss"):
+            raise NotImplementedError(f"loss_type={opt['loss_type']!r} is not implemented")
 
     def _device(self):
         dev = torch.device(self.opt["device"])
@@ -273,6 +275,18 @@ class GNN(nn.Module):
         if opt.get("gad_sync_timestamp", False):
             torch.cuda.current_stream(dev).synchronize()
         self.end_MLmodel = time.time()
+        if opt["loss_type"] == "pde_loss":
+            # src/GNN.py:307-342 (dim == 1): per mesh torch_FEM_1D on its relocated points -> one batched launch.
+            # Returns (coeffs_batched [B*(n-2), 1], x_phys_batched [N], sol_batched [B*Q]) like the reference.
+            from . import fem1d
+            B = len(graph.mesh_sizes) if graph.mesh_sizes is not None else int(data.batch.max().item()) + 1
+            n = int(x_phys.shape[0]) // B
+            if graph.mesh_sizes is not None and any(m != n for m in graph.mesh_sizes):
+                raise NotImplementedError("pde_loss needs meshes of equal size in a batch")
+            centers, scales = fem1d._pde_params_to_tensors(data.pde_params, B, dev)
+            xp = x_phys.squeeze(-1)
+            coeffs, sol = fem1d.fem1d_solve(xp, centers, scales, self.quad_points, n, int(opt.get("load_quad_points", 101)))
+            return coeffs, xp, sol
         return x_phys
 
     def inference_session(self, data) -> "InferenceSession":

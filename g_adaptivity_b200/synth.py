@@ -274,7 +274,7 @@ def make_data(topo: MeshTopology, seed: int, num_gauss: int = 2, burgers: bool =
 
 
 def make_batch(mesh_dims: Sequence[int], num_meshes: int, seed: int = 0, num_gauss: Optional[int] = None,
-               burgers: bool = False, first_mesh_id: int = 0) -> Batch:
+               burgers: bool = False, first_mesh_id: int = 0, eval_quad_points: int = 101) -> Batch:
     """`num_meshes` samples on one shared topology, collated like PyG would.
 
     Vectorised (no per-mesh python graph work), bit-identical to
@@ -313,6 +313,15 @@ def make_batch(mesh_dims: Sequence[int], num_meshes: int, seed: int = 0, num_gau
     out.u_true_tensor = torch.from_numpy(u.reshape(-1).copy())
     out.corner_nodes = [topo.corner_nodes.copy() for _ in range(B)]
     out.pde_params = {"centers": [list(c) for c in cs], "scales": [list(s) for s in ss]}
+    if topo.dim == 1 and not burgers:
+        # target of loss_type='pde_loss' (src/run_GNN.py:109-110): u_true at the evaluation points of every mesh
+        q = np.linspace(0.0, 1.0, eval_quad_points, dtype=np.float32)
+        fine = np.zeros((B, eval_quad_points), dtype=np.float32)
+        for b in range(B):
+            for c, s_ in zip(cs[b], ss[b]):
+                fine[b] += np.exp(-(q - np.float32(np.asarray(c).reshape(-1)[0])) ** 2
+                                  / np.float32(np.asarray(s_).reshape(-1)[0]) ** 2).astype(np.float32)
+        out.u_true_fine_tensor = torch.from_numpy(fine.reshape(-1))
     out._num_graphs = B
     out.mesh_sizes = [N] * B
     return out
@@ -342,7 +351,7 @@ def default_opt(mesh_dims: Sequence[int] = (15, 15), **overrides) -> dict:
         gnn_inc_feat_uu=True, gnn_inc_glob_feat_f=False, gnn_inc_glob_feat_uu=False,
         gnn_normalize=False, global_feat_dim=8, softmax_temp_type=None, softmax_temp=2.0,
         reg_skew=False, show_mesh_evol_plots=True, loss_type="mesh_loss", data_type="randg",
-        device="cpu", eval_quad_points=101, loss_fn="l1", lr=0.001, decay=0.0, seed=42,
+        device="cpu", eval_quad_points=101, load_quad_points=101, stiff_quad_points=3, loss_fn="l1", lr=0.001, decay=0.0, seed=42,
         pde_type="Poisson" if dim == 2 else "Poisson",
     )
     opt.update(overrides)
