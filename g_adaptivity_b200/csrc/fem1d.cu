@@ -21,21 +21,18 @@ namespace {
 
 constexpr int FEM_THREADS = 128;
 
-__device__ __forceinline__ double f_forcing(double x, const double* c, const double* s, int G) {   // :32-36
-    double r = 0.0;
+// f = u_true'' (:32-36) and f' = u_true''' from one exponential per Gaussian; is2 / is4 / is6 hold 1/s^2, 1/s^4,
+// 1/s^6 (no division on the quadrature loop: it is fp64-throughput bound, 20 k .. 40 k evaluations per mesh)
+__device__ __forceinline__ void forcing(double x, const double* c, const double* is2, const double* is4,
+                                        const double* is6, int G, double& fv, double& dfv) {
+    fv = 0.0;
+    dfv = 0.0;
     for (int g = 0; g < G; ++g) {
-        const double d = x - c[g], s2 = s[g] * s[g];
-        r += -2.0 * exp(-d * d / s2) * (s2 - 2.0 * d * d) / (s2 * s2);
+        const double d = x - c[g], d2 = d * d;
+        const double e = exp(-d2 * is2[g]);
+        fv += e * (4.0 * d2 * is4[g] - 2.0 * is2[g]);                 // -2 e (s^2 - 2 d^2) / s^4
+        dfv += e * d * (12.0 * is4[g] - 8.0 * d2 * is6[g]);
     }
-    return r;
-}
-__device__ __forceinline__ double df_forcing(double x, const double* c, const double* s, int G) {  // f' = u'''
-    double r = 0.0;
-    for (int g = 0; g < G; ++g) {
-        const double d = x - c[g], s2 = s[g] * s[g];
-        r += exp(-d * d / s2) * (12.0 * d / (s2 * s2) - 8.0 * d * d * d / (s2 * s2 * s2));
-    }
-    return r;
 }
 __device__ __forceinline__ double u_true(double x, const double* c, const double* s, int G) {      // :38-48
     double r = 0.0;
@@ -48,16 +45,16 @@ __device__ __forceinline__ double u_true(double x, const double* c, const double
 
 // Thomas algorithm for the internal system (size m = n - 2): diag_i = -(1/h_{i-1} + 1/h_i), off_i = 1/h_i
 // (i = internal node 1 .. n-2, stored at i).  rhs / sol / cp are indexed by node; one thread.
-__device__ void thomas(const double* h, int n, const double* rhs, double* cp, double* sol) {
-    // forward sweep (sol doubles as the modified right-hand side)
+__device__ void thomas(const double* ih, int n, const double* rhs, double* cp, double* sol) {
+    // `ih` = 1 / h, precomputed in parallel: the serial chain of a step is one reciprocal and a few FMAs
     double cprev = 0.0, dprev = 0.0;
     for (int i = 1; i <= n - 2; ++i) {
-        const double diag = -(1.0 / h[i - 1] + 1.0 / h[i]);
-        const double lower = (i > 1) ? 1.0 / h[i - 1] : 0.0;
-        const double upper = (i < n - 2) ? 1.0 / h[i] : 0.0;
-        const double den = diag - lower * cprev;
-        cprev = upper / den;
-        dprev = (rhs[i] - lower * dprev) / den;
+        const double diag = -(ih[i - 1] + ih[i]);
+        const double lower = (i > 1) ? ih[i - 1] : 0.0;
+        const double upper = (i < n - 2) ? ih[i] : 0.0;
+        const double r = 1.0 / (diag - lower * cprev);
+        cprev = upper * r;
+        dprev = (rhs[i] - lower * dprev) * r;
         cp[i] = cprev;
         sol[i] = dprev;
     }
@@ -65,7 +62,7 @@ __device__ void thomas(const double* h, int n, const double* rhs, double* cp, do
 }
 
 struct FemSmem {
-    double *x, *h, *rhs, *cp, *u, *lam, *gu, *gxl, *gxr, *c, *s;
+    double *x, *h, *ih, *rhs, *cp, *u, *lam, *gu, *gxl, *gxr, *c, *s, *is2, *is4, *is6;
     int* idx;
 };
 
@@ -74,6 +71,7 @@ __device__ __forceinline__ FemSmem carve(unsigned char* smem, int n, int Q, int 
     double* p = reinterpret_cast<double*>(smem);
     f.x = p; p += n;
     f.h = p; p += n;
+    f.ih = p; p += n;
     f.rhs = p; p += n;
     f.cp = p; p += n;
     f.u = p; p += n;
@@ -83,6 +81,9 @@ __device__ __forceinline__ FemSmem carve(unsigned char* smem, int n, int Q, int 
     f.gxr = p; p += n;
     f.c = p; p += G;
     f.s = p; p += G;
+    f.is2 = p; p += G;
+    f.is4 = p; p += G;
+    f.is6 = p; p += G;
     f.idx = reinterpret_cast<int*>(p);
     return f;
 }
@@ -95,9 +96,16 @@ __device__ void fem_solve(const FemSmem& f, const float* __restrict__ xg, const 
     for (int g = tid; g < G; g += nthr) {
         f.c[g] = (double)cg[g];
         f.s[g] = (double)sg[g];
+        const double i2 = 1.0 / (f.s[g] * f.s[g]);
+        f.is2[g] = i2;
+        f.is4[g] = i2 * i2;
+        f.is6[g] = i2 * i2 * i2;
     }
     __syncthreads();
-    for (int k = tid; k < n - 1; k += nthr) f.h[k] = f.x[k + 1] - f.x[k];
+    for (int k = tid; k < n - 1; k += nthr) {
+        f.h[k] = f.x[k + 1] - f.x[k];
+        f.ih[k] = 1.0 / f.h[k];
+    }
     for (int i = tid; i < n; i += nthr) f.rhs[i] = 0.0;
     __syncthreads();
     // load vector (:134-155): left_k = int f phi_{k+1}, right_k = int f phi_k over interval k, trapezoid on
@@ -107,7 +115,9 @@ __device__ void fem_solve(const FemSmem& f, const float* __restrict__ xg, const 
         double sl = 0.0, sr = 0.0;
         for (int m = 0; m < K; ++m) {
             const double t = m * inv, w = (m == 0 || m == K - 1) ? 0.5 : 1.0;
-            const double fv = w * f_forcing(f.x[k] + f.h[k] * t, f.c, f.s, G);
+            double fv, dfv;
+            forcing(f.x[k] + f.h[k] * t, f.c, f.is2, f.is4, f.is6, G, fv, dfv);
+            fv *= w;
             sl += fv * t;
             sr += fv * (1.0 - t);
         }
@@ -124,7 +134,7 @@ __device__ void fem_solve(const FemSmem& f, const float* __restrict__ xg, const 
         if (n > 2) {
             f.rhs[1] += -bc1 / f.h[0];               // BC1 * A[0, 1]      (:229-232)
             f.rhs[n - 2] += -bc2 / f.h[n - 2];       // A[-1, -2] * BC2
-            thomas(f.h, n, f.rhs, f.cp, f.u);
+            thomas(f.ih, n, f.rhs, f.cp, f.u);
             f.u[0] = bc1;
             f.u[n - 1] = bc2;
         }
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(FEM_THREADS) k_fem1d_bwd(const float* __restri
         f.lam[0] = 0.0;
         f.lam[n - 1] = 0.0;
         if (n > 2) {
-            thomas(f.h, n, f.gu, f.cp, f.lam);
+            thomas(f.ih, n, f.gu, f.cp, f.lam);
             f.lam[0] = 0.0;
             f.lam[n - 1] = 0.0;
         }
@@ -225,7 +235,10 @@ __global__ void __launch_bounds__(FEM_THREADS) k_fem1d_bwd(const float* __restri
         double s0l = 0.0, s0r = 0.0, s1la = 0.0, s1lb = 0.0, s1ra = 0.0, s1rb = 0.0;
         for (int m = 0; m < K; ++m) {
             const double t = m * inv, w = (m == 0 || m == K - 1) ? 0.5 : 1.0, p = f.x[k] + hk * t;
-            const double fv = w * f_forcing(p, f.c, f.s, G), dfv = w * df_forcing(p, f.c, f.s, G);
+            double fv, dfv;
+            forcing(p, f.c, f.is2, f.is4, f.is6, G, fv, dfv);
+            fv *= w;
+            dfv *= w;
             s0l += fv * t;
             s0r += fv * (1.0 - t);
             s1la += dfv * t * (1.0 - t);
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__(FEM_THREADS) k_fem1d_bwd(const float* __restri
         g_x[(size_t)b * n + i] = (float)((i < n - 1 ? f.gxl[i] : 0.0) + (i > 0 ? f.gxr[i - 1] : 0.0));
 }
 
-size_t fem_smem_bytes(int n, int Q, int G) { return (size_t)(9 * n + 2 * G) * sizeof(double) + (size_t)Q * sizeof(int) + 16; }
+size_t fem_smem_bytes(int n, int Q, int G) { return (size_t)(10 * n + 5 * G) * sizeof(double) + (size_t)Q * sizeof(int) + 16; }
 
 }  // namespace
 }  // namespace gad

@@ -131,6 +131,50 @@ def time_module_train_fresh(md, B, iters, content_cache):
             "graph_builds": model._graphs.misses, "content_hits": getattr(model._graphs, "misses_identity", 0)}
 
 
+def time_fem1d(B, n, G=1, K=101, Q=101, iters=10):
+    """Next row f1 (1-D): batched differentiable FEM solve behind pde_loss, forward + backward, against
+    the per-mesh CPU restatement of torch_FEM_1D (what the reference loops over in Python)."""
+    import numpy as np
+    import torch.nn.functional as F
+    from g_adaptivity_b200 import fem1d
+    from oracle import fem1d_oracle as F1
+    rng = np.random.default_rng(0)
+    xs = np.tile(np.linspace(0, 1, n), (B, 1))
+    xs[:, 1:-1] += (rng.random((B, n - 2)) - 0.5) * 0.3 / (n - 1)
+    centers = torch.from_numpy(rng.uniform(0.3, 0.7, (B, G)).astype(np.float32)).cuda()
+    scales = torch.from_numpy(rng.uniform(0.05, 0.2, (B, G)).astype(np.float32)).cuda()
+    x = torch.from_numpy(xs.astype(np.float32)).reshape(-1).cuda().requires_grad_(True)
+    quad = torch.linspace(0, 1, Q).cuda()
+    tgt = torch.zeros(B * Q, device="cuda")
+
+    def step():
+        x.grad = None
+        _, sol = fem1d.fem1d_solve(x, centers, scales, quad, n, K)
+        F.mse_loss(sol, tgt).backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    # CPU: the oracle restatement on a few meshes, as the reference would loop
+    m = 4
+    t0 = time.perf_counter()
+    for b in range(m):
+        xb = torch.from_numpy(xs[b].astype(np.float32)).requires_grad_(True)
+        cs, ss = [c for c in centers[b].cpu()], [s_ for s_ in scales[b].cpu()]
+        _, sol, *_ = F1.torch_fem_1d(xb, torch.linspace(0, 1, Q), cs, ss, load_quad_points=K)
+        F.mse_loss(sol, torch.zeros(Q)).backward()
+    cpu_ms_per_mesh = 1e3 * (time.perf_counter() - t0) / m
+    return {"meshes": B, "nodes_per_mesh": n, "gpu_ms_fwd_bwd": round(ms, 4), "meshes_per_s": round(B / ms * 1e3, 1),
+            "cpu_oracle_ms_per_mesh": round(cpu_ms_per_mesh, 3), "cpu_oracle_ms_for_batch_extrapolated": round(cpu_ms_per_mesh * B, 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -142,6 +186,7 @@ def main():
     res["cfg4_200x200_rk4x64_fwd"] = time_forward((200, 200), 1, {"ode_method": "rk4", "num_layers": 64}, False, it)
     res["cfg2_30x30_b256_train"] = time_train((30, 30), 256, 8, it)
     res["cfg5_50x50_b1024_train"] = time_train((50, 50), 1024, 2, max(2, it // 4))
+    res["fem1d_pde_loss_b4096_n200"] = time_fem1d(4096, 200)
     res["cfg2_module_seam_train_fresh_batches_content_cache"] = time_module_train_fresh((30, 30), 256, it, True)
     res["cfg2_module_seam_train_fresh_batches_identity_cache_only"] = time_module_train_fresh((30, 30), 256, it, False)
     for k, v in res.items():
