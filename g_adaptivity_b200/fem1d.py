@@ -15,12 +15,12 @@ from . import _lib
 def _pde_params_to_tensors(pde_params, B: int, device) -> tuple:
     """`data.pde_params['centers'][b]` is a list (one entry per Gaussian) of 1-element arrays."""
     def stack(key):
-        rows = []
-        for b in range(B):
-            rows.append([float(np.asarray(v).reshape(-1)[0]) for v in pde_params[key][b]])
-        if len({len(r) for r in rows}) != 1:
-            raise ValueError("every mesh of a batch must carry the same number of Gaussians")
-        return torch.tensor(rows, dtype=torch.float32, device=device)
+        try:                                                   # rectangular: one vectorised conversion
+            arr = np.asarray(pde_params[key][:B], dtype=np.float32)
+            arr = arr.reshape(B, -1)
+        except ValueError as e:
+            raise ValueError("every mesh of a batch must carry the same number of Gaussians") from e
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True)
     return stack("centers"), stack("scales")
 
 

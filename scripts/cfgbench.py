@@ -175,6 +175,35 @@ def time_fem1d(B, n, G=1, K=101, Q=101, iters=10):
             "cpu_oracle_ms_per_mesh": round(cpu_ms_per_mesh, 3), "cpu_oracle_ms_for_batch_extrapolated": round(cpu_ms_per_mesh * B, 1)}
 
 
+def time_pde_loss_step(md, B, iters):
+    """loss_type='pde_loss' on 1-D meshes through the module seam: model(data) (deformer + batched FEM) ->
+    mse(sol, u_true_fine) -> backward -> torch Adam; inputs device-resident."""
+    import torch.nn.functional as F
+    from g_adaptivity_b200 import GNN, synth
+    dev = torch.device("cuda", 0)
+    opt = synth.default_opt(md)
+    opt.update(device="cuda:0", gad_store_alpha=False, loss_type="pde_loss")
+    ds = synth.SyntheticDataset(len(md), md)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev).train()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-3)
+    data = synth.make_batch(md, B, seed=0).to(dev)
+    tgt = data.u_true_fine_tensor
+    ts = []
+    for it in range(iters + 3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        optim.zero_grad(set_to_none=True)
+        coeffs, xp, sol = model(data)
+        F.mse_loss(sol, tgt).backward()
+        optim.step()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(time.perf_counter() - t0)
+    ms = 1e3 * statistics.median(ts)
+    return {"meshes": B, "nodes": B * md[0], "ms_per_step": round(ms, 3), "meshes_per_s": round(B / ms * 1e3, 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -187,6 +216,7 @@ def main():
     res["cfg2_30x30_b256_train"] = time_train((30, 30), 256, 8, it)
     res["cfg5_50x50_b1024_train"] = time_train((50, 50), 1024, 2, max(2, it // 4))
     res["fem1d_pde_loss_b4096_n200"] = time_fem1d(4096, 200)
+    res["pde_loss_train_step_module_seam_b4096_n200"] = time_pde_loss_step((200,), 4096, it)
     res["cfg2_module_seam_train_fresh_batches_content_cache"] = time_module_train_fresh((30, 30), 256, it, True)
     res["cfg2_module_seam_train_fresh_batches_identity_cache_only"] = time_module_train_fresh((30, 30), 256, it, False)
     for k, v in res.items():
