@@ -207,6 +207,7 @@ def test_epoch_graph_equals_step_by_step(pdl):
     ((64, 64), 3, {}),                                        # 4096 nodes: cluster of 2
     ((81, 81), 2, {"loss_fn": "mse"}),                         # 6561 nodes: cluster of 4, ragged last slab
     ((64, 64), 2, {"share_conv": False, "learn_step": True, "num_layers": 3}),
+    ((64, 64), 2, {"learn_step": True}),                       # shared weights + step-size partials
 ])
 def test_cluster_train_step_matches_oracle_and_streaming_path(mesh_dims, B, over):
     loss = over.get("loss_fn", "l1")
