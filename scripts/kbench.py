@@ -2,7 +2,7 @@
 """Kernel micro-benchmark: CUDA-event time of the fused forward / backward kernels (and the whole
 graph-replayed train step) for one workload.  Used to compare kernel variants on the GPU box:
 
-    GAD_LIB=/path/to/libvariant.so python scripts/kbench.py --mesh 30 30 --batch 256 [--check]
+    GAD_LIB=/path/to/libvariant.so python scripts/kbench.py --mesh 30 30 --batch 256
 
 (Parity against the CPU oracle lives in tests/; this script only measures.)"""
 import argparse
