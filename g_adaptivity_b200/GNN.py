@@ -6,12 +6,16 @@ as `src/GNN.py:144-306`, so it can stand under `run_GNN.get_model` / `run_pipeli
 unchanged.  What differs is underneath:
 
 * the graph prologue of every call (`src/GNN.py:206-223`) runs once on the GPU and is cached
-  (`graph.MeshGraph`, K0);
-* feature concat + identity encoder (:225-239, :270) is one pack kernel writing the first saved
-  layer state;
-* the per-layer Python loop `x = x + time_step * layer(x, edge_index)` (:273-296) and the decoder
-  slice (:298-299) are ONE fused launch (`gad_deform_fwd`), and autograd's op-by-op backward is
-  one hand-written launch (`gad_deform_bwd`).
+  (`graph.MeshGraph`, K0), found again by tensor identity or by a device content fingerprint when the
+  loader hands over a fresh `Batch`;
+* feature concat + identity encoder (:225-239, :270), the per-layer Python loop
+  `x = x + time_step * layer(x, edge_index)` (:273-296) and the decoder slice (:298-299) are ONE launch
+  (`gad_deform_fwd_ell_raw` on meshes that fit a CTA, `gad_deform_fwd_cluster` on larger ones; the
+  streaming kernels otherwise), with the folded weights cached per parameter version; autograd's
+  op-by-op backward is one hand-written launch plus the reduction;
+* `loss_type='pde_loss'` on 1-D meshes appends the batched differentiable FEM solve (`fem1d.py`) and
+  returns `(coeffs, x_phys, sol)` as `src/GNN.py:307-342` does;
+* `inference_session(data)` replays the call as a CUDA graph for roll-outs.
 
 Options the reference supports but this path does not raise
 `NotImplementedError`; nothing silently falls back to PyTorch, and a non-CUDA device raises.
