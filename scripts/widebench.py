@@ -33,4 +33,4 @@ tr.synchronize()
 N = tr.slots[0].N
 us = 1e3 * e0.elapsed_time(e1) / a.steps
 print(json.dumps({"mesh": list(md), "batch": a.batch, "nodes": N, "step_us": round(us, 2), "gnodes_per_s": round(N / us / 1e3, 3),
-                  "wide": tr.slots[0].graph.wide_in is not None}))
+                  "wide": tr.slots[0].graph.wide_in is not None, "cluster": (tr.slots[0].graph.cl_C if tr._cluster(tr.slots[0]) else 0)}))
