@@ -54,6 +54,55 @@ __device__ __forceinline__ Row<CE> ldg_row(const float* __restrict__ base, int64
     return r;
 }
 
+// State written by the PREVIOUS launch of a programmatic-dependent-launch chain: this kernel is already
+// resident while that launch runs, so its L1 cannot be trusted for these buffers -- read through L2.
+template <int CE>
+__device__ __forceinline__ Row<CE> ldcg_row(const float* base, int64_t i) {
+    Row<CE> r;
+    if constexpr (CE == 2) {
+        const float2 t = __ldcg(reinterpret_cast<const float2*>(base) + i);
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+    } else {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(base) + i);
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+        r.v[2] = t.z;
+        r.v[3] = t.w;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Launch of one link of a chain of dependent kernels.  With `dependent` the kernel may become resident
+// while its predecessor in the stream still runs (programmatic dependent launch): its prologue -- the
+// topology row, the folded weights -- overlaps the predecessor's tail, and it blocks in chain_wait()
+// before touching anything the predecessor writes.
+inline bool chain_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GAD_WIDE_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <typename... KA, typename... A>
+cudaError_t launch_link(void (*kern)(KA...), unsigned G, cudaStream_t st, bool dependent, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(TB);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (dependent && chain_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // cotangent rows: [N, CE], or [N, dim] (dim < CE) for the layer next to the loss
 template <int CE>
 __device__ __forceinline__ Row<CE> load_gplus(const float* __restrict__ g, int64_t i, int gdim) {
@@ -96,7 +145,11 @@ __global__ void __launch_bounds__(TB) k_wide_stage(const int4* __restrict__ rows
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const Wide w = load_wide(rows, i);
-    const Row<CE> yi = ldg_row<CE>(y, i);
+    const float tau0 = tau ? __ldg(tau) : 1.0f;
+    // everything above is independent of the previous launch; everything below reads what it wrote
+    chain_wait();
+    chain_release();
+    const Row<CE> yi = ldcg_row<CE>(y, i);
     // ---- F(y) at node i: project, gather, softmax, aggregate (ell_math.cuh: ell_feval) ----
     const Row<CE> p = project<CE>(Mu, yi);
     Row<CE> xj[W];
@@ -104,7 +157,7 @@ __global__ void __launch_bounds__(TB) k_wide_stage(const int4* __restrict__ rows
     float m = -3.0e38f;
 #pragma unroll
     for (int q = 0; q < W; ++q) {
-        xj[q] = ldg_row<CE>(y, (int64_t)w.nb[q]);
+        xj[q] = ldcg_row<CE>(y, (int64_t)w.nb[q]);
         const float d = dot<CE>(p, xj[q]);
         s[q] = w.has(q) ? d : -CUDART_INF_F;
         m = fmaxf(m, s[q]);
@@ -123,10 +176,10 @@ __global__ void __launch_bounds__(TB) k_wide_stage(const int4* __restrict__ rows
 #pragma unroll
     for (int c = 0; c < CE; ++c) k.v[c] = fmaf(o.v[c], rZ, -yi.v[c]);
     // ---- stage combination ----
-    const float c1 = (tau ? tau[0] : 1.0f) * c1_scale;
+    const float c1 = tau0 * c1_scale;
     Row<CE> a_in = zero_row<CE>(), b_in = zero_row<CE>();
-    if (acc_in) a_in = ldg_row<CE>(acc_in, i);
-    if (base) b_in = (base == y) ? yi : ldg_row<CE>(base, i);
+    if (acc_in) a_in = ldcg_row<CE>(acc_in, i);
+    if (base) b_in = (base == y) ? yi : ldcg_row<CE>(base, i);
     Row<CE> o1;
 #pragma unroll
     for (int c = 0; c < CE; ++c) {
@@ -306,18 +359,20 @@ int wide_forward_t(const int4* rows, int64_t N, const float* x0, int dim, const 
         float* nxt = last ? nullptr : (states ? states + (size_t)(l + 1) * row : ping[l & 1]);
         float* xp = last ? x_phys : nullptr;
         if (method == GAD_METHOD_EULER) {
-            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, cur, cur, nullptr, Mul, tl, 1.0f, 0.f, 0, nxt, nullptr, xp, dim);
-            GAD_LAUNCH_CHECK();
+            GAD_CUDA(launch_link(k_wide_stage<CE, W>, G, st, l > 0, rows, N, cur, cur, (const float*)nullptr, Mul, tl, 1.0f,
+                                 0.f, 0, nxt, (float*)nullptr, xp, dim));
+            count_launch(1);
         } else {
             // classical RK4 on F(y) = A(y) y - y (stream_kernels.cu: stream_forward)
-            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, cur, cur, nullptr, Mul, tl, 0.5f, 1.0f, 0, ybuf, abuf, nullptr, dim);
-            GAD_LAUNCH_CHECK();
-            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, ybuf, cur, abuf, Mul, tl, 0.5f, 2.0f, 0, y3buf, abuf, nullptr, dim);
-            GAD_LAUNCH_CHECK();
-            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, y3buf, cur, abuf, Mul, tl, 1.0f, 2.0f, 0, ybuf, abuf, nullptr, dim);
-            GAD_LAUNCH_CHECK();
-            k_wide_stage<CE, W><<<G, TB, 0, st>>>(rows, N, ybuf, cur, abuf, Mul, tl, 1.0f / 6.0f, 0.f, 1, nxt, nullptr, xp, dim);
-            GAD_LAUNCH_CHECK();
+            GAD_CUDA(launch_link(k_wide_stage<CE, W>, G, st, l > 0, rows, N, cur, cur, (const float*)nullptr, Mul, tl, 0.5f,
+                                 1.0f, 0, ybuf, abuf, (float*)nullptr, dim));
+            GAD_CUDA(launch_link(k_wide_stage<CE, W>, G, st, true, rows, N, (const float*)ybuf, cur, (const float*)abuf,
+                                 Mul, tl, 0.5f, 2.0f, 0, y3buf, abuf, (float*)nullptr, dim));
+            GAD_CUDA(launch_link(k_wide_stage<CE, W>, G, st, true, rows, N, (const float*)y3buf, cur, (const float*)abuf,
+                                 Mul, tl, 1.0f, 2.0f, 0, ybuf, abuf, (float*)nullptr, dim));
+            GAD_CUDA(launch_link(k_wide_stage<CE, W>, G, st, true, rows, N, (const float*)ybuf, cur, (const float*)abuf,
+                                 Mul, tl, 1.0f / 6.0f, 0.f, 1, nxt, (float*)nullptr, xp, dim));
+            count_launch(4);
         }
         cur = nxt;
     }

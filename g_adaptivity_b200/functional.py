@@ -146,7 +146,9 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
     if x_comp.dim() == 1:
         x_comp = x_comp.unsqueeze(-1)
     N = x_comp.shape[0]
-    if graph.tile_ptr is None and not force_stream and not getattr(graph, "_no_cluster", False) and graph.ensure_cluster_fwd(CE):
+    if (graph.tile_ptr is None and not force_stream and not getattr(graph, "_no_cluster", False)
+            and graph.ensure_cluster_fwd(CE)
+            and not graph.stream_fwd_preferred(CE, int(tau.numel()) * (4 if method == METHOD_RK4 else 1))):
         # meshes beyond one CTA: one thread-block cluster per mesh, ONE launch for all layers / RK4 steps
         lib = _lib.load()
         if f is not None and dim >= CE:

@@ -338,8 +338,41 @@ def _ensure_cluster_fwd(self, ce: int) -> bool:
     return True
 
 
+# F-evaluation time of the cluster forward kernel against the nodes of one slab (us; 64 RK4 steps on one
+# 64x64 / 100x100 / 200x200 mesh over 16 CTAs, scripts/fwd_sweep.py)
+_CLUSTER_FEVAL_US = ((256, 1.125), (625, 2.03), (2500, 3.5))
+
+
+def _stream_fwd_preferred(self, ce: int, n_fevals: int) -> bool:
+    """Forward-only dispatch between the cluster kernel (one launch, M x C CTAs, a cluster barrier per
+    F-evaluation) and the streaming wide-row chain (one dependent launch per F-evaluation over ALL SMs,
+    csrc/stream_ell.cu).  With few meshes the clusters leave most of the machine idle: one 200x200 mesh on
+    16 CTAs takes 3.5 us per F-evaluation against 1.85 us for the chain (cfg 4: 0.87 -> 0.46 ms); from
+    ~4 meshes of 100x100 on, and for 64x64 meshes at any batch, the cluster kernel wins.  Measured model:
+    chain = 1.7 us + 12.2 ns per 1000 nodes of the batch per F-evaluation, plus ~3 us once for the extra
+    pack launch.  Call after ensure_cluster_fwd returned True."""
+    import os
+    pol = os.environ.get("GAD_FWD_POLICY")
+    if pol == "cluster":
+        return False
+    M, C = len(self.mesh_sizes), int(self.clf_C)
+    if pol != "stream":
+        if M * C > 128:
+            return False
+        slab = -(-max(self.mesh_sizes) // C)
+        pts = _CLUSTER_FEVAL_US
+        k = 0 if slab <= pts[1][0] else 1
+        (s0, t0), (s1, t1) = pts[k], pts[k + 1]
+        cluster_us = t0 + (slab - s0) * (t1 - t0) / (s1 - s0)
+        stream_us = 1.7 + 1.22e-5 * self.N
+        if n_fevals * (cluster_us - stream_us) <= 3.0:
+            return False
+    return self.ensure_wide(ce)
+
+
 MeshGraph.ensure_cluster = _ensure_cluster
 MeshGraph.ensure_cluster_fwd = _ensure_cluster_fwd
+MeshGraph.stream_fwd_preferred = _stream_fwd_preferred
 
 
 def edge_masks(edge_index: torch.Tensor, side_bits: torch.Tensor):

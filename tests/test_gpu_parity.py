@@ -370,10 +370,21 @@ def test_inference_session_replays_burgers_rollout():
             assert util.rel_err(got, ref(data)) <= COORD_TOL
 
 
-def test_config4_200x200_rk4_64_steps_forward():
+def test_config4_200x200_rk4_64_steps_forward(monkeypatch):
     over = {"ode_method": "rk4", "num_layers": 64}
     model, out, ref_out, data = _compare_with_oracle((200, 200), 1, over=over, backward=False)
-    assert model.last_graph.tile_ptr is None and model.last_graph.clf_C == 16     # one cluster of 16 CTAs, one launch
+    # a single 16-CTA cluster would leave 90 % of the machine idle: the module dispatches the forward to the
+    # chain of 256 dependent streaming launches (graph.stream_fwd_preferred) ...
+    assert model.last_graph.tile_ptr is None and model.last_graph.clf_C == 16 and model.last_graph.wide_in is not None
+    model.eval()
+    with torch.no_grad():
+        got = model(data)
+    assert util.rel_err(got, ref_out) <= COORD_TOL
+    # ... and the cluster kernel (ONE launch for all 64 steps) gives the same mesh
+    monkeypatch.setenv("GAD_FWD_POLICY", "cluster")
+    with torch.no_grad():
+        got2 = model(data)
+    assert util.rel_err(got2, ref_out) <= COORD_TOL and util.rel_err(got2, got) <= COORD_TOL
     model2, *_ = _compare_with_oracle((200, 200), 1, over=over, backward=False, gad_no_cluster=True)   # 256 launches
     assert getattr(model2.last_graph, "clf_in", None) is None
 
