@@ -21,6 +21,7 @@ namespace {
 
 constexpr int TB = 256;
 constexpr int WIDE_SLOTS = 7;
+constexpr int WIDE_TAU_LAYERS = 64;   // columns of deferred step-size partials the backward workspace holds
 
 inline unsigned nblocks(int64_t n, int t = TB) { return (unsigned)((n + t - 1) / t); }
 
@@ -110,6 +111,15 @@ __device__ __forceinline__ Row<CE> load_gplus(const float* __restrict__ g, int64
     Row<CE> r;
 #pragma unroll
     for (int c = 0; c < CE; ++c) r.v[c] = (c < gdim) ? __ldg(g + i * gdim + c) : 0.f;
+    return r;
+}
+
+template <int CE>
+__device__ __forceinline__ Row<CE> ldcg_gplus(const float* g, int64_t i, int gdim) {
+    if (gdim >= CE) return ldcg_row<CE>(g, i);
+    Row<CE> r;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) r.v[c] = (c < gdim) ? __ldcg(g + i * gdim + c) : 0.f;
     return r;
 }
 
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ ro
                                                      const float* __restrict__ Mu_g, const float* __restrict__ tau,
                                                      float a_coef, float* __restrict__ P, float2* __restrict__ DL,
                                                      float* __restrict__ gself, float* __restrict__ partials,
-                                                     int accumulate) {
+                                                     int accumulate, float* __restrict__ tau_part, int tau_stride) {
     constexpr int NACC = CE * CE + CE + 1;
     __shared__ float Mu[CE * CE + CE];
     __shared__ float red[NACC * (TB / 32)];
@@ -220,10 +230,6 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ ro
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const Wide w = load_wide(rows, i);
         const Row<CE> xi = ldg_row<CE>(x, i);
-        const Row<CE> gp = load_gplus<CE>(gplus, i, gplus_dim);
-        Row<CE> go;
-#pragma unroll
-        for (int c = 0; c < CE; ++c) go.v[c] = b * gp.v[c];
         const bool any = w.nb[7] != 0;
         const Row<CE> p = project<CE>(Mu, xi);
         Row<CE> xj[W];
@@ -248,6 +254,13 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ ro
         const float rZ = any ? rcp_refined(Z) : 0.f;
 #pragma unroll
         for (int c = 0; c < CE; ++c) o.v[c] *= rZ;
+        // the recompute above reads only the saved states; the cotangent comes from the previous launch
+        chain_wait();
+        chain_release();
+        const Row<CE> gp = ldcg_gplus<CE>(gplus, i, gplus_dim);
+        Row<CE> go;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) go.v[c] = b * gp.v[c];
         const float D = dot<CE>(go, o);
         const float lse = any ? m + lg2_approx(Z) : 0.f;
         const float scale = rZ * LN2_F;
@@ -278,10 +291,13 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_dst(const int4* __restrict__ ro
     }
     // per-block partial row: (G_M, G_u) accumulate over the layers of a shared weight set (same block,
     // same order every time: deterministic), the step-size column is per layer
+    chain_wait();
     block_reduce<NACC>(acc, red, blk);
     if (threadIdx.x < NACC) {
         float* dst = partials + (size_t)blockIdx.x * NACC + threadIdx.x;
-        *dst = (accumulate && threadIdx.x < NACC - 1) ? *dst + blk[threadIdx.x] : blk[threadIdx.x];
+        *dst = (accumulate && threadIdx.x < NACC - 1) ? __ldcg(dst) + blk[threadIdx.x] : blk[threadIdx.x];
+        // step-size partials of ALL layers side by side ([block][layer]) when the reduction is deferred
+        if (tau_part && threadIdx.x == NACC - 1) tau_part[(size_t)blockIdx.x * tau_stride] = blk[NACC - 1];
     }
 }
 
@@ -297,16 +313,19 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_src(const int4* __restrict__ ro
     const float b = tau ? tau[0] : 1.0f;
     const Wide w = load_wide(rows_out, j);
     const Row<CE> xj = ldg_row<CE>(x, j);
+    // the out-edge row and the saved state do not depend on the destination pass; its outputs do
+    chain_wait();
+    chain_release();
     Row<CE> p[W], gp[W];
     float2 dl[W];
 #pragma unroll
     for (int q = 0; q < W; ++q) {
         const int64_t i = (int64_t)w.nb[q];
-        p[q] = ldg_row<CE>(P, i);
-        gp[q] = load_gplus<CE>(gplus, i, gplus_dim);
-        dl[q] = __ldg(DL + i);
+        p[q] = ldcg_row<CE>(P, i);
+        gp[q] = ldcg_gplus<CE>(gplus, i, gplus_dim);
+        dl[q] = __ldcg(DL + i);
     }
-    Row<CE> accv = ldg_row<CE>(gself, j);
+    Row<CE> accv = ldcg_row<CE>(gself, j);
 #pragma unroll
     for (int q = 0; q < W; ++q) {
         const float sv = dot<CE>(p[q], xj) - dl[q].y;
@@ -396,29 +415,41 @@ int wide_backward_t(const int4* rows_in, const int4* rows_out, int64_t N, const 
     GAD_CUDA(cudaMemsetAsync(gMu, 0, (size_t)Lw * MUSZ * sizeof(float), st));
     const float* gcur = g_xphys;
     int gdim = dim;
+    // Step-size partials of all layers are kept side by side and reduced once at the end, so that (with one
+    // shared weight set) nothing is launched between the passes and the whole backward is one chain of
+    // dependent launches; the workspace holds WIDE_TAU_LAYERS columns.
+    const bool defer_tau = g_tau && L <= WIDE_TAU_LAYERS;
+    float* taup = partials + align_up((size_t)G * NACC, 64);
+    bool first = true;
     for (int l = L - 1; l >= 0; --l) {
         const float* Mul = Mu + (size_t)(Lw > 1 ? l : 0) * MUSZ;
         const float* xl = states + (size_t)l * row;
         const float* tl = tau + l;
         float* gout = (l == 0 && g_x0) ? g_x0 : gping[l & 1];
         const bool shared_w = (Lw == 1);
-        k_wide_bwd_dst<CE, W><<<G, TB, 0, st>>>(rows_in, N, xl, gcur, gdim, Mul, tl, 1.0f, P, DL, gself, partials,
-                                                (shared_w && l < L - 1) ? 1 : 0);
-        GAD_LAUNCH_CHECK();
+        GAD_CUDA(launch_link(k_wide_bwd_dst<CE, W>, (unsigned)G, st, !first, rows_in, N, xl, gcur, gdim, Mul, tl, 1.0f, P, DL,
+                             gself, partials, (shared_w && l < L - 1) ? 1 : 0, defer_tau ? taup + l : (float*)nullptr, L));
+        count_launch(1);
+        first = false;
         if (l > 0 || g_x0) {
-            k_wide_bwd_src<CE, W><<<nblocks(N), TB, 0, st>>>(rows_out, N, xl, gcur, gdim, tl, P, DL, gself, gout);
-            GAD_LAUNCH_CHECK();
+            GAD_CUDA(launch_link(k_wide_bwd_src<CE, W>, nblocks(N), st, true, rows_out, N, xl, gcur, gdim, tl,
+                                 (const float*)P, (const float2*)DL, (const float*)gself, gout));
+            count_launch(1);
         }
         if (!shared_w || l == 0) {   // shared weights: one reduction of the accumulated partials at the end
             k_wide_reduce<<<(MUSZ + 7) / 8, 256, 0, st>>>(partials, G, MUSZ, NACC, gMu + (size_t)(shared_w ? 0 : l) * MUSZ, 1);
             GAD_LAUNCH_CHECK();
         }
-        if (g_tau) {
+        if (g_tau && !defer_tau) {
             k_wide_reduce<<<1, 32, 0, st>>>(partials + MUSZ, G, 1, NACC, g_tau + l, 0);
             GAD_LAUNCH_CHECK();
         }
         gcur = gout;
         gdim = CE;
+    }
+    if (defer_tau) {
+        k_wide_reduce<<<(L + 7) / 8, 256, 0, st>>>(taup, G, L, L, g_tau, 0);
+        GAD_LAUNCH_CHECK();
     }
     return GAD_OK;
 }

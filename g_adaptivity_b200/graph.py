@@ -370,8 +370,30 @@ def _stream_fwd_preferred(self, ce: int, n_fevals: int) -> bool:
     return self.ensure_wide(ce)
 
 
+def _stream_train_preferred(self, ce: int) -> bool:
+    """Training-step dispatch for FEW very large meshes: the one-launch cluster kernel takes 43 us on one
+    100x100 mesh (625 nodes per CTA of a 16-cluster) and 70 us on one 200x200 mesh (2500 per CTA, 16 SMs
+    busy), the chain of ~14 streaming launches 45 us and 51 us; with four meshes or more the cluster
+    kernel always wins (scripts/widebench.py).  Call after ensure_cluster returned True."""
+    import os
+    pol = os.environ.get("GAD_TRAIN_POLICY")
+    if pol == "cluster":
+        return False
+    if pol != "stream":
+        M, C = len(self.mesh_sizes), int(self.cl_C)
+        if M * C > 128:
+            return False
+        slab = -(-max(self.mesh_sizes) // C)
+        cluster_us = 43.0 + max(0, slab - 625) * 0.01435
+        stream_us = 45.0 + max(0, self.N - 10000) * 0.00019
+        if stream_us >= cluster_us - 2.0:
+            return False
+    return self.ensure_wide(ce)
+
+
 MeshGraph.ensure_cluster = _ensure_cluster
 MeshGraph.ensure_cluster_fwd = _ensure_cluster_fwd
+MeshGraph.stream_train_preferred = _stream_train_preferred
 MeshGraph.stream_fwd_preferred = _stream_fwd_preferred
 
 

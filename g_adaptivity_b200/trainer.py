@@ -206,7 +206,9 @@ class DeformerTrainer:
             streaming = T == 0 or self.opt.get("gad_force_stream", False)
             if streaming:
                 s.graph.ensure_wide(self.CE)     # wide rows for the streaming ELL kernels, built outside any capture
+            s.prefer_stream = None
             if T == 0 and not self.opt.get("gad_no_cluster", False) and s.graph.ensure_cluster(self.CE):
+                s.prefer_stream = bool(s.graph.stream_train_preferred(self.CE))   # decided outside any capture
                 need = lib.gad_cluster_workspace_bytes(self.CE, len(s.graph.mesh_sizes), s.graph.cl_C, self.L)
                 if need > s.bwd_ws_bytes:
                     s.bwd_ws_bytes = need
@@ -336,8 +338,12 @@ class DeformerTrainer:
     def _cluster(self, s: _Slot) -> bool:
         """Meshes too large for one CTA run on the cluster-resident kernel (csrc/cl_kernels.cu)."""
         g = s.graph
-        return bool(g.tile_ptr is None and g.cl_in is not None and not self.opt.get("gad_no_cluster", False)
-                    and not self.opt.get("gad_force_stream", False))
+        if not (g.tile_ptr is None and g.cl_in is not None and not self.opt.get("gad_no_cluster", False)
+                and not self.opt.get("gad_force_stream", False)):
+            return False
+        if s.prefer_stream is None:      # one or two very large meshes: the streaming chain uses all SMs
+            s.prefer_stream = bool(g.stream_train_preferred(self.CE))
+        return not s.prefer_stream
 
     def _one_launch(self, s: _Slot) -> bool:
         g = s.graph

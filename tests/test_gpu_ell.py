@@ -258,6 +258,32 @@ def test_cluster_training_is_deterministic_and_matches_streaming_steps():
     assert (finals[0][1] - finals[2][1]).abs().max().item() <= 2e-4 * finals[2][1].abs().max().item()
 
 
+def test_single_very_large_mesh_trains_on_the_streaming_chain(monkeypatch):
+    """One 128x128 mesh would keep a 16-CTA cluster on 16 SMs: the trainer picks the chain of dependent
+    streaming launches (graph.stream_train_preferred); forced onto the cluster kernel it takes the same steps."""
+    opt, ds, data, ref = _case((128, 128), 1, seed=13)
+    finals = []
+    for policy in (None, "cluster"):
+        if policy:
+            monkeypatch.setenv("GAD_TRAIN_POLICY", policy)
+        model = cuda_model(ds, opt, ref.state_dict())
+        tr = DeformerTrainer(model, lr=1e-2)
+        sid = tr.add_batch(data)
+        s = tr.slots[sid]
+        assert s.graph.cl_in is not None and s.graph.cl_C == 16
+        assert tr._cluster(s) == (policy == "cluster")
+        losses = []
+        for _ in range(3):
+            l = tr.step(sid)
+            with torch.cuda.stream(tr.stream):
+                losses.append(l.clone())
+        tr.synchronize()
+        finals.append(([float(x.item()) for x in losses], tr.flat.clone().cpu()))
+    assert finals[0][0][-1] < finals[0][0][0]
+    assert abs(finals[0][0][0] - finals[1][0][0]) <= 1e-5 * abs(finals[1][0][0])
+    assert (finals[0][1] - finals[1][1]).abs().max().item() <= 2e-4 * finals[1][1].abs().max().item()
+
+
 def test_host_fed_loop_packed_buffers_equal_per_tensor_copies():
     """run_from_host over pack_host buffers (one H2D copy per step) == over Batch objects (one copy per
     tensor) == resident-batch steps: same losses, same parameters."""
