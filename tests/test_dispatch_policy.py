@@ -1,0 +1,56 @@
+"""Host logic of the cluster / streaming dispatch (graph.stream_fwd_preferred, stream_train_preferred):
+the measured shapes of profiles/r01_v11_fwd_dispatch_sweep.jsonl must come out on the faster side."""
+import types
+
+import pytest
+
+from g_adaptivity_b200 import graph as G
+
+
+def _fake(n_mesh_nodes, M, C):
+    g = types.SimpleNamespace(mesh_sizes=[n_mesh_nodes] * M, clf_C=C, cl_C=C, N=n_mesh_nodes * M)
+    g.ensure_wide = lambda ce: True
+    return g
+
+
+@pytest.mark.parametrize("nodes,M,C,fevals,want_stream", [
+    (200 * 200, 1, 16, 256, True),      # cfg 4: 0.46 ms on the chain, 0.87 ms on one cluster
+    (200 * 200, 4, 16, 64, False),      # tie -> one launch
+    (100 * 100, 1, 16, 64, True),
+    (100 * 100, 2, 16, 64, True),
+    (100 * 100, 8, 16, 64, False),
+    (100 * 100, 64, 4, 64, False),
+    (64 * 64, 1, 16, 64, False),
+    (64 * 64, 64, 2, 64, False),
+    (100 * 100, 1, 16, 4, False),       # four Euler layers: the extra pack launch costs more than it saves
+])
+def test_forward_dispatch(nodes, M, C, fevals, want_stream, monkeypatch):
+    monkeypatch.delenv("GAD_FWD_POLICY", raising=False)
+    assert G._stream_fwd_preferred(_fake(nodes, M, C), 4, fevals) == want_stream
+
+
+@pytest.mark.parametrize("nodes,M,C,want_stream", [
+    (200 * 200, 1, 16, True),           # 51 us against 70 us
+    (100 * 100, 1, 16, False),          # 45 us against 43 us
+    (100 * 100, 4, 16, False),
+    (100 * 100, 64, 4, False),
+    (64 * 64, 3, 16, False),
+])
+def test_training_dispatch(nodes, M, C, want_stream, monkeypatch):
+    monkeypatch.delenv("GAD_TRAIN_POLICY", raising=False)
+    assert G._stream_train_preferred(_fake(nodes, M, C), 4) == want_stream
+
+
+def test_policy_overrides(monkeypatch):
+    g = _fake(64 * 64, 1, 16)
+    monkeypatch.setenv("GAD_FWD_POLICY", "stream")
+    assert G._stream_fwd_preferred(g, 4, 4)
+    monkeypatch.setenv("GAD_TRAIN_POLICY", "stream")
+    assert G._stream_train_preferred(g, 4)
+    g2 = _fake(200 * 200, 1, 16)
+    monkeypatch.setenv("GAD_FWD_POLICY", "cluster")
+    monkeypatch.setenv("GAD_TRAIN_POLICY", "cluster")
+    assert not G._stream_fwd_preferred(g2, 4, 256) and not G._stream_train_preferred(g2, 4)
+    g2.ensure_wide = lambda ce: False       # no wide rows (degree > 7): never the chain
+    monkeypatch.delenv("GAD_FWD_POLICY")
+    assert not G._stream_fwd_preferred(g2, 4, 256)
