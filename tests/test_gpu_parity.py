@@ -400,6 +400,35 @@ def test_config5_slice_50x50_batch64_fwd_bwd():
     assert model.last_graph.tile_ptr is not None and model.last_graph.max_tile_nodes == 2500
 
 
+def test_config5_per_gpu_shard_through_replication():
+    """cfg 5 at its per-GPU size on 8 GPUs (1024 meshes of 50x50 = 2.56 M nodes, 14.6 M edges), checked
+    through a size-independent property: the batch is 128 copies of an 8-mesh batch, so every copy must come
+    out bit for bit the same, equal the oracle on the 8 meshes, and (mean loss) give the 8-mesh gradient."""
+    mesh_dims, B0, R = (50, 50), 8, 128
+    opt = synth.default_opt(mesh_dims)
+    ds = synth.SyntheticDataset(2, mesh_dims)
+    small = synth.make_batch(mesh_dims, B0, seed=21)
+    big = synth.make_batch(mesh_dims, B0 * R, seed=21)
+    for k in ("x_comp", "x_phys", "f_tensor", "uu_tensor", "u_true_tensor"):
+        v = getattr(small, k)
+        setattr(big, k, v.repeat((R,) + (1,) * (v.dim() - 1)).contiguous())
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    ref_out = ref(small)
+    gnn_oracle.mesh_loss(ref_out, small.x_phys).backward()
+    ref_grads = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    model = cuda_model(ds, opt, ref.state_dict())
+    model.train()
+    out = model(big)
+    assert model.last_graph.T == B0 * R and model.last_graph.max_tile_nodes == 2500
+    o = out.detach().reshape(R, ref_out.shape[0], -1)
+    assert torch.equal(o, o[0:1].expand_as(o))
+    assert util.rel_err(o[0], ref_out) <= COORD_TOL
+    F.l1_loss(out, big.x_phys.cuda()).backward()
+    g64, floor, scale = util.fp64_grads_and_noise_floor(ds, opt, small, ref, ref_grads)
+    util.check_grads_conditioned(grads_of(model), g64, floor, scale, tol=GRAD_TOL)
+
+
 def test_scaled_weights_stress_softmax():
     # x4 weights: logits 16x larger -> near one-hot attention; parity is still within the bar
     _compare_with_oracle((24, 24), 8, wscale=4.0)
