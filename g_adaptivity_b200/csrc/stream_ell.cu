@@ -11,6 +11,13 @@
 // streaming kernels (stream_kernels.cu: two to three passes over col[] per node, each a dependent
 // index load + gather) a node is one pass with no dependent index loads.
 //
+// The launches of one call form a chain of programmatic dependent launches: every kernel loads what
+// does not depend on its predecessor (topology row, folded weights, in the backward destination pass the
+// whole softmax recompute from the saved state) BEFORE griddepcontrol.wait, releases its own dependent
+// right after the wait (so at most two links are ever resident), and reads whatever the predecessor
+// wrote with ld.global.cg -- it was resident while those lines were written, so its L1 may be stale.
+// One 200x200 mesh: 2.5 -> 1.8 us per F-evaluation.
+//
 // Replaces, per layer, `layer(x, edge_index)` + the Euler update (src/GNN.py:273-296) and its
 // autograd (src/run_GNN.py:127,130) for graphs of degree <= 7.
 #include "common.cuh"
