@@ -169,7 +169,15 @@ class GNN(nn.Module):
         g = self._graphs.get(key)
         if g is not None:
             return g
-        # Identity miss (a fresh Batch from the loader): look the topology up by CONTENT before building
+        # Identity miss (a fresh Batch from the loader).  Datasets on one shared mesh: shapes + host samples
+        skey = None
+        if opt.get("gad_shared_topology", False):
+            skey = GraphCache.shared_key_of(data, flags)
+            g = self._graphs.get(skey)
+            if g is not None:
+                self._graphs.shared_hits = getattr(self._graphs, "shared_hits", 0) + 1
+                return g
+        # otherwise look the topology up by CONTENT before building
         ckey, dev_copies = None, {}
         if opt.get("gad_content_cache", True):
             ckey, dev_copies = GraphCache.content_key_of(data, flags, dev, use_masks=bool(opt["fix_boundary"]))
@@ -197,6 +205,8 @@ class GNN(nn.Module):
         self._graphs.put(key, g, keep)
         if ckey is not None:
             self._graphs._d[ckey] = g
+        if skey is not None:
+            self._graphs._d[skey] = g
         return g
 
     def _folded_weights(self, dev):

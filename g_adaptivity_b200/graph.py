@@ -498,6 +498,30 @@ class GraphCache:
         fp = tuple(out.tolist())     # the one synchronisation
         return ("content", fp, tuple(shapes), h.hexdigest()) + tuple(flags), copies
 
+    SHARED_SAMPLES = 64
+
+    @staticmethod
+    def shared_key_of(data, flags) -> tuple:
+        """Key for datasets whose samples all live on ONE mesh (the reference's `randg` data: `dataset.mesh`,
+        `x_comp_shared`, src/data.py:143), opted into with `opt['gad_shared_topology']`: batches of the same
+        shape then have the same topology, so a fresh Batch is recognised from shapes, mesh sizes and
+        SHARED_SAMPLES columns of `edge_index` / entries of the masks read on the host -- no host -> device
+        copy of the topology (26 MB per step on cfg 2), no fingerprint pass.  The samples catch a batch that
+        breaks the promise only with high probability, which is why this is an option and the content
+        fingerprint (content_key_of) the default."""
+        ei = data.edge_index
+        E = int(ei.shape[1])
+        parts = [tuple(ei.shape), int(data.x_comp.shape[0])]
+        sizes = getattr(data, "mesh_sizes", None)
+        parts.append(None if sizes is None else (len(sizes), int(min(sizes)), int(max(sizes))))
+        if E > 0:
+            idx = torch.linspace(0, E - 1, min(E, GraphCache.SHARED_SAMPLES)).long().to(ei.device)
+            parts.append(tuple(ei[:, idx].reshape(-1).tolist()))
+            for name in ("to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask"):
+                t = getattr(data, name, None)
+                parts.append(None if t is None else tuple(t[idx.to(t.device)].tolist()))
+        return ("shared",) + tuple(parts) + tuple(flags)
+
     def alias(self, key, graph, keepalive):
         """Register another identity key for an existing graph (kept alive like any entry)."""
         self._d[key] = graph

@@ -93,14 +93,14 @@ def time_train(md, B, ring, iters):
             "tiles": s.graph.T}
 
 
-def time_module_train_fresh(md, B, iters, content_cache):
+def time_module_train_fresh(md, B, iters, content_cache, shared_topology=False):
     """The reference's loop shape: a FRESH Batch object per iteration, model(data) -> L1 loss ->
     backward -> torch.optim.Adam.step(), all through the module seam (host tensors in)."""
     import torch.nn.functional as F
     from g_adaptivity_b200 import GNN, synth
     dev = torch.device("cuda", 0)
     opt = synth.default_opt(md)
-    opt.update(device="cuda:0", gad_store_alpha=False, gad_content_cache=content_cache)
+    opt.update(device="cuda:0", gad_store_alpha=False, gad_content_cache=content_cache, gad_shared_topology=shared_topology)
     ds = synth.SyntheticDataset(len(md), md)
     torch.manual_seed(42)
     model = GNN(ds, opt).to(dev).train()
@@ -128,7 +128,8 @@ def time_module_train_fresh(md, B, iters, content_cache):
     ms = 1e3 * statistics.median(ts)
     N = base.x_comp.shape[0]
     return {"nodes": N, "ms_per_step": round(ms, 4), "gnodes_per_s": round(N / ms / 1e6, 4),
-            "graph_builds": model._graphs.misses, "content_hits": getattr(model._graphs, "misses_identity", 0)}
+            "graph_builds": model._graphs.misses, "content_hits": getattr(model._graphs, "misses_identity", 0),
+            "shared_hits": getattr(model._graphs, "shared_hits", 0)}
 
 
 def time_fem1d(B, n, G=1, K=101, Q=101, iters=10):
@@ -208,6 +209,7 @@ def main():
     res["fem1d_pde_loss_b4096_n200"] = time_fem1d(4096, 200)
     res["pde_loss_train_step_module_seam_b4096_n200"] = time_pde_loss_step((200,), 4096, it)
     res["cfg2_module_seam_train_fresh_batches_content_cache"] = time_module_train_fresh((30, 30), 256, it, True)
+    res["cfg2_module_seam_train_fresh_batches_shared_topology"] = time_module_train_fresh((30, 30), 256, it, True, True)
     res["cfg2_module_seam_train_fresh_batches_identity_cache_only"] = time_module_train_fresh((30, 30), 256, it, False)
     for k, v in res.items():
         print(k, json.dumps(v), flush=True)

@@ -54,3 +54,23 @@ def test_policy_overrides(monkeypatch):
     g2.ensure_wide = lambda ce: False       # no wide rows (degree > 7): never the chain
     monkeypatch.delenv("GAD_FWD_POLICY")
     assert not G._stream_fwd_preferred(g2, 4, 256)
+
+
+def test_shared_topology_key_is_host_only_and_shape_and_sample_sensitive():
+    """GraphCache.shared_key_of (opt gad_shared_topology): equal for fresh batches on the same mesh, different
+    for another batch size or a changed sampled edge / mask entry; reads host tensors only."""
+    from g_adaptivity_b200 import synth
+    flags = (True, False, 4, "cuda:0")
+    a = synth.make_batch((9, 9), 4, seed=1)
+    b = synth.make_batch((9, 9), 4, seed=2)          # other features, same mesh
+    ka, kb = G.GraphCache.shared_key_of(a, flags), G.GraphCache.shared_key_of(b, flags)
+    assert ka == kb and ka[0] == "shared"
+    assert G.GraphCache.shared_key_of(synth.make_batch((9, 9), 5, seed=1), flags) != ka
+    assert G.GraphCache.shared_key_of(a, flags[:-1] + ("cuda:1",)) != ka
+    c = a.clone()
+    c.edge_index = c.edge_index.clone()
+    c.edge_index[0, 0] += 1                          # column 0 is always sampled
+    assert G.GraphCache.shared_key_of(c, flags) != ka
+    d = a.clone()
+    d.to_boundary_edge_mask = ~d.to_boundary_edge_mask
+    assert G.GraphCache.shared_key_of(d, flags) != ka

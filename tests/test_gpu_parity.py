@@ -348,6 +348,28 @@ def test_graph_cache_finds_fresh_batch_objects_by_content():
     assert not torch.equal(out2, outs[0])
 
 
+def test_shared_topology_option_recognises_batches_without_topology_traffic():
+    """`gad_shared_topology` (datasets whose samples all live on one mesh, src/data.py:143): a fresh Batch
+    of a known shape is served from the cache by shapes + host samples -- no fingerprint pass, no copy of
+    edge_index -- and another batch size is another graph."""
+    mesh_dims, B = (12, 12), 6
+    opt = synth.default_opt(mesh_dims)
+    ds = synth.SyntheticDataset(2, mesh_dims)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    model = cuda_model(ds, opt, ref.state_dict(), gad_shared_topology=True)
+    model.eval()
+    with torch.no_grad():
+        for it in range(3):
+            data = synth.make_batch(mesh_dims, B, seed=5 + it)     # fresh tensors, new features, same mesh
+            assert util.rel_err(model(data), ref(data)) <= COORD_TOL
+        assert model._graphs.misses == 1 and model._graphs.shared_hits == 2
+        assert getattr(model._graphs, "misses_identity", 0) == 0
+        data = synth.make_batch(mesh_dims, B + 1, seed=9)
+        assert util.rel_err(model(data), ref(data)) <= COORD_TOL
+        assert model._graphs.misses == 2 and model._graphs.shared_hits == 2
+
+
 def test_inference_session_replays_burgers_rollout():
     """CUDA-graph replay of the deformer call (GNN.inference_session) == the module call, for a
     sequence of uu fields on a fixed 1-D mesh batch."""
