@@ -74,3 +74,38 @@ def test_shared_topology_key_is_host_only_and_shape_and_sample_sensitive():
     d = a.clone()
     d.to_boundary_edge_mask = ~d.to_boundary_edge_mask
     assert G.GraphCache.shared_key_of(d, flags) != ka
+
+
+def test_module_serves_fresh_batches_from_the_shared_topology_key(monkeypatch):
+    """GNN._graph with gad_shared_topology: one build, then fresh batches on the same mesh hit the cache
+    without the content-fingerprint pass; another batch size builds again.  (Graph build and fingerprint are
+    stubbed: this is the host logic only; the GPU run is tests/test_gpu_parity.py.)"""
+    import importlib
+    import torch
+    from g_adaptivity_b200 import synth
+    M = importlib.import_module("g_adaptivity_b200.GNN")
+    builds, fingerprints = [], []
+
+    def fake_build(*a, **k):
+        builds.append(types.SimpleNamespace())
+        return builds[-1]
+
+    def fake_content(data, flags, dev, use_masks=True):
+        fingerprints.append(1)
+        return ("content", len(fingerprints)), {}
+
+    monkeypatch.setattr(M.MeshGraph, "build", staticmethod(fake_build))
+    monkeypatch.setattr(G.GraphCache, "content_key_of", staticmethod(fake_content))
+    md = (12, 12)
+    model = M.GNN(synth.SyntheticDataset(2, md), synth.default_opt(md, gad_shared_topology=True))
+    dev = torch.device("cpu")
+    gs = [model._graph(synth.make_batch(md, 6, seed=5 + it), dev) for it in range(3)]
+    assert len(builds) == 1 and len(fingerprints) == 1 and gs[0] is gs[1] is gs[2]
+    assert model._graphs.misses == 1 and model._graphs.shared_hits == 2
+    g7 = model._graph(synth.make_batch(md, 7, seed=9), dev)
+    assert g7 is not gs[0] and len(builds) == 2 and model._graphs.shared_hits == 2
+    # without the option every fresh batch goes through the fingerprint
+    model2 = M.GNN(synth.SyntheticDataset(2, md), synth.default_opt(md))
+    for it in range(2):
+        model2._graph(synth.make_batch(md, 6, seed=5 + it), dev)
+    assert len(fingerprints) == 2 + 2 and getattr(model2._graphs, "shared_hits", 0) == 0
