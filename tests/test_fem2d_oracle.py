@@ -1,0 +1,70 @@
+"""The 2-D FEM oracle (oracle/fem2d_oracle.py) against the fixtures minted from the reference's own
+firedrake_difFEM/difFEM_2d.py (oracle/ref_harness/make_golden_fem2d.py).  First step of scope row f1 in
+2-D: no CUDA kernel exists for it yet; the quadrature (torchquad) part of the parity is unpinned, see the
+oracle's header."""
+import glob
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fem2d_oracle as O
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden_fem2d", "fem2d_*.pt")))
+
+
+def _run(fx, dtype=torch.float32):
+    mesh = fx["mesh"].clone().to(dtype).requires_grad_(True)
+    Q = int(fx["eval_points"])
+    x0 = torch.linspace(0, 1, Q)
+    X, Y = torch.meshgrid(x0, x0, indexing="ij")
+    c_list = [c.clone() for c in fx["centers"]]
+    s_list = [s.clone() for s in fx["scales"]]
+    coeffs, sol = O.torch_fem_2d(fx["cells"], fx["bc_nodes"], mesh, [X, Y], int(fx["load_quad_points"]), c_list, s_list)
+    loss = F.mse_loss(sol, O.u_true(torch.stack([X, Y]), c_list, s_list))
+    loss.backward()
+    return coeffs, sol, loss, mesh.grad
+
+
+def test_fixtures_present():
+    assert len(GOLDEN) == 4
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-3] for p in GOLDEN])
+def test_oracle_reproduces_reference_bit_for_bit(path):
+    fx = torch.load(path)
+    coeffs, sol, loss, grad = _run(fx)
+    assert torch.equal(coeffs.detach(), fx["coeffs"])
+    assert torch.equal(sol.detach(), fx["sol"])
+    assert float(loss.item()) == fx["loss"]
+    assert torch.equal(grad, fx["grad_mesh"])
+
+
+def test_simpson_rule_properties():
+    """The restated torchquad rule: points per dimension (odd, >= 3), exactness for cubics per dimension,
+    and the point order the reference's integrands rely on (dimension 0 slowest)."""
+    assert [O.simpson_points_per_dim(N) for N in (1, 9, 100, 121, 441, 50000)] == [3, 3, 9, 11, 21, 223]
+    seen = {}
+
+    def fn(p):
+        seen["p"] = p
+        return p[:, 0] ** 3 * p[:, 1] ** 2 + 2.0
+
+    val = O.simpson_2d(fn, 81, [[0.0, 2.0], [1.0, 3.0]])
+    assert seen["p"].shape == (81, 2) and seen["p"][1, 0] == seen["p"][0, 0] and seen["p"][1, 1] > seen["p"][0, 1]
+    exact = (2.0 ** 4 / 4) * ((3.0 ** 3 - 1.0) / 3) + 2.0 * 4.0
+    assert abs(float(val) - exact) <= 1e-5 * exact
+
+
+def test_basis_is_a_partition_of_unity_and_interpolates():
+    """phim (difFEM_2d.py:28-60): the hat functions sum to one on the domain (edge / vertex repeats are
+    divided out) and phi_m(x_n) = delta_mn."""
+    fx = torch.load(GOLDEN[1])
+    cells, mesh = fx["cells"], fx["mesh"]
+    x0 = torch.linspace(0, 1, 17)
+    X, Y = torch.meshgrid(x0, x0, indexing="ij")
+    total = sum(O.phim([X, Y], m, mesh, cells) for m in range(mesh.shape[0]))
+    assert (total - 1.0).abs().max().item() <= 1e-5
+    at_nodes = torch.stack([O.phim(mesh.t().contiguous(), m, mesh, cells) for m in range(mesh.shape[0])])
+    assert (at_nodes - torch.eye(mesh.shape[0])).abs().max().item() <= 1e-6
