@@ -37,16 +37,23 @@ def star_table(cells: torch.Tensor, num_nodes: int):
 
 def _hat(P, a, b, c):
     """P [..., Q, 2] points, a/b/c [..., 1, 2] vertices: indicator(closed triangle) * barycentric coordinate of c."""
-    def edge(u, v):
-        return (u[..., 1] - v[..., 1]) * P[..., 0] + (v[..., 0] - u[..., 0]) * P[..., 1] - (
-            (u[..., 1] - v[..., 1]) * u[..., 0] + (v[..., 0] - u[..., 0]) * u[..., 1])
-    e1, e2, e3 = edge(a, b), edge(b, c), edge(c, a)
-    left = (e1 >= 0) & (e2 >= 0) & (e3 >= 0)
-    right = (e1 <= 0) & (e2 <= 0) & (e3 <= 0)
-    inside = left.to(P.dtype) + right.to(P.dtype)
+    inside, lin = _hat_parts(P, a, b, c)
+    return inside * lin
+
+
+def _hat_parts(P, a, b, c):
+    # the two sides of every edge test are rounded separately and then compared, exactly as difFEM_2d.py:16-20
+    # does: points ON an edge (ties) are then decided the same way as in the reference
+    def sides(u, v):
+        return ((u[..., 1] - v[..., 1]) * P[..., 0] + (v[..., 0] - u[..., 0]) * P[..., 1],
+                (u[..., 1] - v[..., 1]) * u[..., 0] + (v[..., 0] - u[..., 0]) * u[..., 1])
+    (l1, r1), (l2, r2), (l3, r3) = sides(a, b), sides(b, c), sides(c, a)
+    left = (l1 >= r1).to(P.dtype) * (l2 >= r2).to(P.dtype) * (l3 >= r3).to(P.dtype)
+    right = (l1 <= r1).to(P.dtype) * (l2 <= r2).to(P.dtype) * (l3 <= r3).to(P.dtype)
+    inside = left + right
     lin = 1 + ((P[..., 0] - c[..., 0]) * (a[..., 1] - b[..., 1]) + (P[..., 1] - c[..., 1]) * (b[..., 0] - a[..., 0])) / (
         (a[..., 1] - b[..., 1]) * (c[..., 0] - a[..., 0]) + (c[..., 1] - a[..., 1]) * (b[..., 0] - a[..., 0]))
-    return inside * lin
+    return inside, lin
 
 
 def basis_at(P, nodes, coords, cells, cell_of, loc_of):
@@ -81,13 +88,24 @@ def u_true(P, centers, scales):
     return out
 
 
+def linspace_rows(lo, hi, n):
+    """Row-wise torch.linspace(lo[r], hi[r], n), bit for bit: ATen steps up from `lo` in the first half and down
+    from `hi` in the second, each point one fused multiply-add (a kernel does the same with fmaf) -- the cubature
+    points must be the reference's to the last bit because points ON element edges are decided by comparisons."""
+    step = (hi - lo) / (n - 1)
+    i = torch.arange(n, dtype=torch.float64)
+    up = (lo.double().unsqueeze(1) + step.double().unsqueeze(1) * i).to(lo.dtype)
+    down = (hi.double().unsqueeze(1) - step.double().unsqueeze(1) * (n - 1 - i)).to(lo.dtype)
+    return torch.where((torch.arange(n) < n // 2).unsqueeze(0), up, down)
+
+
 def stiffness(cells, coords):
     """Dense -K (the reference's sign) from closed-form triangle gradients."""
     N = coords.shape[0]
     p = coords[cells]                                            # [T, 3, 2]
     d = p[:, [1, 2, 0]] - p[:, [2, 0, 1]]                        # p_{k+1} - p_{k+2}
     twoA = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1])
-    g = torch.stack([-d[..., 1], d[..., 0]], dim=-1) / twoA.view(-1, 1, 1)     # grad phi_k  [T, 3, 2]
+    g = torch.stack([d[..., 1], -d[..., 0]], dim=-1) / twoA.view(-1, 1, 1)     # grad phi_k  [T, 3, 2]
     Kloc = 0.5 * twoA.abs().view(-1, 1, 1) * (g @ g.transpose(1, 2))           # [T, 3, 3]
     A = torch.zeros(N, N, dtype=coords.dtype)
     rows = cells.unsqueeze(2).expand(-1, 3, 3).reshape(-1)
@@ -114,9 +132,7 @@ def fem2d_fast(cells, bc_nodes, coords, eval_xy, load_quad_points, centers, scal
     pad = (cell_of[inner] < 0).view(len(inner), -1, 1, 1)
     lo = torch.where(pad, torch.full_like(star_pts, float("inf")), star_pts).amin(dim=(1, 2))
     hi = torch.where(pad, torch.full_like(star_pts, float("-inf")), star_pts).amax(dim=(1, 2))
-    t = torch.linspace(0, 1, n, dtype=dt)
-    gx = lo[:, 0:1] + (hi[:, 0:1] - lo[:, 0:1]) * t                               # [M, n]
-    gy = lo[:, 1:2] + (hi[:, 1:2] - lo[:, 1:2]) * t
+    gx, gy = linspace_rows(lo[:, 0], hi[:, 0], n), linspace_rows(lo[:, 1], hi[:, 1], n)   # [M, n]
     P = torch.stack([gx.unsqueeze(2).expand(-1, n, n), gy.unsqueeze(1).expand(-1, n, n)], dim=-1).reshape(len(inner), n * n, 2)
     w1 = torch.ones(n, dtype=dt)
     w1[1:-1:2], w1[2:-1:2] = 4, 2
@@ -134,3 +150,109 @@ def fem2d_fast(cells, bc_nodes, coords, eval_xy, load_quad_points, centers, scal
     phi = basis_at(E.unsqueeze(0).expand(N, -1, -1), allnodes, coords, cells, cell_of, loc_of)       # [N, Q]
     sol = (coeffs * phi).sum(0).reshape(X.shape)
     return coeffs, sol
+
+
+# ---- hand-derived adjoint (what a backward kernel computes; checked against autograd on the CPU) ----------
+# For a triangle with vertices p_k, barycentric coordinates l_k(P) and their (constant) gradients g_k:
+#     d l_c(P) / d p_v = -l_v(P) g_c          d g_c / d p_v [delta] = -g_v (g_c . delta)
+#     d area / d p_v   = area * g_v
+# hence for K_ab = area * g_a . g_b:   sum_ab x_a y_b dK_ab/dp_v = area * ((Gx . Gy) g_v - (g_v . Gy) Gx - (g_v . Gx) Gy)
+# with Gx = sum_a x_a g_a, Gy = sum_b y_b g_b.  The masks of `phim` (which cells count at a point, and the repeat
+# divisor) are piecewise constant and carry no derivative; box and grid of the cubature are detached in the
+# reference (bounds_support_jr, difFEM_2d.py:298-309), as are the Dirichlet values (:172).
+def _bary(P, p, q, r):
+    """barycentric coordinate of vertex r of triangle (p, q, r) at P, and its gradient (constant per triangle)."""
+    den = (p[..., 1] - q[..., 1]) * (r[..., 0] - p[..., 0]) + (r[..., 1] - p[..., 1]) * (q[..., 0] - p[..., 0])
+    g = torch.stack([(p[..., 1] - q[..., 1]), (q[..., 0] - p[..., 0])], dim=-1) / den.unsqueeze(-1)
+    lam = 1 + ((P[..., 0] - r[..., 0]) * g[..., 0] + (P[..., 1] - r[..., 1]) * g[..., 1])
+    return lam, g
+
+
+def _star_parts(P, nodes, coords, cells, cell_of, loc_of):
+    """Per (node m, star slot d, point q): counting mask / repeat divisor, the three barycentric coordinates and
+    the vertex ids (c = m itself, a, b as in phim) of the slot's cell, gradient of l_c."""
+    cid, k = cell_of[nodes], loc_of[nodes]
+    valid = (cid >= 0)
+    tri = cells[cid.clamp(min=0)]
+    vid = lambda off: torch.gather(tri, 2, ((k + off) % 3).unsqueeze(-1)).squeeze(-1)        # [M, D]
+    c_id, a_id, b_id = vid(0), vid(2), vid(1)
+    c, a, b = (coords[i].unsqueeze(2) for i in (c_id, a_id, b_id))                           # [M, D, 1, 2]
+    Pq = P.unsqueeze(1)
+    inside, lin = _hat_parts(Pq, a, b, c)
+    mult = inside * valid.unsqueeze(-1).to(P.dtype)        # 0, 1, or 2 when both orientation tests hold (point on a vertex line)
+    rep = ((mult * lin) > 0).to(P.dtype).sum(1)            # cells that contributed a positive value (phim's divisor)
+    rep = rep + (rep == 0).to(P.dtype)
+    lc, gc = _bary(Pq, a, b, c)
+    la, _ = _bary(Pq, b, c, a)
+    lb, _ = _bary(Pq, c, a, b)
+    # a point ON the edge opposite to m has value 0 (not counted in rep) but a non-zero derivative: mult keeps it
+    return mult, rep, (la, lb, lc), (a_id, b_id, c_id), gc.squeeze(2)
+
+
+def _scatter_basis_grad(grad, coef, parts):
+    """grad[p_v] += sum_{m,d,q} coef[m,q] * d phi_m(P_q)/d p_v  for the three vertices of every star slot."""
+    mult, rep, (la, lb, lc), (a_id, b_id, c_id), gc = parts
+    wq = (coef / rep).unsqueeze(1) * mult                                   # [M, D, Q]
+    for lam, vid_ in ((la, a_id), (lb, b_id), (lc, c_id)):
+        S = -(wq * lam).sum(-1)                                             # [M, D]
+        grad.index_add_(0, vid_.reshape(-1), (S.unsqueeze(-1) * gc).reshape(-1, 2))
+
+
+def fem2d_forward_backward(cells, bc_nodes, coords, eval_xy, load_quad_points, centers, scales, loss_grad_fn):
+    """(coeffs, sol, d loss / d coords) without autograd.  `loss_grad_fn(sol)` returns d loss / d sol."""
+    with torch.no_grad():
+        cells = torch.as_tensor(cells, dtype=torch.long)
+        bcn = torch.as_tensor(bc_nodes, dtype=torch.long)
+        N, dt = coords.shape[0], coords.dtype
+        cell_of, loc_of = star_table(cells, N)
+        A = stiffness(cells, coords)
+        is_bc = torch.zeros(N, dtype=torch.bool)
+        is_bc[bcn] = True
+        A = torch.where(is_bc.view(-1, 1), torch.eye(N, dtype=dt), A)
+        inner = torch.nonzero(~is_bc).reshape(-1)
+        n = simpson_points_per_dim(int(load_quad_points), 2)
+        star_pts = coords[cells[cell_of[inner].clamp(min=0)]]
+        pad = (cell_of[inner] < 0).view(len(inner), -1, 1, 1)
+        lo = torch.where(pad, torch.full_like(star_pts, float("inf")), star_pts).amin(dim=(1, 2))
+        hi = torch.where(pad, torch.full_like(star_pts, float("-inf")), star_pts).amax(dim=(1, 2))
+        gx, gy = linspace_rows(lo[:, 0], hi[:, 0], n), linspace_rows(lo[:, 1], hi[:, 1], n)
+        P = torch.stack([gx.unsqueeze(2).expand(-1, n, n), gy.unsqueeze(1).expand(-1, n, n)], dim=-1).reshape(len(inner), n * n, 2)
+        w1 = torch.ones(n, dtype=dt)
+        w1[1:-1:2], w1[2:-1:2] = 4, 2
+        W = (w1.view(-1, 1) * w1.view(1, -1)).reshape(-1)
+        h = (hi - lo) / (n - 1)
+        wq = W.unsqueeze(0) * (h[:, 0] * h[:, 1] / 9.0).unsqueeze(1) * forcing(P, centers, scales)        # [M, Q]
+        load_parts = _star_parts(P, inner, coords, cells, cell_of, loc_of)
+        mult, rep, (_, _, lc), _, _ = load_parts
+        phi_load = (mult * lc).sum(1) / rep
+        rhs = torch.zeros(N, dtype=dt)
+        rhs[inner] = (phi_load * wq).sum(1)
+        rhs[bcn] = u_true(coords[bcn], centers, scales)
+        u = torch.linalg.solve(A, rhs.unsqueeze(1)).squeeze(1)
+        X, Y = eval_xy
+        E = torch.stack([X.reshape(-1), Y.reshape(-1)], dim=-1).to(dt)
+        allnodes = torch.arange(N)
+        ev_parts = _star_parts(E.unsqueeze(0).expand(N, -1, -1), allnodes, coords, cells, cell_of, loc_of)
+        mult_e, rep_e, (_, _, lc_e), _, _ = ev_parts
+        phi = (mult_e * lc_e).sum(1) / rep_e                                                                # [N, Q]
+        sol = (u.unsqueeze(1) * phi).sum(0).reshape(X.shape)
+        # ---- backward
+        g_sol = loss_grad_fn(sol).reshape(-1).to(dt)
+        g_u = phi @ g_sol
+        lam = torch.linalg.solve(A.t(), g_u.unsqueeze(1)).squeeze(1)
+        grad = torch.zeros(N, 2, dtype=dt)
+        _scatter_basis_grad(grad, u.unsqueeze(1) * g_sol.unsqueeze(0), ev_parts)           # interpolation
+        _scatter_basis_grad(grad, lam[inner].unsqueeze(1) * wq, load_parts)                # load vector
+        lam_in = torch.where(is_bc, torch.zeros_like(lam), lam)                            # matrix rows of interior nodes
+        p = coords[cells]
+        d = p[:, [1, 2, 0]] - p[:, [2, 0, 1]]
+        twoA = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1])
+        g = torch.stack([d[..., 1], -d[..., 0]], dim=-1) / twoA.view(-1, 1, 1)                              # [T, 3, 2]
+        area = 0.5 * twoA.abs()
+        Gl = (lam_in[cells].unsqueeze(-1) * g).sum(1)                                                       # [T, 2]
+        Gu = (u[cells].unsqueeze(-1) * g).sum(1)
+        gv = area.view(-1, 1, 1) * ((Gl * Gu).sum(-1).view(-1, 1, 1) * g
+                                    - (g * Gu.unsqueeze(1)).sum(-1, keepdim=True) * Gl.unsqueeze(1)
+                                    - (g * Gl.unsqueeze(1)).sum(-1, keepdim=True) * Gu.unsqueeze(1))        # [T, 3, 2]
+        grad.index_add_(0, cells.reshape(-1), gv.reshape(-1, 2))
+        return u.unsqueeze(1), sol, grad
