@@ -121,3 +121,42 @@ def test_linspace_rows_is_torch_linspace_bit_for_bit():
         rows = Fz.linspace_rows(lo, hi, n)
         for r in range(64):
             assert torch.equal(rows[r], torch.linspace(float(lo[r]), float(hi[r]), n))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-3] for p in GOLDEN])
+def test_kernel_arithmetic_on_the_host_matches_the_reference(path):
+    """g_adaptivity_b200/csrc/fem2d_math.cuh -- the host/device functions the 2-D FEM kernels are written with --
+    run sequentially on the CPU (oracle/fem2d_host.cpp: triangle geometry, Simpson load vector with the
+    reference's tie handling, matrix-free conjugate gradients on the interior SPD system, point-wise
+    interpolation, hand-derived adjoint) against the fixtures of the reference: forward 1e-5, gradient 5e-5."""
+    import ctypes
+    import numpy as np
+    from oracle import build_host, fem2d_fast as Fz
+    lib = ctypes.CDLL(build_host.build())
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    fx = torch.load(path)
+    N = fx["mesh"].shape[0]
+    cells = fx["cells"].numpy().astype(np.int32)
+    is_bc = np.zeros(N, np.uint8)
+    is_bc[fx["bc_nodes"].numpy()] = 1
+    sc_, sl_ = Fz.star_table(fx["cells"], N)
+    star_cell, star_loc = sc_.numpy().astype(np.int32), sl_.numpy().astype(np.int32)
+    coords = fx["mesh"].numpy().astype(np.float32).copy()
+    cen, scl = fx["centers"].numpy().astype(np.float64).copy(), fx["scales"].numpy().astype(np.float64).copy()
+    Q = int(fx["eval_points"])
+    x0 = torch.linspace(0, 1, Q)
+    X, Y = torch.meshgrid(x0, x0, indexing="ij")
+    ex, ey = X.reshape(-1).numpy().copy(), Y.reshape(-1).numpy().copy()
+    coeffs, sol, grad = np.zeros(N, np.float32), np.zeros(Q * Q, np.float32), np.zeros((N, 2), np.float32)
+    iters = ctypes.c_int(0)
+    args = [ptr(cells), cells.shape[0], ptr(is_bc), N, ptr(star_cell), ptr(star_loc), star_cell.shape[1], ptr(coords), ptr(cen),
+            ptr(scl), cen.shape[0], int(fx["load_quad_points"]), ptr(ex), ptr(ey), Q * Q]
+    assert lib.fem2d_host(*args, None, ptr(coeffs), ptr(sol), None, ctypes.byref(iters)) == 0
+    tgt = Fz.u_true(torch.stack([X, Y], dim=-1), fx["centers"], fx["scales"]).reshape(-1).numpy()
+    g_sol = (2 * (sol - tgt) / sol.size).astype(np.float32)             # d mse_loss / d sol
+    assert lib.fem2d_host(*args, ptr(g_sol), ptr(coeffs), ptr(sol), ptr(grad), ctypes.byref(iters)) == 0
+    scale_c, scale_g = fx["coeffs"].abs().max().item(), fx["grad_mesh"].abs().max().item()
+    assert np.abs(coeffs - fx["coeffs"].reshape(-1).numpy()).max() <= 1e-5 * scale_c
+    assert np.abs(sol - fx["sol"].reshape(-1).numpy()).max() <= 1e-5 * scale_c
+    assert np.abs(grad - fx["grad_mesh"].numpy()).max() <= 5e-5 * scale_g
+    assert 0 < iters.value <= 40 * N
