@@ -93,6 +93,8 @@ SIGNATURES = {
     "gad_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p, _p]),
     "gad_fem1d_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "gad_fem1d_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "gad_fem2d_fwd": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "gad_fem2d_bwd": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p]),
     "gad_peer_exchange_bytes": (_sz, [_i, _i64]),
     "gad_peer_alloc": (_i, [_sz, C.POINTER(_p), _p]),
     "gad_peer_open": (_i, [_p, C.POINTER(_p)]),

@@ -359,6 +359,27 @@ int gad_fem1d_fwd(const float* x, const float* centers, const float* scales, con
 int gad_fem1d_bwd(const float* x, const float* centers, const float* scales, const float* quad, const float* g_sol,
                   int B, int n, int G, int load_quad_points, int Q, float* g_x, void* stream);
 
+/* ---- next row f1 (2-D): batched differentiable FEM solve after the deformer on 2-D meshes ------------------
+ * Replaces the per-mesh Python loop of src/GNN.py:327-335 over torch_FEM_2D
+ * (firedrake_difFEM/difFEM_2d.py:345-372: P1 stiffness matrix from per-triangle gradients, Dirichlet rows,
+ * load vector by torchquad's composite Simpson rule with `load_quad_points` points over the bounding box of
+ * every node's star, linear solve, evaluation of sum_m coeffs_m phi_m at the Q evaluation points with the
+ * edge / vertex repeat rule of `phim`) and its autograd with respect to the mesh points.  One topology per
+ * batch: cells [T,3]; is_bc [N] (DirichletBC(V, 0, "on_boundary").nodes as a mask); star_cell / star_loc [N,D]
+ * = cell id and local vertex index of the cells around every node in ascending cell order, -1 padded.
+ * coords [B,N,2]; centers / scales [B,G,2] fp64 (as the reference passes them); eval_x / eval_y [Q].
+ * fwd: coeffs [B,N], sol [B,Q], u64 [B,N] (fp64 coefficients kept for the backward), cg_iters [B] or NULL.
+ * bwd: g_sol [B,Q] -> grad [B,N,2] (no gradient through Dirichlet values and cubature boxes, as :172, :298-309).
+ * STATUS: arithmetic verified on the host (oracle/fem2d_host.cpp); kernels not yet run on a GPU. */
+int gad_fem2d_fwd(const int32_t* cells, int32_t T, const uint8_t* is_bc, int32_t N, const int32_t* star_cell,
+                  const int32_t* star_loc, int32_t D, const float* coords, const double* centers, const double* scales,
+                  int32_t G, int32_t B, int32_t load_quad_points, const float* eval_x, const float* eval_y, int32_t Q,
+                  float* coeffs, float* sol, double* u64, int32_t* cg_iters, void* stream);
+int gad_fem2d_bwd(const int32_t* cells, int32_t T, const uint8_t* is_bc, int32_t N, const int32_t* star_cell,
+                  const int32_t* star_loc, int32_t D, const float* coords, const double* centers, const double* scales,
+                  int32_t G, int32_t B, int32_t load_quad_points, const float* eval_x, const float* eval_y, int32_t Q,
+                  const double* u64, const float* g_sol, float* grad, void* stream);
+
 /* ---- peer memory for the data-parallel gradient exchange (one process per GPU, one node) -------
  * The reference trains single-process (src/run_GNN.py:95-131); sharding a batch by whole meshes
  * needs exactly one exchange per step, the SUM of the flat gradient.  gad_peer_alloc returns a
