@@ -3,20 +3,27 @@
 // mesh in a Python loop (src/GNN.py:327-335), as one CTA per mesh over a topology shared by the batch.
 //
 // STATUS: first version, correctness-first.  Its arithmetic (fem2d_math.cuh) and phase order are checked on the CPU
-// against the reference's fixtures (oracle/fem2d_host.cpp, tests/test_fem2d_oracle.py); the kernels themselves
-// compile for sm_100a but have NOT yet run on a GPU (the round's GPU budget was spent) -- nothing in the Python
-// package calls them yet, and tests/pending_gpu/check_fem2d.py is the first thing to run next.
+// against the reference's fixtures (oracle/fem2d_host.cpp, tests/test_fem2d_oracle.py), and the kernels below run
+// on the CPU under a thread-per-CUDA-thread emulation (oracle/fem2d_emu.cpp: FEM2D_EMULATE) with the same results;
+// they compile for sm_100a but have NOT yet run on a GPU (the round's GPU budget was spent) -- GNN.forward does not
+// route to them yet, and tests/pending_gpu/check_fem2d.py is the first thing to run next.
 //
 // Phases (forward): triangle geometry -> load vector (Simpson cubature per interior node, Dirichlet values) ->
 // matrix-free conjugate gradients on the interior SPD system (rows gathered through the star table, fixed-order
 // block reductions, fp64) -> interpolation on the evaluation points (brute-force point location for now).
 // Backward: g_u by fp64 shared-memory accumulation, second CG solve for the adjoint, three gradient terms
 // (matrix, load vector, interpolation) accumulated per vertex in shared memory, one store per vertex.
+#ifndef FEM2D_EMULATE
 #include "common.cuh"
+#endif
 #include "fem2d_math.cuh"
 
 namespace gad {
+#ifdef FEM2D_EMULATE          // oracle/fem2d_emu.cpp: the kernels on CPU threads; they must be visible to that file
+inline namespace emu {
+#else
 namespace {
+#endif
 
 using namespace fem2d;
 
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_bwd(F2Args a) {
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) a.grad[(size_t)mesh * a.N * 2 + i] = (float)s.acc[i];
 }
 
+#ifndef FEM2D_EMULATE
 int f2_launch(const F2Args& a, int B, bool backward, cudaStream_t st) {
     const size_t bytes = f2_smem_bytes(a.N, a.T);
     GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "fem2d: a mesh of %d nodes / %d cells needs %zu B of shared memory", a.N, a.T,
@@ -375,10 +383,12 @@ int f2_launch(const F2Args& a, int B, bool backward, cudaStream_t st) {
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
+#endif
 
 }  // namespace
 }  // namespace gad
 
+#ifndef FEM2D_EMULATE
 using namespace gad;
 
 extern "C" int gad_fem2d_fwd(const int32_t* cells, int32_t T, const uint8_t* is_bc, int32_t N, const int32_t* star_cell,
@@ -408,3 +418,4 @@ extern "C" int gad_fem2d_bwd(const int32_t* cells, int32_t T, const uint8_t* is_
     a.T = T, a.N = N, a.D = D, a.G = G, a.K = load_quad_points, a.Q = Q;
     return f2_launch(a, B, true, as_stream(stream));
 }
+#endif  // FEM2D_EMULATE

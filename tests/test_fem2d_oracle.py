@@ -160,3 +160,76 @@ def test_kernel_arithmetic_on_the_host_matches_the_reference(path):
     assert np.abs(sol - fx["sol"].reshape(-1).numpy()).max() <= 1e-5 * scale_c
     assert np.abs(grad - fx["grad_mesh"].numpy()).max() <= 5e-5 * scale_g
     assert 0 < iters.value <= 40 * N
+
+
+def _emu_run(lib, cells, bc_nodes, mesh, centers, scales, K, Q, B=1):
+    import ctypes
+    import numpy as np
+    from oracle import fem2d_fast as Fz
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    N = mesh.shape[0]
+    cells32 = np.ascontiguousarray(cells, dtype=np.int32)
+    is_bc = np.zeros(N, np.uint8)
+    is_bc[np.asarray(bc_nodes)] = 1
+    sc_, sl_ = Fz.star_table(torch.as_tensor(cells, dtype=torch.long), N)
+    star_cell, star_loc = sc_.numpy().astype(np.int32), sl_.numpy().astype(np.int32)
+    coords = np.stack([np.asarray(mesh, dtype=np.float32)] * B).copy()
+    cen = np.stack([np.asarray(centers, dtype=np.float64)] * B).copy()
+    scl = np.stack([np.asarray(scales, dtype=np.float64)] * B).copy()
+    x0 = torch.linspace(0, 1, Q)
+    X, Y = torch.meshgrid(x0, x0, indexing="ij")
+    ex, ey = X.reshape(-1).numpy().copy(), Y.reshape(-1).numpy().copy()
+    coeffs, sol = np.zeros((B, N), np.float32), np.zeros((B, Q * Q), np.float32)
+    grad, u64, iters = np.zeros((B, N, 2), np.float32), np.zeros((B, N), np.float64), np.zeros(B, np.int32)
+    args = [ptr(cells32), cells32.shape[0], ptr(is_bc), N, ptr(star_cell), ptr(star_loc), star_cell.shape[1], ptr(coords), ptr(cen),
+            ptr(scl), cen.shape[1], B, int(K), ptr(ex), ptr(ey), Q * Q]
+    assert lib.fem2d_emu(*args, None, ptr(coeffs), ptr(sol), ptr(u64), None, ptr(iters)) == 0
+    tgt = Fz.u_true(torch.stack([X, Y], dim=-1), torch.as_tensor(centers), torch.as_tensor(scales)).reshape(-1).numpy()
+    g_sol = (2 * (sol - tgt[None]) / sol[0].size).astype(np.float32)
+    assert lib.fem2d_emu(*args, ptr(g_sol), ptr(coeffs), ptr(sol), ptr(u64), ptr(grad), None) == 0
+    return coeffs, sol, grad, iters, g_sol, (cells32, is_bc, star_cell, star_loc, coords, cen, scl, ex, ey)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-3] for p in GOLDEN])
+def test_kernels_emulated_on_cpu_threads_match_the_reference(path):
+    """csrc/fem2d.cu ITSELF compiled for the CPU (oracle/fem2d_emu.cpp + oracle/cuda_emu.h: one std::thread per
+    CUDA thread, pthread barriers for __syncthreads / warp shuffles, CAS for atomicAdd): k_fem2d_fwd and
+    k_fem2d_bwd, a batch of two meshes, against the fixtures of the reference.  Checks the kernels' indexing,
+    shared-memory carving, phase order and barriers while no GPU is at hand (they have not run on one yet)."""
+    import ctypes
+    import numpy as np
+    from oracle import build_host
+    lib = ctypes.CDLL(build_host.build_emu())
+    fx = torch.load(path)
+    coeffs, sol, grad, iters, _, _ = _emu_run(lib, fx["cells"].numpy(), fx["bc_nodes"].numpy(), fx["mesh"].numpy(), fx["centers"].numpy(),
+                                              fx["scales"].numpy(), fx["load_quad_points"], int(fx["eval_points"]), B=2)
+    scale_c, scale_g = fx["coeffs"].abs().max().item(), fx["grad_mesh"].abs().max().item()
+    for b in range(2):
+        assert np.abs(coeffs[b] - fx["coeffs"].reshape(-1).numpy()).max() <= 1e-5 * scale_c
+        assert np.abs(sol[b] - fx["sol"].reshape(-1).numpy()).max() <= 1e-5 * scale_c
+        assert np.abs(grad[b] - fx["grad_mesh"].numpy()).max() <= 5e-5 * scale_g
+    assert iters[0] == iters[1] > 0
+
+
+def test_emulated_kernels_equal_the_sequential_harness_beyond_one_thread_per_node():
+    """20x20 mesh (400 nodes, 722 cells > 256 threads: every strided loop wraps): emulated kernels against the
+    sequential host run of the same arithmetic."""
+    import ctypes
+    import numpy as np
+    from oracle import build_host
+    from oracle.ref_harness.make_golden_fem2d import case_inputs
+    emu, host = ctypes.CDLL(build_host.build_emu()), ctypes.CDLL(build_host.build())
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    n, K, Q = 20, 101, 23
+    cells, bc, pts, centers, scales = case_inputs(n, 2, 0.3, 7)
+    coeffs, sol, grad, iters, g_sol, (cells32, is_bc, star_cell, star_loc, coords, cen, scl, ex, ey) = _emu_run(
+        emu, cells, bc, pts, centers, scales, K, Q)
+    N = pts.shape[0]
+    c2, s2, g2 = np.zeros(N, np.float32), np.zeros(Q * Q, np.float32), np.zeros((N, 2), np.float32)
+    it2 = ctypes.c_int(0)
+    assert host.fem2d_host(ptr(cells32), cells32.shape[0], ptr(is_bc), N, ptr(star_cell), ptr(star_loc), star_cell.shape[1],
+                           ptr(coords[0]), ptr(cen[0]), ptr(scl[0]), cen.shape[1], K, ptr(ex), ptr(ey), Q * Q, ptr(g_sol[0]),
+                           ptr(c2), ptr(s2), ptr(g2), ctypes.byref(it2)) == 0
+    assert np.abs(coeffs[0] - c2).max() <= 2e-6 * np.abs(c2).max()
+    assert np.abs(sol[0] - s2).max() <= 2e-6 * np.abs(c2).max()
+    assert np.abs(grad[0] - g2).max() <= 1e-5 * np.abs(g2).max()
