@@ -10,7 +10,8 @@
 //
 // Phases (forward): triangle geometry -> load vector (Simpson cubature per interior node, Dirichlet values) ->
 // matrix-free conjugate gradients on the interior SPD system (rows gathered through the star table, fixed-order
-// block reductions, fp64) -> interpolation on the evaluation points (brute-force point location for now).
+// block reductions, fp64) -> interpolation on the evaluation points (point location: all cells, bounding-box
+// prefilter; a bin table is the next step).
 // Backward: g_u by fp64 shared-memory accumulation, second CG solve for the adjoint, three gradient terms
 // (matrix, load vector, interpolation) accumulated per vertex in shared memory, one store per vertex.
 #ifndef FEM2D_EMULATE
@@ -49,9 +50,18 @@ struct F2Args {
     int T, N, D, G, K, Q;
 };
 
+struct Box {
+    float lx, ly, hx, hy;
+};
+// A point that passes the (rounded) edge tests of a cell can lie outside the cell's exact bounding box only by the
+// rounding error of those tests (~1e-7 / edge length); the margin is orders of magnitude above that, so the prefilter
+// never changes which cells count.
+constexpr float BOX_MARGIN = 1e-3f;
+
 struct F2Smem {
     float* xy;       // [2N]
     Tri* tri;        // [T]
+    Box* box;        // [T]   bounding boxes of the cells, inflated: prefilter of the point location
     double* u;       // [N]
     double* b;       // [N]
     double* r;       // [N]
@@ -64,8 +74,8 @@ struct F2Smem {
 __host__ __device__ inline size_t f2_align(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t f2_smem_bytes(int N, int T) {
-    return f2_align(2 * (size_t)N * 4) + f2_align((size_t)T * sizeof(Tri)) + 5 * f2_align((size_t)N * 8) + f2_align(2 * (size_t)N * 8) +
-           f2_align(32 * 8);
+    return f2_align(2 * (size_t)N * 4) + f2_align((size_t)T * sizeof(Tri)) + f2_align((size_t)T * sizeof(Box)) +
+           5 * f2_align((size_t)N * 8) + f2_align(2 * (size_t)N * 8) + f2_align(32 * 8);
 }
 
 __device__ inline F2Smem f2_carve(unsigned char* base, int N, int T) {
@@ -73,6 +83,7 @@ __device__ inline F2Smem f2_carve(unsigned char* base, int N, int T) {
     size_t o = 0;
     s.xy = reinterpret_cast<float*>(base + o), o += f2_align(2 * (size_t)N * 4);
     s.tri = reinterpret_cast<Tri*>(base + o), o += f2_align((size_t)T * sizeof(Tri));
+    s.box = reinterpret_cast<Box*>(base + o), o += f2_align((size_t)T * sizeof(Box));
     s.u = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
     s.b = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
     s.r = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
@@ -102,8 +113,12 @@ __device__ void f2_geometry(const F2Args& a, const F2Smem& s, int mesh) {
     const float* c = a.coords + (size_t)mesh * a.N * 2;
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s.xy[i] = c[i];
     __syncthreads();
-    for (int t = threadIdx.x; t < a.T; t += blockDim.x)
-        s.tri[t] = tri_geometry(f2_pt(s.xy, a.cells[3 * t]), f2_pt(s.xy, a.cells[3 * t + 1]), f2_pt(s.xy, a.cells[3 * t + 2]));
+    for (int t = threadIdx.x; t < a.T; t += blockDim.x) {
+        const P2 p0 = f2_pt(s.xy, a.cells[3 * t]), p1 = f2_pt(s.xy, a.cells[3 * t + 1]), p2 = f2_pt(s.xy, a.cells[3 * t + 2]);
+        s.tri[t] = tri_geometry(p0, p1, p2);
+        s.box[t] = Box{fminf(p0.x, fminf(p1.x, p2.x)) - BOX_MARGIN, fminf(p0.y, fminf(p1.y, p2.y)) - BOX_MARGIN,
+                       fmaxf(p0.x, fmaxf(p1.x, p2.x)) + BOX_MARGIN, fmaxf(p0.y, fmaxf(p1.y, p2.y)) + BOX_MARGIN};
+    }
     __syncthreads();
 }
 
@@ -196,6 +211,8 @@ __device__ void f2_points(const F2Args& a, const F2Smem& s, int mesh) {
         const P2 P{a.ex[q], a.ey[q]};
         int ht[MAX_HITS], hm[MAX_HITS], nh = 0;
         for (int t = 0; t < a.T && nh < MAX_HITS; ++t) {
+            const Box bx = s.box[t];
+            if (P.x < bx.lx || P.x > bx.hx || P.y < bx.ly || P.y > bx.hy) continue;
             const int mult = inside_count(P, f2_pt(s.xy, a.cells[3 * t + 2]), f2_pt(s.xy, a.cells[3 * t + 1]), f2_pt(s.xy, a.cells[3 * t]));
             if (mult) ht[nh] = t, hm[nh] = mult, ++nh;
         }
