@@ -370,7 +370,7 @@ int gad_fem1d_bwd(const float* x, const float* centers, const float* scales, con
  * coords [B,N,2]; centers / scales [B,G,2] fp64 (as the reference passes them); eval_x / eval_y [Q].
  * fwd: coeffs [B,N], sol [B,Q], u64 [B,N] (fp64 coefficients kept for the backward), cg_iters [B] or NULL.
  * bwd: g_sol [B,Q] -> grad [B,N,2] (no gradient through Dirichlet values and cubature boxes, as :172, :298-309).
- * STATUS: arithmetic verified on the host (oracle/fem2d_host.cpp); kernels not yet run on a GPU. */
+ * Parity against the reference's fixtures: tests/test_fem2d_gpu.py (B200), oracle/fem2d_host.cpp (host). */
 int gad_fem2d_fwd(const int32_t* cells, int32_t T, const uint8_t* is_bc, int32_t N, const int32_t* star_cell,
                   const int32_t* star_loc, int32_t D, const float* coords, const double* centers, const double* scales,
                   int32_t G, int32_t B, int32_t load_quad_points, const float* eval_x, const float* eval_y, int32_t Q,

@@ -1,15 +1,15 @@
 #!/usr/bin/env python
-"""FIRST GPU CHECK of the 2-D FEM kernels (csrc/fem2d.cu) -- not collected by pytest on purpose: the kernels
-compiled but had not run on a GPU when the round's budget ended.  Run on a B200:
+"""Check + timing of the 2-D FEM kernels (csrc/fem2d.cu) on a B200 -- the script of their first GPU run
+(profiles/r01_v11_fem2d_first_gpu_run.log):
 
-    python tests/pending_gpu/check_fem2d.py
+    python scripts/fem2d_check.py
 
 Compares gad_fem2d_fwd / gad_fem2d_bwd with the fixtures minted from the reference's difFEM_2d.py
 (tests/golden_fem2d) -- forward 1e-5, gradient 5e-5, the bars the host harness of the same arithmetic meets --
-then with the host harness on a 15x15 mesh, and times a batch of 256 meshes of 30x30.  When it passes, move the
-checks into tests/test_fem2d.py (marked gpu) and route GNN.forward's 2-D pde_loss through g_adaptivity_b200.fem2d."""
+and times a batch of 256 meshes of 30x30 at the reference's default quadrature sizes.  The fixture checks are also
+tests/test_fem2d_gpu.py."""
 import glob, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import torch.nn.functional as F

@@ -195,7 +195,7 @@ def test_kernels_emulated_on_cpu_threads_match_the_reference(path):
     """csrc/fem2d.cu ITSELF compiled for the CPU (oracle/fem2d_emu.cpp + oracle/cuda_emu.h: one std::thread per
     CUDA thread, pthread barriers for __syncthreads / warp shuffles, CAS for atomicAdd): k_fem2d_fwd and
     k_fem2d_bwd, a batch of two meshes, against the fixtures of the reference.  Checks the kernels' indexing,
-    shared-memory carving, phase order and barriers while no GPU is at hand (they have not run on one yet)."""
+    shared-memory carving, phase order and barriers without a GPU (the GPU run is tests/test_fem2d_gpu.py)."""
     import ctypes
     import numpy as np
     from oracle import build_host
