@@ -45,6 +45,10 @@ MESHES_PER_GPU = 256
 NUM_LAYERS = 4
 METRIC = "mesh_nodes_per_sec_deformer_fwd_bwd"
 UNIT = "nodes/s"
+# the same string on both arms (the driver compares the arms' `config.workload`)
+WORKLOAD = (f"cfg2: {MESHES_PER_GPU} x {MESH_DIMS[0]}x{MESH_DIMS[1]} meshes per GPU, fwd+bwd train step "
+            f"(L={NUM_LAYERS} Euler layers, hidden 8, L1 mesh loss, Adam)")
+GRAPH_STEPS = 256       # most training steps held by one CUDA graph of the timed region
 
 
 # ------------------------------------------------------------------------------------------
@@ -139,9 +143,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU oracle timing (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------
-def time_cpu_oracle(steps: int, warmup: int, budget_s: float = 25.0):
-    """fwd + L1 loss + autograd backward of the CPU oracle (pure-PyTorch port of the reference
-    path; PyG itself is not installable here) on the full 256-mesh batch, all host threads."""
+def time_cpu_oracle(steps: int, warmup: int, budget_s: float = 25.0, meshes: int = MESHES_PER_GPU):
+    """One training step of the CPU oracle (pure-PyTorch port of the reference path; PyG itself is not
+    installable here): forward + L1 mesh loss + autograd backward + torch.optim.Adam step
+    (src/run_GNN.py:88,99-131) on a batch of `meshes` 30x30 meshes, all host threads."""
     import copy
     from g_adaptivity_b200 import synth
     from oracle import gnn_oracle
@@ -150,16 +155,18 @@ def time_cpu_oracle(steps: int, warmup: int, budget_s: float = 25.0):
     torch.set_num_threads(cores)
     opt = synth.default_opt(MESH_DIMS, num_layers=NUM_LAYERS)
     ds = synth.SyntheticDataset(2, MESH_DIMS)
-    data = synth.make_batch(MESH_DIMS, MESHES_PER_GPU, seed=0)
+    data = synth.make_batch(MESH_DIMS, meshes, seed=0)
     torch.manual_seed(42)
     model = gnn_oracle.GNNRef(ds, copy.deepcopy(opt))
     model.train()
+    optim = torch.optim.Adam(model.parameters(), lr=opt["lr"], weight_decay=opt["decay"])
     n_nodes = data.x_comp.shape[0]
 
     def one():
-        model.zero_grad(set_to_none=True)
+        optim.zero_grad(set_to_none=True)
         out = model(data)
         gnn_oracle.mesh_loss(out, data.x_phys).backward()
+        optim.step()
 
     for _ in range(max(1, warmup)):
         one()
@@ -173,24 +180,30 @@ def time_cpu_oracle(steps: int, warmup: int, budget_s: float = 25.0):
             break
     ms = 1e3 * sum(times) / len(times)
     return {"value": n_nodes / (ms * 1e-3), "ms_per_step": ms, "cores": cores, "steps": len(times),
-            "sample": f"{MESHES_PER_GPU} meshes of {MESH_DIMS[0]}x{MESH_DIMS[1]} ({n_nodes} nodes), "
-                      f"fwd + L1 loss + autograd bwd, torch CPU {torch.get_num_threads()} threads, "
+            "sample": f"{meshes} meshes of {MESH_DIMS[0]}x{MESH_DIMS[1]} ({n_nodes} nodes) per step, "
+                      f"fwd + L1 loss + autograd bwd + torch.optim.Adam, torch CPU {torch.get_num_threads()} threads, "
                       f"mean of {len(times)} steps"}
 
 
 def run_reference(args, rank: int, world: int):
     """Reference arm: the reference's CPU implementation of the path.  The reference itself cannot
-    run here (torch_geometric / Firedrake absent), so this times the oracle port."""
+    run here (torch_geometric / Firedrake absent), so this times the oracle port: exactly
+    `--warmup` + `--steps` steps of the same workload; when that many full batches would take more than a
+    few minutes the step becomes a bounded sample (fewer meshes of the same shape per step)."""
     if rank != 0:
         return
-    r = time_cpu_oracle(min(args.steps, 40), min(args.warmup, 3), budget_s=90.0)
+    W, K = max(3, args.warmup), max(1, args.steps)
+    meshes = MESHES_PER_GPU
+    while meshes > 1 and (W + K) * 1.2 * meshes / MESHES_PER_GPU > 150.0:    # ~1.2 s per full batch on 16 cores
+        meshes //= 2
+    r = time_cpu_oracle(K, W, budget_s=240.0, meshes=meshes)
     n_nodes = MESHES_PER_GPU * MESH_DIMS[0] * MESH_DIMS[1]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": r["steps"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+        "steps": r["steps"], "warmup": W, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2: {MESHES_PER_GPU} x {MESH_DIMS[0]}x{MESH_DIMS[1]} meshes, fwd+bwd, L={NUM_LAYERS}, hidden 8",
-                   "nodes_per_step": n_nodes, "device": "host CPU"},
+        "config": {"workload": WORKLOAD, "nodes_per_step_per_gpu": n_nodes, "device": "host CPU",
+                   "meshes_per_cpu_step": meshes},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -272,38 +285,46 @@ def main():
     if rank == 0:
         clocks.start()
 
-    # ---- device-resident timing: W warm-up + exactly K timed steps -------------------------
-    # The ring is walked as epochs: one CUDA graph holds the R steps of a pass over the resident
-    # batches (consecutive steps linked by programmatic dependent launch); a remainder of K mod R
-    # steps runs as single-step graphs.
-    ring = list(range(R))
+    # ---- device-resident timing: >= W warm-up steps + exactly K timed steps -----------------
+    # The K timed steps are CUDA-graph replays: one graph holds up to GRAPH_STEPS consecutive steps over
+    # the ring of resident batches (consecutive steps linked by programmatic dependent launch); K steps =
+    # n_full replays of the G-step graph + one replay of a (K mod G)-step graph.  EVERY graph the timed
+    # region replays is replayed during warm-up first, so no first-replay upload sits inside the region.
+    G = min(K, GRAPH_STEPS)
+    n_full, rem = divmod(K, G)
+    plan = [tuple(i % R for i in range(G))] * n_full + ([tuple((n_full * G + i) % R for i in range(rem))] if rem else [])
+    graph_mode = not args.no_graph and not args.no_epoch
 
-    def run_steps(n, first=0):
-        i = first
-        while n > 0:
-            if not args.no_graph and not args.no_epoch and i % R == 0 and n >= R:
-                trainer.run_epoch(ring)
-                i += R
-                n -= R
-            else:
+    def run_plan():
+        if graph_mode:
+            for key in plan:
+                trainer.run_epoch(key)
+        else:
+            for i in range(K):
                 trainer.step(i % R)
-                i += 1
-                n -= 1
-        return i
 
-    if not args.no_graph and not args.no_epoch:
-        trainer.capture_epoch(ring)
-    nxt = run_steps(W)
-    nxt = (nxt + R - 1) // R * R      # start the timed region on an epoch boundary
+    warm_steps = 0
+    if graph_mode:
+        for key in set(plan):
+            trainer.capture_epoch(key)
+        while warm_steps < W:
+            for key in dict.fromkeys(plan):      # each distinct graph at least once
+                trainer.run_epoch(key)
+                warm_steps += len(key)
+    else:
+        while warm_steps < max(W, R if not args.no_graph else W):
+            trainer.step(warm_steps % R)
+            warm_steps += 1
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.gad_launch_count()
     clocks.mark(True)
     ev0.record(trainer.stream)
-    run_steps(K, nxt)
+    run_plan()
     ev1.record(trainer.stream)
     barrier()
     clocks.mark(False)
+    trainer.check_peer()
     ms_total = ev0.elapsed_time(ev1)
     eager_launches = lib.gad_launch_count() - launches0
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -312,6 +333,11 @@ def main():
     ms_total = float(t.item())
     ms_step = ms_total / K
     value = world * n_nodes / (ms_step * 1e-3)
+
+    # ---- data-parallel self-check (N > 1): replicas bit-identical, in-kernel exchange == NCCL route ----
+    dp_check = None
+    if world > 1:
+        dp_check = trainer.dp_selfcheck(list(range(min(R, 4))), steps=min(K, 24))
 
     # kernels per step: counted once from an eager issue of the same step
     l0 = lib.gad_launch_count()
@@ -431,20 +457,24 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"cfg2: {MESHES_PER_GPU} x {MESH_DIMS[0]}x{MESH_DIMS[1]} meshes per GPU, fwd+bwd train step "
-                            f"(L={NUM_LAYERS} Euler layers, hidden 8, L1 mesh loss, Adam"
-                            + ("" if world == 1 else (", gradient all-reduce inside the kernel over NVLink peer memory"
-                                                      if trainer.fused_dp else ", NCCL grad all-reduce")) + ")",
+                "workload": WORKLOAD,
+                "gradient_exchange": (None if world == 1 else ("all-reduce inside the train kernel over NVLink peer memory"
+                                                               if trainer.fused_dp else "NCCL all-reduce")),
                 "nodes_per_step_per_gpu": n_nodes, "edges_per_step_per_gpu": n_edges, "live_channels": model.live,
                 "l2": f"ring of {R} distinct resident batches, {ro_bytes / 1e6:.0f} MB read-only inputs (> 126 MB L2)",
                 "launch": "eager" if args.no_graph else ("cuda-graph replay, one graph per step" if args.no_epoch else
-                                                         f"cuda-graph replay, one graph per pass over the ring ({R} steps, "
-                                                         "programmatic dependent launch between steps)"),
+                                                         f"cuda-graph replay: {n_full} x one graph of {G} steps"
+                                                         + (f" + one graph of {rem} steps" if rem else "")
+                                                         + ", programmatic dependent launch between steps; every graph "
+                                                           "replayed during warm-up"),
+                "warmup_steps_run": warm_steps,
                 "tiles": s0.graph.T, "max_tile_nodes": s0.graph.max_tile_nodes,
             },
             "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": int(launches_per_step),
             "roofline": roofline, "cpu_baseline": cpu,
         }
+        if dp_check is not None:
+            line["dp_check"] = dp_check
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without tearing NCCL down: the captured graphs hold collectives and
@@ -455,7 +485,9 @@ def main():
         torch.cuda.synchronize(dev)
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        ok = dp_check is None or (dp_check["ranks_equal"] and dp_check["vs_nccl"] == "bit-exact"
+                                  and dp_check["parameters_moved"])
+        os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

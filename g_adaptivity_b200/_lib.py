@@ -43,7 +43,7 @@ class TrainDesc(C.Structure):
         ("params", _fp), ("grads", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("n_params", _i64),
         ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("weight_decay", _f), ("adam_grad_scale", _f),
         ("step", _fp), ("flags", _i32), ("trace", _fp),
-        ("rank", _i32), ("world", _i32), ("peers", _fp), ("peer_seq", _fp),
+        ("rank", _i32), ("world", _i32), ("peers", _fp), ("peer_seq", _fp), ("peer_timeout_ms", C.c_uint32),
     ]
 
 

@@ -851,12 +851,17 @@ extern "C" int gad_train_step_cluster(const gad_train_desc* d, int cluster_size,
     a.world = d->world;
     a.peers = d->peers;
     a.peer_seq = d->peer_seq;
+    a.peer_timeout_ns = (unsigned long long)(d->peer_timeout_ms ? d->peer_timeout_ms : 10000u) * 1000000ull;
     a.trace = reinterpret_cast<long long*>(d->trace);
     // the in-kernel tail needs its scratch plan to fit and the flat-vector views (as gad_train_step_ell)
     const cl::Layout lay = cl::make_layout(d->CE, S, (threads + 31) / 32);
     const long long np = d->tail >= 2 ? d->n_params : 0;
     auto within = [](const float* q, const float* base, long long n) { return q >= base && q < base + n; };
-    bool ok = ell::plan_tail(d->CE, d->Lw, d->L, d->C, a.tau_partials && a.g_tau, true, np, grid, (threads + 31) / 32, lay.bar).ok;
+    const ell::TailPlan tplan = ell::plan_tail(d->CE, d->Lw, d->L, d->C, a.tau_partials && a.g_tau, true, np, grid,
+                                               (threads + 31) / 32, lay.bar);
+    bool ok = tplan.ok;
+    if (d->world > 1 && d->peers)   // received peer gradients [world][n_params] sit in the tail's staging area
+        ok = ok && d->peer_seq && (size_t)d->world * (size_t)np * sizeof(float) <= tplan.stage_bytes;
     if (d->tail >= 2) {
         const float* views[] = {d->Wq, d->bq, d->Wk};
         const float* gviews[] = {d->gWq, d->gbq, d->gWk, d->gbk};

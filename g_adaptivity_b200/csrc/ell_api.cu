@@ -461,6 +461,7 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     a.world = d->world;
     a.peers = d->peers;
     a.peer_seq = d->peer_seq;
+    a.peer_timeout_ns = (unsigned long long)(d->peer_timeout_ms ? d->peer_timeout_ms : 10000u) * 1000000ull;
     a.trace = reinterpret_cast<long long*>(d->trace);
     cudaStream_t st = as_stream(stream);
     // The in-kernel tail keeps mirrors of the flat parameter / gradient vectors in shared memory: it
@@ -468,8 +469,11 @@ extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     auto within = [](const float* q, const float* base, long long n) { return q >= base && q < base + n; };
     const long long np = d->tail >= 2 ? d->n_params : 0;
     const Layout lay = make_layout(d->CE, KIND_BWD, d->max_tile_nodes, p.ells != 0, (p.threads + 31) / 32);
-    bool fused_tail = plan_tail(d->CE, d->Lw, d->L, d->C, a.tau_partials && a.g_tau, true, np, d->T, (p.threads + 31) / 32,
-                                lay.bar).ok;
+    const TailPlan tplan = plan_tail(d->CE, d->Lw, d->L, d->C, a.tau_partials && a.g_tau, true, np, d->T, (p.threads + 31) / 32,
+                                     lay.bar);
+    bool fused_tail = tplan.ok;
+    if (d->world > 1 && d->peers)   // received peer gradients [world][n_params] sit in the tail's staging area
+        fused_tail = fused_tail && (size_t)d->world * (size_t)np * sizeof(float) <= tplan.stage_bytes;
     if (d->tail >= 2) {
         const float* views[] = {d->Wq, d->bq, d->Wk};
         const float* gviews[] = {d->gWq, d->gbq, d->gWk, d->gbk};

@@ -136,7 +136,8 @@ struct Args {
     // data parallel over peer memory (tail == 2): receive buffers of all ranks, see peer.cu
     int rank, world;
     void* const* peers;
-    unsigned int* peer_seq;
+    unsigned int* peer_seq;   // [0] launch sequence, [1] error word (sequence of a timed-out exchange)
+    unsigned long long peer_timeout_ns;
     long long* trace;       // optional [gridDim, 64] globaltimer marks of the train kernel (profiling aid)
 };
 
@@ -576,6 +577,7 @@ struct TailPlan {
     uint32_t colsum, wp, gmu, ps, gs, stage;   // byte offsets into the scratch
     int ncol, ntau, nloss, ncolT, TC;          // columns of the three partial arrays; tiles per chunk
     int nps;                                   // floats mirrored in `ps`
+    uint32_t stage_bytes;                      // room behind `stage` (partials chunks; received peer gradients)
     bool ok;
 };
 
@@ -604,6 +606,7 @@ __host__ __device__ inline TailPlan plan_tail(int CE, int Lw, int L, int C, bool
     p.nps = (int)nps;
     p.ok = nps < (1 << 24) && o + (size_t)p.ncolT * sizeof(float) <= scratch_bytes;
     if (!p.ok) return p;
+    p.stage_bytes = (uint32_t)(scratch_bytes - o);
     long long tc = (long long)((scratch_bytes - o) / sizeof(float)) / p.ncolT;
     if (tc > T) tc = T;
     if (tc > 32) tc &= ~31LL;
@@ -636,33 +639,61 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
     return v;
 }
 
-__device__ __forceinline__ void peer_allreduce(const Args& a, float* Gs, int n, uint32_t seq,
-                                               unsigned long long* const* s_peers) {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Every (destination rank, parameter) word has its own thread for the store and every (source rank,
+// parameter) word its own thread for the poll, so the `world` NVLink round trips of a parameter are in
+// flight together instead of one after the other; the received values go through shared memory (V,
+// [world][n]) and are summed in RANK ORDER by one thread per parameter -- same bits on every rank.
+// The wait is bounded: a peer that died, skipped a step or took another route (NCCL) leaves its tag
+// stale; after `timeout_ns` the CTA gives up, returns false and the caller raises the device error
+// word instead of taking the Adam step (the host checks it: DeformerTrainer.check_peer).
+__device__ __forceinline__ bool peer_allreduce(const Args& a, float* Gs, float* V, int n, uint32_t seq,
+                                               unsigned long long* const* s_peers, volatile int* s_fail) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const size_t slot = (size_t)(seq & 1u) * a.world;
+    const int total = a.world * n;
 #pragma unroll 1
-    for (int i = tid; i < n; i += nthr) {
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int r = idx / n, i = idx - r * n;
         const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(Gs[i]);
-#pragma unroll 1
-        for (int r = 0; r < a.world; ++r) st_sys_u64(s_peers[r] + (slot + a.rank) * n + i, word);
+        st_sys_u64(s_peers[r] + (slot + a.rank) * n + i, word);
     }
-    const unsigned long long* own = s_peers[a.rank];
+    const unsigned long long* own = s_peers[a.rank] + slot * n;   // [world][n] words of this parity, contiguous
+    const unsigned long long t0 = globaltimer_ns();
+#pragma unroll 1
+    for (int idx = tid; idx < total; idx += nthr) {
+        unsigned long long w;
+        uint32_t spins = 0;
+        while (true) {
+            w = ld_sys_u64(own + idx);
+            if ((uint32_t)(w >> 32) == seq) break;
+            if ((++spins & 255u) == 0u) {
+                if (*s_fail) break;
+                if (globaltimer_ns() - t0 > a.peer_timeout_ns) {
+                    *s_fail = 1;
+                    break;
+                }
+            }
+        }
+        V[idx] = __uint_as_float((uint32_t)w);
+    }
+    __syncthreads();
+    if (*s_fail) return false;
     float* grads_out = const_cast<float*>(a.grads);
 #pragma unroll 1
     for (int i = tid; i < n; i += nthr) {
         float sum = 0.f;
 #pragma unroll 1
-        for (int r = 0; r < a.world; ++r) {
-            const unsigned long long* src = own + (slot + r) * n + i;
-            unsigned long long w;
-            do {
-                w = ld_sys_u64(src);
-            } while ((uint32_t)(w >> 32) != seq);
-            sum += __uint_as_float((uint32_t)w);
-        }
+        for (int r = 0; r < a.world; ++r) sum += V[r * n + i];
         Gs[i] = sum;
         grads_out[i] = sum;
     }
+    return true;
 }
 
 template <int CE>
@@ -841,11 +872,17 @@ __device__ __forceinline__ void tail_finish(const Args& a, unsigned char* scratc
     if (cx.seq) {
         // data parallel: SUM all-reduce of the flat gradient over peer memory (NVLink), in place
         __shared__ unsigned long long* s_peers[GAD_MAX_PEERS];
+        __shared__ int s_fail;
         if (tid < a.world) s_peers[tid] = reinterpret_cast<unsigned long long*>(a.peers[tid]);
+        if (tid == 0) s_fail = (__ldcg(a.peer_seq + 1) != 0u) ? 1 : 0;   // an earlier exchange failed: do not wait again
         __syncthreads();
-        peer_allreduce(a, Gs, np, cx.seq, s_peers);
-        if (tid == 0) *a.peer_seq = cx.seq;
+        const bool arrived = peer_allreduce(a, Gs, S, np, cx.seq, s_peers, &s_fail);   // S: the staging area is free now
+        if (tid == 0) {
+            *a.peer_seq = cx.seq;
+            if (!arrived) a.peer_seq[1] = cx.seq;   // sticky error word: exchange `seq` timed out
+        }
         __syncthreads();
+        if (!arrived) return;                       // no Adam step, no refold: parameters keep their value
     }
     tr.mark();   // chain rule (+ gradient exchange)
 

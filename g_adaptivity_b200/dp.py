@@ -56,6 +56,21 @@ def allreduce_flat(gflat: torch.Tensor, group=None) -> torch.Tensor:
     return gflat
 
 
+def allreduce_flat_ordered(gflat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM all-reduce with a FIXED reduction order: all-gather the per-rank vectors, then add them
+    in rank order in fp32 (0 + g_0 + g_1 + ...), exactly the order of the in-kernel peer exchange
+    (csrc/ell_kernels.cuh: peer_allreduce), so both routes give the same bits on every rank."""
+    world = world_size(group)
+    if world > 1:
+        parts = [torch.empty_like(gflat) for _ in range(world)]
+        dist.all_gather(parts, gflat.contiguous(), group=group)
+        acc = parts[0].clone()
+        for r in range(1, world):
+            acc += parts[r]
+        gflat.copy_(acc)
+    return gflat
+
+
 def broadcast_flat(flat: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
     if world_size(group) > 1:
         dist.broadcast(flat, src=src, group=group)
@@ -76,7 +91,7 @@ class PeerExchange:
         self.own = C.c_void_p()
         self.opened = []
         self.ptrs = None            # int64 [world] device array of receive-buffer pointers
-        self.seq = None             # uint32 launch sequence, advanced by the kernel
+        self.seq = None             # uint32 [2]: launch sequence (advanced by the kernel), error word
         self.ok = False
         self.why = ""
         if self.world <= 1:
@@ -119,10 +134,40 @@ class PeerExchange:
         self.ok = bool(flag.item())
         if self.ok:
             self.ptrs = torch.tensor(addrs, dtype=torch.int64, device=device)
-            self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+            self.seq = torch.zeros(2, dtype=torch.int32, device=device)
         else:
             self.why = self.why or "a peer could not map the buffers"
             self.close()
+
+    @classmethod
+    def loopback(cls, lib, n_params: int, device: torch.device, world: int, rank: int) -> "PeerExchange":
+        """Single-process stand-in used by the self-tests (tests/test_gpu_peer_loopback.py): `world` receive
+        buffers, all on this device, owned by torch.  The training kernel behaves exactly as on `world` GPUs -- it
+        stores its tagged gradient words into every buffer and waits for the other ranks' words in buffer `rank` --
+        and the test plays the peers by writing their words (`peer_words`) into that buffer.  This is how the
+        4- and 8-rank exchange, the fixed summation order and the bounded wait are checked on one GPU."""
+        self = cls.__new__(cls)
+        self.lib, self.dev, self.group = lib, device, None
+        self.world, self.rank = int(world), int(rank)
+        self.own, self.opened, self.why = C.c_void_p(), [], "loopback"
+        if not (1 < self.world <= cls.MAX_PEERS and 0 <= self.rank < self.world):
+            raise ValueError(f"loopback exchange: rank {rank} / world {world}")
+        self.n_params = int(n_params)
+        self.bufs = [torch.zeros(2 * self.world * self.n_params, dtype=torch.int64, device=device)
+                     for _ in range(self.world)]
+        self.ptrs = torch.tensor([b.data_ptr() for b in self.bufs], dtype=torch.int64, device=device)
+        self.seq = torch.zeros(2, dtype=torch.int32, device=device)
+        self.ok = True
+        return self
+
+    def peer_words(self, seq: int, src_rank: int, values: torch.Tensor):
+        """Loopback only: deposit what rank `src_rank` would send in exchange number `seq` (fp32 `values`
+        [n_params]) into this rank's receive buffer: words {value bits, seq} in slot [seq & 1][src_rank]."""
+        n = self.n_params
+        bits = values.detach().to(self.dev, torch.float32).contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        words = bits | (int(seq) << 32)
+        off = ((int(seq) & 1) * self.world + int(src_rank)) * n
+        self.bufs[self.rank][off:off + n].copy_(words)
 
     def close(self):
         """Unmap the peers' buffers and free the own one (all ranks must be past their last step)."""

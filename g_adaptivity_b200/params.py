@@ -15,6 +15,7 @@ reference behaviour):
 from __future__ import annotations
 
 import argparse
+import ast
 import os
 import random
 
@@ -112,7 +113,9 @@ def get_arg_list(arg_list):
     (`src/params.py:190-196`)."""
     if type(arg_list[0]) == int:
         return arg_list
-    return eval(arg_list[0])
+    # the reference calls eval() on the CLI string; a literal parser accepts the same inputs ("[15, 15]") and
+    # nothing else
+    return list(ast.literal_eval(arg_list[0]))
 
 
 def set_seed(seed: int = 42) -> None:

@@ -53,7 +53,23 @@ class DeformerTrainer:
         self.lr = float(opt.get("lr", 1e-3) if lr is None else lr)
         self.wd = float(opt.get("decay", 0.0) if weight_decay is None else weight_decay)
         self.betas, self.eps = betas, eps
+        # Options GNN.forward and the reference training loop honour but this fused step does not implement
+        # raise instead of silently training something else (src/run_GNN.py:80-88,109-131; src/GNN.py:231-237).
+        if loss_fn is None and opt.get("loss_type", "mesh_loss") != "mesh_loss":
+            raise NotImplementedError(
+                f"DeformerTrainer fuses the mesh loss (loss_type='mesh_loss', src/run_GNN.py:105-107); opt['loss_type']="
+                f"{opt['loss_type']!r} trains through GNN.forward + autograd instead.  Pass loss_fn='l1' / 'mse' explicitly "
+                "to train the mesh loss on such a preset")
+        if opt.get("gnn_normalize", False):
+            raise NotImplementedError("DeformerTrainer: gnn_normalize=True (per-batch f / max f, src/GNN.py:231-237) is "
+                                      "only implemented on the GNN.forward path")
+        if opt.get("gnn_dont_train", False):
+            raise NotImplementedError("DeformerTrainer: gnn_dont_train=True skips the optimizer step (src/run_GNN.py:122-131); "
+                                      "evaluate with GNN.forward instead")
         self.loss_kind = (opt.get("loss_fn", "l1") if loss_fn is None else loss_fn)
+        if self.loss_kind not in ("l1", "mse"):
+            raise NotImplementedError(f"DeformerTrainer: loss_fn={self.loss_kind!r} (the reference has 'l1' and 'mse', "
+                                      "src/run_GNN.py:80-84)")
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.use_graph = use_cuda_graph
@@ -74,11 +90,18 @@ class DeformerTrainer:
         # peer memory (dp.PeerExchange); otherwise NCCL between the train kernel and Adam
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.peer = None
-        if self.world > 1 and bool(opt.get("gad_peer_allreduce", True)) and self.dev.type == "cuda":
+        self.loopback = opt.get("gad_peer_loopback")     # (world, rank): single-process self-test of the exchange
+        if self.loopback is not None:
+            if self.world != 1:
+                raise ValueError("gad_peer_loopback is a single-process self-test option")
+            self.world, self.rank = int(self.loopback[0]), int(self.loopback[1])
+            self.peer = dp.PeerExchange.loopback(self.lib, self.flat.numel(), self.dev, self.world, self.rank)
+        elif self.world > 1 and bool(opt.get("gad_peer_allreduce", True)) and self.dev.type == "cuda":
             self.peer = dp.PeerExchange(self.lib, self.flat.numel(), self.dev, group=process_group)
         self.fused_dp = self.peer is not None and self.peer.ok
         # programmatic dependent launch between the train kernels of consecutive steps (one launch per step)
         self.use_pdl = bool(opt.get("gad_pdl", True)) and (self.world == 1 or self.fused_dp)
+        self._route_override = None     # dp_selfcheck: force the NCCL routes on slots that use the peer exchange
         self.stream = torch.cuda.Stream(device=self.dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)   # last-CTA election of k_ell_train
         self.sync_weights()
@@ -153,7 +176,7 @@ class DeformerTrainer:
         d.dim, d.CE = self.dim, self.CE
         d.Mu, d.tau, d.Lw, d.L, d.C, d.inv_temp = P(self.Mu), P(self.tau), self.Lw, self.L, self.C, self.model.inv_temp
         d.loss_kind = 0 if self.loss_kind == "l1" else 1
-        d.grad_scale, d.loss_scale = dp.local_grad_scale(count, world=self.world), 1.0 / count
+        d.grad_scale, d.loss_scale = dp.local_grad_scale(count, s.count_global, world=self.world), 1.0 / count
         d.states, d.gMu, d.g_tau, d.loss, d.x_phys = P(s.states), P(self.gMu), P(self.gtau), P(s.loss), P(s.x_phys)
         d.workspace, d.workspace_bytes = P(s.bwd_ws), s.bwd_ws_bytes
         d.tail, d.counter = tail, P(self.counter)
@@ -164,8 +187,10 @@ class DeformerTrainer:
         d.lr, d.beta1, d.beta2, d.eps, d.weight_decay, d.adam_grad_scale = self.lr, b1, b2, self.eps, self.wd, 1.0
         d.step = P(self.step_count)
         d.flags = 1 if (self.use_pdl and tail == 2) else 0      # GAD_TRAIN_PDL
+        d.peer_timeout_ms = 0
         if self.fused_dp and tail == 2:
             d.rank, d.world, d.peers, d.peer_seq = self.rank, self.world, P(self.peer.ptrs), P(self.peer.seq)
+            d.peer_timeout_ms = int(self.opt.get("gad_peer_timeout_ms", 10000))
         return d
 
     # ------------------------------------------------------------------------------------
@@ -216,6 +241,24 @@ class DeformerTrainer:
             s.fwd_ws_bytes = lib.gad_deform_workspace_bytes(N, self.CE, self.method) if streaming else 0
             s.fwd_ws = torch.empty(max(s.fwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
             s.h2d_bytes = 0
+            # Data parallel: add_batch is COLLECTIVE (every rank adds its shard of the same global batch, in the
+            # same order).  Two things are agreed here, once per slot and outside any capture:
+            #  * the mean of the loss is over the nodes of the GLOBAL batch (F.l1_loss on the whole batch,
+            #    src/run_GNN.py:80-84): the cotangent scale uses the summed count, so ragged shards weigh right;
+            #  * the gradient route.  Whether a rank can run the one-launch kernel (whose tail all-reduces over
+            #    peer memory) depends on ITS shard (degree, mesh sizes, policy); a rank spinning in the peer
+            #    exchange while another calls NCCL would hang both, so the route is the MIN over the ranks.
+            s.count_global = N * self.dim
+            s.peer_route = False
+            if self.loopback is not None:
+                s.count_global, s.peer_route = N * self.dim * self.world, bool(self._one_launch_local(s))
+            elif self.world > 1:
+                mine = 1 if (self.fused_dp and self._one_launch_local(s)) else 0
+                t = torch.tensor([N * self.dim, 1 - mine], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+                t = t.cpu()
+                s.count_global = int(t[0])
+                s.peer_route = bool(int(t[1]) == 0)
         self.slots.append(s)
         sid = len(self.slots) - 1
         self.load_inputs(sid, data)
@@ -275,7 +318,7 @@ class DeformerTrainer:
             # ONE launch per step (csrc/ell_kernels.cuh: k_ell_train): pack + forward + loss + backward per
             # tile, then the last CTA reduces, applies the chain rule and -- single GPU -- takes the Adam step
             # and refolds (M, u) for the next step.  Data parallel: all-reduce, Adam and refold follow.
-            single = (self.world == 1 or self.fused_dp) and with_optimizer
+            single = (self.world == 1 or (s.peer_route and self._route_override is None)) and with_optimizer
             if stage in ("all", "pre") and cluster:
                 chk(lib.gad_train_step_cluster(C.byref(self._train_desc(s, 2 if single else 1)), g.cl_C, stream_ptr),
                     "gad_train_step_cluster")
@@ -307,7 +350,8 @@ class DeformerTrainer:
                                        s.fwd_ws_bytes, stream_ptr),
                     "gad_deform_fwd")
             chk(lib.gad_mesh_loss(P(s.x_phys), P(s.target), s.N * dim, 0 if self.loss_kind == "l1" else 1,
-                                  dp.local_grad_scale(s.N * dim, world=self.world), P(s.loss), P(s.g_out), P(s.loss_ws),
+                                  dp.local_grad_scale(s.N * dim, s.count_global, world=self.world), P(s.loss), P(s.g_out),
+                                  P(s.loss_ws),
                                   stream_ptr),
                 "gad_mesh_loss")
             if wide:
@@ -331,9 +375,12 @@ class DeformerTrainer:
     def _allreduce(self, s: Optional[_Slot] = None):
         """NCCL all-reduce of the flat gradient -- unless the train kernel of this slot does the
         exchange itself over peer memory (fused_dp on the one-launch path)."""
-        if self.fused_dp and s is not None and self._one_launch(s):
+        if s is not None and s.peer_route and self._route_override is None:
             return
-        dp.allreduce_flat(self.gflat, group=self.pg)
+        if self._route_override == "nccl_ordered":
+            dp.allreduce_flat_ordered(self.gflat, group=self.pg)
+        else:
+            dp.allreduce_flat(self.gflat, group=self.pg)
 
     def _cluster(self, s: _Slot) -> bool:
         """Meshes too large for one CTA run on the cluster-resident kernel (csrc/cl_kernels.cu)."""
@@ -346,6 +393,11 @@ class DeformerTrainer:
         return not s.prefer_stream
 
     def _one_launch(self, s: _Slot) -> bool:
+        """The step of this slot is ONE kernel including the optimizer (single GPU, or every rank agreed on the
+        in-kernel peer exchange for it)."""
+        return self._one_launch_local(s) and (self.world == 1 or s.peer_route)
+
+    def _one_launch_local(self, s: _Slot) -> bool:
         g = s.graph
         tiles = g.tile_ptr is not None and not self.opt.get("gad_force_stream", False)
         return bool(tiles and GF.use_ell(g, self.CE) and not self.opt.get("gad_no_fused_train", False)) or self._cluster(s)
@@ -356,7 +408,7 @@ class DeformerTrainer:
         self.graphs.clear()
         self.epoch_graphs.clear()
         if self.peer is not None:
-            if self.world > 1:
+            if self.world > 1 and self.loopback is None:
                 dist.barrier(group=self.pg)
             self.peer.close()
             self.peer = None
@@ -379,6 +431,7 @@ class DeformerTrainer:
             self.stream.synchronize()
             self.sync_weights()
             self.stream.synchronize()
+            self.check_peer(collective=True)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.stream):
                 cs = torch.cuda.current_stream(self.dev).cuda_stream
@@ -399,6 +452,7 @@ class DeformerTrainer:
                 self.capture(sid)
         with torch.cuda.device(self.dev):
             self.stream.synchronize()
+            self.check_peer(collective=True)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.stream):
                 cs = torch.cuda.current_stream(self.dev).cuda_stream
@@ -489,5 +543,93 @@ class DeformerTrainer:
         ms.synchronize()
         return losses
 
+    def check_peer(self, collective: bool = False):
+        """Raise if an in-kernel gradient exchange timed out (device error word, csrc/ell_kernels.cuh:
+        peer_allreduce).  With `collective=True` (every rank calls it, e.g. before a capture) the launch
+        sequence numbers of all ranks are compared as well: the exchange pairs launches by sequence number, so an
+        asymmetric launch on one rank (a warm-up only it ran) would desynchronise the parity slots for good."""
+        if self.peer is None or not self.fused_dp:
+            return
+        seq = self.peer.seq.cpu()
+        if int(seq[1]) != 0:
+            raise RuntimeError(
+                f"rank {self.rank}: the in-kernel gradient all-reduce of exchange #{int(seq[1]) & 0xffffffff} timed out "
+                f"(gad_peer_timeout_ms={int(self.opt.get('gad_peer_timeout_ms', 10000))}): a peer died, skipped a step or "
+                "issued a different launch sequence.  The Adam step of that launch was skipped; the trainer cannot continue")
+        if collective and self.world > 1 and self.loopback is None:
+            mine = torch.tensor([int(seq[0])], dtype=torch.int64, device=self.dev)
+            every = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine, group=self.pg)
+            vals = [int(v.item()) for v in every]
+            if any(v != vals[0] for v in vals):
+                raise RuntimeError(f"peer exchange sequence numbers differ across ranks: {vals} -- every rank must issue "
+                                   "the same sequence of training launches")
+
+    def dp_selfcheck(self, sids, steps: int = 16) -> dict:
+        """Correctness check of the data-parallel step on the live job (collective; every rank calls it).
+
+        From a snapshot of the current optimizer state, `steps` training steps over the resident batches `sids`
+        are run three times -- (a) the route the trainer uses (the gradient all-reduce inside the train kernel
+        over peer memory, where the slots agreed on it), (b) NCCL all-gather of the per-rank gradients followed by
+        the same rank-ordered fp32 sum, Adam and refold as separate kernels, (c) plain `ncclAllReduce` -- and the
+        state is restored afterwards.  Reported: the parameters of all ranks are bit-identical after (a); (a) and
+        (b) agree bit for bit (same operands, same order: anything else is a bug in the exchange); the largest
+        relative deviation of (a) from (c), whose reduction order is NCCL's own (equal at 2 ranks, rounding-level
+        beyond).  The verdicts are MIN-reduced over the ranks, so every rank returns the same dict."""
+        if self.world <= 1:
+            return {"world": 1, "ranks_equal": True, "vs_nccl": "n/a (single rank)"}
+        state = (self.flat, self.exp_avg, self.exp_avg_sq, self.step_count)
+        self.stream.synchronize()
+        saved = [t.clone() for t in state]
+
+        def run(route):
+            with torch.cuda.stream(self.stream):
+                for t, v in zip(state, saved):
+                    t.copy_(v)
+            self.stream.synchronize()
+            self.sync_weights()
+            self._route_override = route
+            try:
+                with torch.cuda.stream(self.stream):
+                    for k in range(steps):
+                        s = self.slots[sids[k % len(sids)]]
+                        self._issue(s, self.stream.cuda_stream, stage="pre")
+                        self._allreduce(s)
+                        self._issue(s, self.stream.cuda_stream, stage="post")
+                self.stream.synchronize()
+            finally:
+                self._route_override = None
+            self.check_peer()
+            return self.flat.detach().clone()
+
+        a = run(None)
+        b = run("nccl_ordered")
+        c = run("nccl")
+        with torch.cuda.stream(self.stream):
+            for t, v in zip(state, saved):
+                t.copy_(v)
+        self.stream.synchronize()
+        self.sync_weights()
+        self.stream.synchronize()
+        every = [torch.empty_like(a) for _ in range(self.world)]
+        dist.all_gather(every, a, group=self.pg)
+        ranks_equal = all(bool(torch.equal(e, a)) for e in every)
+        exact = bool(torch.equal(a, b))
+        dev_c = float(((a - c).abs().max() / c.abs().max().clamp_min(1e-30)).item())
+        moved = float((a - saved[0]).abs().max().item())
+        verdict = torch.tensor([int(ranks_equal), int(exact), int(moved > 0)], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(verdict, op=dist.ReduceOp.MIN, group=self.pg)
+        worst = torch.tensor([dev_c], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.pg)
+        peer_slots = sum(1 for sid in sids if self.slots[sid].peer_route)
+        return {"world": self.world, "steps": steps, "slots": len(sids), "slots_on_peer_route": peer_slots,
+                "ranks_equal": bool(verdict[0].item()),
+                "vs_nccl": "bit-exact" if bool(verdict[1].item()) else "DIFFERS",
+                "nccl_route": "ncclAllGather of the per-rank gradients + rank-ordered fp32 sum, Adam and refold as "
+                              "separate kernels",
+                "vs_nccl_allreduce_max_rel": float(worst.item()),
+                "parameters_moved": bool(verdict[2].item())}
+
     def synchronize(self):
         self.stream.synchronize()
+        self.check_peer()

@@ -279,12 +279,17 @@ typedef struct gad_train_desc {
      * rule and Adam the kernel stores its flat gradient into every rank's receive buffer over
      * NVLink and sums, in rank order, what the peers stored into its own -- the SUM all-reduce of
      * src/run_GNN.py's (single-process) gradient, fused into the step.  `peers` is a DEVICE array of
-     * `world` receive-buffer pointers (entry `rank` = this rank's own buffer), `peer_seq` one
-     * zero-initialised device uint32 that the kernel advances by one per launch; every rank must
-     * issue the same sequence of launches.  world <= 1 or peers == NULL: no exchange. */
+     * `world` receive-buffer pointers (entry `rank` = this rank's own buffer), `peer_seq` TWO
+     * zero-initialised device uint32: [0] the launch sequence, advanced by one per launch (every rank
+     * must issue the same sequence of launches), [1] an error word.  The wait for the peers' words is
+     * bounded by `peer_timeout_ms` (0 = 10 000): when a contribution has not arrived by then (a peer
+     * died, skipped a step or took the NCCL route) the kernel writes the failing sequence number into
+     * peer_seq[1], skips the Adam step and the refold, and every later launch skips its wait as well;
+     * the caller must check the word (it is sticky).  world <= 1 or peers == NULL: no exchange. */
     int32_t rank, world;
     void* const* peers;
     uint32_t* peer_seq;
+    uint32_t peer_timeout_ms;
 } gad_train_desc;
 #define GAD_TRAIN_PDL 1
 #define GAD_MAX_PEERS 16

@@ -264,7 +264,7 @@ def test_cluster_backward_equals_streaming_backward():
 
 def test_config3_burgers_1d_200_repeated_calls():
     """Burgers roll-out pattern (src/utils_eval_Burgers.py:269,297): same graph, new uu each call."""
-    mesh_dims, B = (200,), 1024
+    mesh_dims, B = (200,), 4096          # BASELINE configs[2] at full size: 819 200 nodes per call
     opt = synth.burgers_opt(mesh_dims)
     ds = synth.SyntheticDataset(1, mesh_dims)
     data = synth.make_batch(mesh_dims, B, seed=0, burgers=True)
