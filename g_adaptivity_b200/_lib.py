@@ -47,6 +47,11 @@ class TrainDesc(C.Structure):
     ]
 
 
+class PipelineSlot(C.Structure):
+    """`gad_pipeline_slot` of include/gadapt.h."""
+    _fields_ = [("dev_inputs", _fp), ("bytes", _sz), ("graph_exec", _fp), ("loss_dev", _fp)]
+
+
 # name -> (restype, argtypes); mirrors include/gadapt.h declaration by declaration
 SIGNATURES = {
     "gad_version": (_i, []),
@@ -100,6 +105,7 @@ SIGNATURES = {
     "gad_peer_open": (_i, [_p, C.POINTER(_p)]),
     "gad_peer_close": (_i, [_p]),
     "gad_peer_free": (_i, [_p]),
+    "gad_pipeline_run": (_i, [C.POINTER(PipelineSlot), _i, C.POINTER(_p), _i, _i64, _p, _p, _p]),
 }
 
 

@@ -1,0 +1,72 @@
+// Host side of the end-to-end training loop (the reference's `for data in loader: ... optimizer.step()`,
+// src/run_GNN.py:95-131, with the batches in pinned host memory): a double-buffered H2D / compute / D2H
+// pipeline driven from C, so that the per-step CPU cost is a handful of CUDA API calls instead of a
+// Python loop (which, with one process per GPU on a shared host, becomes the limit long before PCIe).
+//
+//   copy stream   : step k+1's inputs host -> device (ONE cudaMemcpyAsync: the batch is packed in the slot's
+//                   input layout, DeformerTrainer.pack_host) as soon as step k+1-R has released the slot
+//   compute stream: wait for the inputs, replay the slot's captured step (cudaGraphLaunch of the one-launch
+//                   training kernel), copy the 4-byte loss device -> host, release the slot
+//
+// Slot k % n_slots receives host batch k % n_host.  The call returns when the last step has finished
+// (cudaStreamSynchronize of the compute stream).  No hidden allocation besides 2 * n_slots events per call.
+#include <vector>
+
+#include "common.cuh"
+
+using namespace gad;
+
+extern "C" int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, const void* const* host_batches,
+                                int n_host, int64_t steps, float* losses_host, void* compute_stream,
+                                void* copy_stream) {
+    GAD_CHECK_ARG(slots && host_batches && losses_host && n_slots >= 2 && n_host >= 1 && steps >= 0,
+                  "gad_pipeline_run: bad arguments (needs >= 2 slots for double buffering)");
+    for (int s = 0; s < n_slots; ++s)
+        GAD_CHECK_ARG(slots[s].dev_inputs && slots[s].graph_exec && slots[s].loss_dev && slots[s].bytes > 0,
+                      "gad_pipeline_run: slot %d is incomplete", s);
+    cudaStream_t cs = as_stream(copy_stream), ms = as_stream(compute_stream);
+    GAD_CHECK_ARG(cs != ms, "gad_pipeline_run: the copy stream must differ from the compute stream");
+    std::vector<cudaEvent_t> in_ready(n_slots), slot_free(n_slots);
+    for (int s = 0; s < n_slots; ++s) {
+        GAD_CUDA(cudaEventCreateWithFlags(&in_ready[s], cudaEventDisableTiming));
+        GAD_CUDA(cudaEventCreateWithFlags(&slot_free[s], cudaEventDisableTiming));
+    }
+    int rc = GAD_OK;
+    auto fail = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == GAD_OK) {
+            set_error("gad_pipeline_run: %s failed: %s", what, cudaGetErrorString(e));
+            rc = GAD_ERR_CUDA;
+        }
+        return e != cudaSuccess;
+    };
+    // the first upload must not overtake work already queued on the compute stream (it may still read the slot)
+    cudaEvent_t start;
+    GAD_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    fail(cudaEventRecord(start, ms), "cudaEventRecord");
+    fail(cudaStreamWaitEvent(cs, start, 0), "cudaStreamWaitEvent");
+    auto upload = [&](int64_t k) {
+        const int sid = (int)(k % n_slots);
+        if (k >= n_slots) fail(cudaStreamWaitEvent(cs, slot_free[sid], 0), "cudaStreamWaitEvent");
+        fail(cudaMemcpyAsync(slots[sid].dev_inputs, host_batches[k % n_host], slots[sid].bytes, cudaMemcpyHostToDevice, cs),
+             "cudaMemcpyAsync (inputs)");
+        fail(cudaEventRecord(in_ready[sid], cs), "cudaEventRecord");
+    };
+    if (steps > 0) upload(0);
+    for (int64_t k = 0; k < steps && rc == GAD_OK; ++k) {
+        const int sid = (int)(k % n_slots);
+        if (k + 1 < steps) upload(k + 1);
+        fail(cudaStreamWaitEvent(ms, in_ready[sid], 0), "cudaStreamWaitEvent");
+        fail(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(slots[sid].graph_exec), ms), "cudaGraphLaunch");
+        fail(cudaMemcpyAsync(losses_host + k, slots[sid].loss_dev, sizeof(float), cudaMemcpyDeviceToHost, ms),
+             "cudaMemcpyAsync (loss)");
+        fail(cudaEventRecord(slot_free[sid], ms), "cudaEventRecord");
+    }
+    fail(cudaStreamSynchronize(ms), "cudaStreamSynchronize");
+    fail(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
+    for (int s = 0; s < n_slots; ++s) {
+        cudaEventDestroy(in_ready[s]);
+        cudaEventDestroy(slot_free[s]);
+    }
+    cudaEventDestroy(start);
+    return rc;
+}

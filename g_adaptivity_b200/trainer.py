@@ -205,20 +205,22 @@ class DeformerTrainer:
             s.N = N
             f32 = dict(dtype=torch.float32, device=dev)
             xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
-            # node inputs of a step live in ONE device buffer [x_comp | target | f | uu] (segments padded to
-            # 16 bytes, the TMA staging granularity), so that a packed host batch travels in one copy
+            # node inputs of a step live in ONE device buffer [target | f | uu | x_comp] (segments padded to
+            # 16 bytes, the TMA staging granularity), so that a packed host batch travels in one copy.  x_comp
+            # comes last: datasets on one shared mesh (`randg`, src/data.py:143: every sample has the same
+            # computational mesh) send it once, and a step's copy is the [target | f | uu] prefix only.
             has_f, has_uu = bool(self.opt["gnn_inc_feat_f"]), bool(self.opt["gnn_inc_feat_uu"])
-            seg = [N * self.dim, N * self.dim, N if has_f else 0, N if has_uu else 0]
+            seg = [N * self.dim, N if has_f else 0, N if has_uu else 0, N * self.dim]
             offs, o = [], 0
             for n in seg:
                 offs.append(o)
                 o += (n + 3) // 4 * 4
             s.in_offs, s.in_sizes = offs, seg
             s.inbuf = torch.zeros(o, **f32)
-            s.x_comp = s.inbuf[offs[0]:offs[0] + seg[0]].view(N, self.dim)
-            s.target = s.inbuf[offs[1]:offs[1] + seg[1]].view(N, self.dim)
-            s.f = s.inbuf[offs[2]:offs[2] + seg[2]] if has_f else None
-            s.uu = s.inbuf[offs[3]:offs[3] + seg[3]] if has_uu else None
+            s.target = s.inbuf[offs[0]:offs[0] + seg[0]].view(N, self.dim)
+            s.f = s.inbuf[offs[1]:offs[1] + seg[1]] if has_f else None
+            s.uu = s.inbuf[offs[2]:offs[2] + seg[2]] if has_uu else None
+            s.x_comp = s.inbuf[offs[3]:offs[3] + seg[3]].view(N, self.dim)
             s.states = torch.empty((self.L, N, self.CE), **f32)
             s.x_phys = torch.empty((N, self.dim), **f32)
             s.g_out = torch.empty((N, self.dim), **f32)
@@ -264,15 +266,21 @@ class DeformerTrainer:
         self.load_inputs(sid, data)
         return sid
 
-    def pack_host(self, sid: int, data) -> torch.Tensor:
+    def pack_host(self, sid: int, data, with_x_comp: bool = True) -> torch.Tensor:
         """One pinned host buffer holding `data`'s node inputs in the layout of slot `sid`
-        ([x_comp | target | f | uu]): `load_inputs` / `run_from_host` then move a batch host -> device
-        with a single copy."""
+        ([target | f | uu | x_comp]): `load_inputs` / `run_from_host` then move a batch host -> device
+        with a single copy.  `with_x_comp=False` packs the per-sample prefix [target | f | uu] only, for
+        datasets whose samples share one computational mesh (the slot keeps the x_comp it was given by
+        `add_batch`; the caller asserts that it does not change -- checked here against the slot)."""
         s = self.slots[sid]
-        buf = torch.zeros(s.inbuf.numel(), dtype=torch.float32).pin_memory()
         xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
         tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
-        parts = [xc, tg, data.f_tensor if s.f is not None else None, data.uu_tensor if s.uu is not None else None]
+        if not with_x_comp and not torch.equal(xc.to(torch.float32).cpu(), s.x_comp.cpu()):
+            raise ValueError("pack_host(with_x_comp=False): this batch's x_comp differs from the slot's resident one")
+        n_total = s.inbuf.numel() if with_x_comp else s.in_offs[3]
+        buf = torch.zeros(n_total, dtype=torch.float32).pin_memory()
+        parts = [tg, data.f_tensor if s.f is not None else None, data.uu_tensor if s.uu is not None else None,
+                 xc if with_x_comp else None]
         for off, n, t in zip(s.in_offs, s.in_sizes, parts):
             if t is not None and n:
                 buf[off:off + n].copy_(t.reshape(-1))
@@ -280,8 +288,8 @@ class DeformerTrainer:
 
     def _copy_inputs(self, s: "_Slot", data) -> int:
         """Enqueue the host -> device copies of one batch on the current stream; returns the bytes."""
-        if torch.is_tensor(data):                       # packed (pack_host): one copy
-            s.inbuf.copy_(data, non_blocking=True)
+        if torch.is_tensor(data):                       # packed (pack_host): one copy (whole buffer or its prefix)
+            s.inbuf[:data.numel()].copy_(data, non_blocking=True)
             return data.numel() * 4
         xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
         tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
@@ -503,11 +511,15 @@ class DeformerTrainer:
             out = loss.to("cpu", non_blocking=False)
         return float(out)
 
-    def run_from_host(self, host_batches, steps: int) -> torch.Tensor:
+    def run_from_host(self, host_batches, steps: int, native: Optional[bool] = None) -> torch.Tensor:
         """Pipelined end-to-end training loop over host-resident (pinned) batches: the inputs of step
         k + 1 travel host -> device on a copy stream while step k computes, and every step's loss is
         read back device -> host asynchronously into pinned memory.  Slot k % R receives batch
-        k % len(host_batches); needs R = len(self.slots) >= 2.  Returns the `steps` losses (host)."""
+        k % len(host_batches); needs R = len(self.slots) >= 2.  Returns the `steps` losses (host).
+
+        With CUDA graphs and batches packed by `pack_host`, the loop itself runs in the C library
+        (`gad_pipeline_run`, csrc/host_pipeline.cu: seven CUDA API calls per step, no Python); otherwise, or
+        with `native=False`, the same schedule is issued from Python."""
         R = len(self.slots)
         if R < 2:
             raise ValueError("run_from_host needs at least two resident slots (double buffering)")
@@ -517,6 +529,32 @@ class DeformerTrainer:
             self._slot_free = [torch.cuda.Event() for _ in range(R)]
         losses = torch.empty(steps, dtype=torch.float32).pin_memory()
         cs, ms = self._copy_stream, self.stream
+        packed = all(torch.is_tensor(b) and b.is_pinned() and b.dtype == torch.float32 for b in host_batches)
+        pure = all(self._one_launch(s) for s in self.slots)      # the step's graph holds library kernels only
+        if native is None:
+            native = self.use_graph and packed and pure
+        if native:
+            if not (self.use_graph and packed):
+                raise ValueError("the native pipeline needs use_cuda_graph=True and pinned buffers from pack_host")
+            nb = len(host_batches)
+            if len({b.numel() for b in host_batches}) != 1:
+                raise ValueError("packed host batches must have one size")
+            slots = (_lib.PipelineSlot * R)()
+            for sid, s in enumerate(self.slots):
+                if sid not in self.graphs:
+                    self.capture(sid)
+                slots[sid].dev_inputs = s.inbuf.data_ptr()
+                slots[sid].bytes = host_batches[0].numel() * 4
+                slots[sid].graph_exec = self.graphs[sid].raw_cuda_graph_exec()
+                slots[sid].loss_dev = s.loss.data_ptr()
+                s.h2d_bytes = host_batches[0].numel() * 4
+            hosts = (C.c_void_p * nb)(*[b.data_ptr() for b in host_batches])
+            self._touch_params()
+            with torch.cuda.device(self.dev):
+                _lib.check(self.lib.gad_pipeline_run(slots, R, hosts, nb, int(steps), losses.data_ptr(), ms.cuda_stream,
+                                                     cs.cuda_stream), "gad_pipeline_run")
+            self.check_peer()
+            return losses
         cs.wait_stream(ms)
         nb = len(host_batches)
 

@@ -398,6 +398,22 @@ int gad_peer_open(const void* handle, void** dev_ptr);
 int gad_peer_close(void* dev_ptr);
 int gad_peer_free(void* dev_ptr);
 
+/* ---- host side of the end-to-end training loop ------------------------------------------------------
+ * The reference's `for data in loader: ... loss.backward(); optimizer.step()` (src/run_GNN.py:95-131) with
+ * the batches in PINNED host memory, as a double-buffered pipeline driven from C: for step k, slot
+ * k % n_slots receives host batch k % n_host in ONE cudaMemcpyAsync on `copy_stream` (as soon as step
+ * k - n_slots has released the slot), `compute_stream` waits for it, launches the slot's captured step
+ * (`graph_exec`: a cudaGraphExec_t holding gad_train_step_ell on that slot) and copies the 4-byte loss
+ * to losses_host[k] (pinned).  Blocks until the last step has finished.  n_slots >= 2. */
+typedef struct gad_pipeline_slot {
+    void* dev_inputs;        /* device buffer the packed batch is copied to */
+    size_t bytes;            /* bytes per batch */
+    void* graph_exec;        /* cudaGraphExec_t of this slot's training step */
+    const float* loss_dev;   /* device scalar the step writes its loss to */
+} gad_pipeline_slot;
+int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, const void* const* host_batches, int n_host,
+                     int64_t steps, float* losses_host, void* compute_stream, void* copy_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,14 +285,15 @@ def test_single_very_large_mesh_trains_on_the_streaming_chain(monkeypatch):
 
 
 def test_host_fed_loop_packed_buffers_equal_per_tensor_copies():
-    """run_from_host over pack_host buffers (one H2D copy per step) == over Batch objects (one copy per
-    tensor) == resident-batch steps: same losses, same parameters."""
+    """run_from_host over pack_host buffers (one H2D copy per step; loop in the C library, gad_pipeline_run, or
+    the same schedule from Python; whole buffer or the per-sample prefix without the shared x_comp) == over
+    Batch objects (one copy per tensor) == resident-batch steps: same losses, same parameters."""
     opt, ds, _, ref = _case((20, 20), 16, seed=11)
     batches = [synth.make_batch((20, 20), 16, seed=20 + r) for r in range(3)]
     for b in batches:
         b.pin_memory()
     outs = []
-    for mode in ("resident", "batches", "packed"):
+    for mode in ("resident", "batches", "packed_native", "packed_python", "prefix_native"):
         model = cuda_model(ds, opt, ref.state_dict())
         tr = DeformerTrainer(model, lr=1e-2)
         sids = [tr.add_batch(b) for b in batches]
@@ -304,10 +305,20 @@ def test_host_fed_loop_packed_buffers_equal_per_tensor_copies():
                     losses.append(l.clone())
             tr.synchronize()
             losses = torch.stack([x.cpu() for x in losses]).reshape(-1)
+        elif mode == "batches":
+            losses = tr.run_from_host(batches, 9).clone()
         else:
-            src = batches if mode == "batches" else [tr.pack_host(sid, b) for sid, b in zip(sids, batches)]
-            losses = tr.run_from_host(src, 9).clone()
+            src = [tr.pack_host(sid, b, with_x_comp=not mode.startswith("prefix")) for sid, b in zip(sids, batches)]
+            if mode.startswith("prefix"):
+                assert src[0].numel() * 4 == 16 * 400 * 16          # target (8) + f (4) + uu (4) bytes per node
+            losses = tr.run_from_host(src, 9, native=mode.endswith("native")).clone()
+            assert tr.slots[0].h2d_bytes == src[0].numel() * 4
         outs.append((losses, tr.flat.clone().cpu()))
     for losses, flat in outs[1:]:
         assert torch.equal(losses, outs[0][0])
         assert torch.equal(flat, outs[0][1])
+    # a batch on another mesh cannot be sent without its x_comp
+    other = synth.make_batch((20, 20), 16, seed=99)
+    other.x_comp = other.x_comp + 0.5
+    with pytest.raises(ValueError):
+        tr.pack_host(0, other, with_x_comp=False)

@@ -84,8 +84,12 @@ def test_k_steps_match_oracle_trained_by_torch_adam(case, mode):
     live = torch.ones(n, dtype=torch.bool)
     live[n - _flat_views(model)[3].numel():] = False        # lin_key.bias: gradient analytically zero
     # the loss of step k depends on the parameters after k - 1 optimizer steps
+    # (first step: same parameters on both sides, kernel-vs-oracle rounding only; later steps carry the
+    # O(lr)-amplified rounding noise of Adam's normalised update, same bar as the parameters below)
+    assert abs(losses[0] - ref_losses[0]) <= 1e-5 * abs(ref_losses[0])
     for a, b in zip(losses, ref_losses):
-        assert abs(a - b) <= 2e-4 * abs(b), (losses, ref_losses)
+        assert abs(a - b) <= 2e-3 * abs(b), (losses, ref_losses)
+    assert losses[-1] < 0.7 * losses[0]                       # and it trains
     # Adam normalises each entry's gradient: rounding noise on near-zero entries is amplified to O(lr)
     err = (got - want)[live].abs().max().item() / want[live].abs().max().item()
     assert err <= 2e-3, err
