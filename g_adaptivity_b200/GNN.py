@@ -13,8 +13,9 @@ unchanged.  What differs is underneath:
   (`gad_deform_fwd_ell_raw` on meshes that fit a CTA, `gad_deform_fwd_cluster` on larger ones; the
   streaming kernels otherwise), with the folded weights cached per parameter version; autograd's
   op-by-op backward is one hand-written launch plus the reduction;
-* `loss_type='pde_loss'` on 1-D meshes appends the batched differentiable FEM solve (`fem1d.py`) and
-  returns `(coeffs, x_phys, sol)` as `src/GNN.py:307-342` does;
+* `loss_type='pde_loss'` appends the batched differentiable FEM solve (1-D: `fem1d.py`, 2-D: `fem2d.py`, one
+  launch for the whole batch instead of the per-mesh Python loop) and returns `(coeffs, x_phys, sol)` as
+  `src/GNN.py:307-342` does;
 * `inference_session(data)` replays the call as a CUDA graph for roll-outs.
 
 Options the reference supports but this path does not raise
@@ -138,10 +139,10 @@ class GNN(nn.Module):
             raise NotImplementedError("GRAND with a non-identity non_lin (src/GNN.py:286) is not implemented")
         if opt.get("ode_method", "euler") not in GF.METHODS:
             raise ValueError(f"ode_method must be one of {sorted(GF.METHODS)}")
-        if opt["loss_type"] == "pde_loss" and self.dim != 1:
+        if opt["loss_type"] == "pde_loss" and opt.get("data_type") == "randg_mix":
             raise NotImplementedError(
-                "loss_type='pde_loss' on 2-D meshes appends a per-mesh differentiable FEM solve (torch_FEM_2D, "
-                "src/GNN.py:329-336): 'next' row 8f1 of the scope table; only the 1-D solve (csrc/fem1d.cu) is built")
+                "loss_type='pde_loss' with data_type='randg_mix' solves on a different Firedrake mesh per sample "
+                "(data.mesh[b], src/GNN.py:316-318): the batched FEM kernels share one triangulation per batch")
         if opt["loss_type"] not in ("mesh_loss", "modular", "pde_loss"):
             raise NotImplementedError(f"loss_type={opt['loss_type']!r} is not implemented")
 
@@ -289,6 +290,8 @@ class GNN(nn.Module):
         if opt.get("gad_sync_timestamp", False):
             torch.cuda.current_stream(dev).synchronize()
         self.end_MLmodel = time.time()
+        if opt["loss_type"] == "pde_loss" and self.dim == 2:
+            return self._pde_tail_2d(data, graph, x_phys, dev)
         if opt["loss_type"] == "pde_loss":
             # src/GNN.py:307-342 (dim == 1): per mesh torch_FEM_1D on its relocated points -> one batched launch.
             # Returns (coeffs_batched [B*(n-2), 1], x_phys_batched [N], sol_batched [B*Q]) like the reference.
@@ -311,6 +314,65 @@ class GNN(nn.Module):
             coeffs, sol = fem1d.fem1d_solve(xp, centers, scales, self.quad_points, n, int(opt.get("load_quad_points", 101)))
             return coeffs, xp, sol
         return x_phys
+
+    # ------------------------------------------------------------------------------------
+    def _fem2d_topology(self, dev, num_nodes: int):
+        """Triangulation tables of `dataset.mesh` for the batched 2-D FEM kernels, built once per model.
+        The reference reads `mesh.coordinates.cell_node_map().values` and `DirichletBC(V, 0, "on_boundary").nodes`
+        (difFEM_2d.py:354-356,363); a mesh object that carries `bc_nodes` (synth.SyntheticMesh, or any stand-in)
+        is used as is, a Firedrake mesh is asked through Firedrake."""
+        from . import fem2d
+        topo = self.__dict__.get("_fem2d_topo")
+        if topo is not None and topo.N == num_nodes and topo.device == dev:
+            return topo
+        mesh = getattr(self.dataset, "mesh", None)
+        if mesh is None:
+            raise ValueError("loss_type='pde_loss' on 2-D meshes needs dataset.mesh (src/GNN.py:321)")
+        cells = np.asarray(mesh.coordinates.cell_node_map().values)
+        if hasattr(mesh, "bc_nodes"):
+            bc = np.asarray(mesh.bc_nodes)
+        else:
+            from firedrake import DirichletBC, FunctionSpace      # the reference's own route
+            bc = np.asarray(DirichletBC(FunctionSpace(mesh, "CG", 1), 0, "on_boundary").nodes)
+        topo = fem2d.Fem2DTopology(cells, bc, num_nodes, dev)
+        self.__dict__["_fem2d_topo"] = topo
+        return topo
+
+    def _pde_tail_2d(self, data, graph, x_phys, dev):
+        """src/GNN.py:307-342 with dim == 2: per mesh `torch_FEM_2D` on its relocated points, then the solution on
+        the evaluation grid is put into the fine mesh's node order by `reshape_grid_to_fd_tensor(sol.view(-1)
+        .unsqueeze(-1), dataset.mapping_tensor_fine)` (utils_data.py:143-159: for this call shape that is
+        `sol.view(-1)[argsort(mapping_tensor_fine)]`).  Here: ONE batched launch (csrc/fem2d.cu) + one gather.
+        Returns (coeffs [B*n*n, 1], x_phys [B*n*n, 2], sol [B*Q*Q]) like the reference."""
+        from . import fem2d
+        opt = self.opt
+        B = len(graph.mesh_sizes) if graph.mesh_sizes is not None else int(data.batch.max().item()) + 1
+        Nm = int(x_phys.shape[0]) // B
+        if graph.mesh_sizes is not None and any(m != Nm for m in graph.mesh_sizes):
+            raise NotImplementedError("pde_loss needs meshes of equal size in a batch")
+        topo = self._fem2d_topology(dev, Nm)
+        cache = self.__dict__.setdefault("_pde_cache", {})
+        hit = cache.get(id(data.pde_params))
+        if hit is None or hit[0] is not data.pde_params or hit[1].shape[0] != B:
+            if len(cache) >= 64:
+                cache.clear()
+            hit = (data.pde_params,) + fem2d.pde_params_to_tensors(data.pde_params, B, dev)
+            cache[id(data.pde_params)] = hit
+        centers, scales = hit[1], hit[2]
+        ev = self.__dict__.get("_fem2d_eval")
+        if ev is None or ev[0].device != dev:
+            X, Y = self.quad_points
+            mapping = getattr(self.dataset, "mapping_tensor_fine", None)
+            if mapping is None:
+                raise ValueError("loss_type='pde_loss' on 2-D meshes needs dataset.mapping_tensor_fine (src/GNN.py:333)")
+            _, order = torch.sort(torch.as_tensor(mapping).reshape(-1))           # utils_data.py:154
+            ev = (X.reshape(-1).to(dev, torch.float32).contiguous(), Y.reshape(-1).to(dev, torch.float32).contiguous(),
+                  order.to(dev))
+            self.__dict__["_fem2d_eval"] = ev
+        sol, coeffs, _ = fem2d.fem2d_solve(x_phys.view(B, Nm, 2), topo, centers, scales, ev[0], ev[1],
+                                           int(opt.get("load_quad_points", 101)))
+        sol_fd = sol.index_select(1, ev[2])
+        return coeffs.reshape(B * Nm, 1), x_phys, sol_fd.reshape(-1)
 
     def inference_session(self, data) -> "InferenceSession":
         """Replayable deformer call on a fixed topology (extension; the Burgers roll-out of

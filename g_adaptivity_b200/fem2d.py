@@ -2,10 +2,9 @@
 firedrake_difFEM/difFEM_2d.py:345-372 looped per mesh by src/GNN.py:327-335) -- plumbing over
 csrc/fem2d.cu: one CTA per mesh, topology shared by the batch.
 
-STATUS: parity green on the B200 against the fixtures minted from the reference (tests/test_fem2d_gpu.py), first
-version performance-wise (36 ms for 256 meshes of 30x30, forward + backward).  `GNN.forward` does not route 2-D
-`pde_loss` here yet (the dataset-side grid mapping, src/GNN.py:333, is not mirrored); call `fem2d_solve` directly.
-There is no CPU fallback."""
+Parity: green on the B200 against the fixtures minted from the reference (tests/test_fem2d_gpu.py).
+`GNN.forward` routes `loss_type='pde_loss'` on 2-D meshes here (`GNN._pde_tail_2d`, mirroring src/GNN.py:327-335
+including the `mapping_tensor_fine` reordering).  There is no CPU fallback."""
 from __future__ import annotations
 
 from typing import Sequence
@@ -42,6 +41,18 @@ class Fem2DTopology:
         self.star_cell = torch.from_numpy(star_cell).to(dev)
         self.star_loc = torch.from_numpy(star_loc).to(dev)
         self.device = dev
+
+
+def pde_params_to_tensors(pde_params, B: int, device) -> tuple:
+    """`data.pde_params['centers'][b]` is a list (one entry per Gaussian) of float32 arrays [2]
+    (src/data.py:155-156; handed to torch_FEM_2D as tensors, src/GNN.py:319-320) -> fp64 [B, G, 2]."""
+    def stack(key):
+        try:
+            arr = np.asarray(pde_params[key][:B], dtype=np.float32).reshape(B, -1, 2)
+        except ValueError as e:
+            raise ValueError("every mesh of a batch must carry the same number of 2-D Gaussians") from e
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True).double()
+    return stack("centers"), stack("scales")
 
 
 class FEM2DFunction(torch.autograd.Function):

@@ -104,16 +104,45 @@ class Batch(Data):
         return out
 
 
-class SyntheticDataset:
-    """What `GNN.__init__` reads from its `dataset` argument (`src/GNN.py:147-149`)."""
+class SyntheticMesh:
+    """What the 2-D FEM tail asks of `dataset.mesh` (a Firedrake mesh in the reference): the cell-node map
+    (`mesh.coordinates.cell_node_map().values`, difFEM_2d.py:363) and the Dirichlet nodes (the reference gets them
+    from `DirichletBC(V, 0, "on_boundary").nodes`, :354-356; a stand-in carries them as `bc_nodes`)."""
 
-    def __init__(self, dim: int, mesh_dims: Sequence[int]):
+    def __init__(self, cells: np.ndarray, bc_nodes: np.ndarray):
+        self._cells = np.asarray(cells, dtype=np.int32)
+        self.bc_nodes = np.asarray(bc_nodes, dtype=np.int32)
+        self.coordinates = self
+
+    def cell_node_map(self):
+        class _Map:
+            values = self._cells
+        return _Map()
+
+
+class SyntheticDataset:
+    """What `GNN.__init__` / `GNN.forward` read from their `dataset` argument (`src/GNN.py:147-149,321,333`).
+    With `eval_quad_points` (2-D) it also carries what `loss_type='pde_loss'` needs: `mesh` and
+    `mapping_tensor_fine`, the canonical-grid -> fine-mesh-node map of `map_firedrake_to_cannonical_ordering_2d`
+    (utils_data.py:53-77) for a fine mesh numbered row-major (node id = iy * Q + ix)."""
+
+    def __init__(self, dim: int, mesh_dims: Sequence[int], eval_quad_points: Optional[int] = None):
         self.num_x_comp_features = dim
         self.mesh_dims = list(mesh_dims)
         self.mesh = None  # Firedrake mesh in the reference; only used by reg_skew / pde_loss
         self.x_comp_shared = None
         self.mapping_tensor = None
         self.mapping_tensor_fine = None
+        if dim == 2:
+            topo = MeshTopology(mesh_dims)
+            self.mesh = SyntheticMesh(topo.cells, np.nonzero(topo.boundary_nodes)[0])
+            self.x_comp_shared = torch.from_numpy(topo.coords.copy())
+            if eval_quad_points is not None:
+                Q = int(eval_quad_points)
+                # canonical index c = i * Q + j is the grid point (x_i, y_j) (torch.meshgrid 'ij', :60-62,71);
+                # on the row-major fine mesh that point is node j * Q + i
+                i, j = np.meshgrid(np.arange(Q), np.arange(Q), indexing="ij")
+                self.mapping_tensor_fine = torch.from_numpy((j * Q + i).reshape(-1).astype(np.int64))
 
 
 # --------------------------------------------------------------------------------------
@@ -274,7 +303,8 @@ def make_data(topo: MeshTopology, seed: int, num_gauss: int = 2, burgers: bool =
 
 
 def make_batch(mesh_dims: Sequence[int], num_meshes: int, seed: int = 0, num_gauss: Optional[int] = None,
-               burgers: bool = False, first_mesh_id: int = 0, eval_quad_points: int = 101) -> Batch:
+               burgers: bool = False, first_mesh_id: int = 0, eval_quad_points: int = 101,
+               with_u_true_fine: bool = False) -> Batch:
     """`num_meshes` samples on one shared topology, collated like PyG would.
 
     Vectorised (no per-mesh python graph work), bit-identical to
@@ -321,6 +351,17 @@ def make_batch(mesh_dims: Sequence[int], num_meshes: int, seed: int = 0, num_gau
             for c, s_ in zip(cs[b], ss[b]):
                 fine[b] += np.exp(-(q - np.float32(np.asarray(c).reshape(-1)[0])) ** 2
                                   / np.float32(np.asarray(s_).reshape(-1)[0]) ** 2).astype(np.float32)
+        out.u_true_fine_tensor = torch.from_numpy(fine.reshape(-1))
+    if topo.dim == 2 and with_u_true_fine:
+        # target of loss_type='pde_loss' in 2-D (src/run_GNN.py:109-110): u_true at the nodes of the fine mesh
+        # (eval_quad_points x eval_quad_points, row-major numbering: node id = iy * Q + ix)
+        q = np.linspace(0.0, 1.0, eval_quad_points, dtype=np.float32)
+        Xf, Yf = np.meshgrid(q, q, indexing="xy")
+        fine_xy = np.stack([Xf.ravel(), Yf.ravel()], axis=1).astype(np.float32)
+        fine = np.empty((B, fine_xy.shape[0]), dtype=np.float32)
+        for b0 in range(0, B, 64):
+            b1 = min(B, b0 + 64)
+            fine[b0:b1], _ = gaussian_features(fine_xy, cs[b0:b1], ss[b0:b1], amplitude)
         out.u_true_fine_tensor = torch.from_numpy(fine.reshape(-1))
     out._num_graphs = B
     out.mesh_sizes = [N] * B

@@ -6,6 +6,7 @@ result depends on reproducing the reference's tie decisions.
 import glob
 import os
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -47,3 +48,59 @@ def test_fem2d_needs_cuda():
     with pytest.raises(RuntimeError):
         fem2d.FEM2DFunction.apply(fx["mesh"].unsqueeze(0), None, fx["centers"].unsqueeze(0), fx["scales"].unsqueeze(0),
                                   torch.zeros(4), torch.zeros(4), 9)
+
+
+@pytest.mark.parametrize("n,Q,K,B", [(7, 13, 9, 3), (6, 21, 9, 2)])
+def test_pde_loss_through_the_deformer_2d(n, Q, K, B):
+    """`loss_type='pde_loss'` on 2-D meshes -- the reference's default loss (params.py:109; src/GNN.py:307-342,
+    src/run_GNN.py:109-110): the model returns (coeffs, x_phys, sol) with `sol` in the fine mesh's node order
+    (`reshape_grid_to_fd_tensor` with `dataset.mapping_tensor_fine`, GNN.py:333); mse(sol, u_true_fine)
+    back-propagates through the batched FEM solve AND the deformer into the Linear parameters.
+    Against the oracle deformer (fp32, as the reference runs) + the oracle's 2-D FEM per mesh + autograd."""
+    import copy
+    from g_adaptivity_b200 import GNN, synth
+    from oracle import gnn_oracle
+    md = (n, n)
+    opt = synth.default_opt(md, eval_quad_points=Q, load_quad_points=K)
+    ds = synth.SyntheticDataset(2, md, eval_quad_points=Q)
+    data = synth.make_batch(md, B, seed=5, eval_quad_points=Q, with_u_true_fine=True)
+    torch.manual_seed(42)
+    ref = gnn_oracle.GNNRef(ds, copy.deepcopy(opt))
+    xp = ref(data)                                             # [B*n*n, 2]
+    topo = synth.MeshTopology(md)
+    bc = np.nonzero(topo.boundary_nodes)[0]
+    x0 = torch.linspace(0, 1, Q)
+    X, Y = torch.meshgrid(x0, x0, indexing="ij")
+    _, order = torch.sort(ds.mapping_tensor_fine)
+    sols, coefs = [], []
+    for b in range(B):
+        cen = torch.from_numpy(np.stack(data.pde_params["centers"][b])).float()
+        scl = torch.from_numpy(np.stack(data.pde_params["scales"][b])).float()
+        c, s = Fz.fem2d_fast(topo.cells, bc, xp[b * n * n:(b + 1) * n * n], [X, Y], K, cen, scl)
+        coefs.append(c)
+        sols.append(s.reshape(-1)[order])                      # reshape_grid_to_fd_tensor (utils_data.py:143-159)
+    sol_ref, coef_ref = torch.cat(sols), torch.cat(coefs)
+    loss_ref = F.mse_loss(sol_ref, data.u_true_fine_tensor)
+    loss_ref.backward()
+
+    gopt = copy.deepcopy(opt)
+    gopt.update(device="cuda", loss_type="pde_loss")
+    model = GNN(ds, gopt).to("cuda")
+    model.load_state_dict(ref.state_dict())
+    model.train()
+    coeffs, x_phys, sol = model(data)
+    assert coeffs.shape == (B * n * n, 1) and x_phys.shape == (B * n * n, 2) and sol.shape == (B * Q * Q,)
+    loss = F.mse_loss(sol, data.u_true_fine_tensor.cuda())
+    loss.backward()
+    sc = coef_ref.abs().max().item()
+    assert (x_phys.detach().cpu() - xp.detach()).abs().max().item() <= 1e-5 * xp.abs().max().item()
+    assert (coeffs.detach().cpu() - coef_ref.detach()).abs().max().item() <= 2e-5 * sc
+    assert (sol.detach().cpu() - sol_ref.detach()).abs().max().item() <= 2e-5 * sc
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    scale = max(p.grad.abs().max().item() for n_, p in ref.named_parameters() if p.grad is not None and "lin_key.bias" not in n_)
+    for (n_, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        if q.grad is None or "lin_key.bias" in n_:
+            continue
+        err = (p.grad.cpu() - q.grad).abs().max().item() / scale
+        assert err <= 2e-3, (n_, err)
+    assert not torch.equal(order, torch.arange(Q * Q))         # the fine-mesh order is a real permutation here

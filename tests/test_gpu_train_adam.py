@@ -93,7 +93,10 @@ def test_k_steps_match_oracle_trained_by_torch_adam(case, mode):
     # Adam normalises each entry's gradient: rounding noise on near-zero entries is amplified to O(lr)
     err = (got - want)[live].abs().max().item() / want[live].abs().max().item()
     assert err <= 2e-3, err
-    assert torch.equal(got[~live], want[~live])              # zero gradient: Adam leaves lin_key.bias alone
+    # d loss / d lin_key.bias is analytically zero (softmax shift invariance): the kernel writes exact zeros, so
+    # Adam leaves the bias alone, while autograd's rounding noise there makes torch Adam random-walk it by O(lr)
+    # per step -- without any effect on the model's output
+    assert torch.equal(got[~live], state["conv_layers.0.lin_key.bias"].flatten())
     # the model's parameters are views of the trainer's flat vector
     assert torch.equal(model.state_dict()["conv_layers.0.lin_query.weight"].cpu().flatten(), got[:64])
 

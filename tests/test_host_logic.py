@@ -116,7 +116,7 @@ def test_model_surface_matches_reference_contract():
 @pytest.mark.parametrize("over,exc", [
     ({"conv_type": "GCN"}, NotImplementedError), ({"conv_type": "GAT_plus"}, NotImplementedError),
     ({"enc": "lin_layer"}, NotImplementedError), ({"dropout": 0.5}, NotImplementedError),
-    ({"gnn_inc_glob_feat_f": True}, NotImplementedError), ({"loss_type": "pde_loss"}, NotImplementedError),
+    ({"gnn_inc_glob_feat_f": True}, NotImplementedError), ({"loss_type": "pde_loss", "data_type": "randg_mix"}, NotImplementedError),
     ({"reg_skew": True}, NotImplementedError), ({"softmax_temp_type": "learnable_a"}, NotImplementedError),
     ({"residual": False}, NotImplementedError), ({"ode_method": "dopri5"}, ValueError),
 ])
