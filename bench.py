@@ -211,6 +211,104 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------
+# the other BASELINE.json configs under the same clock (device-timed; reported in `configs`, not as `value`)
+# ------------------------------------------------------------------------------------------
+def fwd_bytes_per_node(N, E, ce, fevals, in_dim, dim):
+    return fevals * (8 * ce + 4 * E / N + 4) + 4 * in_dim + 4 * dim
+
+
+def time_forward_config(dev, md, B, over, burgers, iters, peak):
+    """Forward through the module seam (`model(data)` under no_grad, inputs device-resident) and through
+    `model.inference_session(data)` (one CUDA-graph replay per call, new `uu` copied in each time)."""
+    from g_adaptivity_b200 import GNN, synth
+    opt = synth.burgers_opt(md) if burgers else synth.default_opt(md)
+    opt.update(device=str(dev), gad_store_alpha=False, **over)
+    ds = synth.SyntheticDataset(len(md), md)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev).eval()
+    data = synth.make_batch(md, B, seed=0, burgers=burgers).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model(data)
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model(data)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        sess = model.inference_session(data)
+        for _ in range(3):
+            sess()
+        torch.cuda.synchronize(dev)
+        n_rep = max(20, iters)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_rep):
+            sess(uu=data.uu_tensor)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_sess = e0.elapsed_time(e1) / n_rep
+    g = model.last_graph
+    ms = statistics.median(ts)
+    fevals = opt["num_layers"] * (4 if opt.get("ode_method", "euler") == "rk4" else 1)
+    bpn = fwd_bytes_per_node(g.N, g.E, model.live, fevals, sum(model.in_dims), model.dim)
+    return {"nodes": g.N, "edges": g.E, "f_evaluations": fevals, "bytes_per_node": round(bpn, 1),
+            "module_call": {"ms": round(ms, 4), "nodes_per_s": g.N / (ms * 1e-3),
+                            "roofline_frac": g.N * bpn / (ms * 1e-3) / 1e9 / peak},
+            "session_replay": {"ms": round(ms_sess, 4), "nodes_per_s": g.N / (ms_sess * 1e-3),
+                               "roofline_frac": g.N * bpn / (ms_sess * 1e-3) / 1e9 / peak}}
+
+
+def time_cfg5(dev, rank, world, iters, peak, barrier):
+    """BASELINE configs[4]: data-parallel training on 50x50 meshes, GLOBAL batch 8192 (strong scaling: 8192 / N
+    meshes per GPU), one optimizer step per global batch, gradient all-reduce inside the kernel."""
+    import torch.distributed as dist
+    from g_adaptivity_b200 import GNN, synth
+    from g_adaptivity_b200.trainer import DeformerTrainer
+    md, total = (50, 50), 8192
+    per = total // world
+    opt = synth.default_opt(md, device=str(dev), gad_store_alpha=False)
+    ds = synth.SyntheticDataset(2, md)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev)
+    tr = DeformerTrainer(model)
+    tr.broadcast_parameters()
+    ring = 2
+    sids = [tr.add_batch(synth.make_batch_device(md, per, dev, seed=500 + 7 * r + 1000 * rank)) for r in range(ring)]
+    key = tuple(sids) * 2
+    tr.capture_epoch(key)
+    tr.run_epoch(key)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tr.stream)
+    for _ in range(iters):
+        tr.run_epoch(key)
+    e1.record(tr.stream)
+    barrier()
+    tr.check_peer()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / (iters * len(key))
+    s0 = tr.slots[0]
+    N, E = s0.N, s0.graph.E
+    ab = algorithmic_bytes(N, E, model.live, opt["num_layers"], sum(model.in_dims), model.dim)
+    out = {"workload": f"cfg5: global batch {total} x 50x50 meshes, {per} per GPU (strong scaling), train step",
+           "nodes_per_gpu": N, "ms_per_step": round(ms, 4), "nodes_per_s": world * N / (ms * 1e-3),
+           "bytes_per_node": round(ab["step_per_node"], 1),
+           "roofline_frac": N * ab["step_per_node"] / (ms * 1e-3) / 1e9 / peak,
+           "data": "256 distinct samples per GPU tiled on the device (synth.make_batch_device)",
+           "one_launch": bool(tr._one_launch(s0))}
+    tr.close()
+    del tr, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def bind_rank_to_cores(local_rank: int, local_world: int):
     """One process per GPU on a shared host: give every rank its own slice of the cores this job may use, so
     that the ranks' launch / copy threads do not migrate over each other (all GPUs of the box report the same
@@ -243,6 +341,7 @@ def main():
     ap.add_argument("--no-epoch", action="store_true", help="one CUDA graph per step instead of one per pass over the ring")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="do not time the other BASELINE configs (cfg 1, 3, 4, 5)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -447,7 +546,7 @@ def main():
     # ---- end-to-end: pinned host buffers in, loss out, every step --------------------------
     e2e = None
     if not args.skip_e2e:
-        ke = min(K, 2000)
+        ke = min(max(K, 200), 2000)      # the pipeline needs a few steps to fill: never fewer than 200
         # host side of the public API: every batch packed once into ONE pinned buffer in the slot's input
         # layout (DeformerTrainer.pack_host), so a step's inputs travel host -> device in a single copy.
         # The synthetic dataset is on one shared mesh (as the reference's `randg` datasets, src/data.py:143):
@@ -474,6 +573,29 @@ def main():
                "cpu_affinity": affinity}
 
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- the other BASELINE configs, device-timed (cfg 2 stays `value`) ---------------------------
+    configs = None
+    if not args.skip_configs:
+        configs = {}
+        it = 5 if K <= 50 else 20
+        try:
+            configs["cfg5_50x50_global_batch_8192_train"] = time_cfg5(dev, rank, world, max(3, it // 2), peak, barrier)
+        except Exception as e:      # noqa: BLE001 -- the headline line must survive a failing extra
+            if world > 1:
+                raise
+            configs["cfg5_50x50_global_batch_8192_train"] = {"error": repr(e)[:300]}
+        if world == 1:
+            for name, fn in (
+                    ("cfg1_15x15_single_mesh_fwd", lambda: time_forward_config(dev, (15, 15), 1, {}, False, it, peak)),
+                    ("cfg3_burgers_1d_200_batch_4096_fwd",
+                     lambda: time_forward_config(dev, (200,), 4096, {}, True, it, peak)),
+                    ("cfg4_200x200_64_rk4_steps_fwd",
+                     lambda: time_forward_config(dev, (200, 200), 1, {"ode_method": "rk4", "num_layers": 64}, False, it, peak))):
+                try:
+                    configs[name] = fn()
+                except Exception as e:      # noqa: BLE001
+                    configs[name] = {"error": repr(e)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:      # reported at N = 1 only (the other ranks would spin)
@@ -505,6 +627,8 @@ def main():
         }
         if dp_check is not None:
             line["dp_check"] = dp_check
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without tearing NCCL down: the captured graphs hold collectives and

@@ -368,6 +368,39 @@ def make_batch(mesh_dims: Sequence[int], num_meshes: int, seed: int = 0, num_gau
     return out
 
 
+def make_batch_device(mesh_dims: Sequence[int], num_meshes: int, device, seed: int = 0, block: int = 256,
+                      burgers: bool = False) -> Batch:
+    """A large batch assembled ON THE DEVICE for timing runs (BASELINE cfg 5: 8192 meshes of 50x50 = 20 M nodes,
+    120 M edges): `block` distinct samples are generated on the host (`make_batch`) and tiled; the topology tensors
+    are the one-mesh arrays plus per-mesh node offsets, exactly what PyG's collation yields, built with torch ops
+    on `device`.  Sample values repeat every `block` meshes -- irrelevant for throughput, stated by the caller."""
+    B = int(num_meshes)
+    base = make_batch(mesh_dims, min(B, block), seed=seed, burgers=burgers)
+    nb = base.num_graphs
+    topo = MeshTopology(mesh_dims)
+    N1, dev = topo.num_nodes, torch.device(device)
+    reps = (B + nb - 1) // nb
+    out = Batch()
+    ei1 = torch.from_numpy(topo.edge_index).to(dev)                                   # [2, E0]
+    offs = (torch.arange(B, device=dev, dtype=torch.int64) * N1).view(1, B, 1)
+    out.edge_index = (ei1.view(2, 1, -1) + offs).reshape(2, -1).contiguous()
+    out.batch = torch.arange(B, device=dev, dtype=torch.int64).repeat_interleave(N1)
+
+    def tile_nodes(t):
+        t = t.to(dev)
+        per = t.shape[0] // nb
+        return t.repeat((reps,) + (1,) * (t.dim() - 1))[:B * per].contiguous()
+
+    for k in ("x_comp", "x_phys", "f_tensor", "uu_tensor", "u_true_tensor", "boundary_nodes", "to_boundary_edge_mask",
+              "to_corner_nodes_mask", "diff_boundary_edges_mask"):
+        setattr(out, k, tile_nodes(getattr(base, k)))
+    out.corner_nodes = [topo.corner_nodes.copy() for _ in range(B)]
+    out.pde_params = {"centers": (base.pde_params["centers"] * reps)[:B], "scales": (base.pde_params["scales"] * reps)[:B]}
+    out._num_graphs = B
+    out.mesh_sizes = [N1] * B
+    return out
+
+
 def make_mixed_batch(mesh_dims_list: Sequence[Sequence[int]], seed: int = 0) -> Batch:
     """Variable-size batch (the `randg_mix` input shape, `src/data_mixed.py:122-146`)."""
     topos = {}
