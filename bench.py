@@ -336,7 +336,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ring", type=int, default=16, help="distinct resident batches walked by the timed loop")
+    ap.add_argument("--ring", type=int, default=32, help="distinct resident batches walked by the timed loop")
+    ap.add_argument("--no-shared-topology", action="store_true", help="build the general graph of the whole batch")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-epoch", action="store_true", help="one CUDA graph per step instead of one per pass over the ring")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -370,7 +371,10 @@ def main():
     R = max(1, args.ring)
 
     # ---- workload ----------------------------------------------------------------------
-    opt = synth.default_opt(MESH_DIMS, num_layers=NUM_LAYERS, device=str(dev), gad_store_alpha=False)
+    # the synthetic dataset is on one shared mesh, as the reference's `randg` datasets (src/data.py:143): the
+    # graph is built for one tile and every tile of the batch uses that ELL table (row f2, MeshGraph.build_uniform)
+    opt = synth.default_opt(MESH_DIMS, num_layers=NUM_LAYERS, device=str(dev), gad_store_alpha=False,
+                            gad_shared_topology=not args.no_shared_topology)
     ds = synth.SyntheticDataset(2, MESH_DIMS)
     torch.manual_seed(42)
     model = GNN(ds, opt).to(dev)
@@ -387,8 +391,8 @@ def main():
     n_nodes, n_edges = s0.N, s0.graph.E
     in_dim = sum(model.in_dims)
     ab = algorithmic_bytes(n_nodes, n_edges, model.live, NUM_LAYERS, in_dim, model.dim)
-    ro_bytes = sum(t.numel() * t.element_size() for s in trainer.slots for t in
-                   (s.x_comp, s.f, s.uu, s.target, s.graph.rowptr, s.graph.col, s.graph.t_rowptr, s.graph.t_dst))
+    per_slot = lambda s: [s.inbuf] + ([] if s.graph.uniform else [s.graph.ell_in, s.graph.ell_out])
+    ro_bytes = sum(t.numel() * t.element_size() for s in trainer.slots for t in per_slot(s))
     lib = _lib.load()
 
     if not args.no_graph:
@@ -415,10 +419,15 @@ def main():
     plan = [tuple(i % R for i in range(G))] * n_full + ([tuple((n_full * G + i) % R for i in range(rem))] if rem else [])
     graph_mode = not args.no_graph and not args.no_epoch
 
+    # K <= GRAPH_STEPS: the timed region is ONE graph, and its two events are event-record NODES of that graph
+    # (after a 0.1 ms device-side spin), so the K steps are timed on the device without the host -> device
+    # latency of the graph launch; stream-recorded events around the replay are kept next to it.
+    in_graph_events = graph_mode and len(plan) == 1
+
     def run_plan():
         if graph_mode:
             for key in plan:
-                trainer.run_epoch(key)
+                trainer.run_epoch(key, timed=in_graph_events)
         else:
             for i in range(K):
                 trainer.step(i % R)
@@ -426,10 +435,10 @@ def main():
     warm_steps = 0
     if graph_mode:
         for key in set(plan):
-            trainer.capture_epoch(key)
+            trainer.capture_epoch(key, timed=in_graph_events)
         while warm_steps < W:
             for key in dict.fromkeys(plan):      # each distinct graph at least once
-                trainer.run_epoch(key)
+                trainer.run_epoch(key, timed=in_graph_events)
                 warm_steps += len(key)
     else:
         while warm_steps < max(W, R if not args.no_graph else W):
@@ -449,7 +458,8 @@ def main():
     barrier()
     clocks.mark(False)
     trainer.check_peer()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_stream_events = ev0.elapsed_time(ev1)
+    ms_total = trainer.epoch_elapsed_ms(plan[0]) if in_graph_events else ms_stream_events
     eager_launches = lib.gad_launch_count() - launches0
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -613,13 +623,20 @@ def main():
                 "gradient_exchange": (None if world == 1 else ("all-reduce inside the train kernel over NVLink peer memory"
                                                                if trainer.fused_dp else "NCCL all-reduce")),
                 "nodes_per_step_per_gpu": n_nodes, "edges_per_step_per_gpu": n_edges, "live_channels": model.live,
-                "l2": f"ring of {R} distinct resident batches, {ro_bytes / 1e6:.0f} MB read-only inputs (> 126 MB L2)",
+                "l2": f"ring of {R} distinct resident batches, {ro_bytes / 1e6:.0f} MB of read-only per-step inputs walked "
+                      "in order (> 126 MB L2: no step finds its inputs cached)",
+                "topology": ("shared: one ELL table per tile shape (dataset on one mesh), graph built for one tile"
+                             if s0.graph.uniform else "general: ELL rows for every node of the batch"),
                 "launch": "eager" if args.no_graph else ("cuda-graph replay, one graph per step" if args.no_epoch else
                                                          f"cuda-graph replay: {n_full} x one graph of {G} steps"
                                                          + (f" + one graph of {rem} steps" if rem else "")
                                                          + ", programmatic dependent launch between steps; every graph "
                                                            "replayed during warm-up"),
                 "warmup_steps_run": warm_steps,
+                "timing": ("CUDA events recorded as nodes of the K-step graph (device time of the K steps); the same "
+                           f"region between stream-recorded events around the replay: {ms_stream_events / K * 1e3:.2f} us/step "
+                           "(adds the device-side start-up of the graph launch and a 0.1 ms spin)"
+                           if in_graph_events else "CUDA events recorded on the launching stream around the replays"),
                 "tiles": s0.graph.T, "max_tile_nodes": s0.graph.max_tile_nodes,
             },
             "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": int(launches_per_step),

@@ -162,10 +162,17 @@ class GNN(nn.Module):
             return torch.diff(data.ptr).cpu().tolist()
         return torch.bincount(data.batch).cpu().tolist()
 
-    def _graph(self, data, dev) -> MeshGraph:
+    def _graph(self, data, dev, allow_uniform: bool = False) -> MeshGraph:
+        """The cached result of the graph prologue (src/GNN.py:206-223) for this batch.  `allow_uniform`: the caller
+        only runs the mesh-resident ELL kernels and does not read attention weights, so with
+        `opt['gad_shared_topology']` (dataset on one mesh) the graph may be the shared-topology form, built for one
+        tile (`MeshGraph.build_uniform`)."""
         opt = self.opt
+        uniform_ok = bool(allow_uniform and opt.get("gad_shared_topology", False)
+                          and not any(opt.get(k, False) for k in ("gad_no_ell", "gad_force_stream", "gad_no_fused_train")))
         flags = (bool(opt["fix_boundary"]), bool(opt["self_loops"]), self.CE, str(dev), opt.get("gad_tile_nodes"),
-                 bool(opt.get("gad_no_ell", False)), bool(opt.get("gad_no_wide", False)), bool(opt.get("gad_no_cluster", False)))
+                 bool(opt.get("gad_no_ell", False)), bool(opt.get("gad_no_wide", False)), bool(opt.get("gad_no_cluster", False)),
+                 uniform_ok)
         key = GraphCache.key_of(data, flags)
         g = self._graphs.get(key)
         if g is not None:
@@ -177,6 +184,14 @@ class GNN(nn.Module):
             g = self._graphs.get(skey)
             if g is not None:
                 self._graphs.shared_hits = getattr(self._graphs, "shared_hits", 0) + 1
+                return g
+        if uniform_ok:
+            g = MeshGraph.build_uniform(data, self._mesh_sizes(data), self.dim, opt["mesh_dims"], bool(opt["fix_boundary"]),
+                                        bool(opt["self_loops"]), dev, ce=self.CE, tile_target=opt.get("gad_tile_nodes"))
+            if g is not None:
+                keep = (data.edge_index, data.batch) + tuple(getattr(data, n, None) for n in GraphCache.TOPOLOGY_FIELDS)
+                self._graphs.put(key, g, keep)
+                self._graphs._d[skey] = g
                 return g
         # otherwise look the topology up by CONTENT before building
         ckey, dev_copies = None, {}
@@ -247,7 +262,9 @@ class GNN(nn.Module):
     def forward(self, data):
         opt = self.opt
         dev = self._device()
-        graph = self._graph(data, dev)
+        keep_alpha = isinstance(opt.get("show_mesh_evol_plots"), bool) or opt["conv_type"] == "GRAND"
+        keep_alpha = keep_alpha and bool(opt.get("gad_store_alpha", True))
+        graph = self._graph(data, dev, allow_uniform=not keep_alpha)
         x_comp = data.x_comp.to(dev, non_blocking=True)
         f = data.f_tensor.to(dev, non_blocking=True) if opt["gnn_inc_feat_f"] else None
         uu = data.uu_tensor.to(dev, non_blocking=True) if opt["gnn_inc_feat_uu"] else None
@@ -258,8 +275,6 @@ class GNN(nn.Module):
         if x_comp.dim() == 1:
             x_comp = x_comp.unsqueeze(-1)
         tau = self._tau(dev)
-        keep_alpha = isinstance(opt.get("show_mesh_evol_plots"), bool) or opt["conv_type"] == "GRAND"
-        keep_alpha = keep_alpha and bool(opt.get("gad_store_alpha", True))
         Mu_in = self._folded_weights(dev)
         aux = {"keep_states": keep_alpha, "Mu_in": Mu_in}
         method = GF.METHODS[opt.get("ode_method", "euler")]
@@ -394,7 +409,7 @@ class InferenceSession:
         dev = self.dev
         if opt["gnn_normalize"]:
             raise NotImplementedError("inference_session with gnn_normalize=True is not implemented")
-        self.graph = model._graph(data, dev)
+        self.graph = model._graph(data, dev, allow_uniform=True)
         f32 = dict(dtype=torch.float32, device=dev)
         xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
         self.x_comp = xc.to(**f32).contiguous().clone()

@@ -205,6 +205,12 @@ int reduce_partials(int CE, int T, int Lw, int L, float* ws, float* gMu, float* 
 using namespace gad;
 using namespace gad::ell;
 
+// tile_ptr == NULL: shared-topology batch of equal tiles (include/gadapt.h) -- the tile count must match
+#define GAD_UNIFORM_TILES_OK(who)                                                                                  \
+    GAD_CHECK_ARG(tile_ptr || (max_tile_nodes > 0 && (int64_t)T == (N + max_tile_nodes - 1) / max_tile_nodes),     \
+                  who ": tile_ptr == NULL means T = ceil(N / max_tile_nodes) equal tiles (N=%lld T=%d tile=%d)",    \
+                  (long long)N, T, max_tile_nodes)
+
 extern "C" int gad_graph_build_ell(const int32_t* ptr, const int32_t* idx, int64_t N, const int32_t* tile_ptr, int T,
                                    int CE, int max_deg, void* ell_rows, int32_t* info, void* stream) {
     GAD_CHECK_ARG(ptr && idx && tile_ptr && ell_rows && info && N > 0 && T > 0, "gad_graph_build_ell: bad arguments");
@@ -231,7 +237,8 @@ extern "C" size_t gad_ell_workspace_bytes(int CE, int T, int L) { return ws_floa
 extern "C" int gad_deform_fwd_ell(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T, int max_tile_nodes,
                                   int max_deg, const float* x0, int dim, int CE, const float* Mu, int Lw,
                                   const float* tau, int L, int method, float* x_phys, float* states, void* stream) {
-    GAD_CHECK_ARG(ell_in && tile_ptr && x0 && Mu && tau && x_phys, "gad_deform_fwd_ell: null pointer");
+    GAD_CHECK_ARG(ell_in && x0 && Mu && tau && x_phys, "gad_deform_fwd_ell: null pointer");
+    GAD_UNIFORM_TILES_OK("gad_deform_fwd_ell");
     GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
                   "gad_deform_fwd_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
     GAD_CHECK_ARG(method == GAD_METHOD_EULER || method == GAD_METHOD_RK4, "gad_deform_fwd_ell: unknown method %d", method);
@@ -261,7 +268,8 @@ extern "C" int gad_deform_fwd_ell_raw(const void* ell_in, int64_t N, const int32
                                       const float* uu, const float* f_scale, const float* uu_scale, int dim, int CE,
                                       const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
                                       float* states, void* stream) {
-    GAD_CHECK_ARG(ell_in && tile_ptr && x_comp && Mu && tau && x_phys, "gad_deform_fwd_ell_raw: null pointer");
+    GAD_CHECK_ARG(ell_in && x_comp && Mu && tau && x_phys, "gad_deform_fwd_ell_raw: null pointer");
+    GAD_UNIFORM_TILES_OK("gad_deform_fwd_ell_raw");
     GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
                   "gad_deform_fwd_ell_raw: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
     GAD_CHECK_ARG(dim + (f ? 1 : 0) + (uu ? 1 : 0) <= CE, "gad_deform_fwd_ell_raw: %d input features exceed CE=%d",
@@ -297,8 +305,9 @@ extern "C" int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64
                                   int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
                                   int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,
                                   float* g_x0, void* workspace, size_t workspace_bytes, void* stream) {
-    GAD_CHECK_ARG(ell_in && ell_out && tile_ptr && states && g_xphys && Mu && tau && gMu && workspace,
+    GAD_CHECK_ARG(ell_in && ell_out && states && g_xphys && Mu && tau && gMu && workspace,
                   "gad_deform_bwd_ell: null pointer");
+    GAD_UNIFORM_TILES_OK("gad_deform_bwd_ell");
     GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
                   "gad_deform_bwd_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
     GAD_CHECK_ARG(workspace_bytes >= ws_floats(CE, T, L) * sizeof(float), "gad_deform_bwd_ell: workspace too small");
@@ -335,8 +344,9 @@ extern "C" int gad_deform_train_ell(const void* ell_in, const void* ell_out, int
                                     int dim, int CE, const float* Mu, int Lw, const float* tau, int L, int loss_kind,
                                     float grad_scale, float loss_scale, float* states, float* gMu, float* g_tau,
                                     float* loss, float* x_phys, void* workspace, size_t workspace_bytes, void* stream) {
-    GAD_CHECK_ARG(ell_in && ell_out && tile_ptr && x_comp && target && Mu && tau && states && gMu && loss && workspace,
+    GAD_CHECK_ARG(ell_in && ell_out && x_comp && target && Mu && tau && states && gMu && loss && workspace,
                   "gad_deform_train_ell: null pointer");
+    GAD_UNIFORM_TILES_OK("gad_deform_train_ell");
     GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
                   "gad_deform_train_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
     GAD_CHECK_ARG(dim + (f ? 1 : 0) + (uu ? 1 : 0) <= CE, "gad_deform_train_ell: %d input features exceed CE=%d",
@@ -381,9 +391,15 @@ extern "C" int gad_deform_train_ell(const void* ell_in, const void* ell_out, int
 
 extern "C" int gad_train_step_ell(const gad_train_desc* d, void* stream) {
     GAD_CHECK_ARG(d, "gad_train_step_ell: null descriptor");
-    GAD_CHECK_ARG(d->ell_in && d->ell_out && d->tile_ptr && d->x_comp && d->target && d->Mu && d->tau && d->states &&
+    GAD_CHECK_ARG(d->ell_in && d->ell_out && d->x_comp && d->target && d->Mu && d->tau && d->states &&
                       d->gMu && d->loss && d->workspace && d->counter,
                   "gad_train_step_ell: null pointer");
+    {
+        const int32_t* tile_ptr = d->tile_ptr;
+        const int64_t N = d->N;
+        const int T = d->T, max_tile_nodes = d->max_tile_nodes;
+        GAD_UNIFORM_TILES_OK("gad_train_step_ell");
+    }
     GAD_CHECK_ARG(d->N > 0 && d->T > 0 && d->L > 0 && d->dim >= 1 && d->dim <= d->CE && (d->Lw == 1 || d->Lw == d->L),
                   "gad_train_step_ell: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)d->N, d->T, d->L, d->dim, d->CE,
                   d->Lw);

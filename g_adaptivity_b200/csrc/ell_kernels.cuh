@@ -209,6 +209,24 @@ struct EllView {
     }
 };
 
+// Node range of a tile and the first ELL row of its table.  tile_ptr == nullptr is the SHARED-TOPOLOGY form: the
+// batch consists of equal tiles of `cap_nodes` nodes (copies of one mesh, or of one group of meshes; the last
+// tile may be shorter) that all use ONE table of tile-local ELL rows -- the reference's `randg` datasets put
+// every sample on the same mesh (src/data.py:143), so the batch topology is one mesh's, B times.
+__device__ __forceinline__ void tile_range(const Args& a, int tile, int& n0, int& NT, int& e0) {
+    if (a.tile_ptr) {
+        n0 = a.tile_ptr[tile];
+        NT = a.tile_ptr[tile + 1] - n0;
+        e0 = n0;
+    } else {
+        const long long first = (long long)tile * a.cap_nodes;
+        const long long rest = a.N - first;
+        n0 = (int)first;
+        NT = rest < a.cap_nodes ? (int)rest : a.cap_nodes;
+        e0 = 0;
+    }
+}
+
 // features = cat[x_comp, f, uu] (optionally f / max f, uu / max uu) + identity (zero-pad) encoder:
 // src/GNN.py:225-239,75-83,270.  Inputs come from the TMA staging areas (`stage`) or from global
 // memory; rows go to the shared-memory state buffer and, when `states0` is given, to states[0].
@@ -271,8 +289,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
     const size_t state_stride = (size_t)a.N * CE;
 
     for (int tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
-        const int n0 = a.tile_ptr[tile];
-        const int NT = a.tile_ptr[tile + 1] - n0;
+        int n0, NT, e0;
+        tile_range(a, tile, n0, NT, e0);
         __syncthreads();   // previous tile fully consumed (and the mbarrier initialised)
         if (a.x0 == nullptr) {
             // fused feature assembly (gad_deform_fwd_ell with raw inputs): x_comp | f | uu staged by TMA
@@ -292,7 +310,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
             if (tid == 0 && tx) {
                 fence_proxy_async_smem();
                 mbar_expect_tx(bar, tx);
-                if (ELLS) bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
+                if (ELLS) bulk_g2s(smem + lay.ein, a.ell_in + e0, (uint32_t)NT * 16u, bar);
                 if (stage) {
                     bulk_g2s(st_xc, xc_g, xc_bytes, bar);
                     if (a.f) bulk_g2s(st_f, f_g, sc_bytes, bar);
@@ -312,7 +330,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
         if (tid == 0 && tx) {
             fence_proxy_async_smem();
             mbar_expect_tx(bar, tx);
-            if (ELLS) bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
+            if (ELLS) bulk_g2s(smem + lay.ein, a.ell_in + e0, (uint32_t)NT * 16u, bar);
             if (bulk_x) bulk_g2s(Xc, x0t, (uint32_t)NT * RB, bar);
         }
         if (!bulk_x)
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
         }
         }
         __syncthreads();
-        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
+        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + e0};
 
         for (int l = 0; l < a.L; ++l) {
             if (a.Lw > 1 && l > 0) {
@@ -517,8 +535,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd(const Ar
     const size_t state_stride = (size_t)a.N * CE;
 
     for (int tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
-        const int n0 = a.tile_ptr[tile];
-        const int NT = a.tile_ptr[tile + 1] - n0;
+        int n0, NT, e0;
+        tile_range(a, tile, n0, NT, e0);
         __syncthreads();
         const float* xl = a.states + (size_t)(a.L - 1) * state_stride + (size_t)n0 * CE;
         const bool bulk_x = ((reinterpret_cast<uintptr_t>(xl) & 15) == 0) && (((uint32_t)NT * RB) % 16 == 0);
@@ -527,8 +545,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd(const Ar
             fence_proxy_async_smem();
             mbar_expect_tx(bar, tx);
             if (ELLS) {
-                bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
-                bulk_g2s(smem + lay.eout, a.ell_out + n0, (uint32_t)NT * 16u, bar);
+                bulk_g2s(smem + lay.ein, a.ell_in + e0, (uint32_t)NT * 16u, bar);
+                bulk_g2s(smem + lay.eout, a.ell_out + e0, (uint32_t)NT * 16u, bar);
             }
             if (bulk_x) bulk_g2s(X, xl, (uint32_t)NT * RB, bar);
         }
@@ -543,8 +561,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd(const Ar
             parity ^= 1;
         }
         __syncthreads();
-        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
-        EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + n0};
+        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + e0};
+        EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + e0};
         tile_backward<CE, W, ELLS>(a, tile, n0, NT, X, GO, P, DL, GS, Ein, Eout, Mu, red);
     }
 }
@@ -952,8 +970,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
     const bool reducer = a.tail_cta && (int)blockIdx.x == tile_ctas;
 
     for (int tile = reducer ? a.T : (int)blockIdx.x; tile < a.T; tile += tile_ctas) {
-        const int n0 = a.tile_ptr[tile];
-        const int NT = a.tile_ptr[tile + 1] - n0;
+        int n0, NT, e0;
+        tile_range(a, tile, n0, NT, e0);
         __syncthreads();
         // Inputs of the tile by 1-D TMA bulk copies: ELL rows to their buffers, x_comp | f | uu to a
         // staging area in the (not yet used) P buffer, the target mesh to the DL buffer.
@@ -974,8 +992,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
             fence_proxy_async_smem();
             mbar_expect_tx(bar, tx);
             if (ELLS) {
-                bulk_g2s(smem + lay.ein, a.ell_in + n0, (uint32_t)NT * 16u, bar);
-                bulk_g2s(smem + lay.eout, a.ell_out + n0, (uint32_t)NT * 16u, bar);
+                bulk_g2s(smem + lay.ein, a.ell_in + e0, (uint32_t)NT * 16u, bar);
+                bulk_g2s(smem + lay.eout, a.ell_out + e0, (uint32_t)NT * 16u, bar);
             }
             if (stage) {
                 bulk_g2s(st_xc, xc_g, xc_bytes, bar);
@@ -1010,8 +1028,8 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_train(const 
         // 2000 warps at once), then through shared memory
         for (int t = tid; t < MUSZ; t += nthr) Mu[t] = __ldcg(a.Mu + t);
         __syncthreads();
-        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + n0};
-        EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + n0};
+        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + e0};
+        EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + e0};
 
         // ---- forward (Euler), loss and cotangent fused into the last layer --------------------
         float loss_acc = 0.f;

@@ -9,7 +9,7 @@
 //                   training kernel), copy the 4-byte loss device -> host, release the slot
 //
 // Slot k % n_slots receives host batch k % n_host.  The call returns when the last step has finished
-// (cudaStreamSynchronize of the compute stream).  No hidden allocation besides 2 * n_slots events per call.
+// (cudaStreamSynchronize of the compute stream).  No hidden allocation besides a grow-only pool of 2 * n_slots + 1 events.
 #include <vector>
 
 #include "common.cuh"
@@ -26,11 +26,23 @@ extern "C" int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, con
                       "gad_pipeline_run: slot %d is incomplete", s);
     cudaStream_t cs = as_stream(copy_stream), ms = as_stream(compute_stream);
     GAD_CHECK_ARG(cs != ms, "gad_pipeline_run: the copy stream must differ from the compute stream");
-    std::vector<cudaEvent_t> in_ready(n_slots), slot_free(n_slots);
-    for (int s = 0; s < n_slots; ++s) {
-        GAD_CUDA(cudaEventCreateWithFlags(&in_ready[s], cudaEventDisableTiming));
-        GAD_CUDA(cudaEventCreateWithFlags(&slot_free[s], cudaEventDisableTiming));
+    // events come from a grow-only per-thread pool (creating 2 * n_slots + 1 events costs more than a short run)
+    static thread_local std::vector<cudaEvent_t> pool;
+    static thread_local int pool_device = -1;
+    int device = -1;
+    GAD_CUDA(cudaGetDevice(&device));
+    if (device != pool_device) {
+        pool.clear();      // events belong to the device they were created on
+        pool_device = device;
     }
+    while ((int)pool.size() < 2 * n_slots + 1) {
+        cudaEvent_t e;
+        GAD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        pool.push_back(e);
+    }
+    cudaEvent_t* in_ready = pool.data();
+    cudaEvent_t* slot_free = pool.data() + n_slots;
+    cudaEvent_t start = pool[2 * n_slots];
     int rc = GAD_OK;
     auto fail = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess && rc == GAD_OK) {
@@ -40,8 +52,6 @@ extern "C" int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, con
         return e != cudaSuccess;
     };
     // the first upload must not overtake work already queued on the compute stream (it may still read the slot)
-    cudaEvent_t start;
-    GAD_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     fail(cudaEventRecord(start, ms), "cudaEventRecord");
     fail(cudaStreamWaitEvent(cs, start, 0), "cudaStreamWaitEvent");
     auto upload = [&](int64_t k) {
@@ -63,10 +73,5 @@ extern "C" int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, con
     }
     fail(cudaStreamSynchronize(ms), "cudaStreamSynchronize");
     fail(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
-    for (int s = 0; s < n_slots; ++s) {
-        cudaEventDestroy(in_ready[s]);
-        cudaEventDestroy(slot_free[s]);
-    }
-    cudaEventDestroy(start);
     return rc;
 }

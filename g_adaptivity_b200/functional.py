@@ -112,7 +112,7 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
     if use_tiles and use_ell(graph, CE):
         with torch.cuda.device(x0.device):
             _lib.check(lib.gad_deform_fwd_ell(
-                _lib.ptr(graph.ell_in), N, _lib.ptr(graph.tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
+                _lib.ptr(graph.ell_in), N, _lib.ptr(graph.ell_tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
                 _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys),
                 _lib.ptr(states), _stream(x0)), "gad_deform_fwd_ell")
         return x_phys
@@ -181,7 +181,7 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
     x_phys = torch.empty((N, dim), dtype=torch.float32, device=x_comp.device)
     with torch.cuda.device(x_comp.device):
         _lib.check(lib.gad_deform_fwd_ell_raw(
-            _lib.ptr(graph.ell_in), N, _lib.ptr(graph.tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
+            _lib.ptr(graph.ell_in), N, _lib.ptr(graph.ell_tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
             _lib.ptr(x_comp), _lib.ptr(f), _lib.ptr(uu), _lib.ptr(f_scale), _lib.ptr(uu_scale), dim, CE, _lib.ptr(Mu),
             Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys), _lib.ptr(states), _stream(x_comp)), "gad_deform_fwd_ell_raw")
     return x_phys
@@ -206,7 +206,7 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.gad_deform_bwd_ell(
-                _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.tile_ptr), T,
+                _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.ell_tile_ptr), T,
                 graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw,
                 _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes,
                 _stream(states)), "gad_deform_bwd_ell")

@@ -78,6 +78,8 @@ class MeshGraph:
         self.max_tile_nodes = 0
         self.max_tile_edges = 0
         self._keepalive = ()
+        self.uniform = False        # shared-topology batch: equal tiles, ell_in / ell_out are ONE tile's rows
+        self.sub = None             # ... and the general graph of that one tile
 
     # ------------------------------------------------------------------------------------
     @staticmethod
@@ -150,6 +152,73 @@ class MeshGraph:
         return g
 
     # ------------------------------------------------------------------------------------
+    @property
+    def ell_tile_ptr(self):
+        """What the gad_*_ell entry points take as `tile_ptr`: NULL for a shared-topology graph (equal tiles,
+        one ELL table for all of them; include/gadapt.h), the tile offsets otherwise."""
+        return None if self.uniform else self.tile_ptr
+
+    @staticmethod
+    def build_uniform(data, mesh_sizes: Sequence[int], dim: int, mesh_dims, fix_boundary: bool, self_loops: bool,
+                      device, ce: int = 4, tile_target: Optional[int] = None) -> Optional["MeshGraph"]:
+        """Shared-topology batch (every sample on the same mesh: the reference's `randg` datasets,
+        src/data.py:143; PyG's collation only adds node offsets): run the graph prologue of `GNN.forward`
+        (src/GNN.py:206-223) for the meshes of ONE tile and let every tile of the batch use that tile's ELL
+        table.  Build cost and topology memory are O(mesh), not O(batch).
+
+        Returns None when the batch is not of that form (unequal sizes, edge list not mesh-major, the last mesh's
+        block differing from the first, degree > 7, ...): the caller then builds the general graph."""
+        sizes = [int(n) for n in mesh_sizes]
+        B = len(sizes)
+        if B == 0 or any(n != sizes[0] for n in sizes) or ce not in (2, 4):
+            return None
+        N1 = sizes[0]
+        ei = data.edge_index
+        E0 = int(ei.shape[1])
+        if E0 == 0 or E0 % B:
+            return None
+        E1 = E0 // B
+        target = tile_target or _DEFAULT_TILE_TARGET
+        if N1 > _FUSED_MAX_TILE_NODES:
+            return None
+        m = min(B, max(1, target // N1))
+        names = ("to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask")
+        masks_full = [getattr(data, n, None) for n in names] if fix_boundary else [None] * 3
+        if fix_boundary and any(t is None for t in masks_full):
+            return None
+        # the promise, checked where the tensors live: first and last mesh carry the same block
+        head = ei[:, :m * E1]
+        if int(head.min()) < 0 or int(head.max()) >= m * N1:
+            return None
+        if B > 1:
+            if not torch.equal(ei[:, (B - 1) * E1:] - (B - 1) * N1, ei[:, :E1]):
+                return None
+            if any(t is not None and not torch.equal(t[(B - 1) * E1:], t[:E1]) for t in masks_full):
+                return None
+        loops = None
+        if fix_boundary:
+            class _Head:
+                corner_nodes = list(getattr(data, "corner_nodes", []) or [])[:m]
+            loops = corner_loops(_Head, dim, mesh_dims, sizes[:m])
+        sub = MeshGraph.build(head, m * N1, masks=[None if t is None else t[:m * E1] for t in masks_full],
+                              extra_loops=loops, self_loops=self_loops, mesh_sizes=sizes[:m], device=device, ce=ce,
+                              tile_target=tile_target, use_ell=True)
+        if sub.tile_ptr is None or sub.T != 1 or sub.ell_in is None or sub.E % m:
+            return None
+        g = MeshGraph()
+        g.uniform, g.sub = True, sub
+        g.N, g.E, g.device = B * N1, sub.E // m * B, sub.device
+        g.mesh_sizes = sizes
+        g.T = (B + m - 1) // m
+        tp = np.minimum(np.arange(g.T + 1, dtype=np.int64) * (m * N1), B * N1).astype(np.int32)
+        g.tile_ptr = torch.from_numpy(tp).to(sub.device)
+        g.max_tile_nodes, g.max_tile_edges = m * N1, sub.max_tile_edges
+        g.max_in_deg, g.max_out_deg = sub.max_in_deg, sub.max_out_deg
+        g.ell_in, g.ell_out, g.ell_ce, g.ell_deg = sub.ell_in, sub.ell_out, sub.ell_ce, sub.ell_deg
+        g.sm_count = getattr(sub, "sm_count", 148)
+        g._wide_tried = g._cl_tried = True        # no general arrays: the streaming / cluster fallbacks do not apply
+        return g
+
     def plan(self, mesh_sizes: Sequence[int], ce: int = 4, tile_target: Optional[int] = None, use_ell: bool = True):
         """Choose tiles for the mesh-resident kernels; falls back to streaming (tile_ptr = None)
         when a mesh does not fit one CTA's shared memory or the batch is not a disjoint union."""

@@ -170,7 +170,7 @@ class DeformerTrainer:
             d.ell_in, d.ell_out, d.tile_ptr, d.N = P(g.cl_in), P(g.cl_out), P(g.mesh_ptr), s.N
             d.T, d.max_tile_nodes, d.max_deg = len(g.mesh_sizes), max(g.mesh_sizes), g.cl_deg
         else:
-            d.ell_in, d.ell_out, d.tile_ptr, d.N = P(g.ell_in), P(g.ell_out), P(g.tile_ptr), s.N
+            d.ell_in, d.ell_out, d.tile_ptr, d.N = P(g.ell_in), P(g.ell_out), P(g.ell_tile_ptr), s.N
             d.T, d.max_tile_nodes, d.max_deg = g.T, g.max_tile_nodes, g.ell_deg
         d.x_comp, d.f, d.uu, d.f_scale, d.uu_scale, d.target = P(s.x_comp), P(s.f), P(s.uu), None, None, P(s.target)
         d.dim, d.CE = self.dim, self.CE
@@ -200,7 +200,7 @@ class DeformerTrainer:
         m, dev, lib = self.model, self.dev, self.lib
         s = _Slot()
         with torch.cuda.device(dev):
-            s.graph = m._graph(data, dev)
+            s.graph = m._graph(data, dev, allow_uniform=True)      # the trainer never reads attention weights
             N = s.graph.N
             s.N = N
             f32 = dict(dtype=torch.float32, device=dev)
@@ -448,44 +448,70 @@ class DeformerTrainer:
                 self._issue(s, cs, stage="post")
             self.graphs[sid] = g
 
-    def capture_epoch(self, sids) -> tuple:
+    def capture_epoch(self, sids, timed: bool = False) -> tuple:
         """Capture the steps of the resident batches `sids`, in order, into ONE CUDA graph.  On a single
         GPU every step is one kernel and consecutive kernels are linked by programmatic dependent
-        launch: step k + 1 stages its inputs (TMA) while step k still computes, then waits for it."""
+        launch: step k + 1 stages its inputs (TMA) while step k still computes, then waits for it.
+
+        `timed=True` captures a second, instrumented graph of the same steps for benchmarks: a short device-side
+        spin, an event record, the steps, an event record (external events = event-record NODES of the graph).
+        `run_epoch(sids, timed=True)` replays it and `epoch_elapsed_ms(sids)` reads the device time between the two
+        records: the steps' own time, without the latency of getting a graph launch from the host to the device."""
         key = tuple(int(s) for s in sids)
+        if timed:
+            key = ("timed",) + key
         if key in self.epoch_graphs:
             return key
-        for sid in set(key):             # warm-up / attribute set-up happens in the single-step capture
+        for sid in set(key[1:] if timed else key):   # warm-up / attribute set-up happens in the single-step capture
             if sid not in self.graphs:
                 self.capture(sid)
         with torch.cuda.device(self.dev):
             self.stream.synchronize()
             self.check_peer(collective=True)
             g = torch.cuda.CUDAGraph()
+            ev = None
+            if timed:
+                ev = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
             with torch.cuda.graph(g, stream=self.stream):
-                cs = torch.cuda.current_stream(self.dev).cuda_stream
-                for sid in key:
+                cur = torch.cuda.current_stream(self.dev)
+                cs = cur.cuda_stream
+                if timed:
+                    torch.cuda._sleep(200000)          # ~0.1 ms: the graph is fully resident before the first record
+                    ev[0].record(cur)
+                for sid in (key[1:] if timed else key):
                     s = self.slots[sid]
                     self._issue(s, cs, stage="pre")
                     self._allreduce(s)
                     self._issue(s, cs, stage="post")
+                if timed:
+                    ev[1].record(cur)
             self.epoch_graphs[key] = g
+            if timed:
+                self._epoch_events = getattr(self, "_epoch_events", {})
+                self._epoch_events[key] = ev
         return key
+
+    def epoch_elapsed_ms(self, sids) -> float:
+        """Device time of the last `run_epoch(sids, timed=True)` (between the graph's two event-record nodes)."""
+        key = ("timed",) + tuple(int(s) for s in sids)
+        ev = self._epoch_events[key]
+        ev[1].synchronize()
+        return ev[0].elapsed_time(ev[1])
 
     def _touch_params(self):
         # the kernels update the parameters in place without bumping tensor version counters
         self.model._param_epoch = getattr(self.model, "_param_epoch", 0) + 1
 
-    def run_epoch(self, sids):
+    def run_epoch(self, sids, timed: bool = False):
         """One pass over the resident batches `sids` (one training step each) as a single graph replay.
         Returns the per-slot loss tensors (device; each holds the loss of that slot's LAST step)."""
         if not self.use_graph:
             return [self.step(sid) for sid in sids]
-        key = self.capture_epoch(sids)
+        key = self.capture_epoch(sids, timed=timed)
         self._touch_params()
         with torch.cuda.stream(self.stream):
             self.epoch_graphs[key].replay()
-        return [self.slots[sid].loss for sid in key]
+        return [self.slots[sid].loss for sid in (key[1:] if timed else key)]
 
     def step(self, sid: int):
         """One training step on the resident batch `sid` (asynchronous; loss stays on the device)."""
@@ -527,7 +553,9 @@ class DeformerTrainer:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
             self._in_ready = [torch.cuda.Event() for _ in range(R)]
             self._slot_free = [torch.cuda.Event() for _ in range(R)]
-        losses = torch.empty(steps, dtype=torch.float32).pin_memory()
+        if getattr(self, "_loss_pin", None) is None or self._loss_pin.numel() < steps:
+            self._loss_pin = torch.empty(max(steps, 1024), dtype=torch.float32).pin_memory()   # cudaHostAlloc is slow: once
+        losses = self._loss_pin[:steps]
         cs, ms = self._copy_stream, self.stream
         packed = all(torch.is_tensor(b) and b.is_pinned() and b.dtype == torch.float32 for b in host_batches)
         pure = all(self._one_launch(s) for s in self.slots)      # the step's graph holds library kernels only

@@ -180,6 +180,13 @@ int gad_deform_bwd_wide(const void* wide_in, const void* wide_out, int64_t N, in
  *     gMu [Lw, CE*CE+CE], g_tau [L] (may be NULL), loss[0] = loss_scale * sum |out - target| (or ^2),
  * with the cotangent grad_scale * d(sum)/d(out).  `states` [L, N, CE] is scratch (layer inputs),
  * x_phys [N, dim] is optional.  workspace: gad_ell_workspace_bytes(CE, T, L).
+ *
+ * SHARED TOPOLOGY (tile_ptr == NULL, in every gad_*_ell entry point and in gad_train_desc): the batch is
+ * T = ceil(N / max_tile_nodes) equal tiles of max_tile_nodes nodes (the last one may be shorter) and ell_in /
+ * ell_out hold the rows of ONE tile (max_tile_nodes x 8 uint16), used by every tile.  This is the batch the
+ * reference's `randg` datasets produce -- every sample lives on the same mesh (src/data.py:143), PyG's
+ * collation only adds node offsets (a2) -- so the graph is built for one tile (O(mesh), not O(batch)) and
+ * the per-step topology traffic is one table that stays in L2 / shared memory.
  */
 int gad_graph_build_ell(const int32_t* ptr, const int32_t* idx, int64_t N, const int32_t* tile_ptr, int T,
                         int CE, int max_deg, void* ell_rows, int32_t* info, void* stream);

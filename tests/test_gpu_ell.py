@@ -322,3 +322,75 @@ def test_host_fed_loop_packed_buffers_equal_per_tensor_copies():
     other.x_comp = other.x_comp + 0.5
     with pytest.raises(ValueError):
         tr.pack_host(0, other, with_x_comp=False)
+
+
+# ------------------------------------------------------------------------------------------
+# shared-topology batches (row f2): one ELL table per mesh shape, graph build O(mesh)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mesh_dims,B,burgers", [((30, 30), 9, False), ((12, 12), 37, False), ((50, 50), 3, False),
+                                                 ((40,), 70, True)])
+def test_shared_topology_graph_equals_general_graph(mesh_dims, B, burgers):
+    """`opt['gad_shared_topology']` (dataset on one mesh, src/data.py:143): the graph prologue runs for the meshes
+    of ONE tile and every tile uses that tile's ELL table (tile_ptr = NULL in the C ABI).  Module forward +
+    backward and K training steps must equal the general graph's bit for bit -- same kernels, same rows -- with
+    topology tensors the size of one tile."""
+    opt, ds, data, ref = _case(mesh_dims, B, seed=13, burgers=burgers)
+    N1 = int(np.prod(mesh_dims))
+    outs = []
+    for shared in (False, True):
+        model = cuda_model(ds, opt, ref.state_dict(), gad_shared_topology=shared, gad_store_alpha=False)
+        model.train()
+        out = model(data)
+        g = model.last_graph
+        assert g.uniform == shared
+        tgt = data.x_phys.cuda()
+        F.l1_loss(out, tgt if tgt.dim() == 2 else tgt.unsqueeze(-1)).backward()
+        grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        with torch.no_grad():
+            out_inf = model(data)
+        tr = DeformerTrainer(model, lr=1e-2, loss_fn="l1")
+        sid = tr.add_batch(data)
+        assert tr.slots[sid].graph.uniform == shared
+        for _ in range(5):
+            tr.step(sid)
+        tr.synchronize()
+        outs.append((out.detach().clone(), grads, out_inf.clone(), tr.flat.clone(), tr.slots[sid].loss.item(), g))
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    for n in a[1]:
+        assert torch.equal(a[1][n], b[1][n]), n
+    assert torch.equal(a[3], b[3]) and a[4] == b[4]
+    g_gen, g_sh = a[5], b[5]
+    assert g_sh.E == g_gen.E and g_sh.N == g_gen.N and g_sh.T == g_gen.T
+    assert g_sh.max_tile_nodes == g_gen.max_tile_nodes
+    assert g_sh.ell_in.shape[0] == g_sh.max_tile_nodes < g_gen.ell_in.shape[0] or B * N1 == g_sh.max_tile_nodes
+    assert torch.equal(g_sh.ell_in, g_gen.ell_in[:g_sh.max_tile_nodes])          # tile-local rows: tile 0's table
+    assert torch.equal(g_sh.tile_ptr, g_gen.tile_ptr)
+
+
+def test_shared_topology_falls_back_when_the_batch_breaks_the_promise():
+    """Mixed mesh sizes, or a batch whose last mesh carries a different edge block, get the general graph."""
+    opt, ds, data, ref = _case((9, 9), 6, seed=2)
+    model = cuda_model(ds, opt, ref.state_dict(), gad_shared_topology=True, gad_store_alpha=False)
+    bad = data.clone()
+    E1 = bad.edge_index.shape[1] // 6
+    perm = torch.randperm(E1, generator=torch.Generator().manual_seed(0))
+    for name in ("to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask"):
+        t = getattr(bad, name).clone()
+        t[5 * E1:] = t[5 * E1:][perm]
+        setattr(bad, name, t)
+    ei = bad.edge_index.clone()
+    ei[:, 5 * E1:] = ei[:, 5 * E1:][:, perm]
+    bad.edge_index = ei
+    with torch.no_grad():
+        out_bad = model(bad)
+        assert not model.last_graph.uniform
+        out = model(data)
+        assert model.last_graph.uniform
+    assert util.rel_err(out_bad, out) <= 2e-6          # same graph, edges listed in another order
+    mixed = synth.make_mixed_batch([(5, 5), (7, 7), (6, 6)], seed=1)
+    m2 = cuda_model(synth.SyntheticDataset(2, (5, 5)), synth.default_opt((5, 5)), gad_shared_topology=True,
+                    gad_store_alpha=False)
+    with torch.no_grad():
+        m2(mixed)
+    assert not m2.last_graph.uniform
