@@ -309,6 +309,42 @@ def time_cfg5(dev, rank, world, iters, peak, barrier):
     return out
 
 
+def time_pde_loss_2d(dev, iters):
+    """Row f1: the reference's DEFAULT loss (`loss_type='pde_loss'`, params.py:109) on cfg-2-shaped data through the
+    module seam: model(data) = deformer + batched 2-D FEM solve (csrc/fem2d.cu; the reference loops torch_FEM_2D per
+    mesh in Python, src/GNN.py:327-335) -> mse(sol, u_true_fine) -> backward -> torch.optim.Adam; inputs resident."""
+    import torch.nn.functional as F
+    from g_adaptivity_b200 import GNN, synth
+    md, B, Q = MESH_DIMS, MESHES_PER_GPU, 101
+    opt = synth.default_opt(md, device=str(dev), gad_store_alpha=False, loss_type="pde_loss", eval_quad_points=Q,
+                            load_quad_points=101)
+    ds = synth.SyntheticDataset(2, md, eval_quad_points=Q)
+    torch.manual_seed(42)
+    model = GNN(ds, opt).to(dev).train()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-3)
+    data = synth.make_batch(md, B, seed=0, eval_quad_points=Q, with_u_true_fine=True).to(dev)
+    tgt = data.u_true_fine_tensor
+    ts, fem = [], []
+    for it in range(iters + 2):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        optim.zero_grad(set_to_none=True)
+        e0.record()
+        coeffs, xp, sol = model(data)
+        loss = F.mse_loss(sol, tgt)
+        loss.backward()
+        e1.record()
+        optim.step()
+        e2.record()
+        torch.cuda.synchronize(dev)
+        if it >= 2:
+            ts.append(e0.elapsed_time(e2))
+    ms = statistics.median(ts)
+    return {"workload": f"{B} x {md[0]}x{md[1]} meshes, loss_type='pde_loss' (deformer + batched 2-D FEM solve, 101-point "
+                        "load cubature, 101x101 evaluation grid), fwd + bwd + torch Adam through GNN.forward",
+            "ms_per_step": round(ms, 3), "meshes_per_s": B / (ms * 1e-3), "loss": float(loss.item()),
+            "reference": "torch_FEM_2D per mesh in a Python loop: ~3 s per 30x30 mesh on the CPU (DESIGN section 11)"}
+
+
 def bind_rank_to_cores(local_rank: int, local_world: int):
     """One process per GPU on a shared host: give every rank its own slice of the cores this job may use, so
     that the ranks' launch / copy threads do not migrate over each other (all GPUs of the box report the same
@@ -601,7 +637,8 @@ def main():
                     ("cfg3_burgers_1d_200_batch_4096_fwd",
                      lambda: time_forward_config(dev, (200,), 4096, {}, True, it, peak)),
                     ("cfg4_200x200_64_rk4_steps_fwd",
-                     lambda: time_forward_config(dev, (200, 200), 1, {"ode_method": "rk4", "num_layers": 64}, False, it, peak))):
+                     lambda: time_forward_config(dev, (200, 200), 1, {"ode_method": "rk4", "num_layers": 64}, False, it, peak)),
+                    ("f1_pde_loss_2d_cfg2_shape_train_step", lambda: time_pde_loss_2d(dev, 3))):
                 try:
                     configs[name] = fn()
                 except Exception as e:      # noqa: BLE001

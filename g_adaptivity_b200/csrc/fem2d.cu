@@ -2,19 +2,23 @@
 // second half): torch_FEM_2D of /root/reference/firedrake_difFEM/difFEM_2d.py:345-372, which the reference runs per
 // mesh in a Python loop (src/GNN.py:327-335), as one CTA per mesh over a topology shared by the batch.
 //
-// STATUS: first version, correctness-first.  Its arithmetic (fem2d_math.cuh) and phase order are checked on the CPU
-// against the reference's fixtures (oracle/fem2d_host.cpp, tests/test_fem2d_oracle.py), and the kernels below run
-// on the CPU under a thread-per-CUDA-thread emulation (oracle/fem2d_emu.cpp: FEM2D_EMULATE) with the same results;
-// on the B200 they match the fixtures to 4e-6 / 1.2e-5 (forward / gradient; tests/test_fem2d_gpu.py) and take 36 ms
-// for 256 meshes of 30x30, forward + backward (scripts/fem2d_check.py).  Not tuned: scalar CG rows, all-cells point
-// location.  GNN.forward does not route to them yet.
+// Its arithmetic (fem2d_math.cuh) and phase order are checked on the CPU against the reference's fixtures
+// (oracle/fem2d_host.cpp, tests/test_fem2d_oracle.py), the kernels below also run on the CPU under a
+// thread-per-CUDA-thread emulation (oracle/fem2d_emu.cpp: FEM2D_EMULATE), and on the B200 they match the fixtures to
+// 4e-6 / 1.2e-5 (forward / gradient; tests/test_fem2d_gpu.py).  GNN.forward routes 2-D pde_loss here (GNN._pde_tail_2d).
 //
-// Phases (forward): triangle geometry -> load vector (Simpson cubature per interior node, Dirichlet values) ->
-// matrix-free conjugate gradients on the interior SPD system (rows gathered through the star table, fixed-order
-// block reductions, fp64) -> interpolation on the evaluation points (point location: all cells, bounding-box
-// prefilter; a bin table is the next step).
+// Phases (forward): coordinates + cells -> shared memory; load vector (Simpson cubature per interior node, one warp
+// per node; Dirichlet values); the interior stiffness matrix as padded rows in shared memory (<= D + 2 entries per
+// node: uint16 column, fp64 coefficient = sum of the fp32 local entries, column-major so that consecutive threads
+// read consecutive words); conjugate gradients on the SPD interior system in fp64 -- one thread per row, the p.Ap
+// and r.r partial sums fused into the row loops, three barriers per iteration; interpolation on the evaluation
+// points through a uniform bin table over the mesh's bounding box (cells binned by their inflated bounding boxes;
+// a point tests the cells of its bin only, and its hits are sorted by cell id, so the result is that of the
+// reference's scan over all cells in ascending order).
 // Backward: g_u by fp64 shared-memory accumulation, second CG solve for the adjoint, three gradient terms
 // (matrix, load vector, interpolation) accumulated per vertex in shared memory, one store per vertex.
+// Round 1 (one thread per CG row gathering through the global star tables, all-cells point location) took 36 ms
+// for 256 meshes of 30x30, forward + backward.
 #ifndef FEM2D_EMULATE
 #include "common.cuh"
 #endif
@@ -29,8 +33,13 @@ namespace {
 
 using namespace fem2d;
 
-constexpr int FEM2D_THREADS = 256;
+constexpr int FEM2D_THREADS = 512;
 constexpr int MAX_HITS = 12;
+constexpr int MAX_ROWS_PER_THREAD = 8;     // CG keeps r / x / Ap of its rows in registers: N <= 8 * 512 (template R)
+__host__ __device__ inline int f2_rows_per_thread(int N) {
+    const int need = (N + FEM2D_THREADS - 1) / FEM2D_THREADS;
+    return need <= 1 ? 1 : (need <= 2 ? 2 : (need <= 4 ? 4 : 8));
+}
 
 struct F2Args {
     const int* cells;        // [T,3]
@@ -51,125 +60,204 @@ struct F2Args {
     int T, N, D, G, K, Q;
 };
 
-struct Box {
-    float lx, ly, hx, hy;
-};
 // A point that passes the (rounded) edge tests of a cell can lie outside the cell's exact bounding box only by the
 // rounding error of those tests (~1e-7 / edge length); the margin is orders of magnitude above that, so the prefilter
 // never changes which cells count.
 constexpr float BOX_MARGIN = 1e-3f;
 
+// Shared memory of one mesh.  `uni` is time-shared: the matrix rows during a CG solve, the bin table during a point pass.
 struct F2Smem {
-    float* xy;       // [2N]
-    Tri* tri;        // [T]
-    Box* box;        // [T]   bounding boxes of the cells, inflated: prefilter of the point location
-    double* u;       // [N]
-    double* b;       // [N]
-    double* r;       // [N]
-    double* p;       // [N]
-    double* Ap;      // [N]
-    double* acc;     // [2N]  gradient / g_u accumulators
-    double* red;     // [32]
+    float* xy;              // [2N]
+    unsigned short* cell;   // [T,4]   vertices of every cell (4th entry unused): one 8-byte load
+    double* u;              // [N]
+    double* b;              // [N]
+    double* r;              // [N]     backward: lambda
+    double* p;              // [N]
+    double* acc;            // [2N]    gradient / g_u accumulators; CG result
+    double* red;            // [2][32] partial sums of the block reductions (double-buffered: one barrier each)
+    float* bbox;            // [4]     bounding box of the mesh
+    unsigned char* uni;
+    // rows view (RW = D + 2 entries per node, column-major)
+    double* coef;           // [RW, N]
+    unsigned short* col;    // [RW, N]
+    // bin view
+    int* bin_ptr;           // [NB + 1]
+    int* bin_fill;          // [NB]
+    unsigned short* bin_cell;   // [cap]
+    int RW, NBX, cap;
 };
 
 __host__ __device__ inline size_t f2_align(size_t x) { return (x + 15) & ~(size_t)15; }
-
-__host__ __device__ inline size_t f2_smem_bytes(int N, int T) {
-    return f2_align(2 * (size_t)N * 4) + f2_align((size_t)T * sizeof(Tri)) + f2_align((size_t)T * sizeof(Box)) +
-           5 * f2_align((size_t)N * 8) + f2_align(2 * (size_t)N * 8) + f2_align(32 * 8);
+__host__ __device__ inline int f2_nbx(int T) {
+    int n = 4;
+    while (n < 64 && 2 * n * n < T) n *= 2;     // about one or two cells per bin
+    return n;
+}
+__host__ __device__ inline size_t f2_rows_bytes(int N, int D) {
+    return f2_align((size_t)(D + 2) * N * 8) + f2_align((size_t)(D + 2) * N * 2);
+}
+__host__ __device__ inline size_t f2_bins_min_bytes(int T) {
+    const int nb = f2_nbx(T) * f2_nbx(T);
+    return f2_align((size_t)(nb + 1) * 4) + f2_align((size_t)nb * 4) + f2_align((size_t)9 * T * 2);
+}
+__host__ __device__ inline size_t f2_uni_bytes(int N, int T, int D) {
+    const size_t r = f2_rows_bytes(N, D), q = f2_bins_min_bytes(T);
+    return r > q ? r : q;
+}
+__host__ __device__ inline size_t f2_smem_bytes(int N, int T, int D) {
+    return f2_align(2 * (size_t)N * 4) + f2_align((size_t)T * 8) + 4 * f2_align((size_t)N * 8) + f2_align(2 * (size_t)N * 8) +
+           f2_align(64 * 8) + f2_align(16) + f2_uni_bytes(N, T, D);
 }
 
-__device__ inline F2Smem f2_carve(unsigned char* base, int N, int T) {
+__device__ inline F2Smem f2_carve(unsigned char* base, int N, int T, int D) {
     F2Smem s;
     size_t o = 0;
     s.xy = reinterpret_cast<float*>(base + o), o += f2_align(2 * (size_t)N * 4);
-    s.tri = reinterpret_cast<Tri*>(base + o), o += f2_align((size_t)T * sizeof(Tri));
-    s.box = reinterpret_cast<Box*>(base + o), o += f2_align((size_t)T * sizeof(Box));
+    s.cell = reinterpret_cast<unsigned short*>(base + o), o += f2_align((size_t)T * 8);
     s.u = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
     s.b = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
     s.r = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
     s.p = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
-    s.Ap = reinterpret_cast<double*>(base + o), o += f2_align((size_t)N * 8);
     s.acc = reinterpret_cast<double*>(base + o), o += f2_align(2 * (size_t)N * 8);
-    s.red = reinterpret_cast<double*>(base + o);
+    s.red = reinterpret_cast<double*>(base + o), o += f2_align(64 * 8);
+    s.bbox = reinterpret_cast<float*>(base + o), o += f2_align(16);
+    s.uni = base + o;
+    s.RW = D + 2;
+    s.coef = reinterpret_cast<double*>(s.uni);
+    s.col = reinterpret_cast<unsigned short*>(s.uni + f2_align((size_t)s.RW * N * 8));
+    s.NBX = f2_nbx(T);
+    const int nb = s.NBX * s.NBX;
+    s.bin_ptr = reinterpret_cast<int*>(s.uni);
+    s.bin_fill = reinterpret_cast<int*>(s.uni + f2_align((size_t)(nb + 1) * 4));
+    const size_t head = f2_align((size_t)(nb + 1) * 4) + f2_align((size_t)nb * 4);
+    s.bin_cell = reinterpret_cast<unsigned short*>(s.uni + head);
+    s.cap = (int)((f2_uni_bytes(N, T, D) - head) / 2);
     return s;
 }
 
 __device__ inline P2 f2_pt(const float* xy, int i) { return P2{xy[2 * i], xy[2 * i + 1]}; }
 
-// fixed-order block sum (every thread gets the result)
-__device__ double f2_block_sum(double v, double* red) {
+// fixed-order block sum (every thread gets the result); `which` alternates between two buffers so that consecutive
+// reductions need one barrier each
+__device__ double f2_block_sum(double v, double* red, int which) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[w] = v;
+    double* buf = red + 32 * (which & 1);
+    if ((threadIdx.x & 31) == 0) buf[w] = v;
     __syncthreads();
     double s = 0.0;
-    for (int k = 0; k < nw; ++k) s += red[k];
+    for (int k = 0; k < nw; ++k) s += buf[k];
     return s;
 }
 
 __device__ void f2_geometry(const F2Args& a, const F2Smem& s, int mesh) {
     const float* c = a.coords + (size_t)mesh * a.N * 2;
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s.xy[i] = c[i];
-    __syncthreads();
     for (int t = threadIdx.x; t < a.T; t += blockDim.x) {
-        const P2 p0 = f2_pt(s.xy, a.cells[3 * t]), p1 = f2_pt(s.xy, a.cells[3 * t + 1]), p2 = f2_pt(s.xy, a.cells[3 * t + 2]);
-        s.tri[t] = tri_geometry(p0, p1, p2);
-        s.box[t] = Box{fminf(p0.x, fminf(p1.x, p2.x)) - BOX_MARGIN, fminf(p0.y, fminf(p1.y, p2.y)) - BOX_MARGIN,
-                       fmaxf(p0.x, fmaxf(p1.x, p2.x)) + BOX_MARGIN, fmaxf(p0.y, fmaxf(p1.y, p2.y)) + BOX_MARGIN};
+        s.cell[4 * t] = (unsigned short)a.cells[3 * t];
+        s.cell[4 * t + 1] = (unsigned short)a.cells[3 * t + 1];
+        s.cell[4 * t + 2] = (unsigned short)a.cells[3 * t + 2];
+        s.cell[4 * t + 3] = 0;
     }
     __syncthreads();
 }
 
-// y = K_II x over the nodes of this thread
-__device__ void f2_spmv(const F2Args& a, const F2Smem& s, const double* x, double* y) {
-    for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
-        double acc = 0.0;
-        if (!a.is_bc[i])
-            for (int d = 0; d < a.D; ++d) {
-                const int t = a.star_cell[i * a.D + d];
-                if (t < 0) continue;
-                const int k = a.star_loc[i * a.D + d];
-                for (int kk = 0; kk < 3; ++kk) {
-                    const int j = a.cells[3 * t + kk];
-                    if (!a.is_bc[j]) acc += (double)tri_k(s.tri[t], k, kk) * x[j];
+__device__ inline Tri f2_tri(const F2Smem& s, int t) {
+    return tri_geometry(f2_pt(s.xy, s.cell[4 * t]), f2_pt(s.xy, s.cell[4 * t + 1]), f2_pt(s.xy, s.cell[4 * t + 2]));
+}
+
+// Interior stiffness matrix K_II as padded rows in shared memory: row i holds, for every interior neighbour j
+// (i itself included), K_ij = sum over the cells of the star of i that contain j of the fp32 local entry, added in
+// fp64 in ascending star order.  Unused slots: column i, coefficient 0.  Dirichlet rows are empty.
+__device__ void f2_build_rows(const F2Args& a, const F2Smem& s) {
+    const int N = a.N, RW = s.RW;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        for (int q = 0; q < RW; ++q) {
+            s.coef[(size_t)q * N + i] = 0.0;
+            s.col[(size_t)q * N + i] = (unsigned short)i;
+        }
+        if (a.is_bc[i]) continue;
+        int used = 0;
+        for (int d = 0; d < a.D; ++d) {
+            const int t = a.star_cell[i * a.D + d];
+            if (t < 0) continue;
+            const int k = a.star_loc[i * a.D + d];
+            const Tri g = f2_tri(s, t);
+            for (int kk = 0; kk < 3; ++kk) {
+                const int j = s.cell[4 * t + kk];
+                if (a.is_bc[j]) continue;
+                int q = 0;
+                while (q < used && s.col[(size_t)q * N + i] != j) ++q;
+                if (q == used) {
+                    if (used == RW) continue;      // cannot happen: a star of D cells has at most D + 2 vertices
+                    s.col[(size_t)q * N + i] = (unsigned short)j;
+                    ++used;
                 }
+                s.coef[(size_t)q * N + i] += (double)tri_k(g, k, kk);
             }
-        y[i] = acc;
+        }
     }
     __syncthreads();
 }
 
-// conjugate gradients on K_II x = b (b in s.b, zero on Dirichlet nodes); x -> out (all threads see it after return)
+// conjugate gradients on K_II x = b (b in s.b, zero on Dirichlet nodes; rows built by f2_build_rows); x -> out
+// (all threads see it after return).  Thread t owns rows t, t + blockDim, ...: r, x and Ap of those rows never
+// leave its registers; only the search direction p is exchanged through shared memory.
+template <int R>
 __device__ int f2_cg(const F2Args& a, const F2Smem& s, double* out) {
-    double rr_local = 0.0;
-    for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
-        out[i] = 0.0;
-        s.r[i] = s.b[i];
-        s.p[i] = s.b[i];
-        rr_local += s.b[i] * s.b[i];
+    const int N = a.N, RW = s.RW, nthr = blockDim.x;
+    double r[R], x[R], Ap[R];
+    double l = 0.0;
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+        const int i = threadIdx.x + m * nthr;
+        x[m] = 0.0;
+        r[m] = (i < N) ? s.b[i] : 0.0;
+        if (i < N) s.p[i] = r[m];
+        l += r[m] * r[m];
     }
-    double rr = f2_block_sum(rr_local, s.red);
+    int which = 0;
+    double rr = f2_block_sum(l, s.red, which++);      // its barrier also publishes p
     const double bb = rr;
     int it = 0;
-    for (; it < 20 * a.N && rr > 1e-28 * bb && rr > 0.0; ++it) {
-        f2_spmv(a, s, s.p, s.Ap);
-        double l = 0.0;
-        for (int i = threadIdx.x; i < a.N; i += blockDim.x) l += s.p[i] * s.Ap[i];
-        const double alpha = rr / f2_block_sum(l, s.red);
+    for (; it < 20 * N && rr > 1e-28 * bb && rr > 0.0; ++it) {
         l = 0.0;
-        for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
-            out[i] += alpha * s.p[i];
-            s.r[i] -= alpha * s.Ap[i];
-            l += s.r[i] * s.r[i];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = threadIdx.x + m * nthr;
+            double acc = 0.0;
+            if (i < N) {
+                for (int q = 0; q < RW; ++q) acc += s.coef[(size_t)q * N + i] * s.p[s.col[(size_t)q * N + i]];
+                l += s.p[i] * acc;
+            }
+            Ap[m] = acc;
         }
-        const double rr2 = f2_block_sum(l, s.red);
+        const double alpha = rr / f2_block_sum(l, s.red, which++);
+        l = 0.0;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = threadIdx.x + m * nthr;
+            if (i < N) {
+                x[m] += alpha * s.p[i];
+                r[m] -= alpha * Ap[m];
+                l += r[m] * r[m];
+            }
+        }
+        const double rr2 = f2_block_sum(l, s.red, which++);   // after this barrier nobody reads the old p any more
         const double beta = rr2 / rr;
-        for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.p[i] = s.r[i] + beta * s.p[i];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = threadIdx.x + m * nthr;
+            if (i < N) s.p[i] = r[m] + beta * s.p[i];
+        }
         rr = rr2;
         __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+        const int i = threadIdx.x + m * nthr;
+        if (i < N) out[i] = x[m];
     }
     __syncthreads();
     return it;
@@ -182,7 +270,7 @@ __device__ void f2_star_box(const F2Args& a, const F2Smem& s, int i, float& lx, 
         const int t = a.star_cell[i * a.D + d];
         if (t < 0) continue;
         for (int kk = 0; kk < 3; ++kk) {
-            const P2 p = f2_pt(s.xy, a.cells[3 * t + kk]);
+            const P2 p = f2_pt(s.xy, s.cell[4 * t + kk]);
             lx = fminf(lx, p.x), ly = fminf(ly, p.y), hx = fmaxf(hx, p.x), hy = fmaxf(hy, p.y);
         }
     }
@@ -190,7 +278,7 @@ __device__ void f2_star_box(const F2Args& a, const F2Smem& s, int i, float& lx, 
 
 // grad[v] += -coef * l_v(P) * g_c for the three vertices of cell t (c = local vertex k)
 __device__ void f2_scatter(const F2Args& a, const F2Smem& s, int t, int k, P2 P, double coef) {
-    const int ic = a.cells[3 * t + k], ia = a.cells[3 * t + (k + 2) % 3], ib = a.cells[3 * t + (k + 1) % 3];
+    const int ic = s.cell[4 * t + k], ia = s.cell[4 * t + (k + 2) % 3], ib = s.cell[4 * t + (k + 1) % 3];
     const P2 pa = f2_pt(s.xy, ia), pb = f2_pt(s.xy, ib), pc = f2_pt(s.xy, ic);
     float gx, gy, tx, ty;
     const float lc = bary(P, pa, pb, pc, &gx, &gy);
@@ -204,37 +292,124 @@ __device__ void f2_scatter(const F2Args& a, const F2Smem& s, int t, int k, P2 P,
     atomicAdd(&s.acc[2 * ic + 1], -coef * (double)lc * (double)gy);
 }
 
-// The evaluation points of this thread: hit cells, per distinct vertex value / repeat (phim, difFEM_2d.py:28-60).
+// inflated bounding box of a cell (the prefilter of the point location, see BOX_MARGIN)
+__device__ inline void f2_cell_box(const F2Smem& s, int t, float& lx, float& ly, float& hx, float& hy) {
+    const P2 p0 = f2_pt(s.xy, s.cell[4 * t]), p1 = f2_pt(s.xy, s.cell[4 * t + 1]), p2 = f2_pt(s.xy, s.cell[4 * t + 2]);
+    lx = fminf(p0.x, fminf(p1.x, p2.x)) - BOX_MARGIN, ly = fminf(p0.y, fminf(p1.y, p2.y)) - BOX_MARGIN;
+    hx = fmaxf(p0.x, fmaxf(p1.x, p2.x)) + BOX_MARGIN, hy = fmaxf(p0.y, fmaxf(p1.y, p2.y)) + BOX_MARGIN;
+}
+// bin coordinate of x: monotone in x, so lo <= x <= hi implies bin(lo) <= bin(x) <= bin(hi)
+__device__ inline int f2_bin(float x, float lo, float inv, int nbx) {
+    const float f = floorf((x - lo) * inv);
+    return f < 0.f ? 0 : (f > (float)(nbx - 1) ? nbx - 1 : (int)f);
+}
+
+// Uniform bin table over the mesh's bounding box: every cell is listed in the bins its inflated bounding box
+// overlaps (count, exclusive scan, fill).  Returns false (all threads) when the table does not fit the shared
+// memory left for it; the point pass then scans all cells.
+__device__ bool f2_build_bins(const F2Args& a, const F2Smem& s) {
+    const int nbx = s.NBX, nb = nbx * nbx;
+    if (threadIdx.x < 32) {
+        float lx = INFINITY, ly = INFINITY, hx = -INFINITY, hy = -INFINITY;
+        for (int i = threadIdx.x; i < a.N; i += 32) {
+            lx = fminf(lx, s.xy[2 * i]), hx = fmaxf(hx, s.xy[2 * i]);
+            ly = fminf(ly, s.xy[2 * i + 1]), hy = fmaxf(hy, s.xy[2 * i + 1]);
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            lx = fminf(lx, (float)__shfl_xor_sync(0xffffffffu, (double)lx, d));
+            ly = fminf(ly, (float)__shfl_xor_sync(0xffffffffu, (double)ly, d));
+            hx = fmaxf(hx, (float)__shfl_xor_sync(0xffffffffu, (double)hx, d));
+            hy = fmaxf(hy, (float)__shfl_xor_sync(0xffffffffu, (double)hy, d));
+        }
+        if (threadIdx.x == 0) s.bbox[0] = lx, s.bbox[1] = ly, s.bbox[2] = hx, s.bbox[3] = hy;
+    }
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s.bin_fill[k] = 0;
+    __syncthreads();
+    const float LX = s.bbox[0], LY = s.bbox[1];
+    const float ivx = (float)nbx / fmaxf(s.bbox[2] - LX, 1e-30f), ivy = (float)nbx / fmaxf(s.bbox[3] - LY, 1e-30f);
+    for (int t = threadIdx.x; t < a.T; t += blockDim.x) {
+        float lx, ly, hx, hy;
+        f2_cell_box(s, t, lx, ly, hx, hy);
+        const int x0 = f2_bin(lx, LX, ivx, nbx), x1 = f2_bin(hx, LX, ivx, nbx);
+        const int y0 = f2_bin(ly, LY, ivy, nbx), y1 = f2_bin(hy, LY, ivy, nbx);
+        for (int by = y0; by <= y1; ++by)
+            for (int bx = x0; bx <= x1; ++bx) atomicAdd(&s.bin_fill[by * nbx + bx], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < nb; ++k) {
+            s.bin_ptr[k] = run;
+            run += s.bin_fill[k];
+        }
+        s.bin_ptr[nb] = run;
+    }
+    __syncthreads();
+    const bool fits = s.bin_ptr[nb] <= s.cap;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s.bin_fill[k] = s.bin_ptr[k];
+    __syncthreads();
+    if (fits)
+        for (int t = threadIdx.x; t < a.T; t += blockDim.x) {
+            float lx, ly, hx, hy;
+            f2_cell_box(s, t, lx, ly, hx, hy);
+            const int x0 = f2_bin(lx, LX, ivx, nbx), x1 = f2_bin(hx, LX, ivx, nbx);
+            const int y0 = f2_bin(ly, LY, ivy, nbx), y1 = f2_bin(hy, LY, ivy, nbx);
+            for (int by = y0; by <= y1; ++by)
+                for (int bx = x0; bx <= x1; ++bx) s.bin_cell[atomicAdd(&s.bin_fill[by * nbx + bx], 1)] = (unsigned short)t;
+        }
+    __syncthreads();
+    return fits;
+}
+
+__device__ inline void f2_try_cell(const F2Smem& s, P2 P, int t, int* ht, int* hm, int& nh) {
+    float lx, ly, hx, hy;
+    f2_cell_box(s, t, lx, ly, hx, hy);
+    if (P.x < lx || P.x > hx || P.y < ly || P.y > hy) return;
+    const int mult = inside_count(P, f2_pt(s.xy, s.cell[4 * t + 2]), f2_pt(s.xy, s.cell[4 * t + 1]), f2_pt(s.xy, s.cell[4 * t]));
+    if (mult && nh < MAX_HITS) ht[nh] = t, hm[nh] = mult, ++nh;
+}
+
+// The evaluation points of this thread: hit cells (in ascending cell order, as the reference's scan finds them), per
+// distinct vertex value / repeat (phim, difFEM_2d.py:28-60).
 // MODE 0: sol[q].  MODE 1: g_u accumulation (s.acc[v]).  MODE 2: interpolation term of the gradient (s.acc[2v..]).
 template <int MODE>
-__device__ void f2_points(const F2Args& a, const F2Smem& s, int mesh) {
+__device__ void f2_points(const F2Args& a, const F2Smem& s, int mesh, bool bins) {
+    const int nbx = s.NBX;
+    const float LX = s.bbox[0], LY = s.bbox[1];
+    const float ivx = (float)nbx / fmaxf(s.bbox[2] - LX, 1e-30f), ivy = (float)nbx / fmaxf(s.bbox[3] - LY, 1e-30f);
     for (int q = threadIdx.x; q < a.Q; q += blockDim.x) {
         const P2 P{a.ex[q], a.ey[q]};
         int ht[MAX_HITS], hm[MAX_HITS], nh = 0;
-        for (int t = 0; t < a.T && nh < MAX_HITS; ++t) {
-            const Box bx = s.box[t];
-            if (P.x < bx.lx || P.x > bx.hx || P.y < bx.ly || P.y > bx.hy) continue;
-            const int mult = inside_count(P, f2_pt(s.xy, a.cells[3 * t + 2]), f2_pt(s.xy, a.cells[3 * t + 1]), f2_pt(s.xy, a.cells[3 * t]));
-            if (mult) ht[nh] = t, hm[nh] = mult, ++nh;
+        if (bins) {
+            const int k = f2_bin(P.y, LY, ivy, nbx) * nbx + f2_bin(P.x, LX, ivx, nbx);
+            for (int e = s.bin_ptr[k]; e < s.bin_ptr[k + 1]; ++e) f2_try_cell(s, P, s.bin_cell[e], ht, hm, nh);
+            for (int x = 1; x < nh; ++x) {                     // the bin lists are unordered: sort the hits by cell id
+                const int t = ht[x], m = hm[x];
+                int y = x - 1;
+                for (; y >= 0 && ht[y] > t; --y) ht[y + 1] = ht[y], hm[y + 1] = hm[y];
+                ht[y + 1] = t, hm[y + 1] = m;
+            }
+        } else {
+            for (int t = 0; t < a.T && nh < MAX_HITS; ++t) f2_try_cell(s, P, t, ht, hm, nh);
         }
         const double gq = (MODE == 0) ? 0.0 : (double)a.g_sol[(size_t)mesh * a.Q + q];
         double val = 0.0;
         for (int h = 0; h < nh; ++h)
             for (int k = 0; k < 3; ++k) {
-                const int v = a.cells[3 * ht[h] + k];
+                const int v = s.cell[4 * ht[h] + k];
                 bool first = true;
                 for (int h2 = 0; h2 < h && first; ++h2)
                     for (int k2 = 0; k2 < 3; ++k2)
-                        if (a.cells[3 * ht[h2] + k2] == v) first = false;
+                        if (s.cell[4 * ht[h2] + k2] == v) first = false;
                 if (!first) continue;
                 float num = 0.f, rep = 0.f;
                 for (int h2 = h; h2 < nh; ++h2)
                     for (int k2 = 0; k2 < 3; ++k2) {
                         const int t2 = ht[h2];
-                        if (a.cells[3 * t2 + k2] != v) continue;
+                        if (s.cell[4 * t2 + k2] != v) continue;
                         float gx, gy;
-                        const float inc = (float)hm[h2] * bary(P, f2_pt(s.xy, a.cells[3 * t2 + (k2 + 2) % 3]),
-                                                               f2_pt(s.xy, a.cells[3 * t2 + (k2 + 1) % 3]), f2_pt(s.xy, v), &gx, &gy);
+                        const float inc = (float)hm[h2] * bary(P, f2_pt(s.xy, s.cell[4 * t2 + (k2 + 2) % 3]),
+                                                               f2_pt(s.xy, s.cell[4 * t2 + (k2 + 1) % 3]), f2_pt(s.xy, v), &gx, &gy);
                         num += inc;
                         rep += (inc > 0.f) ? 1.f : 0.f;
                     }
@@ -246,7 +421,7 @@ __device__ void f2_points(const F2Args& a, const F2Smem& s, int mesh) {
                 if (MODE == 2)
                     for (int h2 = h; h2 < nh; ++h2)
                         for (int k2 = 0; k2 < 3; ++k2)
-                            if (a.cells[3 * ht[h2] + k2] == v) f2_scatter(a, s, ht[h2], k2, P, uv * gq * hm[h2] / (double)rep);
+                            if (s.cell[4 * ht[h2] + k2] == v) f2_scatter(a, s, ht[h2], k2, P, uv * gq * hm[h2] / (double)rep);
             }
         if (MODE == 0) a.sol[(size_t)mesh * a.Q + q] = (float)val;
     }
@@ -282,8 +457,8 @@ __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, con
                     const int t = a.star_cell[i * a.D + d];
                     if (t < 0) continue;
                     const int k = a.star_loc[i * a.D + d];
-                    const int mult = inside_count(P, f2_pt(s.xy, a.cells[3 * t + (k + 2) % 3]), f2_pt(s.xy, a.cells[3 * t + (k + 1) % 3]),
-                                                  f2_pt(s.xy, a.cells[3 * t + k]));
+                    const int mult = inside_count(P, f2_pt(s.xy, s.cell[4 * t + (k + 2) % 3]), f2_pt(s.xy, s.cell[4 * t + (k + 1) % 3]),
+                                                  f2_pt(s.xy, s.cell[4 * t + k]));
                     if (mult) f2_scatter(a, s, t, k, P, coef * mult);
                 }
             }
@@ -309,42 +484,47 @@ __device__ void f2_interior_rhs(const F2Args& a, const F2Smem& s) {
                 const int t = a.star_cell[i * a.D + d];
                 if (t < 0) continue;
                 const int k = a.star_loc[i * a.D + d];
+                const Tri g = f2_tri(s, t);
                 for (int kk = 0; kk < 3; ++kk) {
-                    const int j = a.cells[3 * t + kk];
-                    if (a.is_bc[j]) v -= (double)tri_k(s.tri[t], k, kk) * s.u[j];
+                    const int j = s.cell[4 * t + kk];
+                    if (a.is_bc[j]) v -= (double)tri_k(g, k, kk) * s.u[j];
                 }
             }
         }
-        s.Ap[i] = v;
+        s.p[i] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.b[i] = s.Ap[i];
+    for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.b[i] = s.p[i];
     __syncthreads();
 }
 
+template <int R>
 __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_fwd(F2Args a) {
     extern __shared__ __align__(16) unsigned char f2_raw[];
-    const F2Smem s = f2_carve(f2_raw, a.N, a.T);
+    const F2Smem s = f2_carve(f2_raw, a.N, a.T, a.D);
     const int mesh = blockIdx.x;
     const double* cen = a.cen + (size_t)mesh * a.G * 2;
     const double* sc = a.sc + (size_t)mesh * a.G * 2;
     f2_geometry(a, s, mesh);
     f2_load<0>(a, s, cen, sc);
     f2_interior_rhs(a, s);
-    const int it = f2_cg(a, s, s.acc);              // interior solution in s.acc[0..N)
+    f2_build_rows(a, s);
+    const int it = f2_cg<R>(a, s, s.acc);              // interior solution in s.acc[0..N)
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
         if (!a.is_bc[i]) s.u[i] = s.acc[i];
         a.coeffs[(size_t)mesh * a.N + i] = (float)s.u[i];
         a.u64[(size_t)mesh * a.N + i] = s.u[i];
     }
     __syncthreads();
-    f2_points<0>(a, s, mesh);
+    const bool bins = f2_build_bins(a, s);           // the rows are no longer needed: their memory holds the bins
+    f2_points<0>(a, s, mesh, bins);
     if (a.cg_iters && threadIdx.x == 0) a.cg_iters[mesh] = it;
 }
 
+template <int R>
 __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_bwd(F2Args a) {
     extern __shared__ __align__(16) unsigned char f2_raw[];
-    const F2Smem s = f2_carve(f2_raw, a.N, a.T);
+    const F2Smem s = f2_carve(f2_raw, a.N, a.T, a.D);
     const int mesh = blockIdx.x;
     const double* cen = a.cen + (size_t)mesh * a.G * 2;
     const double* sc = a.sc + (size_t)mesh * a.G * 2;
@@ -352,30 +532,33 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_bwd(F2Args a) {
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.u[i] = a.u64[(size_t)mesh * a.N + i];
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s.acc[i] = 0.0;
     __syncthreads();
-    f2_points<1>(a, s, mesh);                        // g_u in s.acc[0..N)
+    bool bins = f2_build_bins(a, s);
+    f2_points<1>(a, s, mesh, bins);                  // g_u in s.acc[0..N)
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.b[i] = a.is_bc[i] ? 0.0 : -s.acc[i];
     __syncthreads();
+    f2_build_rows(a, s);                             // (overwrites the bins)
     double* lam = s.acc + a.N;                       // second half of the accumulator array, free until the scatter
-    f2_cg(a, s, lam);                                // K_II lambda_I = -g_I
+    f2_cg<R>(a, s, lam);                             // K_II lambda_I = -g_I
     // keep lambda in s.r (zero on Dirichlet nodes), then reuse s.acc as the gradient accumulator
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.b[i] = a.is_bc[i] ? 0.0 : lam[i];
     __syncthreads();
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.r[i] = s.b[i];
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s.acc[i] = 0.0;
     __syncthreads();
-    f2_points<2>(a, s, mesh);                        // interpolation term
+    bins = f2_build_bins(a, s);
+    f2_points<2>(a, s, mesh, bins);                  // interpolation term
     f2_load<1>(a, s, cen, sc);                       // load-vector term
     for (int t = threadIdx.x; t < a.T; t += blockDim.x) {      // matrix term
-        const Tri& g = s.tri[t];
+        const Tri g = f2_tri(s, t);
         double Glx = 0, Gly = 0, Gux = 0, Guy = 0;
         for (int k = 0; k < 3; ++k) {
-            const int v = a.cells[3 * t + k];
+            const int v = s.cell[4 * t + k];
             Glx += s.r[v] * g.gx[k], Gly += s.r[v] * g.gy[k];
             Gux += s.u[v] * g.gx[k], Guy += s.u[v] * g.gy[k];
         }
         const double dot = Glx * Gux + Gly * Guy;
         for (int k = 0; k < 3; ++k) {
-            const int v = a.cells[3 * t + k];
+            const int v = s.cell[4 * t + k];
             const double gx = g.gx[k], gy = g.gy[k];
             const double gGu = gx * Gux + gy * Guy, gGl = gx * Glx + gy * Gly;
             atomicAdd(&s.acc[2 * v], (double)g.area * (dot * gx - gGu * Glx - gGl * Gux));
@@ -388,16 +571,30 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_bwd(F2Args a) {
 
 #ifndef FEM2D_EMULATE
 int f2_launch(const F2Args& a, int B, bool backward, cudaStream_t st) {
-    const size_t bytes = f2_smem_bytes(a.N, a.T);
+    const size_t bytes = f2_smem_bytes(a.N, a.T, a.D);
     GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "fem2d: a mesh of %d nodes / %d cells needs %zu B of shared memory", a.N, a.T,
                   bytes);
+    GAD_CHECK_ARG(a.N <= MAX_ROWS_PER_THREAD * FEM2D_THREADS && a.N <= 65535 && a.T <= 65535,
+                  "fem2d: %d nodes / %d cells exceed the kernel's limits (%d nodes, 16-bit indices)", a.N, a.T,
+                  MAX_ROWS_PER_THREAD * FEM2D_THREADS);
+    const int R = f2_rows_per_thread(a.N);
+#define F2_LAUNCH(K_)                                                                                        \
+    do {                                                                                                     \
+        GAD_CUDA(cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));         \
+        K_<<<B, FEM2D_THREADS, bytes, st>>>(a);                                                              \
+    } while (0)
     if (backward) {
-        GAD_CUDA(cudaFuncSetAttribute(k_fem2d_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        k_fem2d_bwd<<<B, FEM2D_THREADS, bytes, st>>>(a);
+        if (R == 1) F2_LAUNCH(k_fem2d_bwd<1>);
+        else if (R == 2) F2_LAUNCH(k_fem2d_bwd<2>);
+        else if (R == 4) F2_LAUNCH(k_fem2d_bwd<4>);
+        else F2_LAUNCH(k_fem2d_bwd<8>);
     } else {
-        GAD_CUDA(cudaFuncSetAttribute(k_fem2d_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        k_fem2d_fwd<<<B, FEM2D_THREADS, bytes, st>>>(a);
+        if (R == 1) F2_LAUNCH(k_fem2d_fwd<1>);
+        else if (R == 2) F2_LAUNCH(k_fem2d_fwd<2>);
+        else if (R == 4) F2_LAUNCH(k_fem2d_fwd<4>);
+        else F2_LAUNCH(k_fem2d_fwd<8>);
     }
+#undef F2_LAUNCH
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

@@ -39,6 +39,8 @@ inline double __shfl_xor_sync(unsigned, double v, int d) {
     return r;
 }
 
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
 inline double atomicAdd(double* p, double v) {
     uint64_t* q = reinterpret_cast<uint64_t*>(p);
     uint64_t old = __atomic_load_n(q, __ATOMIC_RELAXED), want;

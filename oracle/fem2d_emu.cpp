@@ -45,14 +45,22 @@ void run_grid(K kernel, const gad::F2Args& a, int B) {
 extern "C" int fem2d_emu(const int* cells, int T, const unsigned char* is_bc, int N, const int* star_cell, const int* star_loc, int D,
                          const float* coords, const double* cen, const double* sc, int G, int B, int load_quad_points, const float* ex,
                          const float* ey, int Q, const float* g_sol, float* coeffs, float* sol, double* u64, float* grad, int* cg_iters) {
-    if (gad::f2_smem_bytes(N, T) > sizeof(gad::f2_raw)) return 1;
+    if (gad::f2_smem_bytes(N, T, D) > sizeof(gad::f2_raw)) return 1;
     gad::F2Args a = {};
     a.cells = cells, a.is_bc = is_bc, a.star_cell = star_cell, a.star_loc = star_loc, a.coords = coords, a.cen = cen, a.sc = sc;
     a.ex = ex, a.ey = ey, a.g_sol = g_sol, a.coeffs = coeffs, a.sol = sol, a.u64 = u64, a.grad = grad, a.cg_iters = cg_iters;
     a.T = T, a.N = N, a.D = D, a.G = G, a.K = load_quad_points, a.Q = Q;
-    if (!g_sol)
-        run_grid(gad::k_fem2d_fwd, a, B);
-    else
-        run_grid(gad::k_fem2d_bwd, a, B);
+    const int R = gad::f2_rows_per_thread(N);
+    if (!g_sol) {
+        if (R == 1) run_grid(gad::k_fem2d_fwd<1>, a, B);
+        else if (R == 2) run_grid(gad::k_fem2d_fwd<2>, a, B);
+        else if (R == 4) run_grid(gad::k_fem2d_fwd<4>, a, B);
+        else run_grid(gad::k_fem2d_fwd<8>, a, B);
+    } else {
+        if (R == 1) run_grid(gad::k_fem2d_bwd<1>, a, B);
+        else if (R == 2) run_grid(gad::k_fem2d_bwd<2>, a, B);
+        else if (R == 4) run_grid(gad::k_fem2d_bwd<4>, a, B);
+        else run_grid(gad::k_fem2d_bwd<8>, a, B);
+    }
     return 0;
 }
