@@ -20,6 +20,8 @@
 // Round 1 (one thread per CG row gathering through the global star tables, all-cells point location) took 36 ms
 // for 256 meshes of 30x30, forward + backward.
 #ifndef FEM2D_EMULATE
+#include <stdlib.h>
+
 #include "common.cuh"
 #endif
 #include "fem2d_math.cuh"
@@ -35,6 +37,7 @@ using namespace fem2d;
 
 constexpr int FEM2D_THREADS = 512;
 constexpr int MAX_HITS = 12;
+constexpr int MAX_GAUSS = 16;
 constexpr int MAX_ROWS_PER_THREAD = 8;     // CG keeps r / x / Ap of its rows in registers: N <= 8 * 512 (template R)
 __host__ __device__ inline int f2_rows_per_thread(int N) {
     const int need = (N + FEM2D_THREADS - 1) / FEM2D_THREADS;
@@ -76,6 +79,7 @@ struct F2Smem {
     double* acc;            // [2N]    gradient / g_u accumulators; CG result
     double* red;            // [2][32] partial sums of the block reductions (double-buffered: one barrier each)
     float* bbox;            // [4]     bounding box of the mesh
+    GaussPre* gp;           // [MAX_GAUSS] per-Gaussian constants of the forcing
     unsigned char* uni;
     // rows view (RW = D + 2 entries per node, column-major)
     double* coef;           // [RW, N]
@@ -93,8 +97,9 @@ __host__ __device__ inline int f2_nbx(int T) {
     while (n < 64 && 2 * n * n < T) n *= 2;     // about one or two cells per bin
     return n;
 }
+__host__ __device__ inline int f2_row_width(int D) { return (D + 2 + 3) & ~3; }   // padded: the CG row loop is unrolled by 4
 __host__ __device__ inline size_t f2_rows_bytes(int N, int D) {
-    return f2_align((size_t)(D + 2) * N * 8) + f2_align((size_t)(D + 2) * N * 2);
+    return f2_align((size_t)f2_row_width(D) * N * 8) + f2_align((size_t)f2_row_width(D) * N * 2);
 }
 __host__ __device__ inline size_t f2_bins_min_bytes(int T) {
     const int nb = f2_nbx(T) * f2_nbx(T);
@@ -106,7 +111,7 @@ __host__ __device__ inline size_t f2_uni_bytes(int N, int T, int D) {
 }
 __host__ __device__ inline size_t f2_smem_bytes(int N, int T, int D) {
     return f2_align(2 * (size_t)N * 4) + f2_align((size_t)T * 8) + 4 * f2_align((size_t)N * 8) + f2_align(2 * (size_t)N * 8) +
-           f2_align(64 * 8) + f2_align(16) + f2_uni_bytes(N, T, D);
+           f2_align(64 * 8) + f2_align(16) + f2_align(MAX_GAUSS * sizeof(GaussPre)) + f2_uni_bytes(N, T, D);
 }
 
 __device__ inline F2Smem f2_carve(unsigned char* base, int N, int T, int D) {
@@ -121,8 +126,9 @@ __device__ inline F2Smem f2_carve(unsigned char* base, int N, int T, int D) {
     s.acc = reinterpret_cast<double*>(base + o), o += f2_align(2 * (size_t)N * 8);
     s.red = reinterpret_cast<double*>(base + o), o += f2_align(64 * 8);
     s.bbox = reinterpret_cast<float*>(base + o), o += f2_align(16);
+    s.gp = reinterpret_cast<GaussPre*>(base + o), o += f2_align(MAX_GAUSS * sizeof(GaussPre));
     s.uni = base + o;
-    s.RW = D + 2;
+    s.RW = f2_row_width(D);
     s.coef = reinterpret_cast<double*>(s.uni);
     s.col = reinterpret_cast<unsigned short*>(s.uni + f2_align((size_t)s.RW * N * 8));
     s.NBX = f2_nbx(T);
@@ -136,6 +142,21 @@ __device__ inline F2Smem f2_carve(unsigned char* base, int N, int T, int D) {
 }
 
 __device__ inline P2 f2_pt(const float* xy, int i) { return P2{xy[2 * i], xy[2 * i + 1]}; }
+
+// Optional phase timeline of CTA 0 (profiling aid, GAD_FEM2D_TRACE=1: f2_launch prints it to stderr)
+#ifndef FEM2D_EMULATE
+__device__ long long g_f2_trace[2][16];
+__device__ int g_f2_trace_on;
+__device__ __forceinline__ void f2_mark(int kernel, int slot) {
+    if (g_f2_trace_on && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_f2_trace[kernel][slot] = t;
+    }
+}
+#else
+inline void f2_mark(int, int) {}
+#endif
 
 // fixed-order block sum (every thread gets the result); `which` alternates between two buffers so that consecutive
 // reductions need one barrier each
@@ -228,7 +249,17 @@ __device__ int f2_cg(const F2Args& a, const F2Smem& s, double* out) {
             const int i = threadIdx.x + m * nthr;
             double acc = 0.0;
             if (i < N) {
-                for (int q = 0; q < RW; ++q) acc += s.coef[(size_t)q * N + i] * s.p[s.col[(size_t)q * N + i]];
+                for (int q = 0; q < RW; q += 4) {          // all loads of four entries in flight before the first FMA
+                    const unsigned short* cq = s.col + (size_t)q * N + i;
+                    const double* kq = s.coef + (size_t)q * N + i;
+                    const int c0 = cq[0], c1 = cq[N], c2 = cq[2 * N], c3 = cq[3 * N];
+                    const double k0 = kq[0], k1 = kq[N], k2 = kq[2 * N], k3 = kq[3 * N];
+                    const double p0 = s.p[c0], p1 = s.p[c1], p2 = s.p[c2], p3 = s.p[c3];
+                    acc += k0 * p0;
+                    acc += k1 * p1;
+                    acc += k2 * p2;
+                    acc += k3 * p3;
+                }
                 l += s.p[i] * acc;
             }
             Ap[m] = acc;
@@ -433,6 +464,8 @@ template <int MODE>
 __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, const double* sc) {
     const int n = simpson_n(a.K);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (threadIdx.x < a.G) s.gp[threadIdx.x] = gauss_pre(cen, sc, threadIdx.x);
+    __syncthreads();
     for (int i = warp; i < a.N; i += nw) {
         if (a.is_bc[i]) {
             if (MODE == 0 && lane == 0) s.b[i] = u_true((double)s.xy[2 * i], (double)s.xy[2 * i + 1], cen, sc, a.G);
@@ -441,32 +474,92 @@ __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, con
         float lx, ly, hx, hy;
         f2_star_box(a, s, i, lx, ly, hx, hy);
         const double hh = (double)((hx - lx) / (float)(n - 1)) * (double)((hy - ly) / (float)(n - 1)) / 9.0;
-        double part = 0.0;
-        for (int pq = lane; pq < n * n; pq += 32) {
-            const int ia = pq / n, ib = pq % n;
-            const P2 P{linspace_at(lx, hx, n, ia), linspace_at(ly, hy, n, ib)};
-            float rep;
-            const float phi = phi_star(P, s.xy, a.cells, a.star_cell + i * a.D, a.star_loc + i * a.D, a.D, &rep);
-            const float f = (float)forcing((double)P.x, (double)P.y, cen, sc, a.G);
-            const double w = (double)(simpson_w(n, ia) * simpson_w(n, ib));
-            if (MODE == 0) {
+        if (MODE == 0) {
+            double part = 0.0;
+            for (int pq = lane; pq < n * n; pq += 32) {
+                const int ia = pq / n, ib = pq % n;
+                const P2 P{linspace_at(lx, hx, n, ia), linspace_at(ly, hy, n, ib)};
+                float rep;
+                const float phi = phi_star(P, s.xy, a.cells, a.star_cell + i * a.D, a.star_loc + i * a.D, a.D, &rep);
+                const float f = (float)forcing_pre((double)P.x, (double)P.y, s.gp, sc, a.G);
+                const double w = (double)(simpson_w(n, ia) * simpson_w(n, ib));
                 part += (double)(phi * f) * w;
-            } else {
-                const double coef = s.r[i] * hh * w * (double)f / (double)rep;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if (lane == 0) s.b[i] = (double)(float)(part * hh);
+        } else {
+            // gradient term: every lane's points contribute to the SAME few vertices (those of the star of i), so the
+            // contributions are summed over the warp per star cell first (registers + shuffles) and only lane 0
+            // touches the fp64 accumulators in shared memory (a compare-and-swap loop per add)
+            constexpr int PTS = 3;
+            for (int base = 0; base < n * n; base += 32 * PTS) {
+                P2 Pm[PTS];
+                double cm[PTS];
+                unsigned mm[PTS];
+#pragma unroll
+                for (int m = 0; m < PTS; ++m) {
+                    const int pq = base + m * 32 + lane;
+                    cm[m] = 0.0;
+                    mm[m] = 0;
+                    Pm[m] = P2{0.f, 0.f};
+                    if (pq < n * n) {
+                        const int ia = pq / n, ib = pq % n;
+                        Pm[m] = P2{linspace_at(lx, hx, n, ia), linspace_at(ly, hy, n, ib)};
+                        // phi_star's repeat count, keeping which star cells contain the point (2 bits per cell)
+                        float rep = 0.f;
+                        unsigned mask = 0;
+                        for (int d = 0; d < a.D; ++d) {
+                            const int t = a.star_cell[i * a.D + d];
+                            if (t < 0) continue;
+                            const int k = a.star_loc[i * a.D + d];
+                            const P2 pa = f2_pt(s.xy, s.cell[4 * t + (k + 2) % 3]), pb = f2_pt(s.xy, s.cell[4 * t + (k + 1) % 3]),
+                                     pc = f2_pt(s.xy, s.cell[4 * t + k]);
+                            const int mult = inside_count(Pm[m], pa, pb, pc);
+                            if (!mult) continue;
+                            mask |= (unsigned)mult << (2 * d);
+                            float gx, gy;
+                            const float inc = (float)mult * bary(Pm[m], pa, pb, pc, &gx, &gy);
+                            rep += (inc > 0.f) ? 1.f : 0.f;
+                        }
+                        if (rep == 0.f) rep = 1.f;
+                        mm[m] = mask;
+                        const float f = (float)forcing_pre((double)Pm[m].x, (double)Pm[m].y, s.gp, sc, a.G);
+                        const double w = (double)(simpson_w(n, ia) * simpson_w(n, ib));
+                        cm[m] = s.r[i] * hh * w * (double)f / (double)rep;
+                    }
+                }
                 for (int d = 0; d < a.D; ++d) {
                     const int t = a.star_cell[i * a.D + d];
                     if (t < 0) continue;
                     const int k = a.star_loc[i * a.D + d];
-                    const int mult = inside_count(P, f2_pt(s.xy, s.cell[4 * t + (k + 2) % 3]), f2_pt(s.xy, s.cell[4 * t + (k + 1) % 3]),
-                                                  f2_pt(s.xy, s.cell[4 * t + k]));
-                    if (mult) f2_scatter(a, s, t, k, P, coef * mult);
+                    const int ic = s.cell[4 * t + k], ia = s.cell[4 * t + (k + 2) % 3], ib = s.cell[4 * t + (k + 1) % 3];
+                    const P2 pa = f2_pt(s.xy, ia), pb = f2_pt(s.xy, ib), pc = f2_pt(s.xy, ic);
+                    double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int m = 0; m < PTS; ++m) {
+                        const int mult = (int)((mm[m] >> (2 * d)) & 3u);
+                        if (!mult || cm[m] == 0.0) continue;
+                        const double coef = cm[m] * mult;
+                        float gx, gy, tx, ty;
+                        const float lc = bary(Pm[m], pa, pb, pc, &gx, &gy);
+                        const float la = bary(Pm[m], pb, pc, pa, &tx, &ty);
+                        const float lb = bary(Pm[m], pc, pa, pb, &tx, &ty);
+                        g[0] += -coef * (double)la * (double)gx, g[1] += -coef * (double)la * (double)gy;
+                        g[2] += -coef * (double)lb * (double)gx, g[3] += -coef * (double)lb * (double)gy;
+                        g[4] += -coef * (double)lc * (double)gx, g[5] += -coef * (double)lc * (double)gy;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; ++c)
+#pragma unroll
+                        for (int sh = 16; sh > 0; sh >>= 1) g[c] += __shfl_xor_sync(0xffffffffu, g[c], sh);
+                    if (lane == 0) {
+                        atomicAdd(&s.acc[2 * ia], g[0]), atomicAdd(&s.acc[2 * ia + 1], g[1]);
+                        atomicAdd(&s.acc[2 * ib], g[2]), atomicAdd(&s.acc[2 * ib + 1], g[3]);
+                        atomicAdd(&s.acc[2 * ic], g[4]), atomicAdd(&s.acc[2 * ic + 1], g[5]);
+                    }
                 }
             }
-        }
-        if (MODE == 0) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-            if (lane == 0) s.b[i] = (double)(float)(part * hh);
         }
     }
     __syncthreads();
@@ -505,11 +598,16 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_fwd(F2Args a) {
     const int mesh = blockIdx.x;
     const double* cen = a.cen + (size_t)mesh * a.G * 2;
     const double* sc = a.sc + (size_t)mesh * a.G * 2;
+    f2_mark(0, 0);
     f2_geometry(a, s, mesh);
+    f2_mark(0, 1);
     f2_load<0>(a, s, cen, sc);
+    f2_mark(0, 2);
     f2_interior_rhs(a, s);
     f2_build_rows(a, s);
+    f2_mark(0, 3);
     const int it = f2_cg<R>(a, s, s.acc);              // interior solution in s.acc[0..N)
+    f2_mark(0, 4);
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
         if (!a.is_bc[i]) s.u[i] = s.acc[i];
         a.coeffs[(size_t)mesh * a.N + i] = (float)s.u[i];
@@ -517,7 +615,9 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_fwd(F2Args a) {
     }
     __syncthreads();
     const bool bins = f2_build_bins(a, s);           // the rows are no longer needed: their memory holds the bins
+    f2_mark(0, 5);
     f2_points<0>(a, s, mesh, bins);
+    f2_mark(0, 6);
     if (a.cg_iters && threadIdx.x == 0) a.cg_iters[mesh] = it;
 }
 
@@ -532,13 +632,18 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_bwd(F2Args a) {
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.u[i] = a.u64[(size_t)mesh * a.N + i];
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s.acc[i] = 0.0;
     __syncthreads();
+    f2_mark(1, 0);
     bool bins = f2_build_bins(a, s);
+    f2_mark(1, 1);
     f2_points<1>(a, s, mesh, bins);                  // g_u in s.acc[0..N)
+    f2_mark(1, 2);
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.b[i] = a.is_bc[i] ? 0.0 : -s.acc[i];
     __syncthreads();
     f2_build_rows(a, s);                             // (overwrites the bins)
+    f2_mark(1, 3);
     double* lam = s.acc + a.N;                       // second half of the accumulator array, free until the scatter
     f2_cg<R>(a, s, lam);                             // K_II lambda_I = -g_I
+    f2_mark(1, 4);
     // keep lambda in s.r (zero on Dirichlet nodes), then reuse s.acc as the gradient accumulator
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) s.b[i] = a.is_bc[i] ? 0.0 : lam[i];
     __syncthreads();
@@ -546,8 +651,11 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_bwd(F2Args a) {
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s.acc[i] = 0.0;
     __syncthreads();
     bins = f2_build_bins(a, s);
+    f2_mark(1, 5);
     f2_points<2>(a, s, mesh, bins);                  // interpolation term
+    f2_mark(1, 6);
     f2_load<1>(a, s, cen, sc);                       // load-vector term
+    f2_mark(1, 7);
     for (int t = threadIdx.x; t < a.T; t += blockDim.x) {      // matrix term
         const Tri g = f2_tri(s, t);
         double Glx = 0, Gly = 0, Gux = 0, Guy = 0;
@@ -566,6 +674,7 @@ __global__ void __launch_bounds__(FEM2D_THREADS) k_fem2d_bwd(F2Args a) {
         }
     }
     __syncthreads();
+    f2_mark(1, 8);
     for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) a.grad[(size_t)mesh * a.N * 2 + i] = (float)s.acc[i];
 }
 
@@ -574,9 +683,15 @@ int f2_launch(const F2Args& a, int B, bool backward, cudaStream_t st) {
     const size_t bytes = f2_smem_bytes(a.N, a.T, a.D);
     GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "fem2d: a mesh of %d nodes / %d cells needs %zu B of shared memory", a.N, a.T,
                   bytes);
+    GAD_CHECK_ARG(a.G <= MAX_GAUSS && a.D <= 16, "fem2d: at most %d Gaussians and 16 cells per node (got %d, %d)", MAX_GAUSS,
+                  a.G, a.D);
     GAD_CHECK_ARG(a.N <= MAX_ROWS_PER_THREAD * FEM2D_THREADS && a.N <= 65535 && a.T <= 65535,
                   "fem2d: %d nodes / %d cells exceed the kernel's limits (%d nodes, 16-bit indices)", a.N, a.T,
                   MAX_ROWS_PER_THREAD * FEM2D_THREADS);
+    static const int trace = getenv("GAD_FEM2D_TRACE") ? atoi(getenv("GAD_FEM2D_TRACE")) : 0;
+    if (trace) {
+        GAD_CUDA(cudaMemcpyToSymbolAsync(g_f2_trace_on, &trace, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    }
     const int R = f2_rows_per_thread(a.N);
 #define F2_LAUNCH(K_)                                                                                        \
     do {                                                                                                     \
@@ -595,6 +710,17 @@ int f2_launch(const F2Args& a, int B, bool backward, cudaStream_t st) {
         else F2_LAUNCH(k_fem2d_fwd<8>);
     }
 #undef F2_LAUNCH
+    if (trace) {
+        long long h[2][16];
+        GAD_CUDA(cudaStreamSynchronize(st));
+        GAD_CUDA(cudaMemcpyFromSymbol(h, g_f2_trace, sizeof(h)));
+        const int k = backward ? 1 : 0, n = backward ? 9 : 7;
+        static const char* names[2][9] = {{"geometry", "load", "rhs+rows", "cg", "bins", "points", "", "", ""},
+                                          {"bins", "points g_u", "rows", "cg", "bins", "points grad", "load grad", "matrix", ""}};
+        fprintf(stderr, "[fem2d %s, CTA 0, us]", backward ? "bwd" : "fwd");
+        for (int i = 0; i + 1 < n; ++i) fprintf(stderr, " %s %.1f", names[k][i], (h[k][i + 1] - h[k][i]) * 1e-3);
+        fprintf(stderr, "\n");
+    }
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
