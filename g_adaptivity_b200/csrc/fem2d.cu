@@ -68,6 +68,55 @@ struct F2Args {
 // never changes which cells count.
 constexpr float BOX_MARGIN = 1e-3f;
 
+// Everything the hat function of node m needs from ONE cell of its star, worked out once per node instead of once
+// per cubature point (c = m's vertex in the cell, a / b the other two, as phi_star orders them): the three edge
+// tests  e?x * P.x + e?y * P.y  against  r?  (inside_count), and the barycentric coordinates of c, a, b at P
+// (bary): numerator coefficients = the edge coefficients, base point, denominator; (gx, gy) = grad l_c.
+// Same operands, same operations as inside_count / bary: bit-identical decisions and values.
+struct StarRec {
+    float e1x, e1y, r1, e2x, e2y, r2, e3x, e3y, r3, valid;
+    float denc, cx, cy, dena, ax, ay, denb, bx, by, gx, gy;
+    float pad[3];
+    int ia, ib, ic;
+    int pad2;
+};
+__device__ inline StarRec f2_star_rec(P2 a, P2 b, P2 c, int ia, int ib, int ic) {
+    StarRec r;
+    r.e1x = a.y - b.y, r.e1y = b.x - a.x;
+    r.r1 = FEM_ADD(FEM_MUL(r.e1x, a.x), FEM_MUL(r.e1y, a.y));
+    r.e2x = b.y - c.y, r.e2y = c.x - b.x;
+    r.r2 = FEM_ADD(FEM_MUL(r.e2x, b.x), FEM_MUL(r.e2y, b.y));
+    r.e3x = c.y - a.y, r.e3y = a.x - c.x;
+    r.r3 = FEM_ADD(FEM_MUL(r.e3x, c.x), FEM_MUL(r.e3y, c.y));
+    r.valid = 1.f;
+    r.denc = FEM_ADD(FEM_MUL(r.e1x, c.x - a.x), FEM_MUL(c.y - a.y, r.e1y));
+    r.dena = FEM_ADD(FEM_MUL(r.e2x, a.x - b.x), FEM_MUL(a.y - b.y, r.e2y));
+    r.denb = FEM_ADD(FEM_MUL(r.e3x, b.x - c.x), FEM_MUL(b.y - c.y, r.e3y));
+    r.cx = c.x, r.cy = c.y, r.ax = a.x, r.ay = a.y, r.bx = b.x, r.by = b.y;
+    r.gx = r.e1x / r.denc, r.gy = r.e1y / r.denc;
+    r.ia = ia, r.ib = ib, r.ic = ic;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0.f;
+    r.pad2 = 0;
+    return r;
+}
+__device__ inline int f2_rec_inside(const StarRec& r, P2 P) {
+    const float l1 = FEM_ADD(FEM_MUL(r.e1x, P.x), FEM_MUL(r.e1y, P.y));
+    const float l2 = FEM_ADD(FEM_MUL(r.e2x, P.x), FEM_MUL(r.e2y, P.y));
+    const float l3 = FEM_ADD(FEM_MUL(r.e3x, P.x), FEM_MUL(r.e3y, P.y));
+    const int left = (l1 >= r.r1) && (l2 >= r.r2) && (l3 >= r.r3);
+    const int right = (l1 <= r.r1) && (l2 <= r.r2) && (l3 <= r.r3);
+    return left + right;
+}
+__device__ inline float f2_rec_lc(const StarRec& r, P2 P) {
+    return FEM_ADD(1.f, FEM_ADD(FEM_MUL(P.x - r.cx, r.e1x), FEM_MUL(P.y - r.cy, r.e1y)) / r.denc);
+}
+__device__ inline float f2_rec_la(const StarRec& r, P2 P) {
+    return FEM_ADD(1.f, FEM_ADD(FEM_MUL(P.x - r.ax, r.e2x), FEM_MUL(P.y - r.ay, r.e2y)) / r.dena);
+}
+__device__ inline float f2_rec_lb(const StarRec& r, P2 P) {
+    return FEM_ADD(1.f, FEM_ADD(FEM_MUL(P.x - r.bx, r.e3x), FEM_MUL(P.y - r.by, r.e3y)) / r.denb);
+}
+
 // Shared memory of one mesh.  `uni` is time-shared: the matrix rows during a CG solve, the bin table during a point pass.
 struct F2Smem {
     float* xy;              // [2N]
@@ -80,6 +129,7 @@ struct F2Smem {
     double* red;            // [2][32] partial sums of the block reductions (double-buffered: one barrier each)
     float* bbox;            // [4]     bounding box of the mesh
     GaussPre* gp;           // [MAX_GAUSS] per-Gaussian constants of the forcing
+    StarRec* star;          // [warps, D]  star records of the node each warp is working on (load vector phases)
     unsigned char* uni;
     // rows view (RW = D + 2 entries per node, column-major)
     double* coef;           // [RW, N]
@@ -111,7 +161,8 @@ __host__ __device__ inline size_t f2_uni_bytes(int N, int T, int D) {
 }
 __host__ __device__ inline size_t f2_smem_bytes(int N, int T, int D) {
     return f2_align(2 * (size_t)N * 4) + f2_align((size_t)T * 8) + 4 * f2_align((size_t)N * 8) + f2_align(2 * (size_t)N * 8) +
-           f2_align(64 * 8) + f2_align(16) + f2_align(MAX_GAUSS * sizeof(GaussPre)) + f2_uni_bytes(N, T, D);
+           f2_align(64 * 8) + f2_align(16) + f2_align(MAX_GAUSS * sizeof(GaussPre)) +
+           f2_align((size_t)(FEM2D_THREADS / 32) * D * sizeof(StarRec)) + f2_uni_bytes(N, T, D);
 }
 
 __device__ inline F2Smem f2_carve(unsigned char* base, int N, int T, int D) {
@@ -127,6 +178,7 @@ __device__ inline F2Smem f2_carve(unsigned char* base, int N, int T, int D) {
     s.red = reinterpret_cast<double*>(base + o), o += f2_align(64 * 8);
     s.bbox = reinterpret_cast<float*>(base + o), o += f2_align(16);
     s.gp = reinterpret_cast<GaussPre*>(base + o), o += f2_align(MAX_GAUSS * sizeof(GaussPre));
+    s.star = reinterpret_cast<StarRec*>(base + o), o += f2_align((size_t)(FEM2D_THREADS / 32) * D * sizeof(StarRec));
     s.uni = base + o;
     s.RW = f2_row_width(D);
     s.coef = reinterpret_cast<double*>(s.uni);
@@ -471,16 +523,43 @@ __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, con
             if (MODE == 0 && lane == 0) s.b[i] = u_true((double)s.xy[2 * i], (double)s.xy[2 * i + 1], cen, sc, a.G);
             continue;
         }
-        float lx, ly, hx, hy;
-        f2_star_box(a, s, i, lx, ly, hx, hy);
+        // star records of node i: lane d builds the record of star cell d (and the bounding box comes with them)
+        StarRec* rec = s.star + (size_t)warp * a.D;
+        __syncwarp();                      // the previous node's records are no longer read
+        if (lane < a.D) {
+            const int t = a.star_cell[i * a.D + lane];
+            if (t < 0) {
+                rec[lane].valid = 0.f;
+            } else {
+                const int k = a.star_loc[i * a.D + lane];
+                const int ic = s.cell[4 * t + k], ia = s.cell[4 * t + (k + 2) % 3], ib = s.cell[4 * t + (k + 1) % 3];
+                rec[lane] = f2_star_rec(f2_pt(s.xy, ia), f2_pt(s.xy, ib), f2_pt(s.xy, ic), ia, ib, ic);
+            }
+        }
+        __syncwarp();
+        float lx = INFINITY, ly = INFINITY, hx = -INFINITY, hy = -INFINITY;
+        for (int d = 0; d < a.D; ++d) {
+            if (rec[d].valid == 0.f) continue;
+            lx = fminf(lx, fminf(rec[d].ax, fminf(rec[d].bx, rec[d].cx))), hx = fmaxf(hx, fmaxf(rec[d].ax, fmaxf(rec[d].bx, rec[d].cx)));
+            ly = fminf(ly, fminf(rec[d].ay, fminf(rec[d].by, rec[d].cy))), hy = fmaxf(hy, fmaxf(rec[d].ay, fmaxf(rec[d].by, rec[d].cy)));
+        }
         const double hh = (double)((hx - lx) / (float)(n - 1)) * (double)((hy - ly) / (float)(n - 1)) / 9.0;
         if (MODE == 0) {
             double part = 0.0;
             for (int pq = lane; pq < n * n; pq += 32) {
                 const int ia = pq / n, ib = pq % n;
                 const P2 P{linspace_at(lx, hx, n, ia), linspace_at(ly, hy, n, ib)};
-                float rep;
-                const float phi = phi_star(P, s.xy, a.cells, a.star_cell + i * a.D, a.star_loc + i * a.D, a.D, &rep);
+                float out = 0.f, rep = 0.f;           // phi_star (fem2d_math.cuh) over the records
+                for (int d = 0; d < a.D; ++d) {
+                    if (rec[d].valid == 0.f) continue;
+                    const int mult = f2_rec_inside(rec[d], P);
+                    if (!mult) continue;
+                    const float inc = (float)mult * f2_rec_lc(rec[d], P);
+                    out += inc;
+                    rep += (inc > 0.f) ? 1.f : 0.f;
+                }
+                if (rep == 0.f) rep = 1.f;
+                const float phi = out / rep;
                 const float f = (float)forcing_pre((double)P.x, (double)P.y, s.gp, sc, a.G);
                 const double w = (double)(simpson_w(n, ia) * simpson_w(n, ib));
                 part += (double)(phi * f) * w;
@@ -510,16 +589,11 @@ __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, con
                         float rep = 0.f;
                         unsigned mask = 0;
                         for (int d = 0; d < a.D; ++d) {
-                            const int t = a.star_cell[i * a.D + d];
-                            if (t < 0) continue;
-                            const int k = a.star_loc[i * a.D + d];
-                            const P2 pa = f2_pt(s.xy, s.cell[4 * t + (k + 2) % 3]), pb = f2_pt(s.xy, s.cell[4 * t + (k + 1) % 3]),
-                                     pc = f2_pt(s.xy, s.cell[4 * t + k]);
-                            const int mult = inside_count(Pm[m], pa, pb, pc);
+                            if (rec[d].valid == 0.f) continue;
+                            const int mult = f2_rec_inside(rec[d], Pm[m]);
                             if (!mult) continue;
                             mask |= (unsigned)mult << (2 * d);
-                            float gx, gy;
-                            const float inc = (float)mult * bary(Pm[m], pa, pb, pc, &gx, &gy);
+                            const float inc = (float)mult * f2_rec_lc(rec[d], Pm[m]);
                             rep += (inc > 0.f) ? 1.f : 0.f;
                         }
                         if (rep == 0.f) rep = 1.f;
@@ -530,21 +604,17 @@ __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, con
                     }
                 }
                 for (int d = 0; d < a.D; ++d) {
-                    const int t = a.star_cell[i * a.D + d];
-                    if (t < 0) continue;
-                    const int k = a.star_loc[i * a.D + d];
-                    const int ic = s.cell[4 * t + k], ia = s.cell[4 * t + (k + 2) % 3], ib = s.cell[4 * t + (k + 1) % 3];
-                    const P2 pa = f2_pt(s.xy, ia), pb = f2_pt(s.xy, ib), pc = f2_pt(s.xy, ic);
+                    if (rec[d].valid == 0.f) continue;
+                    const float gx = rec[d].gx, gy = rec[d].gy;
                     double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                     for (int m = 0; m < PTS; ++m) {
                         const int mult = (int)((mm[m] >> (2 * d)) & 3u);
                         if (!mult || cm[m] == 0.0) continue;
                         const double coef = cm[m] * mult;
-                        float gx, gy, tx, ty;
-                        const float lc = bary(Pm[m], pa, pb, pc, &gx, &gy);
-                        const float la = bary(Pm[m], pb, pc, pa, &tx, &ty);
-                        const float lb = bary(Pm[m], pc, pa, pb, &tx, &ty);
+                        const float lc = f2_rec_lc(rec[d], Pm[m]);
+                        const float la = f2_rec_la(rec[d], Pm[m]);
+                        const float lb = f2_rec_lb(rec[d], Pm[m]);
                         g[0] += -coef * (double)la * (double)gx, g[1] += -coef * (double)la * (double)gy;
                         g[2] += -coef * (double)lb * (double)gx, g[3] += -coef * (double)lb * (double)gy;
                         g[4] += -coef * (double)lc * (double)gx, g[5] += -coef * (double)lc * (double)gy;
@@ -554,6 +624,7 @@ __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, con
 #pragma unroll
                         for (int sh = 16; sh > 0; sh >>= 1) g[c] += __shfl_xor_sync(0xffffffffu, g[c], sh);
                     if (lane == 0) {
+                        const int ia = rec[d].ia, ib = rec[d].ib, ic = rec[d].ic;
                         atomicAdd(&s.acc[2 * ia], g[0]), atomicAdd(&s.acc[2 * ia + 1], g[1]);
                         atomicAdd(&s.acc[2 * ib], g[2]), atomicAdd(&s.acc[2 * ib + 1], g[3]);
                         atomicAdd(&s.acc[2 * ic], g[4]), atomicAdd(&s.acc[2 * ic + 1], g[5]);

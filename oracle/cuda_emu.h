@@ -30,6 +30,8 @@ extern double emu_warp_buf[32][32];
 
 inline void __syncthreads() { pthread_barrier_wait(&emu_block_barrier); }
 
+inline void __syncwarp() { pthread_barrier_wait(&emu_warp_barrier[threadIdx.x >> 5]); }
+
 inline double __shfl_xor_sync(unsigned, double v, int d) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     emu_warp_buf[w][l] = v;
