@@ -338,6 +338,48 @@ extern "C" int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64
     return reduce_partials(CE, T, Lw, L, ws, gMu, g_tau, 0.f, nullptr, st);
 }
 
+extern "C" int gad_deform_bwd_ell_rk4(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
+                                      int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
+                                      int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_x0,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    GAD_CHECK_ARG(ell_in && ell_out && states && g_xphys && Mu && tau && gMu && workspace, "gad_deform_bwd_ell_rk4: null pointer");
+    GAD_UNIFORM_TILES_OK("gad_deform_bwd_ell_rk4");
+    GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
+                  "gad_deform_bwd_ell_rk4: N=%lld T=%d L=%d dim=%d CE=%d Lw=%d", (long long)N, T, L, dim, CE, Lw);
+    GAD_CHECK_ARG(workspace_bytes >= ws_floats(CE, T, L) * sizeof(float), "gad_deform_bwd_ell_rk4: workspace too small");
+    Plan p;
+    int rc = make_plan(CE, KIND_BWD_RK4, max_tile_nodes, max_deg, &p);
+    if (rc) return rc;
+    float* ws = reinterpret_cast<float*>(workspace);
+    Args a{};
+    a.ell_in = reinterpret_cast<const uint4*>(ell_in);
+    a.ell_out = reinterpret_cast<const uint4*>(ell_out);
+    a.tile_ptr = tile_ptr;
+    a.T = T;
+    a.cap_nodes = max_tile_nodes;
+    a.N = N;
+    a.Mu = Mu;
+    a.tau = tau;
+    a.Lw = Lw;
+    a.L = L;
+    a.dim = dim;
+    a.states = const_cast<float*>(states);
+    a.g_xphys = g_xphys;
+    a.partials = ws;
+    a.tau_partials = nullptr;
+    a.g_x0 = g_x0;
+    cudaStream_t st = as_stream(stream);
+    if ((rc = dispatch(CE, p, 3, a, GAD_METHOD_RK4, st))) return rc;
+    return reduce_partials(CE, T, Lw, L, ws, gMu, nullptr, 0.f, nullptr, st);
+}
+
+extern "C" int gad_ell_rk4_bwd_supported(int CE, int max_tile_nodes, int max_deg) {
+    Plan p;
+    if (CE != 2 && CE != 4) return 0;
+    if (max_deg > ELL_SLOTS || max_tile_nodes <= 0 || (long long)max_tile_nodes * CE * 4 > 0x10000) return 0;
+    return make_plan(CE, KIND_BWD_RK4, max_tile_nodes, max_deg, &p) == GAD_OK ? 1 : 0;
+}
+
 extern "C" int gad_deform_train_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                                     int max_tile_nodes, int max_deg, const float* x_comp, const float* f,
                                     const float* uu, const float* f_scale, const float* uu_scale, const float* target,

@@ -39,12 +39,13 @@ namespace ell {
 #define GAD_ELL_MINB 1
 #endif
 
-enum Kind { KIND_FWD = 0, KIND_FWD_RK4 = 1, KIND_BWD = 2 };
+enum Kind { KIND_FWD = 0, KIND_FWD_RK4 = 1, KIND_BWD = 2, KIND_BWD_RK4 = 3 };
 
 constexpr size_t TAIL_SCRATCH_MIN = 24 * 1024;
 
 struct Layout {
     uint32_t xa, xb, p, gs, dl, ein, eout, mu, red, bar, total;
+    uint32_t y2, y3, y4, g, ab;   // RK4 backward: stage inputs, step cotangent, accumulated d/dy
 };
 
 __host__ __device__ inline Layout make_layout(int CE, int kind, int cap_nodes, bool ells, int nwarps) {
@@ -62,13 +63,21 @@ __host__ __device__ inline Layout make_layout(int CE, int kind, int cap_nodes, b
         s.p = bump(rows);    // RK4: base state;   backward: p_i rows
         s.gs = bump(rows);   // RK4: accumulator;  backward: per-node gradient carry
     }
-    if (kind == KIND_BWD) s.dl = bump((size_t)cap_nodes * 8);
+    const bool bwd = (kind == KIND_BWD || kind == KIND_BWD_RK4);
+    if (bwd) s.dl = bump((size_t)cap_nodes * 8);
+    if (kind == KIND_BWD_RK4) {
+        s.y2 = bump(rows);
+        s.y3 = bump(rows);
+        s.y4 = bump(rows);
+        s.g = bump(rows);
+        s.ab = bump(rows);
+    }
     if (ells) {
         s.ein = bump((size_t)cap_nodes * 16);
-        if (kind == KIND_BWD) s.eout = bump((size_t)cap_nodes * 16);
+        if (bwd) s.eout = bump((size_t)cap_nodes * 16);
     }
     s.mu = bump((size_t)(CE * CE + CE) * sizeof(float));
-    if (kind == KIND_BWD) s.red = bump((size_t)(CE * CE + CE + 1) * nwarps * sizeof(float));
+    if (bwd) s.red = bump((size_t)(CE * CE + CE + 1) * nwarps * sizeof(float));
     if (kind == KIND_BWD && o < TAIL_SCRATCH_MIN) o = TAIL_SCRATCH_MIN;   // train tail: [0, bar) is its scratch
     s.bar = bump(16);
     s.total = (uint32_t)o;
@@ -564,6 +573,187 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd(const Ar
         EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + e0};
         EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + e0};
         tile_backward<CE, W, ELLS>(a, tile, n0, NT, X, GO, P, DL, GS, Ein, Eout, Mu, red);
+    }
+}
+
+// ============================================================================================
+// backward of one tile through classical RK4 steps (the forward of k_ell_fwd<..., GAD_METHOD_RK4>)
+// ============================================================================================
+// One step  y' = y + h/6 (k1 + 2 k2 + 2 k3 + k4),  k_s = F(y_s),  y_1 = y, y_2 = y + h/2 k1, y_3 = y + h/2 k2,
+// y_4 = y + h k3,  F(y) = A(y) y - y.  With g = dL/dy' and  vjp(x, c) = J_F(x)^T c = (d(A x)/dx)^T c - c :
+//     c4 = h/6 g              a4 = vjp(y4, c4)
+//     c3 = h/3 g + h   a4     a3 = vjp(y3, c3)
+//     c2 = h/3 g + h/2 a3     a2 = vjp(y2, c2)
+//     c1 = h/6 g + h/2 a2     a1 = vjp(y1, c1)          dL/dy = g + a1 + a2 + a3 + a4
+// Only the step inputs y = x^l are saved by the forward (states[l]); the stage inputs are recomputed (three
+// F-evaluations, same arithmetic as the forward).  Every vjp is the destination / source pass pair of the Euler
+// backward with b = 1, and adds its (G_M, G_u) terms to the same per-thread accumulators.  Buffers (rows of CE
+// floats per node): Y, Y2, Y3, Y4, G (step cotangent), AB (g + sum a_s), C (current cotangent / vjp result), GO, P.
+template <int CE, int W, bool ELLS>
+__device__ __forceinline__ void tile_backward_rk4(const Args& a, int tile, int n0, int NT, unsigned char* smem,
+                                                  const Layout& lay, const EllView<ELLS>& Ein,
+                                                  const EllView<ELLS>& Eout, float* Mu, float* red) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    constexpr int NACC = MUSZ + 1;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    unsigned char* Y = smem + lay.xa;
+    unsigned char* GO = smem + lay.xb;
+    unsigned char* P = smem + lay.p;
+    unsigned char* C = smem + lay.gs;
+    unsigned char* DL = smem + lay.dl;
+    unsigned char* Y2 = smem + lay.y2;
+    unsigned char* Y3 = smem + lay.y3;
+    unsigned char* Y4 = smem + lay.y4;
+    unsigned char* G = smem + lay.g;
+    unsigned char* AB = smem + lay.ab;
+    const bool per_layer = (a.Lw > 1);
+    const int slots = per_layer ? a.L : 1;
+    const size_t state_stride = (size_t)a.N * CE;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+
+    for (int l = a.L - 1; l >= 0; --l) {
+        if (per_layer) {
+            __syncthreads();
+            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+        }
+        const float h = a.tau[l];
+        const float h6 = h * (1.0f / 6.0f), h3 = 2.0f * h6, h2 = 0.5f * h;
+        const float* yl = a.states + (size_t)l * state_stride;
+        for (int i = tid; i < NT; i += nthr) sts_row<CE>(Y, i * RB, load_row_cg<CE>(yl, (int64_t)n0 + i));
+        __syncthreads();
+        // ---- stage inputs y2, y3, y4 (the forward's arithmetic)
+#pragma unroll 1
+        for (int sidx = 0; sidx < 3; ++sidx) {
+            const unsigned char* src = (sidx == 0) ? Y : ((sidx == 1) ? Y2 : Y3);
+            unsigned char* dst = (sidx == 0) ? Y2 : ((sidx == 1) ? Y3 : Y4);
+            const float cs = (sidx == 2) ? h : h2;
+            for (int i = tid; i < NT; i += nthr) {
+                const uint4 e = Ein.get(i);
+                const Row<CE> y = lds_row<CE>(src, i * RB);
+                const Row<CE> k = ell_feval<CE, W>(src, e, y, Mu);
+                const Row<CE> base = lds_row<CE>(Y, i * RB);
+                Row<CE> out;
+#pragma unroll
+                for (int c = 0; c < CE; ++c) out.v[c] = fmaf(cs, k.v[c], base.v[c]);
+                sts_row<CE>(dst, i * RB, out);
+            }
+            __syncthreads();
+        }
+        // ---- four cotangent passes, stage 4 first
+#pragma unroll 1
+        for (int ps = 0; ps < 4; ++ps) {
+            const unsigned char* Xs = (ps == 0) ? Y4 : ((ps == 1) ? Y3 : ((ps == 2) ? Y2 : Y));
+            for (int i = tid; i < NT; i += nthr) {          // destination pass, b = 1
+                const uint4 e = Ein.get(i);
+                const Row<CE> xi = lds_row<CE>(Xs, i * RB);
+                Row<CE> c;
+                if (ps == 0) {
+                    const Row<CE> g = lds_row<CE>(G, i * RB);
+#pragma unroll
+                    for (int ch = 0; ch < CE; ++ch) c.v[ch] = h6 * g.v[ch];
+                } else {
+                    c = lds_row<CE>(C, i * RB);
+                }
+                Row<CE> p, t, o;
+                float D, lse;
+                ell_bwd_dst<CE, W>(Xs, e, xi, c, Mu, p, D, lse, t, o);
+#pragma unroll
+                for (int aa = 0; aa < CE; ++aa)
+#pragma unroll
+                    for (int bb = 0; bb < CE; ++bb) acc[aa * CE + bb] = fmaf(xi.v[aa], t.v[bb], acc[aa * CE + bb]);
+#pragma unroll
+                for (int bb = 0; bb < CE; ++bb) acc[CE * CE + bb] += t.v[bb];
+                const Row<CE> Mt = apply_M<CE>(Mu, t);
+                sts_row<CE>(P, i * RB, p);
+                *reinterpret_cast<float2*>(DL + (size_t)i * 8) = make_float2(D, lse);
+                sts_row<CE>(GO, i * RB, c);
+                sts_row<CE>(C, i * RB, Mt);
+            }
+            __syncthreads();
+            const float wg = (ps == 2) ? h6 : h3, wa = (ps == 0) ? h : h2;     // next cotangent = wg g + wa a_s
+            for (int j = tid; j < NT; j += nthr) {          // source pass + node-local bookkeeping
+                const uint4 e = Eout.get(j);
+                const Row<CE> xj = lds_row<CE>(Xs, j * RB);
+                const Row<CE> sc = ell_bwd_src<CE, W>(P, GO, DL, e, xj);
+                const Row<CE> r = lds_row<CE>(C, j * RB);
+                const Row<CE> cj = lds_row<CE>(GO, j * RB);
+                const Row<CE> g = lds_row<CE>(G, j * RB);
+                Row<CE> as, ab;
+#pragma unroll
+                for (int ch = 0; ch < CE; ++ch) as.v[ch] = (r.v[ch] + sc.v[ch]) - cj.v[ch];
+                if (ps == 0) {
+#pragma unroll
+                    for (int ch = 0; ch < CE; ++ch) ab.v[ch] = g.v[ch] + as.v[ch];
+                } else {
+                    ab = lds_row<CE>(AB, j * RB);
+#pragma unroll
+                    for (int ch = 0; ch < CE; ++ch) ab.v[ch] += as.v[ch];
+                }
+                if (ps < 3) {
+                    Row<CE> cn;
+#pragma unroll
+                    for (int ch = 0; ch < CE; ++ch) cn.v[ch] = fmaf(wg, g.v[ch], wa * as.v[ch]);
+                    sts_row<CE>(AB, j * RB, ab);
+                    sts_row<CE>(C, j * RB, cn);
+                } else {
+                    sts_row<CE>(G, j * RB, ab);             // dL/dx^l: the cotangent of the previous step
+                    if (l == 0 && a.g_x0) store_row<CE>(a.g_x0, (int64_t)n0 + j, ab);
+                }
+            }
+            __syncthreads();
+        }
+        if (per_layer) {
+            acc[NACC - 1] = 0.f;
+            block_reduce<NACC>(acc, red, a.partials + ((size_t)tile * slots + l) * NACC);
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+        }
+    }
+    if (!per_layer) block_reduce<NACC>(acc, red, a.partials + (size_t)tile * NACC);
+}
+
+template <int CE, int W, bool ELLS>
+__global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd_rk4(const Args a) {
+    constexpr uint32_t RB = CE * sizeof(float);
+    constexpr int MUSZ = CE * CE + CE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const Layout lay = make_layout(CE, KIND_BWD_RK4, a.cap_nodes, ELLS, (nthr + 31) >> 5);
+    unsigned char* G = smem + lay.g;
+    float* Mu = reinterpret_cast<float*>(smem + lay.mu);
+    float* red = reinterpret_cast<float*>(smem + lay.red);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    uint32_t parity = 0;
+    for (int tile = blockIdx.x; tile < a.T; tile += gridDim.x) {
+        int n0, NT, e0;
+        tile_range(a, tile, n0, NT, e0);
+        __syncthreads();
+        const uint32_t tx = ELLS ? 2u * (uint32_t)NT * 16u : 0u;
+        if (tid == 0 && tx) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(bar, tx);
+            bulk_g2s(smem + lay.ein, a.ell_in + e0, (uint32_t)NT * 16u, bar);
+            bulk_g2s(smem + lay.eout, a.ell_out + e0, (uint32_t)NT * 16u, bar);
+        }
+        // cotangent of x_phys = x^L[:, :dim]  ->  dL/dx^L (zero in the other channels)
+        for (int i = tid; i < NT; i += nthr) sts_row<CE>(G, i * RB, load_dims<CE>(a.g_xphys, (int64_t)n0 + i, a.dim));
+        const int lw = (a.Lw > 1) ? a.L - 1 : 0;
+        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)lw * MUSZ + t];
+        if (tx) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        __syncthreads();
+        EllView<ELLS> Ein{ELLS ? reinterpret_cast<const uint4*>(smem + lay.ein) : a.ell_in + e0};
+        EllView<ELLS> Eout{ELLS ? reinterpret_cast<const uint4*>(smem + lay.eout) : a.ell_out + e0};
+        tile_backward_rk4<CE, W, ELLS>(a, tile, n0, NT, smem, lay, Ein, Eout, Mu, red);
     }
 }
 
@@ -1187,6 +1377,16 @@ int launch_bwd_t(const Args& a, int threads, cudaStream_t st) {
 }
 
 template <int CE, int W, bool ELLS>
+int launch_bwd_rk4_t(const Args& a, int threads, cudaStream_t st) {
+    int grid = 0, rc;
+    const size_t bytes = make_layout(CE, KIND_BWD_RK4, a.cap_nodes, ELLS, (threads + 31) / 32).total;
+    if ((rc = prepare_launch(k_ell_bwd_rk4<CE, W, ELLS>, threads, bytes, a.T, &grid))) return rc;
+    k_ell_bwd_rk4<CE, W, ELLS><<<grid, threads, bytes, st>>>(a);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+template <int CE, int W, bool ELLS>
 int launch_train_t(const Args& a_in, int threads, cudaStream_t st) {
     int grid = 0, rc;
     const size_t bytes = make_layout(CE, KIND_BWD, a_in.cap_nodes, ELLS, (threads + 31) / 32).total;
@@ -1218,9 +1418,11 @@ int launch_train_t(const Args& a_in, int threads, cudaStream_t st) {
     return GAD_OK;
 }
 
-// which: 0 forward, 1 backward, 2 train
+// which: 0 forward, 1 backward, 2 train, 3 backward through RK4 steps
 #define GAD_ELL_INSTANTIATE(CE_, W_)                                                                         \
     int ell_launch_c##CE_##w##W_(int which, const Args& a, int method, int ells, int threads, cudaStream_t st) { \
+        if (which == 3)                                                                                      \
+            return ells ? launch_bwd_rk4_t<CE_, W_, true>(a, threads, st) : launch_bwd_rk4_t<CE_, W_, false>(a, threads, st); \
         if (which == 0)                                                                                      \
             return ells ? launch_fwd_t<CE_, W_, true>(a, method, threads, st)                                \
                         : launch_fwd_t<CE_, W_, false>(a, method, threads, st);                              \

@@ -623,11 +623,10 @@ __device__ void f2_load(const F2Args& a, const F2Smem& s, const double* cen, con
                     for (int c = 0; c < 6; ++c)
 #pragma unroll
                         for (int sh = 16; sh > 0; sh >>= 1) g[c] += __shfl_xor_sync(0xffffffffu, g[c], sh);
-                    if (lane == 0) {
-                        const int ia = rec[d].ia, ib = rec[d].ib, ic = rec[d].ic;
-                        atomicAdd(&s.acc[2 * ia], g[0]), atomicAdd(&s.acc[2 * ia + 1], g[1]);
-                        atomicAdd(&s.acc[2 * ib], g[2]), atomicAdd(&s.acc[2 * ib + 1], g[3]);
-                        atomicAdd(&s.acc[2 * ic], g[4]), atomicAdd(&s.acc[2 * ic + 1], g[5]);
+                    if (lane < 6) {          // after the butterfly every lane holds the sums: one add per lane, in parallel
+                        const int v = lane < 2 ? rec[d].ia : (lane < 4 ? rec[d].ib : rec[d].ic);
+                        const double gv = lane == 0 ? g[0] : (lane == 1 ? g[1] : (lane == 2 ? g[2] : (lane == 3 ? g[3] : (lane == 4 ? g[4] : g[5]))));
+                        atomicAdd(&s.acc[2 * v + (lane & 1)], gv);
                     }
                 }
             }

@@ -187,6 +187,34 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
     return x_phys
 
 
+def deform_backward_rk4(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tensor, dim: int, Mu: torch.Tensor,
+                        tau: torch.Tensor, want_gx0: bool = False):
+    """Backward through classical RK4 steps (csrc/ell_kernels.cuh: k_ell_bwd_rk4), mesh-resident ELL graphs only:
+    cotangent of x_phys -> (gMu, g_x0 | None).  The step sizes get no gradient (learn_step is an Euler feature)."""
+    _need_cuda(states, g_xphys, Mu, tau)
+    lib = _lib.load()
+    L, N, CE = states.shape
+    if not (graph.tile_ptr is not None and use_ell(graph, CE)
+            and lib.gad_ell_rk4_bwd_supported(CE, graph.max_tile_nodes, graph.ell_deg)):
+        raise NotImplementedError(
+            "backward through ode_method='rk4' runs on the mesh-resident ELL kernel: meshes of at most ~1200 nodes "
+            f"(a tile keeps nine rows per node in shared memory), degree <= 7; this graph has tiles of {graph.max_tile_nodes}")
+    Lw = int(Mu.shape[0])
+    g_xphys = _f32(g_xphys)
+    dev = states.device
+    gMu = torch.empty_like(Mu)
+    g_x0 = torch.empty((N, CE), dtype=torch.float32, device=dev) if want_gx0 else None
+    ws_bytes = lib.gad_ell_workspace_bytes(CE, graph.T, L)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gad_deform_bwd_ell_rk4(
+            _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.ell_tile_ptr), graph.T,
+            graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw,
+            _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes, _stream(states)),
+            "gad_deform_bwd_ell_rk4")
+    return gMu, g_x0
+
+
 def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tensor, dim: int, Mu: torch.Tensor,
                     tau: torch.Tensor, want_gtau: bool = False, want_gx0: bool = False, force_stream: bool = False):
     """Cotangent of x_phys -> (gMu [Lw, CE*CE+CE], g_tau [L] | None, g_x0 [N, CE] | None)."""
@@ -327,15 +355,21 @@ class DeformFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_xphys):
-        if ctx.method != METHOD_EULER:
-            raise NotImplementedError("backward through ode_method='rk4' is not implemented (forward-only extension)")
         states, Mu, tau_d, Wq, bq, Wk = ctx.saved_tensors
         ni = ctx.needs_input_grad
         want_gx0 = ni[0] or ni[1] or ni[2]
         if want_gx0 and ctx.normalised:
             raise NotImplementedError("input gradients with gnn_normalize=True are not implemented")
-        gMu, g_tau, g_x0 = deform_backward(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d,
-                                           want_gtau=ni[9], want_gx0=want_gx0, force_stream=ctx.force_stream)
+        if ctx.method == METHOD_RK4:
+            if ni[9]:
+                raise NotImplementedError("learn_step with ode_method='rk4': the step sizes get no gradient through RK4")
+            if ctx.force_stream:
+                raise NotImplementedError("backward through ode_method='rk4' has no streaming variant (gad_force_stream)")
+            gMu, g_x0 = deform_backward_rk4(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d, want_gx0=want_gx0)
+            g_tau = None
+        else:
+            gMu, g_tau, g_x0 = deform_backward(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d,
+                                               want_gtau=ni[9], want_gx0=want_gx0, force_stream=ctx.force_stream)
         gWq, gbq, gWk, gbk = weight_grads(Wq.detach(), bq.detach(), Wk.detach(), gMu, ctx.CE, ctx.inv_temp)
         g_xc = g_f = g_uu = None
         if want_gx0:

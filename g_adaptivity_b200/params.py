@@ -6,7 +6,7 @@ Only the keys the deformer reads change behaviour here ("confi
 rest are carried so downstream reference code finds them.  New optional keys (default =
 reference behaviour):
 
-    ode_method        'euler' (reference, src/GNN.py:288-291) | 'rk4' (extension, forward only)
+    ode_method        'euler' (reference, src/GNN.py:288-291) | 'rk4' (extension: fused RK4 steps, forward and hand-written backward through GNN.forward)
     gad_tile_nodes    nodes per CTA tile for the mesh-resident kernels (default 1024)
     gad_force_stream  force the per-layer streaming kernels
     gad_store_alpha   keep what `conv.stored_alpha` needs after each forward (default True)

@@ -80,7 +80,8 @@ class DeformerTrainer:
         self.dim = model.dim
         self.method = GF.METHODS[opt.get("ode_method", "euler")]
         if self.method != GF.METHOD_EULER:
-            raise NotImplementedError("training through ode_method='rk4' is not implemented")
+            raise NotImplementedError("DeformerTrainer fuses the Euler step; ode_method='rk4' trains through GNN.forward + "
+                                      "autograd (hand-written RK4 backward kernel, csrc/ell_kernels.cuh: k_ell_bwd_rk4)")
         self._flatten_parameters()
         self.slots: List[_Slot] = []
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}

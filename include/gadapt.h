@@ -209,6 +209,16 @@ int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const
                        int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
                        int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,
                        float* g_x0, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward through classical RK4 steps (the forward of gad_deform_fwd_ell* with method = GAD_METHOD_RK4; the
+ * reference integrates with explicit Euler only, src/GNN.py:288-291 -- RK4 is this library's extension of the fused
+ * ODE step, north_star item 3/4): gad_deform_bwd_ell's contract without g_tau.  Only the step inputs are read from
+ * `states`; stage inputs are recomputed.  gad_ell_rk4_bwd_supported: 1 when a tile of that size fits the kernel's
+ * shared memory (nine rows per node). */
+int gad_deform_bwd_ell_rk4(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
+                           int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
+                           int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_x0,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int gad_ell_rk4_bwd_supported(int CE, int max_tile_nodes, int max_deg);
 int gad_deform_train_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                          int max_tile_nodes, int max_deg, const float* x_comp, const float* f,
                          const float* uu, const float* f_scale, const float* uu_scale, const float* target,

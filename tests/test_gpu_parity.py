@@ -417,6 +417,51 @@ def test_rk4_mesh_resident_matches_oracle():
     assert model.last_graph.tile_ptr is not None
 
 
+@pytest.mark.parametrize("mesh_dims,B,burgers,over", [
+    ((20, 20), 7, False, {"num_layers": 3}),
+    ((30, 30), 5, False, {"num_layers": 2, "share_conv": False}),          # per-step weights, cfg-2-shaped tiles
+    ((12, 12), 9, False, {"num_layers": 4, "self_loops": True, "time_step": 0.3}),
+    ((40,), 33, True, {"num_layers": 3}),                                    # 1-D, CE = 2
+])
+def test_rk4_backward_matches_autograd_through_the_oracle(mesh_dims, B, burgers, over):
+    """Hand-written backward of the fused RK4 step (north_star items 3-4; csrc/ell_kernels.cuh: k_ell_bwd_rk4):
+    parameter gradients against autograd through the oracle's RK4 (fp64 bar as everywhere else), input gradients
+    against autograd as well.  The reference integrates with Euler only; RK4 is pinned by the oracle alone."""
+    over = dict(over, ode_method="rk4")
+    model, out, ref_out, data = _compare_with_oracle(mesh_dims, B, over=over, burgers=burgers, backward=True, seed=3)
+    assert model.last_graph.tile_ptr is not None
+    # input gradients (x_comp, uu) through the same kernel
+    opt = synth.burgers_opt(mesh_dims, **over) if burgers else synth.default_opt(mesh_dims, **over)
+    ds = synth.SyntheticDataset(len(mesh_dims), mesh_dims)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    m2 = cuda_model(ds, opt, ref.state_dict())
+    d_cpu, d_gpu = data.clone(), data.clone().to("cuda")
+    for d in (d_cpu, d_gpu):
+        d.x_comp = d.x_comp.clone().requires_grad_(True)
+        d.uu_tensor = d.uu_tensor.clone().requires_grad_(True)
+    w = torch.randn(ref_out.shape, generator=torch.Generator().manual_seed(5))
+    (ref(d_cpu) * w).sum().backward()
+    (m2(d_gpu) * w.cuda()).sum().backward()
+    assert util.rel_err(d_gpu.x_comp.grad, d_cpu.x_comp.grad) <= 2e-5
+    assert util.rel_err(d_gpu.uu_tensor.grad, d_cpu.uu_tensor.grad) <= 2e-5
+
+
+def test_rk4_backward_refuses_what_it_cannot_do():
+    opt = synth.default_opt((50, 50), ode_method="rk4")          # 2500-node tiles: nine rows per node do not fit
+    ds = synth.SyntheticDataset(2, (50, 50))
+    m = cuda_model(ds, opt)
+    data = synth.make_batch((50, 50), 2)
+    out = m(data)
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()
+    opt = synth.default_opt((10, 10), ode_method="rk4", learn_step=True)
+    m = cuda_model(synth.SyntheticDataset(2, (10, 10)), opt)
+    out = m(synth.make_batch((10, 10), 2))
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()
+
+
 def test_config5_slice_50x50_batch64_fwd_bwd():
     model, *_ = _compare_with_oracle((50, 50), 64)
     assert model.last_graph.tile_ptr is not None and model.last_graph.max_tile_nodes == 2500
