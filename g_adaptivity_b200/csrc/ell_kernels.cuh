@@ -873,14 +873,30 @@ __device__ __forceinline__ bool peer_allreduce(const Args& a, float* Gs, float* 
     }
     const unsigned long long* own = s_peers[a.rank] + slot * n;   // [world][n] words of this parity, contiguous
     const unsigned long long t0 = globaltimer_ns();
+    // polls: four words per thread in flight at a time (a sys-scope load is a full L2 round trip; polling a
+    // thread's words one after the other would put world * n / nthr of them in series)
 #pragma unroll 1
-    for (int idx = tid; idx < total; idx += nthr) {
-        unsigned long long w;
+    for (int base = 0; base < total; base += 4 * nthr) {
+        int idx[4];
+        bool need[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            idx[k] = base + k * nthr + tid;
+            need[k] = idx[k] < total;
+        }
         uint32_t spins = 0;
-        while (true) {
-            w = ld_sys_u64(own + idx);
-            if ((uint32_t)(w >> 32) == seq) break;
-            if ((++spins & 255u) == 0u) {
+        while (need[0] || need[1] || need[2] || need[3]) {
+            unsigned long long w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (need[k]) w[k] = ld_sys_u64(own + idx[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (need[k] && (uint32_t)(w[k] >> 32) == seq) {
+                    V[idx[k]] = __uint_as_float((uint32_t)w[k]);
+                    need[k] = false;
+                }
+            if ((++spins & 63u) == 0u) {
                 if (*s_fail) break;
                 if (globaltimer_ns() - t0 > a.peer_timeout_ns) {
                     *s_fail = 1;
@@ -888,7 +904,6 @@ __device__ __forceinline__ bool peer_allreduce(const Args& a, float* Gs, float* 
                 }
             }
         }
-        V[idx] = __uint_as_float((uint32_t)w);
     }
     __syncthreads();
     if (*s_fail) return false;
