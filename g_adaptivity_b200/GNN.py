@@ -24,7 +24,7 @@ Options the reference supports but this path does not raise
 from __future__ import annotations
 
 import time
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 import torch
@@ -32,6 +32,7 @@ import torch.nn as nn
 
 from . import functional as GF
 from .GRAND_plus import GRAND_conv, GRAND_plusConv, inv_temperature
+from .feature_extractors import GlobalFeatureExtractorCNN
 from .graph import GraphCache, MeshGraph, corner_loops
 from .params import get_arg_list
 
@@ -99,10 +100,12 @@ class GNN(nn.Module):
             self.in_dims += [1]
         if opt["gnn_inc_feat_uu"]:
             self.in_dims += [1]
-        if opt["gnn_inc_glob_feat_f"] or opt["gnn_inc_glob_feat_uu"]:
-            raise NotImplementedError(
-                "gnn_inc_glob_feat_*: the global CNN feature extractor (src/feature_extractors.py) is a "
-                "'next' row of the scope table (SURVEY 8f3), not part of this build")
+        z_dim = sum(self.in_dims)                      # node-varying input channels: x_comp [, f] [, uu]
+        glob_f, glob_uu = bool(opt["gnn_inc_glob_feat_f"]), bool(opt["gnn_inc_glob_feat_uu"])
+        if glob_f:
+            self.in_dims += [opt["global_feat_dim"]]
+        if glob_uu:
+            self.in_dims += [opt["global_feat_dim"]]
         opt["hidden_dims_list"] = self.in_dims
 
         in_dim = sum(self.in_dims)
@@ -111,6 +114,19 @@ class GNN(nn.Module):
         self.conv_layers = build_conv_list(opt)
         self.non_lin = get_nonlin(opt["non_lin"])
         self.dec = get_dec(opt, hid_dim, self.dim, nonlin_type=opt["non_lin"])
+        # global CNN features (src/GNN.py:172-177): created after the conv layers, f before uu, as the reference does
+        # (same parameter order, same random stream)
+        if glob_f:
+            self.global_out_dim = opt["global_feat_dim"]
+            self.global_feature_extractor_cnn_f = GlobalFeatureExtractorCNN(1, hid_dim, self.global_out_dim, dim=self.dim)
+        if glob_uu:
+            self.global_out_dim = opt["global_feat_dim"]
+            self.global_feature_extractor_cnn_uu = GlobalFeatureExtractorCNN(1, hid_dim, self.global_out_dim, dim=self.dim)
+        # The identity encoder keeps the first hidden_dim input channels (src/GNN.py:84-90).  Of the global channels that
+        # survive, every mesh carries a CONSTANT vector: the state rows stay dim + f + uu wide and the global part
+        # enters the kernels as a per-mesh offset of the folded bias (include/gadapt.h: `du`).
+        self.z_dim = z_dim
+        self.n_glob_used = max(0, min(hid_dim, in_dim) - z_dim) if (glob_f or glob_uu) else 0
         if opt["learn_step"]:
             self.steps = nn.ParameterList([nn.Parameter(torch.tensor([opt["time_step"]]))
                                            for _ in range(opt["num_layers"])])
@@ -122,7 +138,7 @@ class GNN(nn.Module):
             self.quad_points = [X, Y]
 
         self._validate(opt)
-        self.live, self.CE = GF.live_channels(in_dim, hid_dim)
+        self.live, self.CE = GF.live_channels(z_dim, hid_dim)
         self.inv_temp = inv_temperature(opt) if opt["conv_type"] == "GRAND_plus" else 1.0
         self._graphs = GraphCache(capacity=int(opt.get("gad_graph_cache", 8)))
         self._tau_const = None
@@ -162,7 +178,7 @@ class GNN(nn.Module):
             return torch.diff(data.ptr).cpu().tolist()
         return torch.bincount(data.batch).cpu().tolist()
 
-    def _graph(self, data, dev, allow_uniform: bool = False) -> MeshGraph:
+    def _graph(self, data, dev, allow_uniform: bool = False, tile_nodes: Optional[int] = None) -> MeshGraph:
         """The cached result of the graph prologue (src/GNN.py:206-223) for this batch.  `allow_uniform`: the caller
         only runs the mesh-resident ELL kernels and does not read attention weights, so with
         `opt['gad_shared_topology']` (dataset on one mesh) the graph may be the shared-topology form, built for one
@@ -170,7 +186,8 @@ class GNN(nn.Module):
         opt = self.opt
         uniform_ok = bool(allow_uniform and opt.get("gad_shared_topology", False)
                           and not any(opt.get(k, False) for k in ("gad_no_ell", "gad_force_stream", "gad_no_fused_train")))
-        flags = (bool(opt["fix_boundary"]), bool(opt["self_loops"]), self.CE, str(dev), opt.get("gad_tile_nodes"),
+        tile_target = tile_nodes if tile_nodes is not None else opt.get("gad_tile_nodes")
+        flags = (bool(opt["fix_boundary"]), bool(opt["self_loops"]), self.CE, str(dev), tile_target,
                  bool(opt.get("gad_no_ell", False)), bool(opt.get("gad_no_wide", False)), bool(opt.get("gad_no_cluster", False)),
                  uniform_ok)
         key = GraphCache.key_of(data, flags)
@@ -187,7 +204,7 @@ class GNN(nn.Module):
                 return g
         if uniform_ok:
             g = MeshGraph.build_uniform(data, self._mesh_sizes(data), self.dim, opt["mesh_dims"], bool(opt["fix_boundary"]),
-                                        bool(opt["self_loops"]), dev, ce=self.CE, tile_target=opt.get("gad_tile_nodes"))
+                                        bool(opt["self_loops"]), dev, ce=self.CE, tile_target=tile_target)
             if g is not None:
                 keep = (data.edge_index, data.batch) + tuple(getattr(data, n, None) for n in GraphCache.TOPOLOGY_FIELDS)
                 self._graphs.put(key, g, keep)
@@ -211,7 +228,7 @@ class GNN(nn.Module):
             loops = corner_loops(data, self.dim, opt["mesh_dims"], sizes)
         g = MeshGraph.build(dev_copies.get("edge_index", data.edge_index), N, masks=masks, extra_loops=loops,
                             self_loops=bool(opt["self_loops"]),
-                            mesh_sizes=sizes, device=dev, ce=self.CE, tile_target=opt.get("gad_tile_nodes"),
+                            mesh_sizes=sizes, device=dev, ce=self.CE, tile_target=tile_target,
                             use_ell=not opt.get("gad_no_ell", False))
         if opt.get("gad_no_wide", False):
             g._wide_tried = True          # keep the CSR streaming kernels (csrc/stream_kernels.cu)
@@ -263,8 +280,14 @@ class GNN(nn.Module):
         opt = self.opt
         dev = self._device()
         keep_alpha = isinstance(opt.get("show_mesh_evol_plots"), bool) or opt["conv_type"] == "GRAND"
-        keep_alpha = keep_alpha and bool(opt.get("gad_store_alpha", True))
-        graph = self._graph(data, dev, allow_uniform=not keep_alpha)
+        keep_alpha = keep_alpha and bool(opt.get("gad_store_alpha", True)) and self.n_glob_used == 0
+        tile_nodes = None
+        if self.n_glob_used:
+            sizes = self._mesh_sizes(data)
+            if any(n != sizes[0] for n in sizes):
+                raise NotImplementedError("global CNN features need meshes of equal size in a batch")
+            tile_nodes = int(sizes[0])              # one mesh per tile: the bias offset is per tile
+        graph = self._graph(data, dev, allow_uniform=not keep_alpha, tile_nodes=tile_nodes)
         x_comp = data.x_comp.to(dev, non_blocking=True)
         f = data.f_tensor.to(dev, non_blocking=True) if opt["gnn_inc_feat_f"] else None
         uu = data.uu_tensor.to(dev, non_blocking=True) if opt["gnn_inc_feat_uu"] else None
@@ -277,6 +300,7 @@ class GNN(nn.Module):
         tau = self._tau(dev)
         Mu_in = self._folded_weights(dev)
         aux = {"keep_states": keep_alpha, "Mu_in": Mu_in}
+        du = self._global_bias_offsets(data, graph, f, uu, f_scale, uu_scale, dev) if self.n_glob_used else None
         method = GF.METHODS[opt.get("ode_method", "euler")]
         force_stream = bool(opt.get("gad_force_stream", False))
         if not torch.is_grad_enabled():
@@ -286,13 +310,13 @@ class GNN(nn.Module):
             states = torch.empty((L, N, self.CE), dtype=torch.float32, device=dev) if keep_alpha else None
             x_phys = GF.deform_forward_raw(graph, x_comp, f, uu, f_scale, uu_scale, self.dim, self.CE, Mu_in,
                                            GF._f32(tau.detach().reshape(-1)), method, states=states,
-                                           force_stream=force_stream)
+                                           force_stream=force_stream, du=None if du is None else du.detach().contiguous())
             aux["states"], aux["Mu"] = states, Mu_in
         else:
             Wq, bq, Wk, bk = self._weights()
             x_phys = GF.DeformFunction.apply(
                 x_comp, f, uu, f_scale, uu_scale, Wq, bq, Wk, bk, tau, graph, self.dim, self.CE, self.inv_temp,
-                method, force_stream, aux)
+                method, force_stream, aux, du)
         if keep_alpha and aux.get("states") is not None:
             states, Mu = aux["states"], aux["Mu"]
             L = opt["num_layers"]
@@ -331,6 +355,55 @@ class GNN(nn.Module):
         return x_phys
 
     # ------------------------------------------------------------------------------------
+    def _global_bias_offsets(self, data, graph, f, uu, f_scale, uu_scale, dev):
+        """Global CNN features (src/GNN.py:242-268) as the per-mesh offset of the folded bias the kernels take.
+
+        The reference appends g_b = [CNN_f(f grid) | CNN_uu(uu grid)] of mesh b to the features of each of its nodes;
+        the identity encoder keeps the first `hidden_dim` channels.  Constant channels stay constant under
+        x <- x + tau (A x - x), and in the logit  x_i^T M x_j + u^T x_j  (M = c Wq^T Wk) every term they enter is
+        constant over the in-edges of i -- it cancels in the softmax -- except  g^T M[z:, :z] z_j.  So the deformer
+        sees them as  u_b = u + M[z:z+n_g, :z]^T g_b : du [B, Lw, CE], differentiable with respect to the CNN
+        parameters (hand-written backward, csrc/glob_cnn.cu) and to Wq / Wk (a [n_g x z] matrix product per
+        weight set, left to autograd)."""
+        opt, lib_c = self.opt, GF.fold_scale(self.inv_temp, int(opt["hidden_dim"]))
+        sizes = self._mesh_sizes(data)
+        B, N1 = len(sizes), int(sizes[0])
+        gather = self.__dict__.get("_cnn_gather")
+        if gather is None or gather.numel() != N1 or gather.device != dev:
+            if self.dim == 2:
+                mapping = getattr(self.dataset, "mapping_tensor", None)
+                if opt.get("data_type") == "randg_mix":
+                    mapping = getattr(data, "mapping_tensor", mapping)
+                if mapping is None:
+                    raise ValueError("global CNN features on 2-D meshes need dataset.mapping_tensor (src/GNN.py:245)")
+                n = int(round(N1 ** 0.5))
+                # reshape_fd_tensor_to_grid (utils_data.py:125-141): gather by the mapping, reshape [n, n], transpose,
+                # flip rows -- as ONE index map applied by the kernel's load: grid[r, c] = u[mapping[c * n + n - 1 - r]]
+                r, c = torch.meshgrid(torch.arange(n), torch.arange(n), indexing="ij")
+                gather = torch.as_tensor(mapping).reshape(-1)[(c * n + (n - 1 - r)).reshape(-1)].to(dev, torch.int32)
+            else:
+                gather = torch.arange(N1, dtype=torch.int32, device=dev)
+            self.__dict__["_cnn_gather"] = gather
+        feats = []
+        if opt["gnn_inc_glob_feat_f"]:
+            src = data.f_tensor.to(dev, non_blocking=True) if f is None else f
+            if opt["gnn_inc_feat_f"] and f_scale is not None:
+                src = src / f_scale                      # the reference normalises f in place before the CNN sees it (:231-233)
+            feats.append(self.global_feature_extractor_cnn_f(src.reshape(B, N1), gather=gather))
+        if opt["gnn_inc_glob_feat_uu"]:
+            src = data.uu_tensor.to(dev, non_blocking=True) if uu is None else uu
+            if opt["gnn_inc_feat_uu"] and uu_scale is not None:
+                src = src / uu_scale
+            feats.append(self.global_feature_extractor_cnn_uu(src.reshape(B, N1), gather=gather))
+        g = torch.cat(feats, dim=1)[:, :self.n_glob_used]                 # what the encoder's truncation keeps
+        Wq, _, Wk, _ = self._weights()
+        z0, z1 = self.z_dim, self.z_dim + self.n_glob_used
+        M = lib_c * torch.matmul(Wq.transpose(1, 2), Wk)                  # [Lw, C, C], log2-domain scale of the kernels
+        du = torch.einsum("bg,lgz->blz", g, M[:, z0:z1, :self.live])      # [B, Lw, live]
+        if self.live < self.CE:
+            du = torch.nn.functional.pad(du, (0, self.CE - self.live))
+        return du.contiguous()
+
     def _fem2d_topology(self, dev, num_nodes: int):
         """Triangulation tables of `dataset.mesh` for the batched 2-D FEM kernels, built once per model.
         The reference reads `mesh.coordinates.cell_node_map().values` and `DirichletBC(V, 0, "on_boundary").nodes`
@@ -409,6 +482,8 @@ class InferenceSession:
         dev = self.dev
         if opt["gnn_normalize"]:
             raise NotImplementedError("inference_session with gnn_normalize=True is not implemented")
+        if model.n_glob_used:
+            raise NotImplementedError("inference_session with global CNN features is not implemented (call the module)")
         self.graph = model._graph(data, dev, allow_uniform=True)
         f32 = dict(dtype=torch.float32, device=dev)
         xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)

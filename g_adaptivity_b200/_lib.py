@@ -79,9 +79,9 @@ SIGNATURES = {
     "gad_ell_supported": (_i, [_i, _i, _i, _i]),
     "gad_ell_workspace_bytes": (_sz, [_i, _i, _i]),
     "gad_deform_fwd_ell": (_i, [_p, _i64, _p, _i, _i, _i, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
-    "gad_deform_fwd_ell_raw": (_i, [_p, _i64, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
-    "gad_deform_bwd_ell": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
-    "gad_deform_bwd_ell_rk4": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
+    "gad_deform_fwd_ell_raw": (_i, [_p, _i64, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "gad_deform_bwd_ell": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "gad_deform_bwd_ell_rk4": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "gad_ell_rk4_bwd_supported": (_i, [_i, _i, _i]),
     "gad_deform_train_ell": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i,
                                   _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -107,6 +107,10 @@ SIGNATURES = {
     "gad_peer_open": (_i, [_p, C.POINTER(_p)]),
     "gad_peer_close": (_i, [_p]),
     "gad_peer_free": (_i, [_p]),
+    "gad_cnn_param_count": (_i64, [_i, _i, _i, _i]),
+    "gad_cnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "gad_cnn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p, _p]),
+    "gad_cnn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p, _p, _p, _sz, _p]),
     "gad_pipeline_run": (_i, [C.POINTER(PipelineSlot), _i, C.POINTER(_p), _i, _i64, _p, _p, _p]),
 }
 

@@ -266,8 +266,8 @@ extern "C" int gad_deform_fwd_ell(const void* ell_in, int64_t N, const int32_t* 
 extern "C" int gad_deform_fwd_ell_raw(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T,
                                       int max_tile_nodes, int max_deg, const float* x_comp, const float* f,
                                       const float* uu, const float* f_scale, const float* uu_scale, int dim, int CE,
-                                      const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
-                                      float* states, void* stream) {
+                                      const float* Mu, const float* du, int Lw, const float* tau, int L, int method,
+                                      float* x_phys, float* states, void* stream) {
     GAD_CHECK_ARG(ell_in && x_comp && Mu && tau && x_phys, "gad_deform_fwd_ell_raw: null pointer");
     GAD_UNIFORM_TILES_OK("gad_deform_fwd_ell_raw");
     GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
@@ -291,6 +291,7 @@ extern "C" int gad_deform_fwd_ell_raw(const void* ell_in, int64_t N, const int32
     a.L = L;
     a.dim = dim;
     a.x0 = nullptr;          // selects the fused feature assembly
+    a.du = du;
     a.x_comp = x_comp;
     a.f = f;
     a.uu = uu;
@@ -303,8 +304,8 @@ extern "C" int gad_deform_fwd_ell_raw(const void* ell_in, int64_t N, const int32
 
 extern "C" int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                                   int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
-                                  int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,
-                                  float* g_x0, void* workspace, size_t workspace_bytes, void* stream) {
+                                  int CE, const float* Mu, const float* du, int Lw, const float* tau, int L, float* gMu,
+                                  float* g_tau, float* g_x0, void* workspace, size_t workspace_bytes, void* stream) {
     GAD_CHECK_ARG(ell_in && ell_out && states && g_xphys && Mu && tau && gMu && workspace,
                   "gad_deform_bwd_ell: null pointer");
     GAD_UNIFORM_TILES_OK("gad_deform_bwd_ell");
@@ -330,6 +331,7 @@ extern "C" int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64
     a.dim = dim;
     a.states = const_cast<float*>(states);
     a.g_xphys = g_xphys;
+    a.du = du;
     a.partials = ws;
     a.tau_partials = (g_tau && Lw == 1) ? ws + (size_t)T * L * NACC : nullptr;
     a.g_x0 = g_x0;
@@ -340,8 +342,8 @@ extern "C" int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64
 
 extern "C" int gad_deform_bwd_ell_rk4(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                                       int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
-                                      int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_x0,
-                                      void* workspace, size_t workspace_bytes, void* stream) {
+                                      int CE, const float* Mu, const float* du, int Lw, const float* tau, int L, float* gMu,
+                                      float* g_x0, void* workspace, size_t workspace_bytes, void* stream) {
     GAD_CHECK_ARG(ell_in && ell_out && states && g_xphys && Mu && tau && gMu && workspace, "gad_deform_bwd_ell_rk4: null pointer");
     GAD_UNIFORM_TILES_OK("gad_deform_bwd_ell_rk4");
     GAD_CHECK_ARG(N > 0 && T > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L),
@@ -365,6 +367,7 @@ extern "C" int gad_deform_bwd_ell_rk4(const void* ell_in, const void* ell_out, i
     a.dim = dim;
     a.states = const_cast<float*>(states);
     a.g_xphys = g_xphys;
+    a.du = du;
     a.partials = ws;
     a.tau_partials = nullptr;
     a.g_x0 = g_x0;

@@ -93,6 +93,7 @@ struct Args {
     int64_t N;
     // model
     const float* Mu;
+    const float* du;        // [T, Lw, CE] or null: per-tile offset of the folded bias u (global CNN features, GNN.py:242-268)
     const float* tau;
     int Lw, L, dim;
     // forward
@@ -236,6 +237,19 @@ __device__ __forceinline__ void tile_range(const Args& a, int tile, int& n0, int
     }
 }
 
+// Folded weights (M, u) of weight set `lw` into shared memory.  With per-mesh global features (row f3) the
+// constant channels g of a mesh act on the attention only through a shift of u:  u_mesh = u + M_gz^T g  (the other
+// terms are constant over the in-edges of a node and cancel in the softmax), handed in per tile as `du`.
+template <int CE>
+__device__ __forceinline__ void load_mu(const Args& a, float* Mu, int lw, int tile) {
+    constexpr int MUSZ = CE * CE + CE;
+    for (int t = threadIdx.x; t < MUSZ; t += blockDim.x) {
+        float v = a.Mu[(size_t)lw * MUSZ + t];
+        if (a.du && t >= CE * CE) v += a.du[((size_t)tile * a.Lw + lw) * CE + (t - CE * CE)];
+        Mu[t] = v;
+    }
+}
+
 // features = cat[x_comp, f, uu] (optionally f / max f, uu / max uu) + identity (zero-pad) encoder:
 // src/GNN.py:225-239,75-83,270.  Inputs come from the TMA staging areas (`stage`) or from global
 // memory; rows go to the shared-memory state buffer and, when `states0` is given, to states[0].
@@ -326,7 +340,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
                     if (a.uu) bulk_g2s(st_uu, uu_g, sc_bytes, bar);
                 }
             }
-            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+            load_mu<CE>(a, Mu, 0, tile);
             if (tx) {
                 mbar_wait(bar, parity);
                 parity ^= 1;
@@ -344,7 +358,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
         }
         if (!bulk_x)
             for (int i = tid; i < NT; i += nthr) sts_row<CE>(Xc, i * RB, load_row<CE>(a.x0, (int64_t)n0 + i));
-        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[t];
+        load_mu<CE>(a, Mu, 0, tile);
         if (tx) {
             mbar_wait(bar, parity);
             parity ^= 1;
@@ -355,7 +369,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_fwd(const Ar
 
         for (int l = 0; l < a.L; ++l) {
             if (a.Lw > 1 && l > 0) {
-                for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+                load_mu<CE>(a, Mu, l, tile);
                 __syncthreads();
             }
             const float h = a.tau[l];
@@ -449,7 +463,7 @@ __device__ __forceinline__ void tile_backward(const Args& a, int tile, int n0, i
 
     for (int l = a.L - 1; l >= 0; --l) {
         if (per_layer && l < a.L - 1) {
-            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+            load_mu<CE>(a, Mu, l, tile);
             __syncthreads();
         }
         const float b = a.tau[l];
@@ -564,7 +578,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd(const Ar
         // cotangent of x_phys = x^L[:, :dim]  ->  dL/dx^L (zero in the other channels)
         for (int i = tid; i < NT; i += nthr) sts_row<CE>(GS, i * RB, load_dims<CE>(a.g_xphys, (int64_t)n0 + i, a.dim));
         const int lw = (a.Lw > 1) ? a.L - 1 : 0;
-        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)lw * MUSZ + t];
+        load_mu<CE>(a, Mu, lw, tile);
         if (tx) {
             mbar_wait(bar, parity);
             parity ^= 1;
@@ -617,7 +631,7 @@ __device__ __forceinline__ void tile_backward_rk4(const Args& a, int tile, int n
     for (int l = a.L - 1; l >= 0; --l) {
         if (per_layer) {
             __syncthreads();
-            for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)l * MUSZ + t];
+            load_mu<CE>(a, Mu, l, tile);
         }
         const float h = a.tau[l];
         const float h6 = h * (1.0f / 6.0f), h3 = 2.0f * h6, h2 = 0.5f * h;
@@ -745,7 +759,7 @@ __global__ void __launch_bounds__(GAD_ELL_MAXT, GAD_ELL_MINB) k_ell_bwd_rk4(cons
         // cotangent of x_phys = x^L[:, :dim]  ->  dL/dx^L (zero in the other channels)
         for (int i = tid; i < NT; i += nthr) sts_row<CE>(G, i * RB, load_dims<CE>(a.g_xphys, (int64_t)n0 + i, a.dim));
         const int lw = (a.Lw > 1) ? a.L - 1 : 0;
-        for (int t = tid; t < MUSZ; t += nthr) Mu[t] = a.Mu[(size_t)lw * MUSZ + t];
+        load_mu<CE>(a, Mu, lw, tile);
         if (tx) {
             mbar_wait(bar, parity);
             parity ^= 1;

@@ -136,9 +136,25 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
     return x_phys
 
 
+def fold_scale(inv_temp: float, C: int) -> float:
+    """Scale of the folded logits (csrc/tail_math.cuh: fold_scale): log2(e) * inv_temp / sqrt(C)."""
+    import math
+    return math.log2(math.e) * float(inv_temp) / math.sqrt(float(C))
+
+
+def _check_du(graph: MeshGraph, du: torch.Tensor, CE: int, Lw: int, force_stream: bool):
+    """Per-tile bias offsets (global CNN features) need the mesh-resident ELL kernels with one mesh per tile."""
+    if force_stream or graph.tile_ptr is None or not use_ell(graph, CE):
+        raise NotImplementedError("global CNN features (per-mesh bias offset) run on the mesh-resident ELL kernels only")
+    if graph.mesh_sizes is None or graph.T != len(graph.mesh_sizes):
+        raise NotImplementedError("global CNN features need one mesh per tile (the module plans tiles that way)")
+    if tuple(du.shape) != (graph.T, Lw, CE) or du.dtype != torch.float32 or not du.is_contiguous():
+        raise ValueError(f"du must be a contiguous float32 [{graph.T}, {Lw}, {CE}] tensor, got {tuple(du.shape)}")
+
+
 def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: int, CE: int, Mu: torch.Tensor,
                        tau: torch.Tensor, method: int = METHOD_EULER, states: Optional[torch.Tensor] = None,
-                       force_stream: bool = False) -> torch.Tensor:
+                       force_stream: bool = False, du: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw inputs -> x_phys [N, dim]: on mesh-resident ELL graphs ONE launch (feature assembly fused
     into the forward kernel's input staging, csrc/ell_kernels.cuh); otherwise pack + forward."""
     _need_cuda(x_comp, f, uu, Mu, tau)
@@ -146,6 +162,8 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
     if x_comp.dim() == 1:
         x_comp = x_comp.unsqueeze(-1)
     N = x_comp.shape[0]
+    if du is not None:
+        _check_du(graph, du, CE, int(Mu.shape[0]), force_stream)
     if (graph.tile_ptr is None and not force_stream and not getattr(graph, "_no_cluster", False)
             and graph.ensure_cluster_fwd(CE)
             and not graph.stream_fwd_preferred(CE, int(tau.numel()) * (4 if method == METHOD_RK4 else 1))):
@@ -183,12 +201,21 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
         _lib.check(lib.gad_deform_fwd_ell_raw(
             _lib.ptr(graph.ell_in), N, _lib.ptr(graph.ell_tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
             _lib.ptr(x_comp), _lib.ptr(f), _lib.ptr(uu), _lib.ptr(f_scale), _lib.ptr(uu_scale), dim, CE, _lib.ptr(Mu),
-            Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys), _lib.ptr(states), _stream(x_comp)), "gad_deform_fwd_ell_raw")
+            _lib.ptr(du), Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys), _lib.ptr(states), _stream(x_comp)),
+            "gad_deform_fwd_ell_raw")
     return x_phys
 
 
+def _tile_bias_grads(ws: torch.Tensor, T: int, Lw: int, L: int, CE: int) -> torch.Tensor:
+    """d loss / d du [T, Lw, CE] from the backward's workspace: it begins with the per-tile partials
+    [T, slots, CE*CE + CE + 1] (include/gadapt.h), whose entries CE*CE .. CE*CE + CE - 1 are sum_i t_i of the tile."""
+    slots, nacc = (L if Lw > 1 else 1), CE * CE + CE + 1
+    part = ws[:T * slots * nacc * 4].view(torch.float32).view(T, slots, nacc)
+    return part[:, :, CE * CE:CE * CE + CE].clone()
+
+
 def deform_backward_rk4(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tensor, dim: int, Mu: torch.Tensor,
-                        tau: torch.Tensor, want_gx0: bool = False):
+                        tau: torch.Tensor, want_gx0: bool = False, du: Optional[torch.Tensor] = None):
     """Backward through classical RK4 steps (csrc/ell_kernels.cuh: k_ell_bwd_rk4), mesh-resident ELL graphs only:
     cotangent of x_phys -> (gMu, g_x0 | None).  The step sizes get no gradient (learn_step is an Euler feature)."""
     _need_cuda(states, g_xphys, Mu, tau)
@@ -209,15 +236,17 @@ def deform_backward_rk4(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.T
     with torch.cuda.device(dev):
         _lib.check(lib.gad_deform_bwd_ell_rk4(
             _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.ell_tile_ptr), graph.T,
-            graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw,
-            _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes, _stream(states)),
+            graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), _lib.ptr(du),
+            Lw, _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes, _stream(states)),
             "gad_deform_bwd_ell_rk4")
-    return gMu, g_x0
+    g_du = _tile_bias_grads(ws, graph.T, Lw, L, CE) if du is not None else None
+    return gMu, g_x0, g_du
 
 
 def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tensor, dim: int, Mu: torch.Tensor,
-                    tau: torch.Tensor, want_gtau: bool = False, want_gx0: bool = False, force_stream: bool = False):
-    """Cotangent of x_phys -> (gMu [Lw, CE*CE+CE], g_tau [L] | None, g_x0 [N, CE] | None)."""
+                    tau: torch.Tensor, want_gtau: bool = False, want_gx0: bool = False, force_stream: bool = False,
+                    du: Optional[torch.Tensor] = None):
+    """Cotangent of x_phys -> (gMu [Lw, CE*CE+CE], g_tau [L] | None, g_x0 [N, CE] | None[, g_du [T, Lw, CE]])."""
     _need_cuda(states, g_xphys, Mu, tau)
     lib = _lib.load()
     L, N, CE = states.shape
@@ -235,10 +264,14 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
         with torch.cuda.device(dev):
             _lib.check(lib.gad_deform_bwd_ell(
                 _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.ell_tile_ptr), T,
-                graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw,
-                _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes,
+                graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu),
+                _lib.ptr(du), Lw, _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes,
                 _stream(states)), "gad_deform_bwd_ell")
+        if du is not None:
+            return gMu, g_tau, g_x0, _tile_bias_grads(ws, T, Lw, L, CE)
         return gMu, g_tau, g_x0
+    if du is not None:
+        raise NotImplementedError("global CNN features (per-mesh bias offset) run on the mesh-resident ELL kernels only")
     if (graph.tile_ptr is None and not force_stream and not getattr(graph, "_no_cluster", False)
             and graph.ensure_cluster(CE)):
         # meshes beyond one CTA (up to 4 slabs): cluster-resident backward, one launch + the reduction
@@ -330,7 +363,7 @@ class DeformFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_comp, f, uu, f_scale, uu_scale, Wq, bq, Wk, bk, tau, graph, dim, CE, inv_temp, method,
-                force_stream, aux):
+                force_stream, aux, du=None):
         L = int(tau.numel())
         N = x_comp.shape[0]
         needs = any(ctx.needs_input_grad)
@@ -342,20 +375,24 @@ class DeformFunction(torch.autograd.Function):
         states = torch.empty((L, N, CE), dtype=torch.float32, device=x_comp.device) if (needs or keep_states) else None
         x_phys = deform_forward_raw(graph, x_comp.detach(), None if f is None else f.detach(),
                                     None if uu is None else uu.detach(), f_scale, uu_scale, dim, CE, Mu, tau_d, method,
-                                    states=states, force_stream=force_stream)
+                                    states=states, force_stream=force_stream,
+                                    du=None if du is None else du.detach().float().contiguous())
         ctx.method = method
+        ctx.has_du = du is not None
         ctx.graph, ctx.dim, ctx.CE, ctx.inv_temp, ctx.force_stream = graph, dim, CE, inv_temp, force_stream
         ctx.has_f, ctx.has_uu = f is not None, uu is not None
         ctx.normalised = (f_scale is not None) or (uu_scale is not None)
         if needs:
-            ctx.save_for_backward(states, Mu, tau_d, Wq, bq, Wk)
+            ctx.save_for_backward(states, Mu, tau_d, Wq, bq, Wk, *([du.detach().float().contiguous()] if du is not None else []))
         if aux is not None:   # side channel for the lazy attention read-out (conv.stored_alpha)
             aux["states"], aux["Mu"] = (states if keep_states else None), Mu
         return x_phys
 
     @staticmethod
     def backward(ctx, g_xphys):
-        states, Mu, tau_d, Wq, bq, Wk = ctx.saved_tensors
+        states, Mu, tau_d, Wq, bq, Wk = ctx.saved_tensors[:6]
+        du = ctx.saved_tensors[6] if ctx.has_du else None
+        g_du = None
         ni = ctx.needs_input_grad
         want_gx0 = ni[0] or ni[1] or ni[2]
         if want_gx0 and ctx.normalised:
@@ -365,11 +402,14 @@ class DeformFunction(torch.autograd.Function):
                 raise NotImplementedError("learn_step with ode_method='rk4': the step sizes get no gradient through RK4")
             if ctx.force_stream:
                 raise NotImplementedError("backward through ode_method='rk4' has no streaming variant (gad_force_stream)")
-            gMu, g_x0 = deform_backward_rk4(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d, want_gx0=want_gx0)
+            gMu, g_x0, g_du = deform_backward_rk4(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d,
+                                                  want_gx0=want_gx0, du=du)
             g_tau = None
         else:
-            gMu, g_tau, g_x0 = deform_backward(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d,
-                                               want_gtau=ni[9], want_gx0=want_gx0, force_stream=ctx.force_stream)
+            res = deform_backward(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d,
+                                  want_gtau=ni[9], want_gx0=want_gx0, force_stream=ctx.force_stream, du=du)
+            gMu, g_tau, g_x0 = res[:3]
+            g_du = res[3] if du is not None else None
         gWq, gbq, gWk, gbk = weight_grads(Wq.detach(), bq.detach(), Wk.detach(), gMu, ctx.CE, ctx.inv_temp)
         g_xc = g_f = g_uu = None
         if want_gx0:
@@ -385,7 +425,7 @@ class DeformFunction(torch.autograd.Function):
         return (g_xc, g_f, g_uu, None, None, gWq if ni[5] else None, gbq if ni[6] else None,
                 gWk if ni[7] else None, gbk if ni[8] else None,
                 g_tau.view_as(tau_d) if (ni[9] and g_tau is not None) else None,
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, g_du)
 
 
 class ConvFunction(torch.autograd.Function):

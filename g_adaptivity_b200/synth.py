@@ -137,6 +137,11 @@ class SyntheticDataset:
             topo = MeshTopology(mesh_dims)
             self.mesh = SyntheticMesh(topo.cells, np.nonzero(topo.boundary_nodes)[0])
             self.x_comp_shared = torch.from_numpy(topo.coords.copy())
+            # canonical-grid -> mesh-node map of the n x n mesh itself (map_firedrake_to_cannonical_ordering_2d,
+            # utils_data.py:53-77; read by the global CNN features, src/GNN.py:245)
+            n = int(mesh_dims[0])
+            i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+            self.mapping_tensor = torch.from_numpy((j * n + i).reshape(-1).astype(np.int64))
             if eval_quad_points is not None:
                 Q = int(eval_quad_points)
                 # canonical index c = i * Q + j is the grid point (x_i, y_j) (torch.meshgrid 'ij', :60-62,71);

@@ -60,6 +60,9 @@ class DeformerTrainer:
                 f"DeformerTrainer fuses the mesh loss (loss_type='mesh_loss', src/run_GNN.py:105-107); opt['loss_type']="
                 f"{opt['loss_type']!r} trains through GNN.forward + autograd instead.  Pass loss_fn='l1' / 'mse' explicitly "
                 "to train the mesh loss on such a preset")
+        if getattr(model, "n_glob_used", 0) or opt.get("gnn_inc_glob_feat_f") or opt.get("gnn_inc_glob_feat_uu"):
+            raise NotImplementedError("DeformerTrainer: global CNN features are trained through GNN.forward + autograd "
+                                      "(the fused step does not update the CNN's parameters)")
         if opt.get("gnn_normalize", False):
             raise NotImplementedError("DeformerTrainer: gnn_normalize=True (per-batch f / max f, src/GNN.py:231-237) is "
                                       "only implemented on the GNN.forward path")

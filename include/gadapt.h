@@ -181,6 +181,15 @@ int gad_deform_bwd_wide(const void* wide_in, const void* wide_out, int64_t N, in
  * with the cotangent grad_scale * d(sum)/d(out).  `states` [L, N, CE] is scratch (layer inputs),
  * x_phys [N, dim] is optional.  workspace: gad_ell_workspace_bytes(CE, T, L).
  *
+ * PER-TILE BIAS OFFSET `du` [T, Lw, CE] (gad_deform_fwd_ell_raw, gad_deform_bwd_ell, gad_deform_bwd_ell_rk4; NULL =
+ * none): added to the folded bias u of every node of the tile.  This is all the global CNN features of the
+ * reference (src/GNN.py:242-268: a per-mesh constant vector appended to every node's features) do to the deformer:
+ * constant channels stay constant under A(x) x - x, and in the logits x_i^T M x_j + u^T x_j every term they enter is
+ * constant over the in-edges of i -- and cancels in the softmax -- except g^T M_gz z_j, a shift of u by M_gz^T g.
+ * One mesh per tile is required (the caller plans tiles that way).  d loss / d du is read from the backward's
+ * workspace, which begins with the per-tile partials [T, slots, CE*CE + CE + 1] (slots = L if Lw > 1 else 1):
+ * entries CE*CE .. CE*CE + CE - 1 of a row are sum_i t_i = d loss / d u restricted to the tile.
+ *
  * SHARED TOPOLOGY (tile_ptr == NULL, in every gad_*_ell entry point and in gad_train_desc): the batch is
  * T = ceil(N / max_tile_nodes) equal tiles of max_tile_nodes nodes (the last one may be shorter) and ell_in /
  * ell_out hold the rows of ONE tile (max_tile_nodes x 8 uint16), used by every tile.  This is the batch the
@@ -203,12 +212,12 @@ int gad_deform_fwd_ell(const void* ell_in, int64_t N, const int32_t* tile_ptr, i
 int gad_deform_fwd_ell_raw(const void* ell_in, int64_t N, const int32_t* tile_ptr, int T, int max_tile_nodes,
                            int max_deg, const float* x_comp, const float* f, const float* uu,
                            const float* f_scale, const float* uu_scale, int dim, int CE, const float* Mu,
-                           int Lw, const float* tau, int L, int method, float* x_phys, float* states,
-                           void* stream);
+                           const float* du, int Lw, const float* tau, int L, int method, float* x_phys,
+                           float* states, void* stream);
 int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                        int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
-                       int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_tau,
-                       float* g_x0, void* workspace, size_t workspace_bytes, void* stream);
+                       int CE, const float* Mu, const float* du, int Lw, const float* tau, int L, float* gMu,
+                       float* g_tau, float* g_x0, void* workspace, size_t workspace_bytes, void* stream);
 /* Backward through classical RK4 steps (the forward of gad_deform_fwd_ell* with method = GAD_METHOD_RK4; the
  * reference integrates with explicit Euler only, src/GNN.py:288-291 -- RK4 is this library's extension of the fused
  * ODE step, north_star item 3/4): gad_deform_bwd_ell's contract without g_tau.  Only the step inputs are read from
@@ -216,8 +225,8 @@ int gad_deform_bwd_ell(const void* ell_in, const void* ell_out, int64_t N, const
  * shared memory (nine rows per node). */
 int gad_deform_bwd_ell_rk4(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                            int max_tile_nodes, int max_deg, const float* states, const float* g_xphys, int dim,
-                           int CE, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_x0,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           int CE, const float* Mu, const float* du, int Lw, const float* tau, int L, float* gMu,
+                           float* g_x0, void* workspace, size_t workspace_bytes, void* stream);
 int gad_ell_rk4_bwd_supported(int CE, int max_tile_nodes, int max_deg);
 int gad_deform_train_ell(const void* ell_in, const void* ell_out, int64_t N, const int32_t* tile_ptr, int T,
                          int max_tile_nodes, int max_deg, const float* x_comp, const float* f,
@@ -414,6 +423,25 @@ int gad_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out);
 int gad_peer_open(const void* handle, void** dev_ptr);
 int gad_peer_close(void* dev_ptr);
 int gad_peer_free(void* dev_ptr);
+
+/* ---- global CNN feature extractor (scope row f3) ----------------------------------------------------
+ * GlobalFeatureExtractorCNN of src/feature_extractors.py:6-34 (wired at src/GNN.py:242-268):
+ *     u / max|u|  ->  L x [conv kernel 3, stride 1, padding 1 + SELU]  ->  global average pool  ->  [B, Co]
+ * on the H x W grid of one mesh's nodal values (Conv2d; H = 1: Conv1d over the W nodes of a 1-D mesh), one CTA per
+ * mesh, all activation planes in shared memory.  u [B, H*W] mesh-major; `gather` [H*W] (or NULL) gives the node
+ * whose value sits in grid cell y * W + x (the reordering of reshape_fd_tensor_to_grid, src/utils_data.py:125-141);
+ * `scale` is one device float, max|u| over the batch.  weights / biases: HOST arrays of L device pointers in
+ * torch's Conv layout [C_out, C_in, (3,) 3]: layer 0 is 1 -> Cm, layers 1 .. L-2 Cm -> Cm, layer L-1 Cm -> Co.
+ * Backward: g_out [B, Co] -> g_params, flat in the order w_0, b_0, w_1, b_1, ... (gad_cnn_param_count entries);
+ * the forward is recomputed, per-mesh parts are summed over the batch in fp64 in a fixed order (workspace of
+ * gad_cnn_workspace_bytes).  The grid values get no gradient.  Limits: L <= 8, channels <= 16, planes in 227 KB. */
+int64_t gad_cnn_param_count(int H, int Cm, int Co, int L);
+size_t gad_cnn_workspace_bytes(int B, int H, int Cm, int Co, int L);
+int gad_cnn_fwd(const float* u, const int32_t* gather, const float* scale, int B, int H, int W, int Cm, int Co, int L,
+                const float* const* weights, const float* const* biases, float* out, void* stream);
+int gad_cnn_bwd(const float* u, const int32_t* gather, const float* scale, int B, int H, int W, int Cm, int Co, int L,
+                const float* const* weights, const float* const* biases, const float* g_out, float* g_params,
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- host side of the end-to-end training loop ------------------------------------------------------
  * The reference's `for data in loader: ... loss.backward(); optimizer.step()` (src/run_GNN.py:95-131) with

@@ -194,6 +194,23 @@ def identity_encoder(in_dim: int, out_dim: int) -> nn.Linear:
     return lin
 
 
+class GlobalCNNRef(nn.Module):
+    """`GlobalFeatureExtractorCNN` (`src/feature_extractors.py:6-34`): same sub-modules, forward by the restatement
+    in oracle/cnn_oracle.py."""
+
+    def __init__(self, in_channels, mid_channels, out_channels, dim=2, num_layers=4):
+        super().__init__()
+        conv = nn.Conv1d if dim == 1 else nn.Conv2d
+        self.convs = nn.ModuleList([conv(in_channels, mid_channels, kernel_size=3, stride=1, padding=1)])
+        for _ in range(num_layers - 2):
+            self.convs.append(conv(mid_channels, mid_channels, kernel_size=3, stride=1, padding=1))
+        self.convs.append(conv(mid_channels, out_channels, kernel_size=3, stride=1, padding=1))
+
+    def forward(self, u):
+        from oracle import cnn_oracle
+        return cnn_oracle.cnn_features(u, [c.weight for c in self.convs], [c.bias for c in self.convs])
+
+
 class GNNRef(nn.Module):
     """`GNN` (`src/GNN.py:144-306`) for the in-scope option set."""
 
@@ -207,8 +224,10 @@ class GNNRef(nn.Module):
             self.in_dims += [1]
         if opt["gnn_inc_feat_uu"]:
             self.in_dims += [1]
-        if opt["gnn_inc_glob_feat_f"] or opt["gnn_inc_glob_feat_uu"]:
-            raise NotImplementedError("global CNN features are off the hot path (SURVEY 8f3)")
+        if opt["gnn_inc_glob_feat_f"]:
+            self.in_dims += [opt["global_feat_dim"]]                 # :156-157
+        if opt["gnn_inc_glob_feat_uu"]:
+            self.in_dims += [opt["global_feat_dim"]]                 # :158-159
         opt["hidden_dims_list"] = self.in_dims                       # :161
         in_dim, hid = sum(self.in_dims), opt["hidden_dim"]
         if opt["enc"] != "identity":
@@ -226,10 +245,43 @@ class GNNRef(nn.Module):
         else:
             self.non_lin = nn.Identity()
         self.dec = nn.Identity()                                     # :170
+        if opt["gnn_inc_glob_feat_f"]:                               # :172-174
+            self.global_feature_extractor_cnn_f = GlobalCNNRef(1, hid, opt["global_feat_dim"], dim=self.dim)
+        if opt["gnn_inc_glob_feat_uu"]:                              # :175-177
+            self.global_feature_extractor_cnn_uu = GlobalCNNRef(1, hid, opt["global_feat_dim"], dim=self.dim)
         if opt["learn_step"]:                                        # :179-180
             self.steps = nn.ParameterList([nn.Parameter(torch.tensor([opt["time_step"]]))
                                            for _ in range(opt["num_layers"])])
         self.end_MLmodel = None
+
+    def _append_global_features(self, data, features):
+        """`src/GNN.py:242-268`: per mesh, the CNN features of the f / uu grid, repeated onto the mesh's nodes and
+        appended.  REFERENCE QUIRK: for `data_type != 'randg_mix'` the reference reshapes to
+        `[num_nodes, num_nodes]` with `num_nodes = dataset.x_comp_shared.shape[0]` (the NODE count, :244-245), which
+        cannot be reshaped to and raises for every 2-D batch; its `randg_mix` branch uses
+        `int(sqrt(data.x_comp.shape[0]))` (:247), the side length only for a batch of one.  The intended grid -- one
+        n x n image per mesh, what that branch computes for a single mesh -- is what is restated here; the 1-D
+        branch (`reshape(batch_size, -1)`, utils_data.py:126-129) is followed as written."""
+        opt = self.opt
+        if not (opt["gnn_inc_glob_feat_f"] or opt["gnn_inc_glob_feat_uu"]):
+            return features
+        from oracle import cnn_oracle
+        batch = data.batch
+        B = int(batch.max().item()) + 1
+        repeats = torch.bincount(batch)
+        n = int(round((data.x_comp.shape[0] // B) ** 0.5)) if self.dim == 2 else data.x_comp.shape[0] // B
+        mapping = getattr(self.dataset, "mapping_tensor", None)
+        for name, on, field, inc in (("f", opt["gnn_inc_glob_feat_f"], data.f_tensor, opt["gnn_inc_feat_f"]),
+                                     ("uu", opt["gnn_inc_glob_feat_uu"], data.uu_tensor, opt["gnn_inc_feat_uu"])):
+            if not on:
+                continue
+            if inc and opt["gnn_normalize"]:
+                field = field / torch.max(field)                     # f / uu were normalised in place above (:231-237)
+            grid = cnn_oracle.reshape_fd_tensor_to_grid(field, mapping, [n, n], B, self.dim)
+            g = getattr(self, f"global_feature_extractor_cnn_{name}")(grid.unsqueeze(1))
+            # (.float() in the reference, :253,266; the input dtype here so that the fp64 cross-checks can run)
+            features = torch.cat([features, g.repeat_interleave(repeats, dim=0)], dim=-1).to(features.dtype)
+        return features
 
     def _vector_field(self, layer, x, edge_index, features):
         if self.opt["conv_type"] == "GRAND_plus":
@@ -246,6 +298,7 @@ class GNNRef(nn.Module):
             raise NotImplementedError("residual=False is only meaningful for non-GRAND convs")
         edge_index = filtered_edge_index(data, opt, self.dim)        # :194,206-223
         features = assemble_features(data, opt, self.dim)            # :225-239
+        features = self._append_global_features(data, features)      # :242-268
         x = self.enc(features)                                       # :270
         x = F.dropout(x, opt["dropout"], training=self.training)     # :271
         states = [x]

@@ -5,8 +5,8 @@ torch_scatter, Firedrake, torchquad, wandb, matplotlib.  This loader
   * puts `oracle/ref_harness/shim` (torch_geometric / torch_scatter stand-ins built on
     `oracle/pyg_semantics.py`) in front of `sys.path`;
   * registers empty stand-ins for the modules that are imported but never reached on the hot
-    path: `firedrake_difFEM.difFEM_1d/_2d` (pde_loss tail), `feature_extractors` (global CNN),
-    `utils_data` (grid reshapes for the CNN);
+    path: `firedrake_difFEM.difFEM_1d/_2d` (pde_loss tail), `wandb`, `matplotlib`; `feature_extractors`
+    (global CNN) and `utils_data` (grid reshapes for the CNN) are the reference's real modules;
   * imports `params`, `GRAND_plus`, `GNN` from the read-only reference tree.
 Nothing is copied: the reference source is executed where it lies.  Only usable where
 /root/reference exists (this container, not the GPU box)."""
@@ -55,12 +55,20 @@ def load():
     pkg.__path__ = []
     _stub("firedrake_difFEM.difFEM_1d", torch_FEM_1D=_unreachable("torch_FEM_1D"))
     _stub("firedrake_difFEM.difFEM_2d", torch_FEM_2D=_unreachable("torch_FEM_2D"))
-    _stub("feature_extractors", GlobalFeatureExtractorGNN=_unreachable("GlobalFeatureExtractorGNN"),
-          GlobalFeatureExtractorCNN=_unreachable("GlobalFeatureExtractorCNN"))
-    _stub("utils_data", reshape_grid_to_fd_tensor=_unreachable("reshape_grid_to_fd_tensor"),
-          reshape_fd_tensor_to_grid=_unreachable("reshape_fd_tensor_to_grid"))
+    # feature_extractors.py (global CNN, row f3) and utils_data.py (grid reorderings) are the reference's REAL
+    # modules: plain torch once wandb / matplotlib (imported at the top of utils_data.py, unused on this path) answer
+    for name in ("wandb", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            _stub(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     import importlib
+    for name in ("feature_extractors", "utils_data"):
+        sys.modules.pop(name, None)
     params = importlib.import_module("params")
+    fe = importlib.import_module("feature_extractors")
+    ud = importlib.import_module("utils_data")
+    assert os.path.realpath(fe.__file__).startswith("/root/reference/"), fe.__file__
+    assert os.path.realpath(ud.__file__).startswith("/root/reference/"), ud.__file__
     grand = importlib.import_module("GRAND_plus")
     gnn = importlib.import_module("GNN")
     assert os.path.realpath(gnn.__file__).startswith("/root/reference/"), gnn.__file__

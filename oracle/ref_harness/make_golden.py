@@ -53,6 +53,18 @@ CASES = [
 ]
 
 
+# global CNN features (row f3) through the reference's own forward: 1-D only -- the reference's 2-D branch reshapes to
+# [num_nodes, num_nodes] with num_nodes = the NODE count (src/GNN.py:244-245) and raises for every 2-D batch.
+# Written to tests/golden_glob/ (own test file: these cases have no streaming / attention read-out variants).
+GLOB_DIR = os.path.join(_REPO, "tests", "golden_glob")
+GLOB_CASES = [
+    ("globfeat_1d_15x3", [[15]] * 3, {"gnn_inc_glob_feat_f": True, "gnn_inc_glob_feat_uu": True}, {}),
+    ("globfeat_f_1d_21x2_hidden16", [[21]] * 2, {"gnn_inc_glob_feat_f": True, "hidden_dim": 16}, {}),
+    ("globfeat_uu_1d_12x4_noshare", [[12]] * 4, {"gnn_inc_glob_feat_uu": True, "share_conv": False, "num_layers": 3,
+                                                  "gnn_inc_feat_f": False}, {}),
+]
+
+
 def build_inputs(mesh_dims_list, burgers: bool, seed: int):
     if len({tuple(m) for m in mesh_dims_list}) == 1:
         return synth.make_batch(mesh_dims_list[0], len(mesh_dims_list), seed=seed, burgers=burgers)
@@ -70,6 +82,8 @@ def run_case(gnn_mod, name, mesh_dims_list, overrides, extras, seed=0):
     data = build_inputs(mesh_dims_list, burgers, seed)
     dim = len(mesh_dims_list[0])
     dataset = synth.SyntheticDataset(dim, mesh_dims_list[0])
+    if dataset.x_comp_shared is None:        # read for its length by the global-feature branch (src/GNN.py:244)
+        dataset.x_comp_shared = synth.make_batch(mesh_dims_list[0], 1).x_comp
     torch.manual_seed(opt["seed"])
     with load_reference.quiet():
         model = gnn_mod.GNN(dataset, opt)
@@ -115,9 +129,12 @@ def run_case(gnn_mod, name, mesh_dims_list, overrides, extras, seed=0):
 def main():
     gnn_mod, grand_mod, params_mod = load_reference.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for name, mesh_dims_list, overrides, extras in CASES:
+    only_glob = "--glob-only" in sys.argv
+    os.makedirs(GLOB_DIR, exist_ok=True)
+    todo = ([] if only_glob else [(GOLDEN_DIR, c) for c in CASES]) + [(GLOB_DIR, c) for c in GLOB_CASES]
+    for out_dir, (name, mesh_dims_list, overrides, extras) in todo:
         fx = run_case(gnn_mod, name, mesh_dims_list, overrides, extras)
-        path = os.path.join(GOLDEN_DIR, name + ".pt")
+        path = os.path.join(out_dir, name + ".pt")
         torch.save(fx, path)
         print(f"{name:24s} N={fx['x_phys'].shape[0]:5d} E={fx['edge_index_filtered'].shape[1]:6d} "
               f"loss={fx['loss']:.6e} grads={sorted(fx['grads'])[:2]}.. -> {os.path.relpath(path, _REPO)}")

@@ -116,7 +116,7 @@ def test_model_surface_matches_reference_contract():
 @pytest.mark.parametrize("over,exc", [
     ({"conv_type": "GCN"}, NotImplementedError), ({"conv_type": "GAT_plus"}, NotImplementedError),
     ({"enc": "lin_layer"}, NotImplementedError), ({"dropout": 0.5}, NotImplementedError),
-    ({"gnn_inc_glob_feat_f": True}, NotImplementedError), ({"loss_type": "pde_loss", "data_type": "randg_mix"}, NotImplementedError),
+    ({"loss_type": "pde_loss", "data_type": "randg_mix"}, NotImplementedError),
     ({"reg_skew": True}, NotImplementedError), ({"softmax_temp_type": "learnable_a"}, NotImplementedError),
     ({"residual": False}, NotImplementedError), ({"ode_method": "dopri5"}, ValueError),
 ])
@@ -124,6 +124,22 @@ def test_unsupported_options_raise(over, exc):
     opt = synth.default_opt((6, 6), **over)
     with pytest.raises(exc):
         gad.GNN(synth.SyntheticDataset(2, (6, 6)), opt)
+
+
+def test_global_feature_models_construct_like_the_reference():
+    """gnn_inc_glob_feat_* (on by CLI default, params.py:259-260): the two CNNs exist under the reference's names,
+    in_dims grows by global_feat_dim each, the state rows stay as wide as the node-varying inputs."""
+    opt = synth.default_opt((6, 6), gnn_inc_glob_feat_f=True, gnn_inc_glob_feat_uu=True)
+    m = gad.GNN(synth.SyntheticDataset(2, (6, 6)), opt)
+    assert m.in_dims == [2, 1, 1, 8, 8] and opt["hidden_dims_list"] == [2, 1, 1, 8, 8]
+    keys = set(m.state_dict().keys())
+    for which in ("f", "uu"):
+        for i in range(4):
+            assert f"global_feature_extractor_cnn_{which}.convs.{i}.weight" in keys
+    assert m.enc.weight.shape == (8, 20) and m.CE == 4 and m.n_glob_used == 4
+    assert m.global_feature_extractor_cnn_f.convs[0].weight.shape == (8, 1, 3, 3)
+    m1 = gad.GNN(synth.SyntheticDataset(1, (9,)), synth.default_opt((9,), gnn_inc_glob_feat_uu=True))
+    assert m1.global_feature_extractor_cnn_uu.convs[1].weight.shape == (8, 8, 3) and m1.n_glob_used == 5
 
 
 def test_params_mirror_defaults_and_presets():
