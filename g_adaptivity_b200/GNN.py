@@ -365,7 +365,8 @@ class GNN(nn.Module):
         sees them as  u_b = u + M[z:z+n_g, :z]^T g_b : du [B, Lw, CE], differentiable with respect to the CNN
         parameters (hand-written backward, csrc/glob_cnn.cu) and to Wq / Wk (a [n_g x z] matrix product per
         weight set, left to autograd)."""
-        opt, lib_c = self.opt, GF.fold_scale(self.inv_temp, int(opt["hidden_dim"]))
+        opt = self.opt
+        lib_c = GF.fold_scale(self.inv_temp, int(opt["hidden_dim"]))
         sizes = self._mesh_sizes(data)
         B, N1 = len(sizes), int(sizes[0])
         gather = self.__dict__.get("_cnn_gather")

@@ -34,6 +34,8 @@ struct CnnArgs {
     float* out;              // [B, Co]
     const float* g_out;      // [B, Co]             (backward)
     float* g_part;           // [B, n_params]       (backward: per-mesh parameter gradients)
+    float* act_global;       // [B, L, Cmax, H*W] or null: activation planes in global memory (L2) when they do not
+                             // fit the shared memory next to the other buffers
     int B, H, W, Cm, Co, L, KH;
     int n_params;
 };
@@ -51,12 +53,14 @@ __host__ __device__ inline int cnn_param_offset(const CnnArgs& a, int l) {      
 }
 __host__ __device__ inline int cnn_cmax(const CnnArgs& a) { return a.Cm > a.Co ? a.Cm : a.Co; }
 
-// shared memory: input plane [HW] | L activation planes [Cmax * HW] | (backward) two gradient planes | weights | bias
-__host__ __device__ inline size_t cnn_smem_bytes(const CnnArgs& a, bool backward) {
+// shared memory: input plane [HW] | L activation planes [Cmax * HW] (unless in global memory) | (backward) two
+// gradient planes | weights | bias
+__host__ __device__ inline size_t cnn_smem_bytes(const CnnArgs& a, bool backward, bool act_in_smem) {
     const size_t HW = (size_t)a.H * a.W, C = cnn_cmax(a);
-    size_t fl = HW + (size_t)a.L * C * HW + (backward ? 2 * C * HW : 0) + C * C * a.KH * 3 + C + 64;
+    size_t fl = HW + (act_in_smem ? (size_t)a.L * C * HW : 0) + (backward ? 2 * C * HW : 0) + C * C * a.KH * 3 + C + 64;
     return fl * sizeof(float);
 }
+__host__ __device__ inline size_t cnn_act_floats(const CnnArgs& a) { return (size_t)a.L * cnn_cmax(a) * a.H * a.W; }
 
 // layers 0 .. L-1 into the activation planes (all threads; ends with a barrier)
 __device__ void cnn_forward_planes(const CnnArgs& a, int mesh, float* in, float* act, float* wsm, float* bsm) {
@@ -111,11 +115,11 @@ __device__ __forceinline__ float cnn_warp_plane_sum(const float* plane, int HW, 
 __global__ void __launch_bounds__(CNN_THREADS) k_cnn_fwd(const CnnArgs a) {
     extern __shared__ __align__(16) float cnn_sm[];
     const int HW = a.H * a.W, C = cnn_cmax(a);
-    float* in = cnn_sm;
-    float* act = in + HW;
-    float* wsm = act + (size_t)a.L * C * HW;
-    float* bsm = wsm + C * C * a.KH * 3;
     const int mesh = blockIdx.x;
+    float* in = cnn_sm;
+    float* act = a.act_global ? a.act_global + (size_t)mesh * cnn_act_floats(a) : in + HW;
+    float* wsm = in + HW + (a.act_global ? 0 : cnn_act_floats(a));
+    float* bsm = wsm + C * C * a.KH * 3;
     cnn_forward_planes(a, mesh, in, act, wsm, bsm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const float* last = act + (size_t)(a.L - 1) * C * HW;
@@ -128,13 +132,13 @@ __global__ void __launch_bounds__(CNN_THREADS) k_cnn_fwd(const CnnArgs a) {
 __global__ void __launch_bounds__(CNN_THREADS) k_cnn_bwd(const CnnArgs a) {
     extern __shared__ __align__(16) float cnn_sm[];
     const int HW = a.H * a.W, C = cnn_cmax(a), KH = a.KH, tid = threadIdx.x, nthr = blockDim.x;
+    const int mesh = blockIdx.x;
     float* in = cnn_sm;
-    float* act = in + HW;
-    float* gA = act + (size_t)a.L * C * HW;
+    float* act = a.act_global ? a.act_global + (size_t)mesh * cnn_act_floats(a) : in + HW;
+    float* gA = in + HW + (a.act_global ? 0 : cnn_act_floats(a));
     float* gB = gA + (size_t)C * HW;
     float* wsm = gB + (size_t)C * HW;
     float* bsm = wsm + C * C * KH * 3;
-    const int mesh = blockIdx.x;
     cnn_forward_planes(a, mesh, in, act, wsm, bsm);
     float* gpart = a.g_part + (size_t)mesh * a.n_params;
     // d(mean over pixels) -> last layer's pre-activation gradient
@@ -246,20 +250,39 @@ extern "C" int64_t gad_cnn_param_count(int H, int Cm, int Co, int L) {
     return cnn_param_offset(a, L);
 }
 
-extern "C" size_t gad_cnn_workspace_bytes(int B, int H, int Cm, int Co, int L) {
-    return (size_t)B * (size_t)gad_cnn_param_count(H, Cm, Co, L) * sizeof(float);
+// workspace: [B, n_params] per-mesh parameter gradients (backward), then -- when the activation planes do not fit the
+// shared memory -- [B, L, Cmax, H*W] activations
+static size_t cnn_plan(CnnArgs& a, bool backward, bool* act_in_smem) {
+    *act_in_smem = (int)cnn_smem_bytes(a, backward, true) <= smem_optin_bytes();
+    return cnn_smem_bytes(a, backward, *act_in_smem);
+}
+
+extern "C" size_t gad_cnn_workspace_bytes(int B, int H, int W, int Cm, int Co, int L) {
+    CnnArgs a{};
+    a.B = B, a.H = H, a.W = W, a.Cm = Cm, a.Co = Co, a.L = L, a.KH = (H == 1) ? 1 : 3;
+    bool in_smem;
+    cnn_plan(a, true, &in_smem);
+    const size_t grads = (size_t)B * (size_t)gad_cnn_param_count(H, Cm, Co, L) * sizeof(float);
+    return ((grads + 255) & ~(size_t)255) + (in_smem ? 0 : (size_t)B * cnn_act_floats(a) * sizeof(float)) + 256;
 }
 
 extern "C" int gad_cnn_fwd(const float* u, const int32_t* gather, const float* scale, int B, int H, int W, int Cm, int Co,
-                           int L, const float* const* weights, const float* const* biases, float* out, void* stream) {
+                           int L, const float* const* weights, const float* const* biases, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
     CnnArgs a{};
     int rc = cnn_fill(a, u, gather, scale, B, H, W, Cm, Co, L, weights, biases);
     if (rc) return rc;
     GAD_CHECK_ARG(out, "gad_cnn_fwd: null output");
     a.out = out;
-    const size_t bytes = cnn_smem_bytes(a, false);
-    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "gad_cnn_fwd: a %d x %d grid with %d layers of %d channels needs %zu B of "
-                                                    "shared memory (> %d)", H, W, L, cnn_cmax(a), bytes, smem_optin_bytes());
+    bool in_smem;
+    const size_t bytes = cnn_plan(a, false, &in_smem);
+    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "gad_cnn_fwd: a %d x %d grid with %d channels needs %zu B of shared "
+                                                    "memory (> %d)", H, W, cnn_cmax(a), bytes, smem_optin_bytes());
+    if (!in_smem) {
+        GAD_CHECK_ARG(workspace && workspace_bytes >= (size_t)B * cnn_act_floats(a) * sizeof(float),
+                      "gad_cnn_fwd: the activation planes need a workspace of gad_cnn_workspace_bytes");
+        a.act_global = reinterpret_cast<float*>(workspace);
+    }
     GAD_CUDA(cudaFuncSetAttribute(k_cnn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     k_cnn_fwd<<<B, CNN_THREADS, bytes, as_stream(stream)>>>(a);
     GAD_LAUNCH_CHECK();
@@ -273,12 +296,17 @@ extern "C" int gad_cnn_bwd(const float* u, const int32_t* gather, const float* s
     int rc = cnn_fill(a, u, gather, scale, B, H, W, Cm, Co, L, weights, biases);
     if (rc) return rc;
     GAD_CHECK_ARG(g_out && g_params && workspace, "gad_cnn_bwd: null argument");
-    GAD_CHECK_ARG(workspace_bytes >= (size_t)B * a.n_params * sizeof(float), "gad_cnn_bwd: workspace too small");
+    GAD_CHECK_ARG(workspace_bytes >= gad_cnn_workspace_bytes(B, H, W, Cm, Co, L), "gad_cnn_bwd: workspace too small");
     a.g_out = g_out;
     a.g_part = reinterpret_cast<float*>(workspace);
-    const size_t bytes = cnn_smem_bytes(a, true);
-    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "gad_cnn_bwd: a %d x %d grid with %d layers of %d channels needs %zu B of "
-                                                    "shared memory (> %d)", H, W, L, cnn_cmax(a), bytes, smem_optin_bytes());
+    bool in_smem;
+    const size_t bytes = cnn_plan(a, true, &in_smem);
+    GAD_CHECK_ARG((int)bytes <= smem_optin_bytes(), "gad_cnn_bwd: a %d x %d grid with %d channels needs %zu B of shared "
+                                                    "memory (> %d)", H, W, cnn_cmax(a), bytes, smem_optin_bytes());
+    if (!in_smem) {
+        const size_t grads = ((size_t)B * a.n_params * sizeof(float) + 255) & ~(size_t)255;
+        a.act_global = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + grads);
+    }
     GAD_CUDA(cudaFuncSetAttribute(k_cnn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     cudaStream_t st = as_stream(stream);
     k_cnn_bwd<<<B, CNN_THREADS, bytes, st>>>(a);

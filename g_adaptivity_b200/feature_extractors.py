@@ -34,10 +34,12 @@ class _CnnFunction(torch.autograd.Function):
         u = u.detach().float().contiguous()
         B = u.numel() // (H * W)
         out = torch.empty((B, Co), dtype=torch.float32, device=u.device)
+        wsb = lib.gad_cnn_workspace_bytes(B, H, W, Cm, Co, L)
+        work = torch.empty(wsb, dtype=torch.uint8, device=u.device)
         with torch.cuda.device(u.device):
             _lib.check(lib.gad_cnn_fwd(_lib.ptr(u), _lib.ptr(gather), _lib.ptr(scale), B, H, W, Cm, Co, L, _ptr_array(ws),
-                                       _ptr_array(bs), _lib.ptr(out), torch.cuda.current_stream(u.device).cuda_stream),
-                       "gad_cnn_fwd")
+                                       _ptr_array(bs), _lib.ptr(out), _lib.ptr(work), wsb,
+                                       torch.cuda.current_stream(u.device).cuda_stream), "gad_cnn_fwd")
         ctx.save_for_backward(u, scale, *ws, *bs)
         ctx.gather, ctx.shape = gather, (B, H, W, Cm, Co, L)
         ctx.param_shapes = [p.shape for p in params]
@@ -51,7 +53,7 @@ class _CnnFunction(torch.autograd.Function):
         u, scale, ws, bs = saved[0], saved[1], saved[2:2 + L], saved[2 + L:2 + 2 * L]
         n = int(lib.gad_cnn_param_count(H, Cm, Co, L))
         g_flat = torch.empty(n, dtype=torch.float32, device=u.device)
-        wsb = lib.gad_cnn_workspace_bytes(B, H, Cm, Co, L)
+        wsb = lib.gad_cnn_workspace_bytes(B, H, W, Cm, Co, L)
         work = torch.empty(wsb, dtype=torch.uint8, device=u.device)
         g_out = g_out.float().contiguous()
         with torch.cuda.device(u.device):

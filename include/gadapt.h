@@ -434,11 +434,14 @@ int gad_peer_free(void* dev_ptr);
  * torch's Conv layout [C_out, C_in, (3,) 3]: layer 0 is 1 -> Cm, layers 1 .. L-2 Cm -> Cm, layer L-1 Cm -> Co.
  * Backward: g_out [B, Co] -> g_params, flat in the order w_0, b_0, w_1, b_1, ... (gad_cnn_param_count entries);
  * the forward is recomputed, per-mesh parts are summed over the batch in fp64 in a fixed order (workspace of
- * gad_cnn_workspace_bytes).  The grid values get no gradient.  Limits: L <= 8, channels <= 16, planes in 227 KB. */
+ * gad_cnn_workspace_bytes; the same workspace size serves the forward).  When the L activation planes do not fit
+ * the shared memory next to the other buffers (16 channels on a 30 x 30 grid) they live in the workspace instead
+ * (L2-resident).  The grid values get no gradient.  Limits: L <= 8, channels <= 16. */
 int64_t gad_cnn_param_count(int H, int Cm, int Co, int L);
-size_t gad_cnn_workspace_bytes(int B, int H, int Cm, int Co, int L);
+size_t gad_cnn_workspace_bytes(int B, int H, int W, int Cm, int Co, int L);
 int gad_cnn_fwd(const float* u, const int32_t* gather, const float* scale, int B, int H, int W, int Cm, int Co, int L,
-                const float* const* weights, const float* const* biases, float* out, void* stream);
+                const float* const* weights, const float* const* biases, float* out, void* workspace,
+                size_t workspace_bytes, void* stream);
 int gad_cnn_bwd(const float* u, const int32_t* gather, const float* scale, int B, int H, int W, int Cm, int Co, int L,
                 const float* const* weights, const float* const* biases, const float* g_out, float* g_params,
                 void* workspace, size_t workspace_bytes, void* stream);
