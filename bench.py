@@ -223,7 +223,7 @@ def time_forward_config(dev, md, B, over, burgers, iters, peak):
     `model.inference_session(data)` (one CUDA-graph replay per call, new `uu` copied in each time)."""
     from g_adaptivity_b200 import GNN, synth
     opt = synth.burgers_opt(md) if burgers else synth.default_opt(md)
-    opt.update(device=str(dev), gad_store_alpha=False, **over)
+    opt.update(device=str(dev), gad_store_alpha=False, gad_sync_timestamp=False, **over)     # throughput: no per-call sync
     ds = synth.SyntheticDataset(len(md), md)
     torch.manual_seed(42)
     model = GNN(ds, opt).to(dev).eval()

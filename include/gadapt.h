@@ -339,8 +339,6 @@ size_t gad_cluster_workspace_bytes(int CE, int M, int cluster_size, int L);
 /* Planning aid: clusters of this shape the device can hold at once (cudaOccupancyMaxActiveClusters). */
 int gad_cluster_occupancy(int CE, int cluster_size, int slab_nodes, int threads, int* max_active_clusters);
 int gad_train_step_cluster(const gad_train_desc* desc, int cluster_size, void* stream);
-/* Forward only (module seam / inference), all L Euler layers or RK4 steps in ONE launch with the state
- * resident in the cluster's shared memory: gad_deform_fwd_ell_raw's contract over cluster rows. */
 /* Backward only (autograd of the module seam) from the states the forward saved: gad_deform_bwd_ell's
  * contract over cluster rows; workspace of gad_cluster_workspace_bytes. */
 int gad_deform_bwd_cluster(const void* crows_in, const void* crows_out, const int32_t* mesh_ptr, int M,
@@ -348,6 +346,8 @@ int gad_deform_bwd_cluster(const void* crows_in, const void* crows_out, const in
                            const float* g_xphys, int dim, int CE, const float* Mu, int Lw, const float* tau, int L,
                            float* gMu, float* g_tau, float* g_x0, void* workspace, size_t workspace_bytes,
                            void* stream);
+/* Forward only (module seam / inference), all L Euler layers or RK4 steps in ONE launch with the state
+ * resident in the cluster's shared memory: gad_deform_fwd_ell_raw's contract over cluster rows. */
 int gad_deform_fwd_cluster(const void* crows_in, const int32_t* mesh_ptr, int M, int max_mesh_nodes, int max_deg,
                            int cluster_size, int64_t N, const float* x_comp, const float* f, const float* uu,
                            const float* f_scale, const float* uu_scale, int dim, int CE, const float* Mu, int Lw,
