@@ -394,3 +394,32 @@ def test_shared_topology_falls_back_when_the_batch_breaks_the_promise():
     with torch.no_grad():
         m2(mixed)
     assert not m2.last_graph.uniform
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_train_batch_keeps_the_reference_loop_shape(shared):
+    """`for data in loader: loss = trainer.train_batch(data)` -- a fresh host Batch per iteration, slots found by
+    topology -- trains exactly like stepping over resident batches: same losses, same parameters."""
+    opt, ds, _, ref = _case((20, 20), 12, seed=3)
+    fresh = [synth.make_batch((20, 20), 12, seed=50 + k) for k in range(7)]
+    for b in fresh:
+        b.pin_memory()
+    model = cuda_model(ds, opt, ref.state_dict(), gad_shared_topology=shared, gad_store_alpha=False)
+    tr = DeformerTrainer(model, lr=1e-2)
+    got = []
+    for b in fresh:
+        loss = tr.train_batch(b if shared else b)
+        tr.synchronize()
+        got.append(float(loss.item()))
+    n_slots = len(tr.slots)
+    assert n_slots == (3 if shared else 7)                 # a shared mesh: three slots serve every batch
+    model2 = cuda_model(ds, opt, ref.state_dict(), gad_store_alpha=False)
+    tr2 = DeformerTrainer(model2, lr=1e-2)
+    want = []
+    for b in fresh:
+        sid = tr2.add_batch(b)
+        l = tr2.step(sid)
+        tr2.synchronize()
+        want.append(float(l.item()))
+    assert got == want
+    assert torch.equal(tr.flat, tr2.flat)
