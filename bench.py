@@ -345,6 +345,54 @@ def time_pde_loss_2d(dev, iters):
             "reference": "torch_FEM_2D per mesh in a Python loop: ~3 s per 30x30 mesh on the CPU (DESIGN section 11)"}
 
 
+def time_loop_shape(dev, iters):
+    """cfg 2 in the REFERENCE's loop shape (src/run_GNN.py:97-131): a fresh pinned host Batch per iteration.
+    (a) the module seam exactly as the reference writes it: model(data) -> F.l1_loss -> backward() ->
+    torch.optim.Adam.step(); (b) the same loop body as ONE call, `DeformerTrainer.train_batch(data)` (H2D of the
+    batch's node inputs on a copy stream + the one-launch training step).  Wall clock per iteration, pipelined."""
+    import torch.nn.functional as F
+    from g_adaptivity_b200 import GNN, synth
+    from g_adaptivity_b200.trainer import DeformerTrainer
+    md, B = MESH_DIMS, MESHES_PER_GPU
+    opt = synth.default_opt(md, device=str(dev), gad_store_alpha=False, gad_shared_topology=True)
+    ds = synth.SyntheticDataset(2, md)
+    base = synth.make_batch(md, B, seed=0)
+    batches = []
+    for _ in range(iters + 6):
+        b = base.clone()
+        b.pin_memory()
+        batches.append(b)
+    out = {}
+    torch.manual_seed(42)
+    model = GNN(ds, dict(opt)).to(dev).train()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    for k, d in enumerate(batches):
+        if k == 6:
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+        optim.zero_grad(set_to_none=True)
+        F.l1_loss(model(d), d.x_phys.to(dev, non_blocking=True)).backward()
+        optim.step()
+    torch.cuda.synchronize(dev)
+    out["module_seam_ms"] = round(1e3 * (time.perf_counter() - t0) / iters, 4)
+    torch.manual_seed(42)
+    model2 = GNN(ds, dict(opt)).to(dev).train()
+    tr = DeformerTrainer(model2)
+    for k, d in enumerate(batches):
+        if k == 6:
+            tr.synchronize()
+            t0 = time.perf_counter()
+        loss = tr.train_batch(d)
+    tr.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / iters
+    out["train_batch_ms"] = round(ms, 4)
+    out["train_batch_nodes_per_s"] = B * md[0] * md[1] / (ms * 1e-3)
+    out["workload"] = (f"{B} x {md[0]}x{md[1]} meshes, a fresh pinned host Batch per iteration: model(data) + F.l1_loss + "
+                       "backward + torch.optim.Adam(fused) vs DeformerTrainer.train_batch(data)")
+    tr.close()
+    return out
+
+
 def bind_rank_to_cores(local_rank: int, local_world: int):
     """One process per GPU on a shared host: give every rank its own slice of the cores this job may use, so
     that the ranks' launch / copy threads do not migrate over each other (all GPUs of the box report the same
@@ -638,7 +686,8 @@ def main():
                      lambda: time_forward_config(dev, (200,), 4096, {}, True, it, peak)),
                     ("cfg4_200x200_64_rk4_steps_fwd",
                      lambda: time_forward_config(dev, (200, 200), 1, {"ode_method": "rk4", "num_layers": 64}, False, it, peak)),
-                    ("f1_pde_loss_2d_cfg2_shape_train_step", lambda: time_pde_loss_2d(dev, 3))):
+                    ("f1_pde_loss_2d_cfg2_shape_train_step", lambda: time_pde_loss_2d(dev, 3)),
+                    ("cfg2_reference_loop_shape", lambda: time_loop_shape(dev, 20))):
                 try:
                     configs[name] = fn()
                 except Exception as e:      # noqa: BLE001
