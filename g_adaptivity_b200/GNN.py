@@ -301,6 +301,12 @@ class GNN(nn.Module):
         Mu_in = self._folded_weights(dev)
         aux = {"keep_states": keep_alpha, "Mu_in": Mu_in}
         du = self._global_bias_offsets(data, graph, f, uu, f_scale, uu_scale, dev) if self.n_glob_used else None
+        temp = None
+        if opt.get("softmax_temp_type") == "learnable_a":      # per weight set, src/GRAND_plus.py:152-154,328-329
+            convs = [self.conv_layers[0]] if opt["share_conv"] else list(self.conv_layers)
+            temp = torch.cat([c.sm_temp_a.reshape(1) for c in convs])
+            if du is not None:
+                du = du / temp.reshape(1, -1, 1)                 # the bias offset is a logit term too
         method = GF.METHODS[opt.get("ode_method", "euler")]
         force_stream = bool(opt.get("gad_force_stream", False))
         if not torch.is_grad_enabled():
@@ -308,15 +314,16 @@ class GNN(nn.Module):
             N = x_comp.shape[0]
             L = int(tau.numel())
             states = torch.empty((L, N, self.CE), dtype=torch.float32, device=dev) if keep_alpha else None
-            x_phys = GF.deform_forward_raw(graph, x_comp, f, uu, f_scale, uu_scale, self.dim, self.CE, Mu_in,
+            Mu_eff = Mu_in if temp is None else (Mu_in / temp.detach().float().reshape(-1, 1)).contiguous()
+            x_phys = GF.deform_forward_raw(graph, x_comp, f, uu, f_scale, uu_scale, self.dim, self.CE, Mu_eff,
                                            GF._f32(tau.detach().reshape(-1)), method, states=states,
                                            force_stream=force_stream, du=None if du is None else du.detach().contiguous())
-            aux["states"], aux["Mu"] = states, Mu_in
+            aux["states"], aux["Mu"] = states, Mu_eff
         else:
             Wq, bq, Wk, bk = self._weights()
             x_phys = GF.DeformFunction.apply(
                 x_comp, f, uu, f_scale, uu_scale, Wq, bq, Wk, bk, tau, graph, self.dim, self.CE, self.inv_temp,
-                method, force_stream, aux, du)
+                method, force_stream, aux, du, temp)
         if keep_alpha and aux.get("states") is not None:
             states, Mu = aux["states"], aux["Mu"]
             L = opt["num_layers"]
@@ -488,6 +495,8 @@ class InferenceSession:
             raise NotImplementedError("inference_session with gnn_normalize=True is not implemented")
         if model.n_glob_used:
             raise NotImplementedError("inference_session with global CNN features is not implemented (call the module)")
+        if opt.get("softmax_temp_type") == "learnable_a":
+            raise NotImplementedError("inference_session with a learnable temperature is not implemented (call the module)")
         self.graph = model._graph(data, dev, allow_uniform=True)
         f32 = dict(dtype=torch.float32, device=dev)
         xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)

@@ -22,17 +22,20 @@ import torch.nn as nn
 from . import functional as GF
 from .graph import GraphCache, MeshGraph
 
-_UNSUPPORTED_TEMP = ("learnable_a", "learnable_v")
+_UNSUPPORTED_TEMP = ("learnable_v",)
 
 
 def inv_temperature(opt: dict) -> float:
-    """`softmax_temp_type == 'fixed'` divides the logits by `softmax_temp`
-    (`src/GRAND_plus.py:326-327`); every other CLI value falls through to the plain softmax (:332-333)."""
+    """`softmax_temp_type == 'fixed'` divides the logits by `softmax_temp` (`src/GRAND_plus.py:326-327`);
+    `'learnable_a'` divides them by the layer's learnable scalar `sm_temp_a` (:152-154,328-329), which the model
+    applies as a factor on the folded weights (so this returns 1); every other CLI value falls through to the plain
+    softmax (:332-333).  `'learnable_v'` applies `Linear(C, H)` to the `[E, H]` logits in the reference (:158,331), a
+    shape error there: rejected."""
     t = opt.get("softmax_temp_type")
     if t in _UNSUPPORTED_TEMP:
         raise NotImplementedError(
-            f"softmax_temp_type={t!r} is unreachable from the reference CLI and broken there "
-            "(uninitialised parameter / shape mismatch, src/GRAND_plus.py:152-163); not implemented")
+            f"softmax_temp_type={t!r} is unreachable from the reference CLI and a shape error there "
+            "(src/GRAND_plus.py:158,331); not implemented")
     if t == "fixed":
         return 1.0 / float(opt["softmax_temp"])
     return 1.0
@@ -77,6 +80,10 @@ class GRAND_plusConv(nn.Module):
         self.lin_query = nn.Linear(in_channels, heads * out_channels)
         self.lin_value = nn.Identity()
         self.lin_skip = nn.Linear(in_channels, out_channels if not concat else heads * out_channels, bias=bias)
+        if opt.get("softmax_temp_type") == "learnable_a":
+            # `nn.Parameter(torch.Tensor(1, heads, 1))` in the reference (:154): uninitialised memory until a value is
+            # loaded.  Same name and shape (a reference state_dict loads), initialised to opt['softmax_temp'].
+            self.sm_temp_a = nn.Parameter(torch.full((1, heads, 1), float(opt.get("softmax_temp", 1.0))))
         self.reset_parameters()
         self.stored_ei = None
         self._alpha_src: Optional[_AlphaSource] = None
@@ -124,6 +131,9 @@ class GRAND_plusConv(nn.Module):
             raise NotImplementedError("edge_attr is off the deformer hot path")
         if x.device.type != "cuda":
             raise RuntimeError("GRAND_plusConv runs on CUDA only: the sm_100a kernels have no CPU fallback")
+        if self.opt.get("softmax_temp_type") == "learnable_a":
+            raise NotImplementedError("softmax_temp_type='learnable_a' is implemented on the module seam (GNN.forward); "
+                                      "the single-layer operator seam takes a fixed temperature")
         graph = edge_index if isinstance(edge_index, MeshGraph) else self._graph_for(edge_index, x.shape[0])
         res = GF.ConvFunction.apply(x, self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,
                                     self.lin_key.bias, graph, self.inv_temp)

@@ -363,7 +363,7 @@ class DeformFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_comp, f, uu, f_scale, uu_scale, Wq, bq, Wk, bk, tau, graph, dim, CE, inv_temp, method,
-                force_stream, aux, du=None):
+                force_stream, aux, du=None, temp=None):
         L = int(tau.numel())
         N = x_comp.shape[0]
         needs = any(ctx.needs_input_grad)
@@ -371,6 +371,12 @@ class DeformFunction(torch.autograd.Function):
         Mu = aux.get("Mu_in") if aux is not None else None     # folded weights cached by the module
         if Mu is None:
             Mu = prepare_weights(Wq.detach(), bq.detach(), Wk.detach(), CE, inv_temp)
+        # learnable temperature (softmax_temp_type='learnable_a'): the logits are divided by T_l, i.e. the folded
+        # weights of set l are scaled by 1 / T_l -- (M, u) are linear in the logit scale
+        ctx.has_temp = temp is not None
+        if temp is not None:
+            inv_t = (1.0 / temp.detach().float().reshape(-1, 1))
+            Mu = (Mu * inv_t).contiguous()
         keep_states = aux is not None and aux.get('keep_states', False)
         states = torch.empty((L, N, CE), dtype=torch.float32, device=x_comp.device) if (needs or keep_states) else None
         x_phys = deform_forward_raw(graph, x_comp.detach(), None if f is None else f.detach(),
@@ -383,7 +389,9 @@ class DeformFunction(torch.autograd.Function):
         ctx.has_f, ctx.has_uu = f is not None, uu is not None
         ctx.normalised = (f_scale is not None) or (uu_scale is not None)
         if needs:
-            ctx.save_for_backward(states, Mu, tau_d, Wq, bq, Wk, *([du.detach().float().contiguous()] if du is not None else []))
+            ctx.save_for_backward(states, Mu, tau_d, Wq, bq, Wk,
+                                  du.detach().float().contiguous() if du is not None else torch.empty(0, device=Mu.device),
+                                  temp.detach().float().reshape(-1) if temp is not None else torch.empty(0, device=Mu.device))
         if aux is not None:   # side channel for the lazy attention read-out (conv.stored_alpha)
             aux["states"], aux["Mu"] = (states if keep_states else None), Mu
         return x_phys
@@ -392,7 +400,8 @@ class DeformFunction(torch.autograd.Function):
     def backward(ctx, g_xphys):
         states, Mu, tau_d, Wq, bq, Wk = ctx.saved_tensors[:6]
         du = ctx.saved_tensors[6] if ctx.has_du else None
-        g_du = None
+        temp = ctx.saved_tensors[7] if ctx.has_temp else None
+        g_du = g_temp = None
         ni = ctx.needs_input_grad
         want_gx0 = ni[0] or ni[1] or ni[2]
         if want_gx0 and ctx.normalised:
@@ -410,6 +419,10 @@ class DeformFunction(torch.autograd.Function):
                                   want_gtau=ni[9], want_gx0=want_gx0, force_stream=ctx.force_stream, du=du)
             gMu, g_tau, g_x0 = res[:3]
             g_du = res[3] if du is not None else None
+        if temp is not None:
+            # Mu_l = Mu_base_l / T_l:  dL/dT_l = -<gMu_l, Mu_l> / T_l ,  dL/dMu_base_l = gMu_l / T_l
+            g_temp = (-(gMu * Mu).sum(dim=1) / temp).reshape(-1)
+            gMu = (gMu / temp.reshape(-1, 1)).contiguous()
         gWq, gbq, gWk, gbk = weight_grads(Wq.detach(), bq.detach(), Wk.detach(), gMu, ctx.CE, ctx.inv_temp)
         g_xc = g_f = g_uu = None
         if want_gx0:
@@ -425,7 +438,7 @@ class DeformFunction(torch.autograd.Function):
         return (g_xc, g_f, g_uu, None, None, gWq if ni[5] else None, gbq if ni[6] else None,
                 gWk if ni[7] else None, gbk if ni[8] else None,
                 g_tau.view_as(tau_d) if (ni[9] and g_tau is not None) else None,
-                None, None, None, None, None, None, None, g_du)
+                None, None, None, None, None, None, None, g_du, g_temp)
 
 
 class ConvFunction(torch.autograd.Function):

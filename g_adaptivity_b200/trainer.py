@@ -63,6 +63,8 @@ class DeformerTrainer:
         if getattr(model, "n_glob_used", 0) or opt.get("gnn_inc_glob_feat_f") or opt.get("gnn_inc_glob_feat_uu"):
             raise NotImplementedError("DeformerTrainer: global CNN features are trained through GNN.forward + autograd "
                                       "(the fused step does not update the CNN's parameters)")
+        if opt.get("softmax_temp_type") == "learnable_a":
+            raise NotImplementedError("DeformerTrainer: the learnable temperature is trained through GNN.forward + autograd")
         if opt.get("gnn_normalize", False):
             raise NotImplementedError("DeformerTrainer: gnn_normalize=True (per-batch f / max f, src/GNN.py:231-237) is "
                                       "only implemented on the GNN.forward path")

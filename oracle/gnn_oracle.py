@@ -77,8 +77,13 @@ class GRANDPlusConvRef(nn.Module):
         self.lin_key = LinearRef(in_channels, heads * out_channels)      # GRAND_plus.py:146
         self.lin_query = LinearRef(in_channels, heads * out_channels)    # GRAND_plus.py:147
         self.lin_skip = LinearRef(in_channels, out_channels, bias=False)  # :178 (never used, root_weight=False)
-        if opt.get("softmax_temp_type") in ("learnable_a", "learnable_v"):
-            raise NotImplementedError("learnable temperatures are broken in the reference (SURVEY 8a)")
+        if opt.get("softmax_temp_type") == "learnable_v":
+            raise NotImplementedError("softmax_temp_type='learnable_v' applies Linear(C, H) to the [E, H] logits "
+                                      "(GRAND_plus.py:158,331): a shape error in the reference")
+        if opt.get("softmax_temp_type") == "learnable_a":
+            # :152-154 -- `nn.Parameter(torch.Tensor(1, heads, 1))`, i.e. UNINITIALISED memory in the reference; usable
+            # once a value is loaded / assigned.  Initialised to opt['softmax_temp'] here.
+            self.sm_temp_a = nn.Parameter(torch.full((1, heads, 1), float(opt.get("softmax_temp", 1.0))))
         if opt.get("reg_skew"):
             raise NotImplementedError("reg_skew needs a Firedrake mesh (GRAND_plus.py:280-324)")
         self.stored_ei = None
@@ -96,6 +101,8 @@ class GRANDPlusConvRef(nn.Module):
             alpha = (query_i * key_j).sum(dim=-1) / math.sqrt(self.out_channels)   # :279
             if self.opt.get("softmax_temp_type") == "fixed":                        # :326-327
                 alpha = pyg.softmax(alpha / self.opt["softmax_temp"], index, None, size_i)
+            elif self.opt.get("softmax_temp_type") == "learnable_a":                # :328-329
+                alpha = pyg.softmax(alpha / self.sm_temp_a.squeeze(2), index, None, size_i)
             else:                                                                   # :332-333
                 alpha = pyg.softmax(alpha, index, None, size_i)
             store["alpha"] = alpha

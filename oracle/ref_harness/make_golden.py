@@ -50,6 +50,11 @@ CASES = [
     ("scaled_w4_8x8", [[8, 8]] * 2, {}, {"weight_scale": 4.0}),
     ("nofeat_f_6x6", [[6, 6]] * 2, {"gnn_inc_feat_f": False}, {}),
     ("layers8_tau02_6x6", [[6, 6]] * 2, {"num_layers": 8, "time_step": 0.2}, {}),
+    # learnable global temperature (GRAND_plus.py:152-154,328-329): the reference leaves the parameter uninitialised;
+    # it is assigned here, as loading a checkpoint would
+    ("temp_learnable_a_7x7", [[7, 7]] * 3, {"softmax_temp_type": "learnable_a"}, {"sm_temp_a": 1.7}),
+    ("temp_learnable_a_noshare_6x6", [[6, 6]] * 2, {"softmax_temp_type": "learnable_a", "share_conv": False,
+                                                    "num_layers": 3}, {"sm_temp_a": [0.6, 1.3, 2.5]}),
 ]
 
 
@@ -95,6 +100,11 @@ def run_case(gnn_mod, name, mesh_dims_list, overrides, extras, seed=0):
         if "steps" in extras:
             for p, v in zip(model.steps, extras["steps"]):
                 p.fill_(v)
+        if "sm_temp_a" in extras:
+            vals = extras["sm_temp_a"]
+            convs = [model.conv_layers[0]] if opt["share_conv"] else list(model.conv_layers)
+            for k, c in enumerate(convs):
+                c.sm_temp_a.fill_(vals[k] if isinstance(vals, (list, tuple)) else vals)
     model.train()
     out = model(data)
     target = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
@@ -130,6 +140,14 @@ def main():
     gnn_mod, grand_mod, params_mod = load_reference.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     only_glob = "--glob-only" in sys.argv
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    if only:            # mint the named cases without touching the other fixtures
+        todo = [(GOLDEN_DIR, c) for c in CASES if c[0] in only] + [(GLOB_DIR, c) for c in GLOB_CASES if c[0] in only]
+        for out_dir, (name, mesh_dims_list, overrides, extras) in todo:
+            fx = run_case(gnn_mod, name, mesh_dims_list, overrides, extras)
+            torch.save(fx, os.path.join(out_dir, name + ".pt"))
+            print(f"{name}: loss={fx['loss']:.6e} grads={sorted(fx['grads'])}")
+        return
     os.makedirs(GLOB_DIR, exist_ok=True)
     todo = ([] if only_glob else [(GOLDEN_DIR, c) for c in CASES]) + [(GLOB_DIR, c) for c in GLOB_CASES]
     for out_dir, (name, mesh_dims_list, overrides, extras) in todo:

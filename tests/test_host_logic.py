@@ -117,7 +117,7 @@ def test_model_surface_matches_reference_contract():
     ({"conv_type": "GCN"}, NotImplementedError), ({"conv_type": "GAT_plus"}, NotImplementedError),
     ({"enc": "lin_layer"}, NotImplementedError), ({"dropout": 0.5}, NotImplementedError),
     ({"loss_type": "pde_loss", "data_type": "randg_mix"}, NotImplementedError),
-    ({"reg_skew": True}, NotImplementedError), ({"softmax_temp_type": "learnable_a"}, NotImplementedError),
+    ({"reg_skew": True}, NotImplementedError), ({"softmax_temp_type": "learnable_v"}, NotImplementedError),
     ({"residual": False}, NotImplementedError), ({"ode_method": "dopri5"}, ValueError),
 ])
 def test_unsupported_options_raise(over, exc):
