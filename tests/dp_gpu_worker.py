@@ -58,12 +58,14 @@ def main():
             for k in range(K):
                 losses.append(tr.step(sids[k % 2]).clone())
         tr.synchronize()
+        selfcheck = tr.dp_selfcheck(sids, steps=4) if mode == "peer" else None      # restores the optimizer state
         flat = tr.flat.detach().clone()
         gathered = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
         res[mode] = {"fused_dp": bool(tr.fused_dp), "why": (tr.peer.why if tr.peer is not None else "off"),
                      "flat": flat.cpu().tolist(), "ranks_equal": all(bool(torch.equal(g, flat)) for g in gathered),
-                     "steps": int(tr.step_count.item()), "loss_last": float(losses[-1].item()), "g_first": g_first}
+                     "steps": int(tr.step_count.item()), "loss_last": float(losses[-1].item()), "g_first": g_first,
+                     "selfcheck": selfcheck}
         tr.close()
     if rank == 0:
         with open(out_path, "w") as fh:

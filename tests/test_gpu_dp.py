@@ -34,6 +34,8 @@ def test_two_gpu_peer_allreduce_matches_nccl_and_oracle(tmp_path):
         assert res[mode]["ranks_equal"], mode
         assert res[mode]["steps"] == K
     assert res["peer"]["flat"] == res["nccl"]["flat"]
+    sc = res["peer"]["selfcheck"]          # the check bench.py runs on the live job (DeformerTrainer.dp_selfcheck)
+    assert sc["ranks_equal"] and sc["vs_nccl"] == "bit-exact" and sc["parameters_moved"] and sc["slots_on_peer_route"] == 2
     assert res["peer_graph"]["flat"] == res["peer"]["flat"]
 
     # single-process oracle on the global batch, torch.optim.Adam
