@@ -426,6 +426,7 @@ def main():
     ap.add_argument("--no-epoch", action="store_true", help="one CUDA graph per step instead of one per pass over the ring")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--write-combined", action="store_true", help="e2e: packed host batches in write-combined pinned memory")
     ap.add_argument("--skip-configs", action="store_true", help="do not time the other BASELINE configs (cfg 1, 3, 4, 5)")
     args = ap.parse_args()
 
@@ -645,7 +646,8 @@ def main():
         # layout (DeformerTrainer.pack_host), so a step's inputs travel host -> device in a single copy.
         # The synthetic dataset is on one shared mesh (as the reference's `randg` datasets, src/data.py:143):
         # x_comp is resident per slot and the per-step copy is the per-sample part, target | f | uu.
-        packed = [trainer.pack_host(r, host_batches[r], with_x_comp=False) for r in range(R)]
+        packed = [trainer.pack_host(r, host_batches[r], with_x_comp=False, write_combined=args.write_combined)
+                  for r in range(R)]
         trainer.run_from_host(packed, min(2 * R, ke))
         barrier()
         t0 = time.perf_counter()
@@ -664,7 +666,7 @@ def main():
                       "per step ONE pinned H2D copy of the per-sample inputs target|f|uu (16 B/node; x_comp of the "
                       "shared mesh is resident) on a copy stream, overlapped with the previous step's kernel; graph "
                       "replay of the one-launch step; async D2H of the loss",
-               "cpu_affinity": affinity}
+               "cpu_affinity": affinity, "host_memory": "pinned, write-combined" if args.write_combined else "pinned"}
 
     clk = clocks.stop() if rank == 0 else None
 

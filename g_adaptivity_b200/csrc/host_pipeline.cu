@@ -75,3 +75,19 @@ extern "C" int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, con
     fail(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
     return rc;
 }
+
+// Pinned host staging buffers for the packed batches.  write_combined != 0: cudaHostAllocWriteCombined -- the host
+// writes a batch once and never reads it back, and device reads of write-combined memory are not snooped through the
+// CPU caches, which matters when eight processes pull their batches through one host memory system.
+extern "C" int gad_host_alloc(size_t bytes, int write_combined, void** host_ptr) {
+    GAD_CHECK_ARG(bytes > 0 && host_ptr, "gad_host_alloc: bad arguments");
+    void* p = nullptr;
+    GAD_CUDA(cudaHostAlloc(&p, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    *host_ptr = p;
+    return GAD_OK;
+}
+
+extern "C" int gad_host_free(void* host_ptr) {
+    if (host_ptr) GAD_CUDA(cudaFreeHost(host_ptr));
+    return GAD_OK;
+}

@@ -272,19 +272,34 @@ class DeformerTrainer:
         self.load_inputs(sid, data)
         return sid
 
-    def pack_host(self, sid: int, data, with_x_comp: bool = True) -> torch.Tensor:
+    def _host_buffer(self, numel: int, write_combined: bool) -> torch.Tensor:
+        """Pinned fp32 host buffer.  Write-combined pages come from the library (`gad_host_alloc`); the tensor is a view
+        of that allocation, which lives as long as the trainer (released by `close()`)."""
+        if not write_combined:
+            return torch.zeros(numel, dtype=torch.float32).pin_memory()
+        p = C.c_void_p()
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.gad_host_alloc(numel * 4, 1, C.byref(p)), "gad_host_alloc")
+        self.__dict__.setdefault("_host_allocs", []).append(p)
+        buf = torch.frombuffer((C.c_float * numel).from_address(p.value), dtype=torch.float32)
+        buf.zero_()
+        buf._gad_pinned = True
+        return buf
+
+    def pack_host(self, sid: int, data, with_x_comp: bool = True, write_combined: bool = False) -> torch.Tensor:
         """One pinned host buffer holding `data`'s node inputs in the layout of slot `sid`
         ([target | f | uu | x_comp]): `load_inputs` / `run_from_host` then move a batch host -> device
         with a single copy.  `with_x_comp=False` packs the per-sample prefix [target | f | uu] only, for
         datasets whose samples share one computational mesh (the slot keeps the x_comp it was given by
-        `add_batch`; the caller asserts that it does not change -- checked here against the slot)."""
+        `add_batch`; the caller asserts that it does not change -- checked here against the slot).
+        `write_combined=True`: write-combined pinned pages (written once here, read only by the device)."""
         s = self.slots[sid]
         xc = data.x_comp if data.x_comp.dim() == 2 else data.x_comp.unsqueeze(-1)
         tg = data.x_phys if data.x_phys.dim() == 2 else data.x_phys.unsqueeze(-1)
         if not with_x_comp and not torch.equal(xc.to(torch.float32).cpu(), s.x_comp.cpu()):
             raise ValueError("pack_host(with_x_comp=False): this batch's x_comp differs from the slot's resident one")
         n_total = s.inbuf.numel() if with_x_comp else s.in_offs[3]
-        buf = torch.zeros(n_total, dtype=torch.float32).pin_memory()
+        buf = self._host_buffer(n_total, write_combined)
         parts = [tg, data.f_tensor if s.f is not None else None, data.uu_tensor if s.uu is not None else None,
                  xc if with_x_comp else None]
         for off, n, t in zip(s.in_offs, s.in_sizes, parts):
@@ -423,6 +438,8 @@ class DeformerTrainer:
         self.stream.synchronize()
         self.graphs.clear()
         self.epoch_graphs.clear()
+        for p in self.__dict__.pop("_host_allocs", []):
+            self.lib.gad_host_free(p)
         if self.peer is not None:
             if self.world > 1 and self.loopback is None:
                 dist.barrier(group=self.pg)
@@ -614,7 +631,8 @@ class DeformerTrainer:
             self._loss_pin = torch.empty(max(steps, 1024), dtype=torch.float32).pin_memory()   # cudaHostAlloc is slow: once
         losses = self._loss_pin[:steps]
         cs, ms = self._copy_stream, self.stream
-        packed = all(torch.is_tensor(b) and b.is_pinned() and b.dtype == torch.float32 for b in host_batches)
+        packed = all(torch.is_tensor(b) and (b.is_pinned() or getattr(b, "_gad_pinned", False)) and b.dtype == torch.float32
+                     for b in host_batches)
         pure = all(self._one_launch(s) for s in self.slots)      # the step's graph holds library kernels only
         if native is None:
             native = self.use_graph and packed and pure

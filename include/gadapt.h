@@ -461,6 +461,10 @@ typedef struct gad_pipeline_slot {
 } gad_pipeline_slot;
 int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, const void* const* host_batches, int n_host,
                      int64_t steps, float* losses_host, void* compute_stream, void* copy_stream);
+/* Pinned host staging memory for packed batches (cudaHostAlloc); write_combined != 0 asks for write-combined pages:
+ * written once by the host, read by the device without snooping the CPU caches. */
+int gad_host_alloc(size_t bytes, int write_combined, void** host_ptr);
+int gad_host_free(void* host_ptr);
 
 #ifdef __cplusplus
 }
