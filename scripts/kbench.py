@@ -79,7 +79,7 @@ def main():
         g = s.graph
         if ell:
             lib.gad_deform_bwd_ell(P(g.ell_in), P(g.ell_out), s.N, P(g.tile_ptr), g.T, g.max_tile_nodes, g.ell_deg,
-                                   P(s.states), P(s.g_out), model.dim, tr.CE, P(tr.Mu), tr.Lw, P(tr.tau), tr.L,
+                                   P(s.states), P(s.g_out), model.dim, tr.CE, P(tr.Mu), None, tr.Lw, P(tr.tau), tr.L,
                                    P(tr.gMu), P(tr.gtau), None, P(s.bwd_ws), s.bwd_ws_bytes, st)
             return
         lib.gad_deform_bwd(P(g.rowptr), P(g.col_walk), P(g.t_rowptr), P(g.t_dst_walk), s.N, g.E, P(g.tile_ptr), g.T,
