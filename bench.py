@@ -641,7 +641,7 @@ def main():
     # ---- end-to-end: pinned host buffers in, loss out, every step --------------------------
     e2e = None
     if not args.skip_e2e:
-        ke = min(max(K, 200), 2000)      # the pipeline needs a few steps to fill: never fewer than 200
+        ke = min(max(K, 400), 2000)      # the pipeline needs a few steps to fill: never fewer than 400
         # host side of the public API: every batch packed once into ONE pinned buffer in the slot's input
         # layout (DeformerTrainer.pack_host), so a step's inputs travel host -> device in a single copy.
         # The synthetic dataset is on one shared mesh (as the reference's `randg` datasets, src/data.py:143):
