@@ -271,7 +271,7 @@ def time_cfg5(dev, rank, world, iters, peak, barrier):
     from g_adaptivity_b200.trainer import DeformerTrainer
     md, total = (50, 50), 8192
     per = total // world
-    opt = synth.default_opt(md, device=str(dev), gad_store_alpha=False)
+    opt = synth.default_opt(md, device=str(dev), gad_store_alpha=False, gad_shared_topology=True)
     ds = synth.SyntheticDataset(2, md)
     torch.manual_seed(42)
     model = GNN(ds, opt).to(dev)
@@ -302,6 +302,7 @@ def time_cfg5(dev, rank, world, iters, peak, barrier):
            "bytes_per_node": round(ab["step_per_node"], 1),
            "roofline_frac": N * ab["step_per_node"] / (ms * 1e-3) / 1e9 / peak,
            "data": "256 distinct samples per GPU tiled on the device (synth.make_batch_device)",
+           "topology": "shared (one ELL table)" if s0.graph.uniform else "general",
            "one_launch": bool(tr._one_launch(s0))}
     tr.close()
     del tr, model
