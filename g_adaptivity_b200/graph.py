@@ -584,7 +584,9 @@ class GraphCache:
         sizes = getattr(data, "mesh_sizes", None)
         parts.append(None if sizes is None else (len(sizes), int(min(sizes)), int(max(sizes))))
         if E > 0:
-            idx = torch.linspace(0, E - 1, min(E, GraphCache.SHARED_SAMPLES)).long().to(ei.device)
+            n = min(E, GraphCache.SHARED_SAMPLES)
+            # integer arithmetic: a float32 linspace rounds E - 1 up past the end beyond 2^24 edges
+            idx = ((torch.arange(n, dtype=torch.int64) * (E - 1)) // max(n - 1, 1)).to(ei.device)
             parts.append(tuple(ei[:, idx].reshape(-1).tolist()))
             for name in ("to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask"):
                 t = getattr(data, name, None)
