@@ -570,6 +570,13 @@ class GraphCache:
     SHARED_SAMPLES = 64
 
     @staticmethod
+    def sample_positions(E: int) -> torch.Tensor:
+        """SHARED_SAMPLES evenly spaced positions in [0, E), first and last included.  Integer arithmetic: a float32
+        `linspace(0, E - 1, n)` rounds its end point up past the array beyond 2^24 edges (cfg 5 has 1.2e8)."""
+        n = min(int(E), GraphCache.SHARED_SAMPLES)
+        return (torch.arange(n, dtype=torch.int64) * (int(E) - 1)) // max(n - 1, 1)
+
+    @staticmethod
     def shared_key_of(data, flags) -> tuple:
         """Key for datasets whose samples all live on ONE mesh (the reference's `randg` data: `dataset.mesh`,
         `x_comp_shared`, src/data.py:143), opted into with `opt['gad_shared_topology']`: batches of the same
@@ -584,9 +591,7 @@ class GraphCache:
         sizes = getattr(data, "mesh_sizes", None)
         parts.append(None if sizes is None else (len(sizes), int(min(sizes)), int(max(sizes))))
         if E > 0:
-            n = min(E, GraphCache.SHARED_SAMPLES)
-            # integer arithmetic: a float32 linspace rounds E - 1 up past the end beyond 2^24 edges
-            idx = ((torch.arange(n, dtype=torch.int64) * (E - 1)) // max(n - 1, 1)).to(ei.device)
+            idx = GraphCache.sample_positions(E).to(ei.device)
             parts.append(tuple(ei[:, idx].reshape(-1).tolist()))
             for name in ("to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask"):
                 t = getattr(data, name, None)

@@ -165,3 +165,26 @@ def test_corner_loops_follow_reference_order():
     assert ids == [0, 4, 20, 24, 25, 29, 45, 49, 50, 54, 70, 74]
     d1 = synth.make_batch((7,), 2)
     assert graph.corner_loops(d1, 1, [7], [7, 7]).tolist() == [0, 6, 7, 13]
+
+
+def test_shared_topology_sample_positions_stay_inside_huge_edge_lists():
+    """cfg 5 on one GPU has 1.2e8 edges: float32 positions would round E - 1 up to E (found by the bench)."""
+    for E in (1, 2, 63, 64, 65, 1000, 119_619_584, 2 ** 31 - 1):
+        idx = graph.GraphCache.sample_positions(E)
+        assert idx.dtype == torch.int64 and int(idx.min()) == 0 and int(idx.max()) == E - 1
+        assert bool((idx[1:] >= idx[:-1]).all()) and idx.numel() == min(E, 64)
+
+
+def test_device_batch_builder_equals_host_collation():
+    """synth.make_batch_device (used by the bench for the 8192-mesh cfg 5 batch) tiles `block` host samples and
+    builds the topology tensors with torch ops: identical to make_batch when block covers the batch."""
+    a = synth.make_batch((6, 6), 9, seed=3)
+    b = synth.make_batch_device((6, 6), 9, "cpu", seed=3, block=9)
+    for k in a.keys():
+        va, vb = getattr(a, k), getattr(b, k)
+        if torch.is_tensor(va):
+            assert torch.equal(va, vb), k
+    c = synth.make_batch_device((6, 6), 9, "cpu", seed=3, block=4)
+    assert torch.equal(c.edge_index, a.edge_index) and torch.equal(c.batch, a.batch)
+    assert torch.equal(c.f_tensor[:4 * 36], a.f_tensor[:4 * 36]) and torch.equal(c.f_tensor[4 * 36:8 * 36], a.f_tensor[:4 * 36])
+    assert c.mesh_sizes == a.mesh_sizes and len(c.corner_nodes) == 9
