@@ -327,11 +327,50 @@ class GNNRef(nn.Module):
         x = self.dec(x)                                              # :298
         x_phys = x[:, :self.dim]                                     # :299
         self.end_MLmodel = time.time()                               # :301
-        if opt["loss_type"] not in ("mesh_loss", "modular"):
-            raise NotImplementedError("pde_loss tail (GNN.py:307-342) is off the hot path")
+        if opt["loss_type"] == "pde_loss" and not return_states:
+            return self._pde_tail(data, x_phys)                      # :307-342
         if return_states:
             return x_phys, states, edge_index
         return x_phys
+
+    def _pde_tail(self, data, x_phys):
+        """`loss_type == 'pde_loss'` (GNN.py:307-342): per mesh, the differentiable FEM solve on the relocated nodes
+        (1-D: difFEM_1d.py:159-186 = fem1d_oracle.torch_fem_1d; 2-D: difFEM_2d.py:345-372 = fem2d_oracle.torch_fem_2d,
+        the line-by-line restatement, or with opt['oracle_fem2d'] == 'fast' the vectorised formulation of
+        fem2d_fast.py), the 2-D solution re-ordered to the fine mesh's node order (`reshape_grid_to_fd_tensor` of a
+        [Q*Q, 1] column, utils_data.py:143-159 = a gather by argsort(mapping_tensor_fine)); returns
+        (coeffs, x_phys, sol) concatenated over the batch."""
+        import numpy as np
+        from . import fem1d_oracle, fem2d_fast, fem2d_oracle
+        opt, dim = self.opt, self.dim
+        Q = opt["eval_quad_points"]
+        coefs, xs, sols = [], [], []
+        if dim == 2:
+            x0 = torch.linspace(0, 1, Q)
+            X, Y = torch.meshgrid(x0, x0, indexing="ij")                 # :185-188
+            mesh = self.dataset.mesh
+            cells = np.asarray(mesh.coordinates.cell_node_map().values)
+            bc = np.asarray(mesh.bc_nodes)
+            _, order = torch.sort(self.dataset.mapping_tensor_fine)
+        for b in range(int(data.batch.max().item()) + 1):
+            c_list = [torch.as_tensor(np.asarray(c)) for c in data.pde_params["centers"][b]]   # :311-316
+            s_list = [torch.as_tensor(np.asarray(s)) for s in data.pde_params["scales"][b]]
+            xb = x_phys.squeeze()[data.batch == b]                   # :320,327
+            if dim == 1:
+                coef, sol, _, _ = fem1d_oracle.torch_fem_1d(xb, torch.linspace(0, 1, Q), c_list, s_list,
+                                                            load_quad_points=opt["load_quad_points"],
+                                                            stiff_quad_points=opt["stiff_quad_points"])
+            elif opt.get("oracle_fem2d", "reference") == "fast":
+                coef, sol = fem2d_fast.fem2d_fast(cells, bc, xb, [X, Y], opt["load_quad_points"],
+                                                  torch.stack(c_list).float(), torch.stack(s_list).float())
+                sol = sol.reshape(-1)[order]
+            else:
+                coef, sol = fem2d_oracle.torch_fem_2d(cells, bc, xb, [X, Y], opt["load_quad_points"], c_list, s_list)
+                sol = sol.reshape(-1)[order]                         # :333
+            coefs.append(coef)
+            xs.append(xb)
+            sols.append(sol)
+        return torch.cat(coefs, dim=0), torch.cat(xs, dim=0), torch.cat(sols, dim=0)
 
 
 # --------------------------------------------------------------------------------------
