@@ -215,6 +215,276 @@ __global__ void __launch_bounds__(TB) k_wide_stage(const int4* __restrict__ rows
     }
 }
 
+// ---- persistent forward: all L steps (x 4 RK4 stages) of one call in ONE launch --------------------------------
+// For graphs whose nodes fit the co-resident threads of the GPU (one 200x200 mesh: 157 CTAs on 148 SMs) the chain of
+// one launch per F-evaluation above spends half of every link on the launch hand-over, and a grid barrier per
+// F-evaluation (release fence + counter + acquire poll) was measured at the same 2 us.  Here neither exists:
+//   * every thread keeps its node -- topology row, state x, RK4 accumulator -- in registers for the whole call;
+//   * a CTA owns S = 256 consecutive nodes and keeps the stage input y of its WINDOW (the strips of the CTAs within
+//     r = ceil(reach / S) of it, reach = max |j - i| over the edges) in shared memory: all gathers are LDS;
+//   * after each F-evaluation a thread publishes its new row to one of two global (L2-resident) buffers as
+//     (value, epoch) pairs, written and read with 16-byte relaxed accesses whose 8-byte halves are single-copy
+//     atomic (the layout of NCCL's LL protocol: data is valid when its own tag matches -- no fence, no barrier),
+//     and the CTA polls the 2 r S halo rows of its window into shared memory.
+// A CTA waits only for the CTAs within r of it, so the machine synchronises locally.  Two buffers suffice because the
+// windows are symmetric: B overwrites its epoch-e rows with epoch e+2 only after it has read the epoch-(e+1) rows of
+// every CTA within r, each of which published them after it finished reading B's epoch-e rows.
+// The arithmetic is k_wide_stage's, expression for expression: results are bit-identical to the chain.  The launch
+// is cooperative (all CTAs co-resident or the launch fails); a poll that sees no progress for 2 s traps.
+template <int CE>
+__device__ __forceinline__ void publish_row(float* buf, int64_t i, const Row<CE>& r, unsigned tag) {
+    if constexpr (CE == 4) {      // one 32-byte store (256-bit accesses exist from sm_100 on)
+        asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(buf + i * 8),
+                     "r"(__float_as_uint(r.v[0])), "r"(tag), "r"(__float_as_uint(r.v[1])), "r"(tag),
+                     "r"(__float_as_uint(r.v[2])), "r"(tag), "r"(__float_as_uint(r.v[3])), "r"(tag)
+                     : "memory");
+    } else {
+        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(buf + i * 4), "r"(__float_as_uint(r.v[0])),
+                     "r"(tag), "r"(__float_as_uint(r.v[1])), "r"(tag)
+                     : "memory");
+    }
+}
+
+// One poll of a row: true when every (value, tag) pair carries `tag`.
+template <int CE>
+__device__ __forceinline__ bool try_row(const float* p, unsigned tag, Row<CE>& r) {
+    if constexpr (CE == 4) {
+        unsigned v[8];
+        asm volatile("ld.relaxed.gpu.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "l"(p)
+                     : "memory");
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r.v[c] = __uint_as_float(v[2 * c]);
+        return v[1] == tag && v[3] == tag && v[5] == tag && v[7] == tag;
+    } else {
+        uint4 v;
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(p)
+                     : "memory");
+        r.v[0] = __uint_as_float(v.x);
+        r.v[1] = __uint_as_float(v.z);
+        return v.y == tag && v.w == tag;
+    }
+}
+
+template <int CE>
+__device__ __forceinline__ Row<CE> lds_row(const float* sm, int j) {
+    Row<CE> r;
+    if constexpr (CE == 2) {
+        const float2 t = reinterpret_cast<const float2*>(sm)[j];
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+    } else {
+        const float4 t = reinterpret_cast<const float4*>(sm)[j];
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+        r.v[2] = t.z;
+        r.v[3] = t.w;
+    }
+    return r;
+}
+
+template <int CE>
+__device__ __forceinline__ void sts_row(float* sm, int j, const Row<CE>& r) {
+    if constexpr (CE == 2) reinterpret_cast<float2*>(sm)[j] = make_float2(r.v[0], r.v[1]);
+    else reinterpret_cast<float4*>(sm)[j] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+
+// F(y) at one node, neighbours at LOCAL window indices (same expression order as k_wide_stage)
+template <int CE, int W>
+__device__ __forceinline__ Row<CE> window_feval(const float* Mu, const int* nbl, int valid, const float* ysm,
+                                                const Row<CE>& yi) {
+    const Row<CE> p = project<CE>(Mu, yi);
+    Row<CE> xj[W];
+    float s[W];
+    float m = -3.0e38f;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        xj[q] = lds_row<CE>(ysm, nbl[q]);
+        const float d = dot<CE>(p, xj[q]);
+        s[q] = ((valid >> q) & 1) ? d : -CUDART_INF_F;
+        m = fmaxf(m, s[q]);
+    }
+    float Z = 0.f;
+    Row<CE> o = zero_row<CE>();
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const float e = ex2_approx(s[q] - m);
+        Z += e;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) o.v[c] = fmaf(e, xj[q].v[c], o.v[c]);
+    }
+    const float rZ = (valid != 0) ? rcp_refined(Z) : 0.f;
+    Row<CE> k;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) k.v[c] = fmaf(o.v[c], rZ, -yi.v[c]);
+    return k;
+}
+
+#ifndef GAD_PERSIST_MINB
+#define GAD_PERSIST_MINB 3      // co-resident CTAs per SM the register budget allows (capacity = 148 x this x 256 nodes)
+#endif
+template <int CE, int W>
+__global__ void __launch_bounds__(TB, GAD_PERSIST_MINB) k_wide_persist(const int4* __restrict__ rows, int64_t N, int r,
+                                                     const float* __restrict__ x0, const float* __restrict__ Mu_g, int Lw,
+                                                     const float* __restrict__ tau, int L, int method, float* tbuf0,
+                                                     float* tbuf1, float* states, float* __restrict__ xphys, int dim) {
+    constexpr int MUSZ = CE * CE + CE;
+    constexpr int S = TB;
+    __shared__ float Mu[MUSZ];
+    extern __shared__ float4 ysm4[];
+    float* ysm = reinterpret_cast<float*>(ysm4);             // [(2 r + 1) S][CE], row w <-> node wlo + w
+    const int64_t n0 = (int64_t)blockIdx.x * S;
+    const int64_t wlo = n0 - (int64_t)r * S;
+    const int64_t i = n0 + threadIdx.x;
+    const bool live = i < N;
+    const int64_t ic = live ? i : n0;                        // idle threads of the last CTA shadow its first node
+    const int own = r * S + threadIdx.x;                     // this thread's row of the window
+    const int halo = 2 * r * S;
+    int nbl[W], valid;
+    {
+        const Wide w = load_wide(rows, ic);
+#pragma unroll
+        for (int q = 0; q < W; ++q) nbl[q] = (int)((int64_t)w.nb[q] - wlo);
+        valid = live ? w.nb[7] : 0;
+    }
+    Row<CE> x = ldg_row<CE>(x0, ic);
+    // Needed part of the halo (window rows), widened so that every strip of the window contributes at least one row:
+    // that keeps the dependencies between CTAs symmetric, which is what makes two buffers enough (see above).
+    __shared__ int need[2];
+    if (threadIdx.x == 0) {
+        need[0] = r * S - 1 - (r - 1) * S;                   // last row of the farthest strip on the left  (= S - 1)
+        need[1] = (r + 1) * S + (r - 1) * S;                 // first row of the farthest strip on the right (= 2 r S)
+    }
+    __syncthreads();
+    if (live) {
+        int lo = own, hi = own;
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            lo = min(lo, nbl[q]);
+            hi = max(hi, nbl[q]);
+        }
+        atomicMin(&need[0], lo);
+        atomicMax(&need[1], hi);
+    }
+    __syncthreads();
+    const int need_lo = max(need[0], 0), need_hi = min(need[1], halo + S - 1);
+    const int n_left = r * S - need_lo, n_need = n_left + (need_hi - (r + 1) * S + 1);
+    // window of the initial state (an input of the call: plain loads)
+    for (int h = threadIdx.x; h < halo + S; h += TB) {
+        const int64_t j = wlo + h;
+        if (j >= 0 && j < N) sts_row<CE>(ysm, h, ldg_row<CE>(x0, j));
+    }
+    unsigned epoch = 0;
+    const size_t row = (size_t)N * CE;
+    // This thread's share of the needed halo rows (two per pass; one pass when the halo has at most 2 TB rows): window
+    // row and offset into a tagged buffer, fixed for the whole call.
+    int hrow[2];
+    int64_t hoff[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int k = threadIdx.x + u * TB;
+        const int wr = k < n_left ? need_lo + k : (r + 1) * S + (k - n_left);
+        const int64_t j = wlo + wr;
+        hrow[u] = (k < n_need && j >= 0 && j < N) ? wr : -1;
+        hoff[u] = j * (2 * CE);
+    }
+    const bool one_pass = n_need <= 2 * TB;
+    auto poll_pair = [&](const float* buf, const int* wr, const int64_t* off) {
+        bool pending[2] = {wr[0] >= 0, wr[1] >= 0};
+        unsigned long long t0 = 0;
+        for (unsigned spins = 1; pending[0] || pending[1]; ++spins) {
+            Row<CE> t[2];
+            bool ok[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) ok[u] = pending[u] && try_row<CE>(buf + off[u], epoch, t[u]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ok[u]) {
+                    sts_row<CE>(ysm, wr[u], t[u]);
+                    pending[u] = false;
+                }
+            if ((spins & 0xfff) == 0) {                      // a neighbour that never publishes must not hang the device
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 2000000000ull) __trap();
+            }
+        }
+    };
+    // hand the next stage input to the window: own row to shared memory and to the world, halo rows from the world
+    auto exchange = [&](const Row<CE>& y) {
+        ++epoch;
+        float* buf = (epoch & 1) ? tbuf1 : tbuf0;
+        if (live) publish_row<CE>(buf, i, y, epoch);
+        __syncthreads();                                     // every thread has finished reading the old window
+        sts_row<CE>(ysm, own, y);
+        if (one_pass) {
+            poll_pair(buf, hrow, hoff);
+        } else {
+            for (int h = threadIdx.x; h < n_need; h += 2 * TB) {
+                int wr[2];
+                int64_t off[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int k = h + u * TB;
+                    wr[u] = k < n_left ? need_lo + k : (r + 1) * S + (k - n_left);
+                    const int64_t j = wlo + wr[u];
+                    if (!(k < n_need && j >= 0 && j < N)) wr[u] = -1;
+                    off[u] = j * (2 * CE);
+                }
+                poll_pair(buf, wr, off);
+            }
+        }
+        __syncthreads();
+    };
+    // One flat loop over the F-evaluations (ONE copy of the F-evaluation and of the exchange in the instruction
+    // stream: with two warps per scheduler nothing hides instruction fetches).  RK4 stage sg of step l:
+    //   sg < 3: y = x + c1 k, acc += c2 k          sg = 3: x += (tau / 6) (acc + k), y = x
+    const bool rk4 = method == GAD_METHOD_RK4;
+    const int per_step = rk4 ? 4 : 1, E = L * per_step;
+    Row<CE> y = x, acc = zero_row<CE>();
+    float tau0 = 0.f;
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        const int l = rk4 ? (e >> 2) : e, sg = rk4 ? (e & 3) : 3;
+        if (sg == 0 || !rk4) {
+            if (e == 0 || Lw > 1) {
+                __syncthreads();
+                for (int t = threadIdx.x; t < MUSZ; t += blockDim.x) Mu[t] = Mu_g[(size_t)(Lw > 1 ? l : 0) * MUSZ + t];
+                __syncthreads();
+            }
+            tau0 = __ldg(tau + l);
+        }
+        const Row<CE> k = window_feval<CE, W>(Mu, nbl, valid, ysm, y);
+        if (sg < 3) {
+            const float c1 = tau0 * (sg == 2 ? 1.0f : 0.5f), c2 = (sg == 0 ? 1.0f : 2.0f);
+#pragma unroll
+            for (int c = 0; c < CE; ++c) {
+                y.v[c] = fmaf(c1, k.v[c], x.v[c]);
+                acc.v[c] = fmaf(c2, k.v[c], acc.v[c]);
+            }
+        } else {
+            const float c1 = tau0 * (rk4 ? 1.0f / 6.0f : 1.0f);
+#pragma unroll
+            for (int c = 0; c < CE; ++c) {
+                x.v[c] = fmaf(c1, rk4 ? acc.v[c] + k.v[c] : k.v[c], x.v[c]);
+                y.v[c] = x.v[c];
+                acc.v[c] = 0.f;
+            }
+            if (e == E - 1) {
+                if (live)
+                    for (int d = 0; d < dim && d < CE; ++d) xphys[i * dim + d] = x.v[d];
+            } else if (states && live) {
+                store_row<CE>(states + (size_t)(l + 1) * row, i, x);
+            }
+        }
+        if (e < E - 1) exchange(y);
+    }
+}
+
 // ---- backward, destination pass (contract of k_bwd_dst; math of ell_bwd_dst) ----------------------
 // grid-stride over nodes so that the number of weight-gradient partials is bounded.
 template <int CE, int W>
@@ -364,11 +634,59 @@ int grid_for_partials(int64_t N) {
     return (int)(want < cap ? want : cap);
 }
 
+// Can the persistent kernel take this call?  G CTAs of TB nodes with a window of (2 r + 1) TB rows in shared memory
+// must all be co-resident on the current device (cooperative launch).  GAD_WIDE_PERSIST=0 keeps the chain of
+// dependent launches (read per call: the tests switch between the two routes).
+constexpr size_t PERSIST_SMEM_MAX = 96 * 1024;
+
+template <int CE, int W>
+bool persist_fits(unsigned G, int r, size_t smem) {
+    const char* e = getenv("GAD_WIDE_PERSIST");
+    if ((e && e[0] == '0') || r < 0 || smem > PERSIST_SMEM_MAX) return false;
+    auto kern = k_wide_persist<CE, W>;
+    static thread_local int cached_dev = -1, sms = 0, coop = 0;
+    static thread_local size_t cached_smem = 0;
+    static thread_local int per_sm = 0;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (dev != cached_dev || smem != cached_smem) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess ||
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PERSIST_SMEM_MAX) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem) != cudaSuccess)
+            return false;
+        cached_dev = dev;
+        cached_smem = smem;
+    }
+    const bool fits = coop && (int)G <= sms * per_sm;
+    if (getenv("GAD_TRACE_ROUTE"))
+        fprintf(stderr, "[gad] k_wide_persist<%d,%d>: G=%u r=%d smem=%zu capacity=%d CTAs -> %s\n", CE, W, G, r, smem,
+                sms * per_sm, fits ? "one launch" : "launch chain");
+    return fits;
+}
+
+template <int CE, int W>
+int persist_capacity_t(int64_t reach, int64_t* nodes) {
+    const int r = (int)((reach + TB - 1) / TB);
+    const size_t smem = (size_t)(2 * r + 1) * TB * CE * sizeof(float);
+    int64_t lo = 0, hi = 1 << 20;                    // largest G that fits, by bisection over the cached occupancy
+    if (!persist_fits<CE, W>(1, r, smem)) {
+        *nodes = 0;
+        return GAD_OK;
+    }
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) / 2;
+        (persist_fits<CE, W>((unsigned)mid, r, smem) ? lo : hi) = mid;
+    }
+    *nodes = lo * TB;
+    return GAD_OK;
+}
+
 int slots_for(int max_deg) { return max_deg <= 2 ? 2 : (max_deg <= 3 ? 3 : (max_deg <= 6 ? 6 : 7)); }
 
 template <int CE, int W>
-int wide_forward_t(const int4* rows, int64_t N, const float* x0, int dim, const float* Mu, int Lw, const float* tau, int L,
-                   int method, float* x_phys, float* states, float* ws, cudaStream_t st) {
+int wide_forward_t(const int4* rows, int64_t N, int64_t reach, const float* x0, int dim, const float* Mu, int Lw,
+                   const float* tau, int L, int method, float* x_phys, float* states, float* ws, cudaStream_t st) {
     const size_t row = (size_t)N * CE;
     const int MUSZ = CE * CE + CE;
     const size_t rowa = align_up(row, 64);
@@ -378,6 +696,29 @@ int wide_forward_t(const int4* rows, int64_t N, const float* x0, int dim, const 
     float* y3buf = ws + 4 * rowa;   // RK4: stage input y3
     const float* cur = x0;
     const unsigned G = nblocks(N);
+    const int r = reach < 0 ? -1 : (int)((reach + TB - 1) / TB);
+    const size_t smem = (size_t)(2 * (r < 0 ? 0 : r) + 1) * TB * CE * sizeof(float);
+    if ((L > 1 || method == GAD_METHOD_RK4) && persist_fits<CE, W>(G, r, smem)) {
+        // ONE cooperative launch for the whole call.  The two tagged buffers (2 floats per state value) live in the
+        // workspace and start with tag 0 everywhere; epochs count from 1.
+        float* tb0 = ws;
+        float* tb1 = ws + 2 * rowa;
+        GAD_CUDA(cudaMemsetAsync(ws, 0, 4 * rowa * sizeof(float), st));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(G);
+        cfg.blockDim = dim3(TB);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GAD_CUDA(cudaLaunchKernelEx(&cfg, k_wide_persist<CE, W>, rows, N, r, x0, Mu, Lw, tau, L, method, tb0, tb1, states,
+                                    x_phys, dim));
+        count_launch(1);
+        return GAD_OK;
+    }
     for (int l = 0; l < L; ++l) {
         const float* Mul = Mu + (size_t)(Lw > 1 ? l : 0) * MUSZ;
         const float* tl = tau + l;
@@ -494,7 +835,7 @@ extern "C" int gad_graph_build_wide(const int32_t* ptr, const int32_t* idx, int6
     return GAD_OK;
 }
 
-extern "C" int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, const float* x0, int dim, int CE,
+extern "C" int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, int64_t reach, const float* x0, int dim, int CE,
                                    const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
                                    float* states, void* workspace, size_t workspace_bytes, void* stream) {
     GAD_CHECK_ARG(wide_in && x0 && Mu && tau && x_phys && workspace, "gad_deform_fwd_wide: null pointer");
@@ -507,7 +848,14 @@ extern "C" int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, 
     const int4* rows = reinterpret_cast<const int4*>(wide_in);
     float* ws = reinterpret_cast<float*>(workspace);
     cudaStream_t st = as_stream(stream);
-    GAD_WIDE_DISPATCH(wide_forward_t, rows, N, x0, dim, Mu, Lw, tau, L, method, x_phys, states, ws, st);
+    GAD_WIDE_DISPATCH(wide_forward_t, rows, N, reach, x0, dim, Mu, Lw, tau, L, method, x_phys, states, ws, st);
+}
+
+extern "C" int64_t gad_wide_persist_nodes(int CE, int max_deg, int64_t reach) {
+    int64_t nodes = 0;
+    if (reach < 0 || max_deg < 0 || max_deg > WIDE_SLOTS || (CE != 2 && CE != 4)) return 0;
+    auto run = [&]() -> int { GAD_WIDE_DISPATCH(persist_capacity_t, reach, &nodes); };
+    return run() == GAD_OK ? nodes : 0;
 }
 
 extern "C" int gad_deform_bwd_wide(const void* wide_in, const void* wide_out, int64_t N, int max_deg,

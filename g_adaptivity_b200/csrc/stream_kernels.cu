@@ -335,7 +335,8 @@ GAD_INSTANTIATE(4)
 GAD_INSTANTIATE(8)
 
 size_t stream_fwd_ws_floats(int64_t N, int CE, int method) {
-    return align_up((size_t)N * CE, 64) * (method == GAD_METHOD_RK4 ? 5 : 2) + 64;
+    // at least 4 rows: the persistent streaming forward keeps two tagged buffers of 2 floats per value there
+    return align_up((size_t)N * CE, 64) * (method == GAD_METHOD_RK4 ? 5 : 4) + 64;
 }
 
 size_t stream_bwd_ws_floats(int64_t N, int CE) {

@@ -124,8 +124,8 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
         if graph.ensure_wide(CE):      # streaming ELL kernels (csrc/stream_ell.cu)
             with torch.cuda.device(x0.device):
                 _lib.check(lib.gad_deform_fwd_wide(
-                    _lib.ptr(graph.wide_in), N, graph.wide_deg, _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L,
-                    method, _lib.ptr(x_phys), _lib.ptr(states), _lib.ptr(ws), ws_bytes, _stream(x0)), "gad_deform_fwd_wide")
+                    _lib.ptr(graph.wide_in), N, graph.wide_deg, graph.wide_reach, _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw,
+                    _lib.ptr(tau), L, method, _lib.ptr(x_phys), _lib.ptr(states), _lib.ptr(ws), ws_bytes, _stream(x0)), "gad_deform_fwd_wide")
             return x_phys
     with torch.cuda.device(x0.device):
         _lib.check(lib.gad_deform_fwd(

@@ -66,6 +66,7 @@ class MeshGraph:
         self.tile_ptr = None        # int32 [T+1] on device, or None -> streaming kernels
         self.ell_in = self.ell_out = None   # uint16 [N, 8] ELL rows (mesh-resident ELL kernels), or None
         self.wide_in = self.wide_out = None  # int32 [N, 8] wide rows (streaming ELL kernels), built on demand
+        self.wide_reach = -1                 # max |j - i| over the edges, known once the wide rows exist
         self._wide_tried = False
         self.cl_in = self.cl_out = None      # int32 [N, 8] cluster rows (cluster-resident training kernel)
         self.cl_C = self.cl_S = 0            # cluster size, slab size
@@ -308,6 +309,11 @@ def _ensure_wide(self, ce: int) -> bool:
         return False
     self.wide_in, self.wide_out = wi, wo
     self.wide_deg = max(self.max_in_deg, self.max_out_deg)
+    # bandwidth of the node numbering, max |j - i| over the edges: the persistent streaming forward sizes its
+    # shared-memory window with it (csrc/stream_ell.cu: k_wide_persist)
+    ids = torch.arange(self.N, device=self.device, dtype=torch.int32).unsqueeze(1)
+    live = (wi[:, 7:8] >> torch.arange(7, device=self.device, dtype=torch.int32)) & 1
+    self.wide_reach = int(((wi[:, :7] - ids).abs() * live).max().item())
     return True
 
 
@@ -416,10 +422,11 @@ def _stream_fwd_preferred(self, ce: int, n_fevals: int) -> bool:
     """Forward-only dispatch between the cluster kernel (one launch, M x C CTAs, a cluster barrier per
     F-evaluation) and the streaming wide-row chain (one dependent launch per F-evaluation over ALL SMs,
     csrc/stream_ell.cu).  With few meshes the clusters leave most of the machine idle: one 200x200 mesh on
-    16 CTAs takes 3.5 us per F-evaluation against 1.85 us for the chain (cfg 4: 0.87 -> 0.46 ms); from
-    ~4 meshes of 100x100 on, and for 64x64 meshes at any batch, the cluster kernel wins.  Measured model:
-    chain = 1.7 us + 12.2 ns per 1000 nodes of the batch per F-evaluation, plus ~3 us once for the extra
-    pack launch.  Call after ensure_cluster_fwd returned True."""
+    16 CTAs takes 3.5 us per F-evaluation against 1.85 us for the chain and 1.6 us for the persistent one-launch
+    streaming kernel (cfg 4: 0.87 -> 0.46 -> 0.41 ms); for 64x64 meshes at any batch, and for many large meshes,
+    the cluster kernel wins.  Measured model: chain = 1.7 us + 12.2 ns per 1000 nodes of the batch per
+    F-evaluation, persistent kernel = 1.37 us + 5.5 ns per 1000 nodes, plus ~3 us once for the extra pack
+    launch.  Call after ensure_cluster_fwd returned True."""
     import os
     pol = os.environ.get("GAD_FWD_POLICY")
     if pol == "cluster":
@@ -433,7 +440,16 @@ def _stream_fwd_preferred(self, ce: int, n_fevals: int) -> bool:
         k = 0 if slab <= pts[1][0] else 1
         (s0, t0), (s1, t1) = pts[k], pts[k + 1]
         cluster_us = t0 + (slab - s0) * (t1 - t0) / (s1 - s0)
-        stream_us = 1.7 + 1.22e-5 * self.N
+        if not self.ensure_wide(ce):
+            return False
+        # the persistent one-launch forward (k_wide_persist) where the nodes fit the co-resident threads: measured
+        # 1.45 us per F-evaluation at 14 400 nodes, 1.59 us at 40 000; beyond that the chain of dependent launches
+        with torch.cuda.device(self.device):
+            fits = self.N <= int(_lib.load().gad_wide_persist_nodes(ce, self.wide_deg, self.wide_reach))
+        if fits and os.environ.get("GAD_WIDE_PERSIST", "1") != "0":
+            stream_us = 1.37 + 5.5e-6 * self.N
+        else:
+            stream_us = 1.7 + 1.22e-5 * self.N
         if n_fevals * (cluster_us - stream_us) <= 3.0:
             return False
     return self.ensure_wide(ce)

@@ -371,7 +371,7 @@ class DeformerTrainer:
                 "gad_pack_features")
             wide = (not tiles) and g.ensure_wide(CE)      # streaming ELL kernels (csrc/stream_ell.cu)
             if wide:
-                chk(lib.gad_deform_fwd_wide(P(g.wide_in), s.N, g.wide_deg, P(s.states), dim, CE, P(self.Mu), Lw, P(self.tau), L,
+                chk(lib.gad_deform_fwd_wide(P(g.wide_in), s.N, g.wide_deg, g.wide_reach, P(s.states), dim, CE, P(self.Mu), Lw, P(self.tau), L,
                                             self.method, P(s.x_phys), P(s.states), P(s.fwd_ws), s.fwd_ws_bytes, stream_ptr),
                     "gad_deform_fwd_wide")
             else:

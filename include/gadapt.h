@@ -149,10 +149,18 @@ int gad_deform_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_r
  * over rows  wide[i] = { int32 j_0 .. j_6, int32 valid }  (32 bytes; absolute neighbour ids, unused
  * slots = i, masked by `valid`): a node is ONE branch-free pass with no dependent index loads.
  * gad_graph_build_wide converts a (row-sorted) CSR or CSC; rows with more than 7 entries are counted
- * into info[GAD_INFO_ELL_BAD].  Workspaces: gad_deform_workspace_bytes / gad_deform_bwd_workspace_bytes. */
+ * into info[GAD_INFO_ELL_BAD].  Workspaces: gad_deform_workspace_bytes / gad_deform_bwd_workspace_bytes.
+ * `reach` = max |j - i| over the edges (the bandwidth of the node numbering), or -1 when unknown.  With a known
+ * reach, and when all N / 256 CTAs with a window of (2 ceil(reach / 256) + 1) * 256 state rows in shared memory can
+ * be co-resident, the forward runs ALL its F-evaluations in ONE cooperative launch (k_wide_persist: state in
+ * registers, gathers from shared memory, halo rows exchanged through L2 as (value, epoch) pairs, no barrier);
+ * same arithmetic, bit-identical results.  GAD_WIDE_PERSIST=0 in the environment keeps the launch chain. */
 int gad_graph_build_wide(const int32_t* ptr, const int32_t* idx, int64_t N, void* wide_rows, int32_t* info,
                          void* stream);
-int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, const float* x0, int dim, int CE,
+/* Largest node count the one-launch persistent forward takes on the current device for rows of this shape
+ * (0: never -- reach unknown, window beyond 96 KB of shared memory, no cooperative launch). */
+int64_t gad_wide_persist_nodes(int CE, int max_deg, int64_t reach);
+int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, int64_t reach, const float* x0, int dim, int CE,
                         const float* Mu, int Lw, const float* tau, int L, int method, float* x_phys,
                         float* states, void* workspace, size_t workspace_bytes, void* stream);
 int gad_deform_bwd_wide(const void* wide_in, const void* wide_out, int64_t N, int max_deg, const float* states,

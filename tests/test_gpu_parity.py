@@ -411,6 +411,50 @@ def test_config4_200x200_rk4_64_steps_forward(monkeypatch):
     assert getattr(model2.last_graph, "clf_in", None) is None
 
 
+@pytest.mark.parametrize("mesh_dims,B,burgers,over", [
+    ((64, 64), 1, False, {}), ((64, 64), 1, False, {"ode_method": "rk4", "num_layers": 5}),
+    ((200, 200), 1, False, {"ode_method": "rk4", "num_layers": 8}),
+    ((90, 90), 1, False, {"share_conv": False, "learn_step": True, "num_layers": 6}),
+    ((100, 100), 3, False, {"num_layers": 7}), ((20000,), 2, True, {"ode_method": "rk4", "num_layers": 6})])
+def test_persistent_streaming_forward_equals_the_launch_chain(mesh_dims, B, burgers, over, monkeypatch):
+    """Graphs whose nodes fit the GPU's co-resident threads run all steps of the streaming forward in ONE cooperative
+    launch (k_wide_persist: state in registers, window in shared memory, halo rows exchanged through L2 as tagged
+    words); same arithmetic as the chain of one launch per F-evaluation, so the result is bit-identical -- forward
+    values and, where the backward exists (Euler), the gradients computed from the states it saved."""
+    from g_adaptivity_b200 import _lib
+    lib = _lib.load()
+    outs, launches = [], []
+    for persist in ("1", "0"):
+        monkeypatch.setenv("GAD_WIDE_PERSIST", persist)
+        model, out, ref_out, data = _compare_with_oracle(mesh_dims, B, over=over, burgers=burgers, backward=False,
+                                                         gad_no_cluster=True)
+        assert model.last_graph.wide_in is not None and model.last_graph.wide_reach >= 1
+        model.eval()
+        with torch.no_grad():
+            model(data)
+            torch.cuda.synchronize()
+            n0 = lib.gad_launch_count()
+            o = model(data)
+            torch.cuda.synchronize()
+            launches.append(lib.gad_launch_count() - n0)
+            for _ in range(3):                     # run to run: the exchange has no data-dependent ordering
+                assert torch.equal(model(data), o)
+        grads = []
+        if over.get("ode_method", "euler") == "euler":
+            model.train()
+            o_train = model(data)
+            assert torch.equal(o_train.detach(), o)
+            g = torch.autograd.grad(o_train.square().sum(), [p for p in model.parameters() if p.requires_grad],
+                                    allow_unused=True)
+            grads = [t.clone() for t in g if t is not None]
+        outs.append((o.clone(), grads))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert len(outs[0][1]) == len(outs[1][1])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+    assert launches[0] < launches[1], launches          # one launch instead of one per F-evaluation
+
+
 def test_rk4_mesh_resident_matches_oracle():
     over = {"ode_method": "rk4", "num_layers": 6}
     model, *_ = _compare_with_oracle((20, 20), 7, over=over, backward=False)
