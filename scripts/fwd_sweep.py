@@ -30,17 +30,26 @@ def run(md, batch, method, layers, no_cluster):
     return e0.elapsed_time(e1) / 10, getattr(sess.graph, "clf_C", None)
 
 
-cases = [((64, 64), b) for b in (1, 4, 16, 64)] + [((100, 100), b) for b in (1, 2, 4, 8, 16, 64)] + \
-        [((200, 200), b) for b in (1, 4)]
+cases = [((64, 64), b) for b in (1, 4, 16)] + [((100, 100), b) for b in (1, 2, 4, 8, 16)] + \
+        [((200, 200), b) for b in (1, 2)]
+# routes: the cluster kernel (forced), the persistent one-launch streaming kernel, the chain of dependent launches, and
+# what graph.stream_fwd_preferred picks when left alone
+ROUTES = (("cluster_ms", {"GAD_FWD_POLICY": "cluster"}, False), ("persist_ms", {}, True),
+          ("chain_ms", {"GAD_WIDE_PERSIST": "0"}, True), ("default_ms", {}, False))
 for method, layers in (("rk4", 16), ("euler", 4)):
     for md, b in cases:
         row = {"mesh": md, "batch": b, "method": method, "layers": layers}
-        for nc in (False, True):
+        for key, env, nc in ROUTES:
+            for k in ("GAD_FWD_POLICY", "GAD_WIDE_PERSIST"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
             try:
                 ms, C = run(md, b, method, layers, nc)
-                row["stream_ms" if nc else "cluster_ms"] = round(ms, 4)
-                if not nc:
+                row[key] = round(ms, 4)
+                if key == "cluster_ms":
                     row["C"] = C
             except Exception as ex:  # noqa
-                row["stream_err" if nc else "cluster_err"] = str(ex)[:80]
+                row[key.replace("_ms", "_err")] = str(ex)[:80]
+        best = min((row[k], k) for k in ("cluster_ms", "persist_ms", "chain_ms") if k in row)
+        row["policy_loss_pct"] = round(100.0 * (row.get("default_ms", best[0]) / best[0] - 1.0), 1)
         print(json.dumps(row), flush=True)
