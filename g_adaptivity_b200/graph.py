@@ -444,8 +444,7 @@ def _stream_fwd_preferred(self, ce: int, n_fevals: int) -> bool:
             return False
         # the persistent one-launch forward (k_wide_persist) where the nodes fit the co-resident threads: measured
         # 1.45 us per F-evaluation at 14 400 nodes, 1.59 us at 40 000; beyond that the chain of dependent launches
-        with torch.cuda.device(self.device):
-            fits = self.N <= int(_lib.load().gad_wide_persist_nodes(ce, self.wide_deg, self.wide_reach))
+        fits = self.N <= self.persist_nodes(ce)
         if fits and os.environ.get("GAD_WIDE_PERSIST", "1") != "0":
             stream_us = 1.37 + 5.5e-6 * self.N
         else:
@@ -453,6 +452,17 @@ def _stream_fwd_preferred(self, ce: int, n_fevals: int) -> bool:
         if n_fevals * (cluster_us - stream_us) <= 3.0:
             return False
     return self.ensure_wide(ce)
+
+
+def _persist_nodes(self, ce: int) -> int:
+    """Largest node count the persistent streaming forward (k_wide_persist) takes for this graph's wide rows on its
+    device: 148 SMs x 3 co-resident CTAs x 256 nodes on a B200 while the window fits shared memory; 0 = never."""
+    cached = getattr(self, "_persist_nodes_cache", None)
+    if cached is None or cached[0] != ce:
+        with torch.cuda.device(self.device):
+            cached = (ce, int(_lib.load().gad_wide_persist_nodes(ce, self.wide_deg, self.wide_reach)))
+        self._persist_nodes_cache = cached
+    return cached[1]
 
 
 def _stream_train_preferred(self, ce: int) -> bool:
@@ -480,6 +490,7 @@ MeshGraph.ensure_cluster = _ensure_cluster
 MeshGraph.ensure_cluster_fwd = _ensure_cluster_fwd
 MeshGraph.stream_train_preferred = _stream_train_preferred
 MeshGraph.stream_fwd_preferred = _stream_fwd_preferred
+MeshGraph.persist_nodes = _persist_nodes
 
 
 def edge_masks(edge_index: torch.Tensor, side_bits: torch.Tensor):

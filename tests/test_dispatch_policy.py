@@ -7,18 +7,24 @@ import pytest
 from g_adaptivity_b200 import graph as G
 
 
-def _fake(n_mesh_nodes, M, C):
+B200_PERSIST_NODES = 148 * 3 * 256      # what gad_wide_persist_nodes answers on a B200 for a 12 KB window
+
+
+def _fake(n_mesh_nodes, M, C, persist_nodes=B200_PERSIST_NODES):
     g = types.SimpleNamespace(mesh_sizes=[n_mesh_nodes] * M, clf_C=C, cl_C=C, N=n_mesh_nodes * M)
     g.ensure_wide = lambda ce: True
+    g.persist_nodes = lambda ce: persist_nodes
     return g
 
 
 @pytest.mark.parametrize("nodes,M,C,fevals,want_stream", [
-    (200 * 200, 1, 16, 256, True),      # cfg 4: 0.46 ms on the chain, 0.87 ms on one cluster
-    (200 * 200, 4, 16, 64, False),      # tie -> one launch
+    (200 * 200, 1, 16, 256, True),      # cfg 4: 0.41 ms on the persistent kernel, 0.87 ms on one cluster
+    (200 * 200, 2, 16, 64, True),       # 0.142 against 0.223 ms (profiles/r02_v3_fwd_dispatch_sweep.jsonl)
+    (200 * 200, 4, 16, 64, False),      # beyond the co-resident threads: chain against cluster is a tie -> one launch
     (100 * 100, 1, 16, 64, True),
     (100 * 100, 2, 16, 64, True),
-    (100 * 100, 8, 16, 64, False),
+    (100 * 100, 8, 16, 64, True),       # 0.130 against 0.152 ms since the persistent kernel
+    (100 * 100, 16, 16, 64, False),     # 160 000 nodes: chain 0.234 against cluster 0.183 ms
     (100 * 100, 64, 4, 64, False),
     (64 * 64, 1, 16, 64, False),
     (64 * 64, 64, 2, 64, False),
@@ -26,7 +32,19 @@ def _fake(n_mesh_nodes, M, C):
 ])
 def test_forward_dispatch(nodes, M, C, fevals, want_stream, monkeypatch):
     monkeypatch.delenv("GAD_FWD_POLICY", raising=False)
+    monkeypatch.delenv("GAD_WIDE_PERSIST", raising=False)
     assert G._stream_fwd_preferred(_fake(nodes, M, C), 4, fevals) == want_stream
+
+
+def test_forward_dispatch_without_the_persistent_kernel(monkeypatch):
+    """GAD_WIDE_PERSIST=0 (or a device where the cooperative launch does not fit): the chain's cost model decides, as
+    in round 1 (profiles/r01_v11_fwd_dispatch_sweep.jsonl)."""
+    monkeypatch.delenv("GAD_FWD_POLICY", raising=False)
+    monkeypatch.setenv("GAD_WIDE_PERSIST", "0")
+    assert G._stream_fwd_preferred(_fake(200 * 200, 1, 16), 4, 256)
+    assert not G._stream_fwd_preferred(_fake(100 * 100, 8, 16), 4, 64)
+    monkeypatch.delenv("GAD_WIDE_PERSIST")
+    assert not G._stream_fwd_preferred(_fake(100 * 100, 8, 16, persist_nodes=0), 4, 64)
 
 
 @pytest.mark.parametrize("nodes,M,C,want_stream", [
