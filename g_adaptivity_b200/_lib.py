@@ -73,6 +73,8 @@ SIGNATURES = {
     "gad_deform_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p,
                             _p, _sz, _p]),
     "gad_graph_build_wide": (_i, [_p, _p, _i64, _p, _p, _p]),
+    "gad_deform_bwd_wide_rk4_workspace_bytes": (_sz, [_i64, _i]),
+    "gad_deform_bwd_wide_rk4": (_i, [_p, _p, _i64, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "gad_wide_persist_nodes": (_i64, [_i, _i, _i64]),
     "gad_deform_fwd_wide": (_i, [_p, _i64, _i, _i64, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "gad_deform_bwd_wide": (_i, [_p, _p, _i64, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),

@@ -615,6 +615,33 @@ __global__ void __launch_bounds__(TB) k_wide_bwd_src(const int4* __restrict__ ro
     store_row<CE>(gout, j, accv);
 }
 
+// ---- RK4 backward on the streaming kernels: bookkeeping between the four vjp passes of a step ------------------
+//   a_out = ca_g * g + ca_gy * gy   (cotangent of the next stage to differentiate, in units of 1 / tau)
+//   gs    = (first ? g : gs) + gy    (running cotangent of the step input)
+// g is [N, gdim] (gdim < CE next to the loss), everything else [N, CE].
+template <int CE>
+__global__ void __launch_bounds__(TB) k_wide_rk4_comb(int64_t N, const float* __restrict__ g, int gdim,
+                                                      const float* __restrict__ gy, float ca_g, float ca_gy,
+                                                      float* __restrict__ a_out, float* __restrict__ gs, int first) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const Row<CE> gi = load_gplus<CE>(g, i, gdim);
+    Row<CE> yi = zero_row<CE>();
+    if (gy) yi = load_row<CE>(gy, i);
+    if (a_out) {
+        Row<CE> a;
+#pragma unroll
+        for (int c = 0; c < CE; ++c) a.v[c] = fmaf(ca_gy, yi.v[c], ca_g * gi.v[c]);
+        store_row<CE>(a_out, i, a);
+    }
+    if (gs) {
+        Row<CE> o = first ? gi : load_row<CE>(gs, i);
+#pragma unroll
+        for (int c = 0; c < CE; ++c) o.v[c] += yi.v[c];
+        store_row<CE>(gs, i, o);
+    }
+}
+
 // Fixed-order reduction of the per-block partials (one warp per accumulator): out[k] (+)= sum_r part[r, k].
 __global__ void k_wide_reduce(const float* __restrict__ partials, int rows, int nacc, int stride, float* __restrict__ out,
                               int accumulate) {
@@ -811,6 +838,82 @@ size_t stream_bwd_ws_floats(int64_t N, int CE);
 
 using namespace gad;
 
+size_t wide_bwd_rk4_ws_floats(int64_t N, int CE) {
+    const int NACC = CE * CE + CE + 1;
+    return align_up((size_t)N * CE, 64) * 9 + align_up(2 * (size_t)N, 64) +
+           align_up((size_t)grid_for_partials(N) * NACC, 64) + 64;
+}
+
+// Backward through L classical RK4 steps of F(y) = A(y) y - y on the streaming kernels, from the saved step inputs
+// x^0 .. x^{L-1}.  Per step, in reverse: recompute the stage inputs y2, y3, y4 (three k_wide_stage launches), then four
+// vjp passes (k_wide_bwd_dst + k_wide_bwd_src with a_coef = 0: gout = tau J(y_s)^T a) on the cotangents
+//   a4 = g / 6,  a3 = g / 3 + gy4,  a2 = g / 3 + gy3 / 2,  a1 = g / 6 + gy2 / 2      (a_s = dL/dk_s / tau)
+// and g(step input) = g + gy1 + gy2 + gy3 + gy4.  The weight-gradient partials accumulate over the four passes (and,
+// with one shared weight set, over all steps) in the same blocks in the same order: deterministic.  No step-size
+// gradient (learn_step is an Euler feature, as in k_ell_bwd_rk4).
+template <int CE, int W>
+int wide_backward_rk4_t(const int4* rows_in, const int4* rows_out, int64_t N, const float* states, const float* g_xphys,
+                        int dim, const float* Mu, int Lw, const float* tau, int L, float* gMu, float* g_x0, float* ws,
+                        cudaStream_t st) {
+    constexpr int NACC = CE * CE + CE + 1;
+    const int MUSZ = CE * CE + CE;
+    const size_t row = (size_t)N * CE;
+    const int G = grid_for_partials(N);
+    const unsigned GN = nblocks(N);
+    const size_t rowa = align_up(row, 64);
+    float* P = ws;
+    float* gself = ws + rowa;
+    float* a = ws + 2 * rowa;
+    float* gy = ws + 3 * rowa;
+    float* gsb[2] = {ws + 4 * rowa, ws + 5 * rowa};
+    float* yb[3] = {ws + 6 * rowa, ws + 7 * rowa, ws + 8 * rowa};       // y2, y3, y4
+    float2* DL = reinterpret_cast<float2*>(ws + 9 * rowa);
+    float* partials = ws + 9 * rowa + align_up(2 * (size_t)N, 64);
+    GAD_CUDA(cudaMemsetAsync(gMu, 0, (size_t)Lw * MUSZ * sizeof(float), st));
+    const float* gcur = g_xphys;
+    int gdim = dim;
+    const bool shared_w = (Lw == 1);
+    bool first_of_set = true;
+    static const float ca_g[4] = {1.0f / 6.0f, 1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 6.0f};      // of a1 .. a4
+    for (int l = L - 1; l >= 0; --l) {
+        const float* Mul = Mu + (size_t)(Lw > 1 ? l : 0) * MUSZ;
+        const float* xl = states + (size_t)l * row;
+        const float* tl = tau + l;
+        float* gs = (l == 0 && g_x0) ? g_x0 : gsb[l & 1];
+        // stage inputs: y2 = x + tau/2 F(x), y3 = x + tau/2 F(y2), y4 = x + tau F(y3)
+        const float* yin = xl;
+        for (int sgi = 0; sgi < 3; ++sgi) {
+            GAD_CUDA(launch_link(k_wide_stage<CE, W>, GN, st, false, rows_in, N, yin, xl, (const float*)nullptr, Mul, tl,
+                                 sgi == 2 ? 1.0f : 0.5f, 0.f, 0, yb[sgi], (float*)nullptr, (float*)nullptr, dim));
+            yin = yb[sgi];
+        }
+        count_launch(3);
+        if (!shared_w) first_of_set = true;
+        k_wide_rk4_comb<CE><<<GN, TB, 0, st>>>(N, gcur, gdim, (const float*)nullptr, ca_g[3], 0.f, a, (float*)nullptr, 0);
+        GAD_LAUNCH_CHECK();
+        for (int sgi = 3; sgi >= 0; --sgi) {
+            const float* ys = sgi == 0 ? xl : yb[sgi - 1];
+            GAD_CUDA(launch_link(k_wide_bwd_dst<CE, W>, (unsigned)G, st, false, rows_in, N, ys, (const float*)a, CE, Mul, tl,
+                                 0.0f, P, DL, gself, partials, first_of_set ? 0 : 1, (float*)nullptr, 0));
+            first_of_set = false;
+            GAD_CUDA(launch_link(k_wide_bwd_src<CE, W>, GN, st, false, rows_out, N, ys, (const float*)a, CE, tl,
+                                 (const float*)P, (const float2*)DL, (const float*)gself, gy));
+            count_launch(2);
+            // next cotangent (a3 = g/3 + gy4, a2 = g/3 + gy3/2, a1 = g/6 + gy2/2) and the running sum g + sum gy
+            k_wide_rk4_comb<CE><<<GN, TB, 0, st>>>(N, gcur, gdim, (const float*)gy, sgi > 0 ? ca_g[sgi - 1] : 0.f,
+                                                 sgi == 3 ? 1.0f : 0.5f, sgi > 0 ? a : (float*)nullptr, gs, sgi == 3);
+            GAD_LAUNCH_CHECK();
+        }
+        if (!shared_w || l == 0) {
+            k_wide_reduce<<<(MUSZ + 7) / 8, 256, 0, st>>>(partials, G, MUSZ, NACC, gMu + (size_t)(shared_w ? 0 : l) * MUSZ, 1);
+            GAD_LAUNCH_CHECK();
+        }
+        gcur = gs;
+        gdim = CE;
+    }
+    return GAD_OK;
+}
+
 #define GAD_WIDE_DISPATCH(FN, ...)                                                     \
     do {                                                                               \
         const int w__ = slots_for(max_deg);                                            \
@@ -849,6 +952,27 @@ extern "C" int gad_deform_fwd_wide(const void* wide_in, int64_t N, int max_deg, 
     float* ws = reinterpret_cast<float*>(workspace);
     cudaStream_t st = as_stream(stream);
     GAD_WIDE_DISPATCH(wide_forward_t, rows, N, reach, x0, dim, Mu, Lw, tau, L, method, x_phys, states, ws, st);
+}
+
+extern "C" size_t gad_deform_bwd_wide_rk4_workspace_bytes(int64_t N, int CE) {
+    return wide_bwd_rk4_ws_floats(N, CE) * sizeof(float);
+}
+
+extern "C" int gad_deform_bwd_wide_rk4(const void* wide_in, const void* wide_out, int64_t N, int max_deg,
+                                       const float* states, const float* g_xphys, int dim, int CE, const float* Mu, int Lw,
+                                       const float* tau, int L, float* gMu, float* g_x0, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+    GAD_CHECK_ARG(wide_in && wide_out && states && g_xphys && Mu && tau && gMu && workspace,
+                  "gad_deform_bwd_wide_rk4: null pointer");
+    GAD_CHECK_ARG(N > 0 && L > 0 && dim >= 1 && dim <= CE && (Lw == 1 || Lw == L) && max_deg >= 0 && max_deg <= WIDE_SLOTS,
+                  "gad_deform_bwd_wide_rk4: N=%lld L=%d dim=%d CE=%d Lw=%d max_deg=%d", (long long)N, L, dim, CE, Lw, max_deg);
+    GAD_CHECK_ARG(workspace_bytes >= wide_bwd_rk4_ws_floats(N, CE) * sizeof(float),
+                  "gad_deform_bwd_wide_rk4: workspace too small");
+    const int4* rin = reinterpret_cast<const int4*>(wide_in);
+    const int4* rout = reinterpret_cast<const int4*>(wide_out);
+    float* ws = reinterpret_cast<float*>(workspace);
+    cudaStream_t st = as_stream(stream);
+    GAD_WIDE_DISPATCH(wide_backward_rk4_t, rin, rout, N, states, g_xphys, dim, Mu, Lw, tau, L, gMu, g_x0, ws, st);
 }
 
 extern "C" int64_t gad_wide_persist_nodes(int CE, int max_deg, int64_t reach) {

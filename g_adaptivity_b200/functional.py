@@ -215,22 +215,39 @@ def _tile_bias_grads(ws: torch.Tensor, T: int, Lw: int, L: int, CE: int) -> torc
 
 
 def deform_backward_rk4(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tensor, dim: int, Mu: torch.Tensor,
-                        tau: torch.Tensor, want_gx0: bool = False, du: Optional[torch.Tensor] = None):
-    """Backward through classical RK4 steps (csrc/ell_kernels.cuh: k_ell_bwd_rk4), mesh-resident ELL graphs only:
-    cotangent of x_phys -> (gMu, g_x0 | None).  The step sizes get no gradient (learn_step is an Euler feature)."""
+                        tau: torch.Tensor, want_gx0: bool = False, du: Optional[torch.Tensor] = None,
+                        force_stream: bool = False):
+    """Backward through classical RK4 steps: cotangent of x_phys -> (gMu, g_x0 | None, g_du | None).  Meshes that fit a
+    CTA: one launch of the mesh-resident kernel (csrc/ell_kernels.cuh: k_ell_bwd_rk4).  Larger meshes (or
+    `force_stream`): the streaming kernels, three stage recomputes and four vjp passes per step
+    (csrc/stream_ell.cu: wide_backward_rk4_t).  The step sizes get no gradient (learn_step is an Euler feature)."""
     _need_cuda(states, g_xphys, Mu, tau)
     lib = _lib.load()
     L, N, CE = states.shape
-    if not (graph.tile_ptr is not None and use_ell(graph, CE)
-            and lib.gad_ell_rk4_bwd_supported(CE, graph.max_tile_nodes, graph.ell_deg)):
-        raise NotImplementedError(
-            "backward through ode_method='rk4' runs on the mesh-resident ELL kernel: meshes of at most ~1200 nodes "
-            f"(a tile keeps nine rows per node in shared memory), degree <= 7; this graph has tiles of {graph.max_tile_nodes}")
     Lw = int(Mu.shape[0])
     g_xphys = _f32(g_xphys)
     dev = states.device
     gMu = torch.empty_like(Mu)
     g_x0 = torch.empty((N, CE), dtype=torch.float32, device=dev) if want_gx0 else None
+    resident = (graph.tile_ptr is not None and not force_stream and use_ell(graph, CE)
+                and lib.gad_ell_rk4_bwd_supported(CE, graph.max_tile_nodes, graph.ell_deg))
+    if not resident:
+        if du is not None:
+            raise NotImplementedError("global CNN features reach the kernels as a per-tile bias offset: meshes that fit "
+                                      "a CTA only (backward through ode_method='rk4' on the streaming kernels has none)")
+        if not graph.ensure_wide(CE):
+            raise NotImplementedError(
+                "backward through ode_method='rk4': meshes of at most ~1200 nodes run on the mesh-resident ELL kernel, "
+                "larger ones on the streaming ELL kernels, both for degree <= 7 and 2 or 4 live channels; this graph "
+                f"has max degree {max(graph.max_in_deg, graph.max_out_deg)}, CE = {CE}")
+        ws_bytes = lib.gad_deform_bwd_wide_rk4_workspace_bytes(N, CE)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gad_deform_bwd_wide_rk4(
+                _lib.ptr(graph.wide_in), _lib.ptr(graph.wide_out), N, graph.wide_deg, _lib.ptr(states), _lib.ptr(g_xphys),
+                dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes,
+                _stream(states)), "gad_deform_bwd_wide_rk4")
+        return gMu, g_x0, None
     ws_bytes = lib.gad_ell_workspace_bytes(CE, graph.T, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
@@ -409,10 +426,8 @@ class DeformFunction(torch.autograd.Function):
         if ctx.method == METHOD_RK4:
             if ni[9]:
                 raise NotImplementedError("learn_step with ode_method='rk4': the step sizes get no gradient through RK4")
-            if ctx.force_stream:
-                raise NotImplementedError("backward through ode_method='rk4' has no streaming variant (gad_force_stream)")
             gMu, g_x0, g_du = deform_backward_rk4(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d,
-                                                  want_gx0=want_gx0, du=du)
+                                                  want_gx0=want_gx0, du=du, force_stream=ctx.force_stream)
             g_tau = None
         else:
             res = deform_backward(ctx.graph, states, g_xphys.contiguous(), ctx.dim, Mu, tau_d,

@@ -157,6 +157,15 @@ int gad_deform_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* t_r
  * same arithmetic, bit-identical results.  GAD_WIDE_PERSIST=0 in the environment keeps the launch chain. */
 int gad_graph_build_wide(const int32_t* ptr, const int32_t* idx, int64_t N, void* wide_rows, int32_t* info,
                          void* stream);
+/* Backward through classical RK4 steps on the streaming kernels (graphs without tiles, or tiles bypassed): from the
+ * saved step inputs states [L, N, CE], per step three stage recomputes and four vjp passes of the Euler backward
+ * kernels; cotangent g_xphys [N, dim] -> gMu [Lw, CE*CE+CE] (deterministic fixed-order reduction), g_x0 [N, CE] or
+ * NULL.  No step-size gradient (as gad_deform_bwd_ell_rk4).  Replaces autograd through the reference's loop with an
+ * RK4 step (north_star item 3; template classical_meshing/ma_mesh_1d.py:65-70). */
+size_t gad_deform_bwd_wide_rk4_workspace_bytes(int64_t N, int CE);
+int gad_deform_bwd_wide_rk4(const void* wide_in, const void* wide_out, int64_t N, int max_deg, const float* states,
+                            const float* g_xphys, int dim, int CE, const float* Mu, int Lw, const float* tau, int L,
+                            float* gMu, float* g_x0, void* workspace, size_t workspace_bytes, void* stream);
 /* Largest node count the one-launch persistent forward takes on the current device for rows of this shape
  * (0: never -- reach unknown, window beyond 96 KB of shared memory, no cooperative launch). */
 int64_t gad_wide_persist_nodes(int CE, int max_deg, int64_t reach);

@@ -491,14 +491,71 @@ def test_rk4_backward_matches_autograd_through_the_oracle(mesh_dims, B, burgers,
     assert util.rel_err(d_gpu.uu_tensor.grad, d_cpu.uu_tensor.grad) <= 2e-5
 
 
+@pytest.mark.parametrize("mesh_dims,B,burgers,over,extra", [
+    ((50, 50), 2, False, {"num_layers": 3}, {}),                  # 2500-node tiles: nine rows per node do not fit a CTA
+    ((64, 64), 1, False, {"num_layers": 2}, {}),                  # beyond one CTA: cluster forward, streaming backward
+    ((64, 64), 1, False, {"num_layers": 2, "share_conv": False}, {"gad_no_cluster": True}),
+    ((12, 12), 3, False, {"num_layers": 4}, {"gad_force_stream": True}),
+    ((3000,), 2, True, {"num_layers": 3}, {}),
+])
+def test_rk4_backward_on_the_streaming_kernels(mesh_dims, B, burgers, over, extra):
+    """RK4 backward beyond the mesh-resident kernel (csrc/stream_ell.cu: wide_backward_rk4_t -- three stage recomputes
+    and four vjp passes of the Euler backward kernels per step): parameter gradients against autograd through the
+    oracle's RK4 on the fp64 bar, input gradients against autograd."""
+    over = dict(over, ode_method="rk4")
+    model, out, ref_out, data = _compare_with_oracle(mesh_dims, B, over=over, burgers=burgers, backward=True, seed=3,
+                                                     **extra)
+    assert model.last_graph.wide_in is not None                   # the streaming rows were built for the backward
+    opt = synth.burgers_opt(mesh_dims, **over) if burgers else synth.default_opt(mesh_dims, **over)
+    ds = synth.SyntheticDataset(len(mesh_dims), mesh_dims)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    m2 = cuda_model(ds, opt, ref.state_dict(), **extra)
+    # input gradients against the oracle in fp64; the bar widens to 4 x the fp32 oracle's own deviation from fp64 where
+    # that is larger (3000-node chains: signed sums, gad_testutil.fp64_grads_and_noise_floor has the argument)
+    ref64 = oracle_model(ds, opt)
+    ref64.load_state_dict(ref.state_dict())
+    ref64 = ref64.double()
+    d_cpu, d_gpu, d64 = data.clone(), data.clone().to("cuda"), data.clone()
+    for k in d64.keys():
+        v = getattr(d64, k)
+        if torch.is_tensor(v) and v.dtype == torch.float32:
+            setattr(d64, k, v.double())
+    for d in (d_cpu, d_gpu, d64):
+        d.x_comp = d.x_comp.clone().requires_grad_(True)
+        d.uu_tensor = d.uu_tensor.clone().requires_grad_(True)
+    w = torch.randn(ref_out.shape, generator=torch.Generator().manual_seed(5))
+    (ref(d_cpu) * w).sum().backward()
+    (ref64(d64) * w.double()).sum().backward()
+    (m2(d_gpu) * w.cuda()).sum().backward()
+    for name in ("x_comp", "uu_tensor"):
+        g64 = getattr(d64, name).grad
+        floor = util.rel_err(getattr(d_cpu, name).grad, g64)
+        assert util.rel_err(getattr(d_gpu, name).grad, g64) <= max(2e-5, 4.0 * floor), (name, floor)
+
+
+def test_rk4_streaming_backward_equals_the_mesh_resident_one():
+    """Same batch, same weights: the streaming RK4 backward (gad_force_stream) against the one-launch mesh-resident
+    kernel -- two independent implementations of the same adjoint."""
+    md, B = (14, 14), 4
+    over = {"ode_method": "rk4", "num_layers": 3}
+    opt = synth.default_opt(md, **over)
+    ds = synth.SyntheticDataset(2, md)
+    torch.manual_seed(42)
+    ref = oracle_model(ds, opt)
+    data = synth.make_batch(md, B, seed=2)
+    grads = []
+    for extra in ({}, {"gad_force_stream": True}):
+        m = cuda_model(ds, opt, ref.state_dict(), **extra)
+        m.train()
+        F.l1_loss(m(data), data.x_phys.cuda()).backward()
+        grads.append(grads_of(m))
+    scale = max(float(g.abs().max()) for g in grads[0].values())
+    for k in grads[0]:
+        assert float((grads[0][k] - grads[1][k]).abs().max()) <= 2e-5 * scale, k
+
+
 def test_rk4_backward_refuses_what_it_cannot_do():
-    opt = synth.default_opt((50, 50), ode_method="rk4")          # 2500-node tiles: nine rows per node do not fit
-    ds = synth.SyntheticDataset(2, (50, 50))
-    m = cuda_model(ds, opt)
-    data = synth.make_batch((50, 50), 2)
-    out = m(data)
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()
     opt = synth.default_opt((10, 10), ode_method="rk4", learn_step=True)
     m = cuda_model(synth.SyntheticDataset(2, (10, 10)), opt)
     out = m(synth.make_batch((10, 10), 2))
