@@ -517,6 +517,7 @@ class InferenceSession:
             self.cuda_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.cuda_graph, stream=self.stream):
                 self.out = self._call()
+            torch.cuda.current_stream(dev).wait_stream(self.stream)
 
     def _call(self):
         m = self.model
@@ -524,22 +525,19 @@ class InferenceSession:
                                      self.method, states=None, force_stream=self.force_stream)
 
     def refresh_weights(self):
-        with torch.cuda.stream(self.stream):
-            self.Mu.copy_(self.model._folded_weights(self.dev))
-            self.tau.copy_(GF._f32(self.model._tau(self.dev).detach().reshape(-1)))
+        """Re-read the model's parameters (on the caller's current stream, like the replays)."""
+        self.Mu.copy_(self.model._folded_weights(self.dev))
+        self.tau.copy_(GF._f32(self.model._tau(self.dev).detach().reshape(-1)))
 
     def __call__(self, x_comp=None, f=None, uu=None) -> torch.Tensor:
-        """Replay with (optionally) new node inputs; returns the static output tensor [N, dim].  The
-        replay is ordered after the caller's current stream and the caller's stream after it."""
-        cur = torch.cuda.current_stream(self.dev)
-        self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            if x_comp is not None:
-                self.x_comp.copy_(x_comp if x_comp.dim() == 2 else x_comp.unsqueeze(-1), non_blocking=True)
-            if f is not None and self.f is not None:
-                self.f.copy_(f, non_blocking=True)
-            if uu is not None and self.uu is not None:
-                self.uu.copy_(uu, non_blocking=True)
-            self.cuda_graph.replay()
-        cur.wait_stream(self.stream)
+        """Replay with (optionally) new node inputs; returns the static output tensor [N, dim].  The input copies
+        and the replay are issued on the CALLER's current stream (a captured graph replays on whatever stream is
+        current), so the call is ordered like any other op of that stream and costs no cross-stream events."""
+        if x_comp is not None:
+            self.x_comp.copy_(x_comp if x_comp.dim() == 2 else x_comp.unsqueeze(-1), non_blocking=True)
+        if f is not None and self.f is not None:
+            self.f.copy_(f, non_blocking=True)
+        if uu is not None and self.uu is not None:
+            self.uu.copy_(uu, non_blocking=True)
+        self.cuda_graph.replay()
         return self.out
