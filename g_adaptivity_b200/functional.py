@@ -34,8 +34,35 @@ def use_ell(graph: MeshGraph, CE: int) -> bool:
     return graph.ell_in is not None and graph.ell_ce == CE and graph.tile_ptr is not None
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(t: torch.Tensor) -> int:
+    """cudaStream_t of the tensor's device's current stream (the raw getter skips building a Stream object: this is on
+    the host path of every module call)."""
+    if _raw_stream is not None:
+        return _raw_stream(t.device.index if t.device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on_device(dev):
+    """`torch.cuda.device(dev)` only when `dev` is not the current device already (the context manager costs several
+    microseconds of host time on every call otherwise)."""
+    idx = dev.index if isinstance(dev, torch.device) else dev
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(idx)
 
 
 def _need_cuda(*ts):
@@ -60,7 +87,7 @@ def prepare_weights(Wq: torch.Tensor, bq: torch.Tensor, Wk: torch.Tensor, CE: in
     Wq, bq, Wk = _f32(Wq), _f32(bq), _f32(Wk)
     Lw, C = Wq.shape[0], Wq.shape[1]
     Mu = torch.empty((Lw, CE * CE + CE), dtype=torch.float32, device=Wq.device)
-    with torch.cuda.device(Wq.device):
+    with _on_device(Wq.device):
         _lib.check(lib.gad_prepare_weights(_lib.ptr(Wq), _lib.ptr(bq), _lib.ptr(Wk), Lw, C, CE, float(inv_temp),
                                            _lib.ptr(Mu), _stream(Wq)), "gad_prepare_weights")
     return Mu
@@ -72,7 +99,7 @@ def weight_grads(Wq, bq, Wk, gMu, CE: int, inv_temp: float):
     Lw, C = Wq.shape[0], Wq.shape[1]
     gWq, gWk = torch.empty_like(Wq), torch.empty_like(Wk)
     gbq, gbk = torch.empty_like(bq), torch.empty_like(bq)
-    with torch.cuda.device(Wq.device):
+    with _on_device(Wq.device):
         _lib.check(lib.gad_weight_grads(_lib.ptr(Wq), _lib.ptr(bq), _lib.ptr(Wk), _lib.ptr(gMu), Lw, C, CE,
                                         float(inv_temp), _lib.ptr(gWq), _lib.ptr(gbq), _lib.ptr(gWk), _lib.ptr(gbk),
                                         _stream(Wq)), "gad_weight_grads")
@@ -90,7 +117,7 @@ def pack_features(x_comp, f, uu, f_scale, uu_scale, CE: int, out: Optional[torch
     f, uu = _f32(f), _f32(uu)
     if out is None:
         out = torch.empty((N, CE), dtype=torch.float32, device=x_comp.device)
-    with torch.cuda.device(x_comp.device):
+    with _on_device(x_comp.device):
         _lib.check(lib.gad_pack_features(_lib.ptr(x_comp), _lib.ptr(f), _lib.ptr(uu), _lib.ptr(f_scale),
                                          _lib.ptr(uu_scale), N, dim, CE, _lib.ptr(out), _stream(x_comp)),
                    "gad_pack_features")
@@ -110,7 +137,7 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
     x_phys = torch.empty((N, dim), dtype=torch.float32, device=x0.device)
     use_tiles = graph.tile_ptr is not None and not force_stream
     if use_tiles and use_ell(graph, CE):
-        with torch.cuda.device(x0.device):
+        with _on_device(x0.device):
             _lib.check(lib.gad_deform_fwd_ell(
                 _lib.ptr(graph.ell_in), N, _lib.ptr(graph.ell_tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
                 _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, method, _lib.ptr(x_phys),
@@ -122,12 +149,12 @@ def deform_forward(graph: MeshGraph, x0: torch.Tensor, dim: int, Mu: torch.Tenso
         ws_bytes = lib.gad_deform_workspace_bytes(N, CE, method)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
         if graph.ensure_wide(CE):      # streaming ELL kernels (csrc/stream_ell.cu)
-            with torch.cuda.device(x0.device):
+            with _on_device(x0.device):
                 _lib.check(lib.gad_deform_fwd_wide(
                     _lib.ptr(graph.wide_in), N, graph.wide_deg, graph.wide_reach, _lib.ptr(x0), dim, CE, _lib.ptr(Mu), Lw,
                     _lib.ptr(tau), L, method, _lib.ptr(x_phys), _lib.ptr(states), _lib.ptr(ws), ws_bytes, _stream(x0)), "gad_deform_fwd_wide")
             return x_phys
-    with torch.cuda.device(x0.device):
+    with _on_device(x0.device):
         _lib.check(lib.gad_deform_fwd(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col_walk), N, graph.E,
             _lib.ptr(graph.tile_ptr) if use_tiles else None, graph.T if use_tiles else 0,
@@ -176,7 +203,7 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
         f, uu = _f32(f), _f32(uu)
         L, Lw = int(tau.numel()), int(Mu.shape[0])
         x_phys = torch.empty((N, dim), dtype=torch.float32, device=x_comp.device)
-        with torch.cuda.device(x_comp.device):
+        with _on_device(x_comp.device):
             _lib.check(lib.gad_deform_fwd_cluster(
                 _lib.ptr(graph.clf_in), _lib.ptr(graph.clf_mesh_ptr), len(graph.mesh_sizes), max(graph.mesh_sizes),
                 graph.clf_deg, graph.clf_C, N, _lib.ptr(x_comp), _lib.ptr(f), _lib.ptr(uu), _lib.ptr(f_scale),
@@ -197,7 +224,7 @@ def deform_forward_raw(graph: MeshGraph, x_comp, f, uu, f_scale, uu_scale, dim: 
     L, Lw = int(tau.numel()), int(Mu.shape[0])
     assert graph.N == N
     x_phys = torch.empty((N, dim), dtype=torch.float32, device=x_comp.device)
-    with torch.cuda.device(x_comp.device):
+    with _on_device(x_comp.device):
         _lib.check(lib.gad_deform_fwd_ell_raw(
             _lib.ptr(graph.ell_in), N, _lib.ptr(graph.ell_tile_ptr), graph.T, graph.max_tile_nodes, graph.ell_deg,
             _lib.ptr(x_comp), _lib.ptr(f), _lib.ptr(uu), _lib.ptr(f_scale), _lib.ptr(uu_scale), dim, CE, _lib.ptr(Mu),
@@ -242,7 +269,7 @@ def deform_backward_rk4(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.T
                 f"has max degree {max(graph.max_in_deg, graph.max_out_deg)}, CE = {CE}")
         ws_bytes = lib.gad_deform_bwd_wide_rk4_workspace_bytes(N, CE)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.gad_deform_bwd_wide_rk4(
                 _lib.ptr(graph.wide_in), _lib.ptr(graph.wide_out), N, graph.wide_deg, _lib.ptr(states), _lib.ptr(g_xphys),
                 dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_x0), _lib.ptr(ws), ws_bytes,
@@ -250,7 +277,7 @@ def deform_backward_rk4(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.T
         return gMu, g_x0, None
     ws_bytes = lib.gad_ell_workspace_bytes(CE, graph.T, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(lib.gad_deform_bwd_ell_rk4(
             _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.ell_tile_ptr), graph.T,
             graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), _lib.ptr(du),
@@ -278,7 +305,7 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
     if use_tiles and use_ell(graph, CE):
         ws_bytes = lib.gad_ell_workspace_bytes(CE, T, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.gad_deform_bwd_ell(
                 _lib.ptr(graph.ell_in), _lib.ptr(graph.ell_out), N, _lib.ptr(graph.ell_tile_ptr), T,
                 graph.max_tile_nodes, graph.ell_deg, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu),
@@ -295,7 +322,7 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
         M = len(graph.mesh_sizes)
         ws_bytes = lib.gad_cluster_workspace_bytes(CE, M, graph.cl_C, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.gad_deform_bwd_cluster(
                 _lib.ptr(graph.cl_in), _lib.ptr(graph.cl_out), _lib.ptr(graph.mesh_ptr), M, max(graph.mesh_sizes),
                 graph.cl_deg, graph.cl_C, N, _lib.ptr(states), _lib.ptr(g_xphys), dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau),
@@ -305,13 +332,13 @@ def deform_backward(graph: MeshGraph, states: torch.Tensor, g_xphys: torch.Tenso
     ws_bytes = lib.gad_deform_bwd_workspace_bytes(N, CE, T, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if not use_tiles and graph.ensure_wide(CE):
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.gad_deform_bwd_wide(
                 _lib.ptr(graph.wide_in), _lib.ptr(graph.wide_out), N, graph.wide_deg, _lib.ptr(states), _lib.ptr(g_xphys),
                 dim, CE, _lib.ptr(Mu), Lw, _lib.ptr(tau), L, _lib.ptr(gMu), _lib.ptr(g_tau), _lib.ptr(g_x0), _lib.ptr(ws),
                 ws_bytes, _stream(states)), "gad_deform_bwd_wide")
         return gMu, g_tau, g_x0
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(lib.gad_deform_bwd(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col_walk), _lib.ptr(graph.t_rowptr), _lib.ptr(graph.t_dst_walk), N, graph.E,
             _lib.ptr(graph.tile_ptr) if use_tiles else None, T, graph.max_tile_nodes, graph.max_tile_edges,
@@ -328,7 +355,7 @@ def conv_forward(graph: MeshGraph, x: torch.Tensor, Mu: torch.Tensor, want_res: 
     N, CE = x.shape
     res = torch.empty_like(x) if want_res else None
     alpha = torch.empty(graph.E, dtype=torch.float32, device=x.device) if want_alpha else None
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _lib.check(lib.gad_conv_fwd(_lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.eid), N, graph.E,
                                     _lib.ptr(x), CE, _lib.ptr(Mu), _lib.ptr(res), _lib.ptr(alpha), _stream(x)),
                    "gad_conv_fwd")
@@ -342,7 +369,7 @@ def conv_backward(graph: MeshGraph, x: torch.Tensor, g_res: torch.Tensor, Mu: to
     g_x = torch.empty_like(x)
     ws_bytes = lib.gad_deform_bwd_workspace_bytes(N, CE, 0, 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _lib.check(lib.gad_conv_bwd(_lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.t_rowptr),
                                     _lib.ptr(graph.t_dst), N, graph.E, _lib.ptr(x), _lib.ptr(_f32(g_res)), CE,
                                     _lib.ptr(Mu), _lib.ptr(gMu), _lib.ptr(g_x), _lib.ptr(ws), ws_bytes, _stream(x)),
@@ -362,7 +389,7 @@ def mesh_loss(out: torch.Tensor, target: torch.Tensor, kind: str = "l1", want_gr
     loss = torch.empty(1, dtype=torch.float32, device=out.device)
     g = torch.empty_like(out) if want_grad else None
     ws = torch.empty(lib.gad_mesh_loss_workspace_bytes(count), dtype=torch.uint8, device=out.device)
-    with torch.cuda.device(out.device):
+    with _on_device(out.device):
         _lib.check(lib.gad_mesh_loss(_lib.ptr(out), _lib.ptr(target), count, 0 if kind == "l1" else 1,
                                      1.0 / count, _lib.ptr(loss), _lib.ptr(g), _lib.ptr(ws), _stream(out)),
                    "gad_mesh_loss")
