@@ -600,8 +600,26 @@ class GraphCache:
     def sample_positions(E: int) -> torch.Tensor:
         """SHARED_SAMPLES evenly spaced positions in [0, E), first and last included.  Integer arithmetic: a float32
         `linspace(0, E - 1, n)` rounds its end point up past the array beyond 2^24 edges (cfg 5 has 1.2e8)."""
-        n = min(int(E), GraphCache.SHARED_SAMPLES)
-        return (torch.arange(n, dtype=torch.int64) * (int(E) - 1)) // max(n - 1, 1)
+        E = int(E)
+        pos = GraphCache._positions.get(E)
+        if pos is None:
+            n = min(E, GraphCache.SHARED_SAMPLES)
+            pos = (torch.arange(n, dtype=torch.int64) * (E - 1)) // max(n - 1, 1)
+            if len(GraphCache._positions) < 64:          # a handful of batch shapes per run
+                GraphCache._positions[E] = pos
+        return pos
+
+    _positions: dict = {}
+
+    @staticmethod
+    def _sampled(t: torch.Tensor, idx: torch.Tensor, columns: bool):
+        """The sampled entries of a topology tensor as a hashable value: bytes for host tensors (this runs on every
+        module call with a fresh Batch), a tuple after one small copy for device tensors."""
+        if t.device.type == "cpu":
+            a, ix = t.detach().numpy(), idx.numpy()
+            return (a[:, ix] if columns else a[ix]).tobytes()
+        sel = t[:, idx.to(t.device)] if columns else t[idx.to(t.device)]
+        return tuple(sel.reshape(-1).tolist())
 
     @staticmethod
     def shared_key_of(data, flags) -> tuple:
@@ -616,13 +634,18 @@ class GraphCache:
         E = int(ei.shape[1])
         parts = [tuple(ei.shape), int(data.x_comp.shape[0])]
         sizes = getattr(data, "mesh_sizes", None)
-        parts.append(None if sizes is None else (len(sizes), int(min(sizes)), int(max(sizes))))
+        if sizes is None:
+            parts.append(None)
+        else:       # equal-size batches (the shared-mesh case) compare as one C-level pass over the list
+            n0 = sizes[0] if len(sizes) else 0
+            same = sizes.count(n0) == len(sizes) if isinstance(sizes, list) else False
+            parts.append((len(sizes), int(n0), int(n0)) if same else (len(sizes), int(min(sizes)), int(max(sizes))))
         if E > 0:
-            idx = GraphCache.sample_positions(E).to(ei.device)
-            parts.append(tuple(ei[:, idx].reshape(-1).tolist()))
+            idx = GraphCache.sample_positions(E)
+            parts.append(GraphCache._sampled(ei, idx, True))
             for name in ("to_boundary_edge_mask", "to_corner_nodes_mask", "diff_boundary_edges_mask"):
                 t = getattr(data, name, None)
-                parts.append(None if t is None else tuple(t[idx.to(t.device)].tolist()))
+                parts.append(None if t is None else GraphCache._sampled(t, idx, False))
         return ("shared",) + tuple(parts) + tuple(flags)
 
     def alias(self, key, graph, keepalive):
