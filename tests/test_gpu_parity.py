@@ -415,7 +415,9 @@ def test_config4_200x200_rk4_64_steps_forward(monkeypatch):
     ((64, 64), 1, False, {}), ((64, 64), 1, False, {"ode_method": "rk4", "num_layers": 5}),
     ((200, 200), 1, False, {"ode_method": "rk4", "num_layers": 8}),
     ((90, 90), 1, False, {"share_conv": False, "learn_step": True, "num_layers": 6}),
-    ((100, 100), 3, False, {"num_layers": 7}), ((20000,), 2, True, {"ode_method": "rk4", "num_layers": 6})])
+    ((100, 100), 3, False, {"num_layers": 7}), ((20000,), 2, True, {"ode_method": "rk4", "num_layers": 6}),
+    ((70, 70), 2, False, {"self_loops": True, "num_layers": 3, "ode_method": "rk4"}),        # degree 7: the widest rows
+    ((70, 70), 1, False, {"fix_boundary": False, "num_layers": 5})])
 def test_persistent_streaming_forward_equals_the_launch_chain(mesh_dims, B, burgers, over, monkeypatch):
     """Graphs whose nodes fit the GPU's co-resident threads run all steps of the streaming forward in ONE cooperative
     launch (k_wide_persist: state in registers, window in shared memory, halo rows exchanged through L2 as tagged
