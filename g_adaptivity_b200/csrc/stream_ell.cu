@@ -223,50 +223,53 @@ __global__ void __launch_bounds__(TB) k_wide_stage(const int4* __restrict__ rows
 //   * a CTA owns S = 256 consecutive nodes and keeps the stage input y of its WINDOW (the strips of the CTAs within
 //     r = ceil(reach / S) of it, reach = max |j - i| over the edges) in shared memory: all gathers are LDS;
 //   * after each F-evaluation a thread publishes its new row to one of two global (L2-resident) buffers as
-//     (value, epoch) pairs, written and read with 16-byte relaxed accesses whose 8-byte halves are single-copy
-//     atomic (the layout of NCCL's LL protocol: data is valid when its own tag matches -- no fence, no barrier),
+//     (value, epoch) pairs, each pair one 64-bit element of a 256-bit relaxed vector access (the idea of NCCL's LL
+//     protocol: a datum is valid when the tag that travels in the same atomic word matches -- no fence, no barrier),
 //     and the CTA polls the 2 r S halo rows of its window into shared memory.
 // A CTA waits only for the CTAs within r of it, so the machine synchronises locally.  Two buffers suffice because the
 // windows are symmetric: B overwrites its epoch-e rows with epoch e+2 only after it has read the epoch-(e+1) rows of
 // every CTA within r, each of which published them after it finished reading B's epoch-e rows.
 // The arithmetic is k_wide_stage's, expression for expression: results are bit-identical to the chain.  The launch
 // is cooperative (all CTAs co-resident or the launch fails); a poll that sees no progress for 2 s traps.
+// A row travels as CE (value, epoch) pairs, each ONE 64-bit element of a vector access: whatever the hardware does
+// with the vector as a whole, a 64-bit element is a single-copy-atomic access, so a value can never be seen with
+// another epoch's tag.
+__device__ __forceinline__ unsigned long long tagged(float v, unsigned tag) {
+    return ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+}
+
 template <int CE>
 __device__ __forceinline__ void publish_row(float* buf, int64_t i, const Row<CE>& r, unsigned tag) {
     if constexpr (CE == 4) {      // one 32-byte store (256-bit accesses exist from sm_100 on)
-        asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(buf + i * 8),
-                     "r"(__float_as_uint(r.v[0])), "r"(tag), "r"(__float_as_uint(r.v[1])), "r"(tag),
-                     "r"(__float_as_uint(r.v[2])), "r"(tag), "r"(__float_as_uint(r.v[3])), "r"(tag)
+        asm volatile("st.relaxed.gpu.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(buf + i * 8), "l"(tagged(r.v[0], tag)),
+                     "l"(tagged(r.v[1], tag)), "l"(tagged(r.v[2], tag)), "l"(tagged(r.v[3], tag))
                      : "memory");
     } else {
-        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(buf + i * 4), "r"(__float_as_uint(r.v[0])),
-                     "r"(tag), "r"(__float_as_uint(r.v[1])), "r"(tag)
+        asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(buf + i * 4), "l"(tagged(r.v[0], tag)),
+                     "l"(tagged(r.v[1], tag))
                      : "memory");
     }
 }
 
-// One poll of a row: true when every (value, tag) pair carries `tag`.
+// One poll of a row: true when every (value, epoch) pair carries `tag`.
 template <int CE>
 __device__ __forceinline__ bool try_row(const float* p, unsigned tag, Row<CE>& r) {
+    unsigned long long v[CE];
     if constexpr (CE == 4) {
-        unsigned v[8];
-        asm volatile("ld.relaxed.gpu.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        asm volatile("ld.relaxed.gpu.global.v4.b64 {%0, %1, %2, %3}, [%4];"
+                     : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
                      : "l"(p)
                      : "memory");
-#pragma unroll
-        for (int c = 0; c < 4; ++c) r.v[c] = __uint_as_float(v[2 * c]);
-        return v[1] == tag && v[3] == tag && v[5] == tag && v[7] == tag;
     } else {
-        uint4 v;
-        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "l"(p)
-                     : "memory");
-        r.v[0] = __uint_as_float(v.x);
-        r.v[1] = __uint_as_float(v.z);
-        return v.y == tag && v.w == tag;
+        asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "l"(p) : "memory");
     }
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < CE; ++c) {
+        r.v[c] = __uint_as_float((unsigned)v[c]);
+        ok = ok && (unsigned)(v[c] >> 32) == tag;
+    }
+    return ok;
 }
 
 template <int CE>
