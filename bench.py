@@ -446,6 +446,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--write-combined", action="store_true", help="e2e: packed host batches in write-combined pinned memory")
+    ap.add_argument("--relay", default="off", choices=["auto", "off"],
+                    help="e2e at N > 1 (experimental, off by default): balance unequal host->device paths by relaying "
+                         "part of the slow ranks' batches through the fast ranks' GPUs (NVLink); the in-run probe that "
+                         "picks the pairs misjudged the one box it was tried on (DESIGN section 15)")
     ap.add_argument("--skip-configs", action="store_true", help="do not time the other BASELINE configs (cfg 1, 3, 4, 5)")
     args = ap.parse_args()
 
@@ -667,10 +671,18 @@ def main():
         # x_comp is resident per slot and the per-step copy is the per-sample part, target | f | uu.
         packed = [trainer.pack_host(r, host_batches[r], with_x_comp=False, write_combined=args.write_combined)
                   for r in range(R)]
-        trainer.run_from_host(packed, min(2 * R, ke))
+        relay, path_rates = None, None
+        if world > 1 and args.relay == "auto":
+            from g_adaptivity_b200 import dp as gdp
+            relay, path_rates = gdp.balance_host_paths(dev)
+            if os.environ.get("GAD_RELAY_FRACTION") and relay is not None:
+                relay = (relay[0], float(os.environ["GAD_RELAY_FRACTION"]))
+            if os.environ.get("GAD_RELAY_FORCE"):      # testing aid: every rank relays through its right neighbour
+                relay = ((dev.index + 1) % world, float(os.environ["GAD_RELAY_FORCE"]))
+        trainer.run_from_host(packed, min(2 * R, ke), relay=relay)
         barrier()
         t0 = time.perf_counter()
-        losses = trainer.run_from_host(packed, ke)
+        losses = trainer.run_from_host(packed, ke, relay=relay)
         barrier()
         dt = time.perf_counter() - t0
         assert losses.numel() == ke and bool(torch.isfinite(losses).all())
@@ -686,6 +698,17 @@ def main():
                       "shared mesh is resident) on a copy stream, overlapped with the previous step's kernel; graph "
                       "replay of the one-launch step; async D2H of the loss",
                "cpu_affinity": affinity, "host_memory": "pinned, write-combined" if args.write_combined else "pinned"}
+        if world > 1:
+            mine = torch.tensor([-1.0, 0.0] if relay is None else [float(relay[0]), float(relay[1])],
+                                dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            e2e["host_paths"] = {
+                "gb_s_per_rank_under_load": None if path_rates is None else [round(x, 1) for x in path_rates],
+                "relay": {str(q): {"via_device": int(a[0]), "fraction": round(float(a[1]), 3)}
+                          for q, a in enumerate(allr) if a[0] >= 0},
+                "what": "ranks whose host->device path is slower under load send that fraction of every batch through "
+                        "the partner GPU (host -> staging there, then NVLink): gad_pipeline_run_relay"}
 
     clk = clocks.stop() if rank == 0 else None
 

@@ -52,6 +52,12 @@ class PipelineSlot(C.Structure):
     _fields_ = [("dev_inputs", _fp), ("bytes", _sz), ("graph_exec", _fp), ("loss_dev", _fp)]
 
 
+class PipelineRelay(C.Structure):
+    """`gad_pipeline_relay` of include/gadapt.h."""
+    _fields_ = [("device", C.c_int), ("direct_bytes", C.c_size_t), ("stream", C.c_void_p), ("staging", C.c_void_p),
+                ("staging_stride", C.c_size_t)]
+
+
 # name -> (restype, argtypes); mirrors include/gadapt.h declaration by declaration
 SIGNATURES = {
     "gad_version": (_i, []),
@@ -117,6 +123,9 @@ SIGNATURES = {
     "gad_host_alloc": (_i, [_sz, _i, C.POINTER(_p)]),
     "gad_host_free": (_i, [_p]),
     "gad_pipeline_run": (_i, [C.POINTER(PipelineSlot), _i, C.POINTER(_p), _i, _i64, _p, _p, _p]),
+    "gad_pipeline_run_relay": (_i, [C.POINTER(PipelineSlot), _i, C.POINTER(_p), _i, _i64, _p, _p, _p,
+                                    C.POINTER(PipelineRelay)]),
+    "gad_enable_peer_access": (_i, [_i, _i]),
 }
 
 

@@ -77,6 +77,70 @@ def broadcast_flat(flat: torch.Tensor, src: int = 0, group=None) -> torch.Tensor
     return flat
 
 
+def probe_host_path(dev: torch.device, mbytes: int = 4, seconds: float = 0.15) -> float:
+    """GB/s of pinned host -> device copies of `mbytes` MB on `dev`, in a loop for `seconds` (call it on every rank at
+    the same time to see the paths under load)."""
+    import time
+    host = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
+    buf = torch.empty(mbytes << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    n = 0
+    with torch.cuda.stream(st):
+        for _ in range(2):
+            buf.copy_(host, non_blocking=True)
+        st.synchronize()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(4):
+                buf.copy_(host, non_blocking=True)
+            st.synchronize()
+            n += 4
+        dt = time.perf_counter() - t0
+    return n * host.numel() / dt / 1e9
+
+
+def plan_host_relays(rates, devices, min_fraction: float = 0.12):
+    """Pair the ranks with the slowest host -> device paths with those with the fastest and choose, per pair, the
+    fraction y of the slow rank's bytes that should travel through the fast rank's GPU so that both finish together:
+    (1 - y) / R_slow = (1 + y) / R_fast, i.e. y = (R_fast - R_slow) / (R_fast + R_slow).  `rates[q]` GB/s of rank q
+    under load, `devices[q]` its device ordinal.  Returns {rank: (partner device, y)} for the ranks that relay."""
+    order = sorted(range(len(rates)), key=lambda q: (rates[q], q))
+    plan = {}
+    for i in range(len(order) // 2):
+        slow, fast = order[i], order[-1 - i]
+        rs, rf = float(rates[slow]), float(rates[fast])
+        if rs <= 0 or rf <= rs:
+            continue
+        y = (rf - rs) / (rf + rs)
+        if y >= min_fraction and devices[slow] != devices[fast]:
+            plan[slow] = (int(devices[fast]), y)
+    return plan
+
+
+def balance_host_paths(dev: torch.device, group=None, min_fraction: float = 0.12, rounds: int = 3):
+    """One node, one process per GPU, every GPU visible to every process: measure all host -> device paths at once
+    (median of `rounds` synchronised probes: a single short probe is noisy) and return (this rank's relay (partner
+    device, fraction) or None, all rates).  Paths closer than a factor 1.27 (fraction < 0.12) are left alone.
+    Collective."""
+    import statistics
+    import torch.distributed as dist
+    world = world_size(group)
+    if world < 2 or torch.cuda.device_count() < world:
+        return None, None
+    samples = []
+    for _ in range(rounds):
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        samples.append(probe_host_path(dev, seconds=0.2))
+    t = torch.tensor([statistics.median(samples), float(dev.index)], dtype=torch.float64, device=dev)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    rates = [float(o[0]) for o in out]
+    devices = [int(o[1]) for o in out]
+    plan = plan_host_relays(rates, devices, min_fraction)
+    return plan.get(dist.get_rank(group)), rates
+
+
 class PeerExchange:
     """Receive buffers of all ranks of `group`, mapped into this process (CUDA IPC), for the
     in-kernel gradient all-reduce.  `ok` is the same on every rank: the set-up ends with a MIN

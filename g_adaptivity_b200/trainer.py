@@ -611,7 +611,30 @@ class DeformerTrainer:
             self.slots[sid]._free.record(self.stream)
         return loss
 
-    def run_from_host(self, host_batches, steps: int, native: Optional[bool] = None) -> torch.Tensor:
+    def _relay_descriptor(self, relay, batch_bytes: int, R: int):
+        """`gad_pipeline_relay` for run_from_host(relay=(device, fraction)): a staging buffer and a stream on the other
+        device (allocated once, this creates a context there), peer access both ways."""
+        dev2, frac = int(relay[0]), float(relay[1])
+        mine = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+        if dev2 == mine or not (0.0 < frac < 1.0):
+            raise ValueError("relay = (another visible device, fraction in (0, 1))")
+        rest = int(batch_bytes * frac) // 256 * 256
+        if rest <= 0:
+            return None
+        direct = batch_bytes - rest
+        key = (dev2, rest, R)
+        if getattr(self, "_relay_key", None) != key:
+            _lib.check(self.lib.gad_enable_peer_access(mine, dev2), "gad_enable_peer_access")
+            self._relay_staging = torch.empty(R * rest, dtype=torch.uint8, device=f"cuda:{dev2}")
+            self._relay_stream = torch.cuda.Stream(device=dev2)
+            torch.cuda.synchronize(dev2)
+            self._relay_key = key
+        d = _lib.PipelineRelay()
+        d.device, d.direct_bytes = dev2, direct
+        d.stream, d.staging, d.staging_stride = self._relay_stream.cuda_stream, self._relay_staging.data_ptr(), rest
+        return d
+
+    def run_from_host(self, host_batches, steps: int, native: Optional[bool] = None, relay=None) -> torch.Tensor:
         """Pipelined end-to-end training loop over host-resident (pinned) batches: the inputs of step
         k + 1 travel host -> device on a copy stream while step k computes, and every step's loss is
         read back device -> host asynchronously into pinned memory.  Slot k % R receives batch
@@ -619,7 +642,11 @@ class DeformerTrainer:
 
         With CUDA graphs and batches packed by `pack_host`, the loop itself runs in the C library
         (`gad_pipeline_run`, csrc/host_pipeline.cu: seven CUDA API calls per step, no Python); otherwise, or
-        with `native=False`, the same schedule is issued from Python."""
+        with `native=False`, the same schedule is issued from Python.
+
+        `relay=(device, fraction)` (native loop only): that fraction of every batch reaches this GPU through another
+        visible GPU -- host -> staging there over ITS path to host memory, then NVLink -- for boxes whose GPUs do not
+        have equal host paths (gad_pipeline_run_relay; `dp.balance_host_paths` picks partner and fraction)."""
         R = len(self.slots)
         if R < 2:
             raise ValueError("run_from_host needs at least two resident slots (double buffering)")
@@ -653,11 +680,19 @@ class DeformerTrainer:
                 s.h2d_bytes = host_batches[0].numel() * 4
             hosts = (C.c_void_p * nb)(*[b.data_ptr() for b in host_batches])
             self._touch_params()
+            rdesc = self._relay_descriptor(relay, host_batches[0].numel() * 4, R) if relay is not None else None
             with torch.cuda.device(self.dev):
-                _lib.check(self.lib.gad_pipeline_run(slots, R, hosts, nb, int(steps), losses.data_ptr(), ms.cuda_stream,
-                                                     cs.cuda_stream), "gad_pipeline_run")
+                if rdesc is None:
+                    _lib.check(self.lib.gad_pipeline_run(slots, R, hosts, nb, int(steps), losses.data_ptr(),
+                                                         ms.cuda_stream, cs.cuda_stream), "gad_pipeline_run")
+                else:
+                    _lib.check(self.lib.gad_pipeline_run_relay(slots, R, hosts, nb, int(steps), losses.data_ptr(),
+                                                               ms.cuda_stream, cs.cuda_stream, C.byref(rdesc)),
+                               "gad_pipeline_run_relay")
             self.check_peer()
             return losses
+        if relay is not None:
+            raise ValueError("relay needs the native pipeline (use_cuda_graph=True, buffers from pack_host)")
         cs.wait_stream(ms)
         nb = len(host_batches)
 

@@ -478,6 +478,22 @@ typedef struct gad_pipeline_slot {
 } gad_pipeline_slot;
 int gad_pipeline_run(const gad_pipeline_slot* slots, int n_slots, const void* const* host_batches, int n_host,
                      int64_t steps, float* losses_host, void* compute_stream, void* copy_stream);
+/* The same loop with a second path into the GPU (boxes whose GPUs do not have equal paths to host memory): the first
+ * `direct_bytes` of every batch travel as above, the rest goes host -> `staging + slot * staging_stride` on ANOTHER
+ * device (`device`, over that GPU's PCIe path, on `stream`, a stream of that device) and from there into the slot
+ * over NVLink (cudaMemcpyPeerAsync; call gad_enable_peer_access first).  All of it inside the calling process.
+ * relay == NULL: gad_pipeline_run. */
+typedef struct gad_pipeline_relay {
+    int device;              /* ordinal of the device the tail of each batch is relayed through */
+    size_t direct_bytes;     /* bytes of each batch copied directly (multiple of 256) */
+    void* stream;            /* cudaStream_t of `device` */
+    void* staging;           /* buffer on `device`: n_slots * staging_stride bytes */
+    size_t staging_stride;
+} gad_pipeline_relay;
+int gad_pipeline_run_relay(const gad_pipeline_slot* slots, int n_slots, const void* const* host_batches, int n_host,
+                           int64_t steps, float* losses_host, void* compute_stream, void* copy_stream,
+                           const gad_pipeline_relay* relay);
+int gad_enable_peer_access(int dev_a, int dev_b);
 /* Pinned host staging memory for packed batches (cudaHostAlloc); write_combined != 0 asks for write-combined pages:
  * written once by the host, read by the device without snooping the CPU caches. */
 int gad_host_alloc(size_t bytes, int write_combined, void** host_ptr);

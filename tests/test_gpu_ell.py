@@ -324,6 +324,33 @@ def test_host_fed_loop_packed_buffers_equal_per_tensor_copies():
         tr.pack_host(0, other, with_x_comp=False)
 
 
+@pytest.mark.parametrize("fraction", [0.3, 0.77])
+def test_host_fed_loop_with_a_relay_through_another_gpu(fraction):
+    """run_from_host(relay=(device, fraction)): part of every batch reaches the GPU through ANOTHER GPU's path to host
+    memory (host -> staging there -> NVLink, gad_pipeline_run_relay).  Same losses, same parameters as the direct
+    loop, bit for bit.  Needs two visible GPUs (the driver's single-GPU lease skips it)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    opt, ds, _, ref = _case((20, 20), 16, seed=11)
+    batches = [synth.make_batch((20, 20), 16, seed=20 + r) for r in range(3)]
+    outs = []
+    for relay in (None, (1, fraction)):
+        model = cuda_model(ds, opt, ref.state_dict())
+        tr = DeformerTrainer(model, lr=1e-2)
+        sids = [tr.add_batch(b) for b in batches]
+        src = [tr.pack_host(sid, b, with_x_comp=False) for sid, b in zip(sids, batches)]
+        losses = tr.run_from_host(src, 11, relay=relay).clone()
+        again = tr.run_from_host(src, 5, relay=relay).clone()        # staging and events are reused
+        outs.append((losses, again, tr.flat.clone().cpu()))
+        tr.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        tr2 = DeformerTrainer(cuda_model(ds, opt, ref.state_dict()), lr=1e-2)
+        s2 = [tr2.add_batch(b) for b in batches]
+        tr2.run_from_host([tr2.pack_host(i, b) for i, b in zip(s2, batches)], 3, relay=(0, 0.5))   # itself
+
+
 # ------------------------------------------------------------------------------------------
 # shared-topology batches (row f2): one ELL table per mesh shape, graph build O(mesh)
 # ------------------------------------------------------------------------------------------

@@ -188,3 +188,19 @@ def test_device_batch_builder_equals_host_collation():
     assert torch.equal(c.edge_index, a.edge_index) and torch.equal(c.batch, a.batch)
     assert torch.equal(c.f_tensor[:4 * 36], a.f_tensor[:4 * 36]) and torch.equal(c.f_tensor[4 * 36:8 * 36], a.f_tensor[:4 * 36])
     assert c.mesh_sizes == a.mesh_sizes and len(c.corner_nodes) == 9
+
+
+def test_host_path_relay_plan():
+    """dp.plan_host_relays: slowest paths paired with fastest, fraction (R_fast - R_slow) / (R_fast + R_slow); the
+    rates are the ones measured on an 8-GPU box (profiles/r02_h2d_probe_8gpu.json)."""
+    from g_adaptivity_b200 import dp
+    rates = [20.69, 20.93, 20.8, 20.93, 36.11, 36.45, 36.23, 36.21]
+    plan = dp.plan_host_relays(rates, list(range(8)))
+    assert sorted(plan) == [0, 1, 2, 3]                               # only the slow class relays
+    assert sorted(v[0] for v in plan.values()) == [4, 5, 6, 7]        # each through a different fast GPU
+    for q, (via, y) in plan.items():
+        assert abs(y - (rates[via] - rates[q]) / (rates[via] + rates[q])) < 1e-12 and 0.25 < y < 0.29
+        # both links finish together under the model
+        assert abs((1 - y) / rates[q] - (1 + y) / rates[via]) < 1e-12
+    assert dp.plan_host_relays([50.0, 51.0], [0, 1]) == {}            # equal paths: nothing to balance
+    assert dp.plan_host_relays([20.0, 40.0, 30.0], [0, 1, 2]) == {0: (1, (40.0 - 20.0) / 60.0)}
