@@ -446,10 +446,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--write-combined", action="store_true", help="e2e: packed host batches in write-combined pinned memory")
-    ap.add_argument("--relay", default="off", choices=["auto", "off"],
-                    help="e2e at N > 1 (experimental, off by default): balance unequal host->device paths by relaying "
-                         "part of the slow ranks' batches through the fast ranks' GPUs (NVLink); the in-run probe that "
-                         "picks the pairs misjudged the one box it was tried on (DESIGN section 15)")
+    ap.add_argument("--relay", default="auto", choices=["auto", "off"],
+                    help="e2e at N > 1: balance unequal host->device paths by relaying part of some ranks' batches "
+                         "through other ranks' GPUs (NVLink); proposals are timed on the real loop and the direct loop "
+                         "stays unless one of them is at least 3%% faster (DESIGN section 15)")
     ap.add_argument("--skip-configs", action="store_true", help="do not time the other BASELINE configs (cfg 1, 3, 4, 5)")
     args = ap.parse_args()
 
@@ -671,14 +671,74 @@ def main():
         # x_comp is resident per slot and the per-step copy is the per-sample part, target | f | uu.
         packed = [trainer.pack_host(r, host_batches[r], with_x_comp=False, write_combined=args.write_combined)
                   for r in range(R)]
-        relay, path_rates = None, None
+        relay, path_rates, relay_trials = None, None, None
         if world > 1 and args.relay == "auto":
+            # Unequal host->device paths: a probe proposes pairs and a fraction; the proposal, its
+            # mirror image and the direct loop are then TIMED on the real loop (short trials, max over ranks) and the
+            # fastest is kept -- the probe alone has been wrong about the direction.
             from g_adaptivity_b200 import dp as gdp
-            relay, path_rates = gdp.balance_host_paths(dev)
-            if os.environ.get("GAD_RELAY_FRACTION") and relay is not None:
-                relay = (relay[0], float(os.environ["GAD_RELAY_FRACTION"]))
-            if os.environ.get("GAD_RELAY_FORCE"):      # testing aid: every rank relays through its right neighbour
-                relay = ((dev.index + 1) % world, float(os.environ["GAD_RELAY_FORCE"]))
+            try:
+                _, path_rates = gdp.balance_host_paths(dev)
+                plans = {"direct": {}}
+                if path_rates is not None:
+                    devs = list(range(world))
+                    fwd = gdp.plan_host_relays(path_rates, devs)
+                    if fwd:
+                        plans["probe"] = fwd
+                        plans["mirror"] = {via: (q, y) for q, (via, y) in fwd.items()}
+                    # a prior from the boxes measured so far (profiles/r02_h2d_probe_8gpu.json: the lower half of the
+                    # GPUs has the slower paths, 21 against 37 GB/s, i.e. y = 0.27), and its mirror image; like every
+                    # proposal it only survives if the timed trial says so
+                    if world >= 2 and world % 2 == 0:
+                        h = world // 2
+                        plans["halves"] = {q: (q + h, 0.27) for q in range(h)}
+                        plans["halves_mirror"] = {q + h: (q, 0.27) for q in range(h)}
+                if os.environ.get("GAD_RELAY_PLAN"):       # testing aid: "rank:device:fraction,..." as the only proposal
+                    forced = {}
+                    for item in os.environ["GAD_RELAY_PLAN"].split(","):
+                        q, via, y = item.split(":")
+                        forced[int(q)] = (int(via), float(y))
+                    plans = {"direct": {}, "forced": forced}
+                relay_trials = {}
+                trainer.run_from_host(packed, 2 * R)
+                nbytes = packed[0].numel() * 4
+                for name, plan in plans.items():
+                    cand = plan.get(rank)
+                    # set-up (context + staging on the partner GPU, peer access) may fail on ONE rank only: agree on
+                    # it before any rank enters a loop whose steps exchange gradients with the others
+                    ok = 1.0
+                    try:
+                        if cand is not None:
+                            trainer._relay_descriptor(cand, nbytes, R)
+                    except Exception:      # noqa: BLE001
+                        ok = 0.0
+                    okt = torch.tensor([ok], dtype=torch.float64, device=dev)
+                    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                    if float(okt.item()) < 1.0:
+                        relay_trials[name] = "set-up failed on a rank"
+                        continue
+                    trainer.run_from_host(packed, 2 * R, relay=cand)          # warm the candidate's path
+                    barrier()
+                    t1 = time.perf_counter()
+                    trainer.run_from_host(packed, 120, relay=cand)
+                    barrier()
+                    tt1 = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tt1, op=dist.ReduceOp.MAX)
+                    relay_trials[name] = float(tt1.item()) / 120
+                timed = {k: v for k, v in relay_trials.items() if isinstance(v, float)}
+                best = min(timed, key=timed.get)
+                if best != "direct" and timed[best] < 0.97 * timed["direct"]:
+                    relay = plans[best].get(rank)
+                    relay_trials["chosen"] = best
+                else:
+                    relay_trials["chosen"] = "direct"
+            except Exception as e:      # noqa: BLE001 -- the direct loop always works
+                relay, relay_trials = None, {"error": repr(e)[:200]}
+            # one more agreement: a rank that fell out of the selection makes everybody run the direct loop
+            okt = torch.tensor([0.0 if (relay_trials or {}).get("error") else 1.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if float(okt.item()) < 1.0:
+                relay = None
         trainer.run_from_host(packed, min(2 * R, ke), relay=relay)
         barrier()
         t0 = time.perf_counter()
@@ -707,6 +767,8 @@ def main():
                 "gb_s_per_rank_under_load": None if path_rates is None else [round(x, 1) for x in path_rates],
                 "relay": {str(q): {"via_device": int(a[0]), "fraction": round(float(a[1]), 3)}
                           for q, a in enumerate(allr) if a[0] >= 0},
+                "trials_ms_per_step": None if relay_trials is None else
+                {k: (round(1e3 * v, 4) if isinstance(v, float) else v) for k, v in relay_trials.items()},
                 "what": "ranks whose host->device path is slower under load send that fraction of every batch through "
                         "the partner GPU (host -> staging there, then NVLink): gad_pipeline_run_relay"}
 
