@@ -672,7 +672,9 @@ def main():
         packed = [trainer.pack_host(r, host_batches[r], with_x_comp=False, write_combined=args.write_combined)
                   for r in range(R)]
         relay, path_rates, relay_trials = None, None, None
-        if world > 1 and args.relay == "auto" and trainer.use_graph:      # the relay lives in the native (graph) loop
+        # the relay lives in the native loop (graph replay of the one-launch step; the route is agreed across ranks)
+        native_loop = trainer.use_graph and all(trainer._one_launch(s) for s in trainer.slots)
+        if world > 1 and args.relay == "auto" and native_loop:
             # Unequal host->device paths: a probe proposes pairs and a fraction; the proposal, its
             # mirror image and the direct loop are then TIMED on the real loop (short trials, max over ranks) and the
             # fastest is kept -- the probe alone has been wrong about the direction.
